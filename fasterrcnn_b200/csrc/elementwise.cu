@@ -1,0 +1,364 @@
+// HBM-bound elementwise / pooling / optimizer kernels.  All are grid-stride with grids sized in
+// multiples of the SM count, 128-bit accesses where the channel count allows, read-only loads
+// through the non-coherent path.
+#include "common.cuh"
+
+namespace frcnn {
+
+// ---- layout: (N, C, HW) <-> (N, HW, C) through a 32x33 shared tile -------------------------
+__global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols, int tiles_r, int tiles_c, int batch)
+{
+  // src: (batch, rows, cols) -> dst: (batch, cols, rows)
+  __shared__ float tile[32][33];
+  const int total = batch * tiles_r * tiles_c;
+  for (int tidx = blockIdx.x; tidx < total; tidx += gridDim.x) {
+    int b = tidx / (tiles_r * tiles_c);
+    int rem = tidx - b * tiles_r * tiles_c;
+    int tr = rem / tiles_c, tc = rem - tr * tiles_c;
+    const float *s = src + (size_t)b * rows * cols;
+    float *d = dst + (size_t)b * rows * cols;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int r = tr * 32 + i, c = tc * 32 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < rows && c < cols) ? __ldg(s + (size_t)r * cols + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int c = tc * 32 + i, r = tr * 32 + threadIdx.x;
+      if (r < rows && c < cols) d[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_transpose(const float *src, float *dst, int batch, int rows, int cols, cudaStream_t st)
+{
+  int tiles_r = ceil_div(rows, 32), tiles_c = ceil_div(cols, 32);
+  long long total = (long long)batch * tiles_r * tiles_c;
+  int grid = (int)(total < (long long)kNumSMs * 16 ? total : (long long)kNumSMs * 16);
+  if (grid < 1) grid = 1;
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, rows, cols, tiles_r, tiles_c, batch);
+  FRCNN_CHECK_LAUNCH("transpose_kernel");
+  return FRCNN_OK;
+}
+
+// ---- relu backward / add / sgd ---------------------------------------------------------------
+__global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, size_t count)
+{
+  size_t n4 = count / 4;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g = __ldg(reinterpret_cast<const float4 *>(dy) + i);
+    float4 v = __ldg(reinterpret_cast<const float4 *>(y) + i);
+    g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f;
+    g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    reinterpret_cast<float4 *>(dz)[i] = g;
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride)
+    dz[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+__global__ void add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, size_t count)
+{
+  size_t n4 = count / 4;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 u = __ldg(reinterpret_cast<const float4 *>(a) + i);
+    float4 v = __ldg(reinterpret_cast<const float4 *>(b) + i);
+    reinterpret_cast<float4 *>(out)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) out[i] = a[i] + b[i];
+}
+
+// torch.optim.SGD (momentum, dampening 0, no nesterov, L2 weight decay folded into the gradient):
+// separate mul/add roundings as torch's foreach kernels produce them (no FMA contraction).
+__device__ __forceinline__ float sgd_one(float p, float g, float &buf, float lr, float mom, float wd, float gs, int first)
+{
+  float gg = __fmul_rn(g, gs);
+  if (wd != 0.f) gg = __fadd_rn(gg, __fmul_rn(wd, p));
+  float b = first ? gg : __fadd_rn(__fmul_rn(buf, mom), gg);
+  buf = b;
+  return __fadd_rn(p, __fmul_rn(-lr, b));
+}
+
+__global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, size_t count,
+                           float lr, float mom, float wd, float gs, int first)
+{
+  size_t n4 = count / 4;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4 *>(p)[i];
+    float4 gv = __ldg(reinterpret_cast<const float4 *>(g) + i);
+    float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4 *>(buf)[i];
+    pv.x = sgd_one(pv.x, gv.x, bv.x, lr, mom, wd, gs, first);
+    pv.y = sgd_one(pv.y, gv.y, bv.y, lr, mom, wd, gs, first);
+    pv.z = sgd_one(pv.z, gv.z, bv.z, lr, mom, wd, gs, first);
+    pv.w = sgd_one(pv.w, gv.w, bv.w, lr, mom, wd, gs, first);
+    reinterpret_cast<float4 *>(p)[i] = pv;
+    reinterpret_cast<float4 *>(buf)[i] = bv;
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
+    float b = first ? 0.f : buf[i];
+    p[i] = sgd_one(p[i], g[i], b, lr, mom, wd, gs, first);
+    buf[i] = b;
+  }
+}
+
+// ---- bias gradient: column sums of (rows, C), two deterministic stages ----------------------
+constexpr int kBiasRowsPerBlock = 256;
+
+__global__ void bias_grad_stage1(const float *__restrict__ dz, float *__restrict__ partial, size_t rows, int C)
+{
+  // block b sums rows [b*256, b*256+256) for every channel; threads stride over channels
+  size_t r0 = (size_t)blockIdx.x * kBiasRowsPerBlock;
+  size_t r1 = r0 + kBiasRowsPerBlock < rows ? r0 + kBiasRowsPerBlock : rows;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (size_t r = r0; r < r1; r++) s += __ldg(dz + r * C + c);
+    partial[(size_t)blockIdx.x * C + c] = s;
+  }
+}
+
+__global__ void bias_grad_stage2(const float *__restrict__ partial, float *__restrict__ dbias, int blocks, int C)
+{
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < blocks; b++) s += partial[(size_t)b * C + c];
+    dbias[c] = s;
+  }
+}
+
+// ---- pooling ---------------------------------------------------------------------------------
+template <int VEC>
+__global__ void maxpool2x2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
+{
+  const int Ho = H / 2, Wo = W / 2, Cv = C / VEC;
+  size_t total = (size_t)N * Ho * Wo * Cv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int cv = (int)(e % Cv);
+    size_t r = e / Cv;
+    int ow = (int)(r % Wo); r /= Wo;
+    int oh = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    const float *base = x + (((size_t)n * H + 2 * oh) * W + 2 * ow) * C + cv * VEC;
+    if (VEC == 4) {
+      float4 a = __ldg(reinterpret_cast<const float4 *>(base));
+      float4 b = __ldg(reinterpret_cast<const float4 *>(base + C));
+      float4 c = __ldg(reinterpret_cast<const float4 *>(base + (size_t)W * C));
+      float4 d = __ldg(reinterpret_cast<const float4 *>(base + (size_t)W * C + C));
+      float4 o;
+      o.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)); o.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+      o.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)); o.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+      *reinterpret_cast<float4 *>(y + (((size_t)n * Ho + oh) * Wo + ow) * C + cv * 4) = o;
+    } else {
+      float o = fmaxf(fmaxf(__ldg(base), __ldg(base + C)), fmaxf(__ldg(base + (size_t)W * C), __ldg(base + (size_t)W * C + C)));
+      y[(((size_t)n * Ho + oh) * Wo + ow) * C + cv] = o;
+    }
+  }
+}
+
+// first maximum of the 2x2 window in (kh,kw) scan order with strict '>' (torch max_pool2d),
+// gradient passes only where the pre-pool activation is > 0 (ReLU backward of the producer).
+__device__ __forceinline__ float pool_relu_grad(float v00, float v01, float v10, float v11, int pos, float g)
+{
+  int best = 0; float bv = v00;
+  if (v01 > bv) { bv = v01; best = 1; }
+  if (v10 > bv) { bv = v10; best = 2; }
+  if (v11 > bv) { bv = v11; best = 3; }
+  return (best == pos && bv > 0.f) ? g : 0.f;
+}
+
+__global__ void maxpool2x2_relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dz, int N, int H, int W, int C)
+{
+  // one thread per (n, window-or-edge cell, channel); windows cover rows/cols < 2*Ho / 2*Wo, the
+  // odd trailing row/column (floor mode) receives zero gradient.
+  const int Ho = H / 2, Wo = W / 2;
+  const int Hc = (H + 1) / 2, Wc = (W + 1) / 2;
+  size_t total = (size_t)N * Hc * Wc * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    size_t r = e / C;
+    int cw = (int)(r % Wc); r /= Wc;
+    int ch = (int)(r % Hc);
+    int n = (int)(r / Hc);
+    int h0 = 2 * ch, w0 = 2 * cw;
+    size_t base = (((size_t)n * H + h0) * W + w0) * C + c;
+    if (ch < Ho && cw < Wo) {
+      float v00 = __ldg(x + base), v01 = __ldg(x + base + C);
+      float v10 = __ldg(x + base + (size_t)W * C), v11 = __ldg(x + base + (size_t)W * C + C);
+      float g = __ldg(dy + (((size_t)n * Ho + ch) * Wo + cw) * C + c);
+      dz[base] = pool_relu_grad(v00, v01, v10, v11, 0, g);
+      dz[base + C] = pool_relu_grad(v00, v01, v10, v11, 1, g);
+      dz[base + (size_t)W * C] = pool_relu_grad(v00, v01, v10, v11, 2, g);
+      dz[base + (size_t)W * C + C] = pool_relu_grad(v00, v01, v10, v11, 3, g);
+    } else {
+      // edge cells outside every window
+      dz[base] = 0.f;
+      if (w0 + 1 < W) dz[base + C] = 0.f;
+      if (h0 + 1 < H) {
+        dz[base + (size_t)W * C] = 0.f;
+        if (w0 + 1 < W) dz[base + (size_t)W * C + C] = 0.f;
+      }
+    }
+  }
+}
+
+__global__ void maxpool3x3s2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int Ho, int Wo)
+{
+  size_t total = (size_t)N * Ho * Wo * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    size_t r = e / C;
+    int ow = (int)(r % Wo); r /= Wo;
+    int oh = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    float best = -INFINITY;
+    for (int kh = 0; kh < 3; kh++) {
+      int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 3; kw++) {
+        int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        best = fmaxf(best, __ldg(x + (((size_t)n * H + ih) * W + iw) * C + c));
+      }
+    }
+    y[e] = best;
+  }
+}
+
+__global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int HW, int C)
+{
+  // torch: y.mean(-1).mean(-1) on (N,C,4,4) == mean over W then over H; HW is laid out (h, w)
+  // here we reproduce mean-of-row-means only for square maps handled by the caller; generic
+  // path: plain mean in (h,w) order.
+  size_t total = (size_t)N * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    int n = (int)(e / C);
+    float s = 0.f;
+    for (int p = 0; p < HW; p++) s += __ldg(x + ((size_t)n * HW + p) * C + c);
+    y[e] = s / (float)HW;
+  }
+}
+
+__global__ void spatial_mean_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, int N, int HW, int C)
+{
+  size_t total = (size_t)N * HW * C;
+  const float inv = 1.0f / (float)HW;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    int n = (int)(e / ((size_t)HW * C));
+    dx[e] = __ldg(dy + (size_t)n * C + c) * inv;
+  }
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+int frcnn_nchw_to_nhwc(const float *src, float *dst, int N, int C, int H, int W, void *stream)
+{
+  FRCNN_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad argument");
+  return launch_transpose(src, dst, N, C, H * W, as_stream(stream));
+}
+
+int frcnn_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H, int W, void *stream)
+{
+  FRCNN_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad argument");
+  return launch_transpose(src, dst, N, H * W, C, as_stream(stream));
+}
+
+int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream)
+{
+  FRCNN_REQUIRE(dy && y && dz, "relu_bwd: null pointer");
+  if (count == 0) return FRCNN_OK;
+  relu_bwd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(dy, y, dz, count);
+  FRCNN_CHECK_LAUNCH("relu_bwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_add(const float *a, const float *b, float *out, size_t count, void *stream)
+{
+  FRCNN_REQUIRE(a && b && out, "add: null pointer");
+  if (count == 0) return FRCNN_OK;
+  add_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(a, b, out, count);
+  FRCNN_CHECK_LAUNCH("add_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                   float grad_scale, int first_step, void *stream)
+{
+  FRCNN_REQUIRE(param && grad && momentum_buf, "sgd_step: null pointer");
+  if (count == 0) return FRCNN_OK;
+  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step);
+  FRCNN_CHECK_LAUNCH("sgd_kernel");
+  return FRCNN_OK;
+}
+
+size_t frcnn_bias_grad_workspace_bytes(size_t rows, int C)
+{
+  size_t blocks = ceil_div<size_t>(rows, kBiasRowsPerBlock);
+  return blocks * (size_t)C * sizeof(float);
+}
+
+int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dz && dbias && rows > 0 && C > 0, "bias_grad: bad argument");
+  if (workspace == nullptr || workspace_bytes < frcnn_bias_grad_workspace_bytes(rows, C)) return fail(FRCNN_E_WORKSPACE, "bias_grad: workspace too small");
+  int blocks = (int)ceil_div<size_t>(rows, kBiasRowsPerBlock);
+  float *partial = reinterpret_cast<float *>(workspace);
+  bias_grad_stage1<<<blocks, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream)>>>(dz, partial, rows, C);
+  FRCNN_CHECK_LAUNCH("bias_grad_stage1");
+  bias_grad_stage2<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partial, dbias, blocks, C);
+  FRCNN_CHECK_LAUNCH("bias_grad_stage2");
+  return FRCNN_OK;
+}
+
+int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)
+{
+  FRCNN_REQUIRE(x && y && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2x2_fwd: bad argument");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  if (C % 4 == 0) maxpool2x2_fwd_kernel<4><<<elementwise_grid(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
+  else maxpool2x2_fwd_kernel<1><<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
+  FRCNN_CHECK_LAUNCH("maxpool2x2_fwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_maxpool2x2_relu_bwd(const float *dy, const float *x, float *dz, int N, int H, int W, int C, void *stream)
+{
+  FRCNN_REQUIRE(dy && x && dz && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2x2_relu_bwd: bad argument");
+  size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * C;
+  maxpool2x2_relu_bwd_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, x, dz, N, H, W, C);
+  FRCNN_CHECK_LAUNCH("maxpool2x2_relu_bwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)
+{
+  FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "maxpool3x3s2_fwd: bad argument");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  size_t total = (size_t)N * Ho * Wo * C;
+  maxpool3x3s2_fwd_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, Ho, Wo);
+  FRCNN_CHECK_LAUNCH("maxpool3x3s2_fwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int HW, int C, void *stream)
+{
+  FRCNN_REQUIRE(x && y && N > 0 && HW > 0 && C > 0, "spatial_mean_fwd: bad argument");
+  spatial_mean_fwd_kernel<<<elementwise_grid((size_t)N * C, 256), 256, 0, as_stream(stream)>>>(x, y, N, HW, C);
+  FRCNN_CHECK_LAUNCH("spatial_mean_fwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_spatial_mean_bwd(const float *dy, float *dx, int N, int HW, int C, void *stream)
+{
+  FRCNN_REQUIRE(dy && dx && N > 0 && HW > 0 && C > 0, "spatial_mean_bwd: bad argument");
+  spatial_mean_bwd_kernel<<<elementwise_grid((size_t)N * HW * C, 256), 256, 0, as_stream(stream)>>>(dy, dx, N, HW, C);
+  FRCNN_CHECK_LAUNCH("spatial_mean_bwd_kernel");
+  return FRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// RPN proposal path: fused anchor generation + delta decode + clip + min-size flag (K5),
+// top-N ordering, order-preserving compaction, greedy NMS (K6).
+//
+// Parity discipline: every fp32 operation that the reference performs as a separate torch
+// kernel is an explicit __f*_rn intrinsic here so that ptxas cannot contract mul+add into FMA;
+// anchors are built in fp64 from the 9x2 size table and rounded to fp32 exactly where
+// models/anchors.py:118-135 rounds them.
+#include <math.h>
+#include "common.cuh"
+
+namespace frcnn {
+
+struct AnchorSizes {
+  double h[9];
+  double w[9];
+};
+
+// models/anchors.py:25-41: k = area*3 + aspect; w = sqrt(area/aspect); h = aspect*w  (fp64)
+static AnchorSizes make_anchor_sizes()
+{
+  AnchorSizes s;
+  const double areas[3] = {128.0 * 128.0, 256.0 * 256.0, 512.0 * 512.0};
+  const double aspects[3] = {0.5, 1.0, 2.0};
+  int k = 0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double w = sqrt(areas[i] / aspects[j]);
+      s.w[k] = w;
+      s.h[k] = aspects[j] * w;
+      k++;
+    }
+  return s;
+}
+
+// ---- K5 ---------------------------------------------------------------------------------------
+__global__ void rpn_decode_kernel(const float *__restrict__ deltas, const float *__restrict__ anchors_in, int fh, int fw, double feature_pixels, float img_h, float img_w,
+                                  float min_size, AnchorSizes sizes, float *__restrict__ boxes, uint8_t *__restrict__ size_ok,
+                                  float *__restrict__ anchors_out, float *__restrict__ valid_out)
+{
+  const int A = fh * fw * 9;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+    int k = a % 9;
+    int cell = a / 9;
+    int x = cell % fw, y = cell / fw;
+    // cell centre: fp64 value rounded to fp32 (anchors.py:104,118), then fp64 template added
+    double cy = (double)__double2float_rn((double)y * feature_pixels + 0.5 * feature_pixels);
+    double cx = (double)__double2float_rn((double)x * feature_pixels + 0.5 * feature_pixels);
+    double y1 = cy + (-0.5 * sizes.h[k]), x1 = cx + (-0.5 * sizes.w[k]);
+    double y2 = cy + (0.5 * sizes.h[k]), x2 = cx + (0.5 * sizes.w[k]);
+    float acy = __double2float_rn(0.5 * (y1 + y2));
+    float acx = __double2float_rn(0.5 * (x1 + x2));
+    float ah = __double2float_rn(y2 - y1);
+    float aw = __double2float_rn(x2 - x1);
+    if (anchors_in) {
+      float4 u = __ldg(reinterpret_cast<const float4 *>(anchors_in) + a);
+      acy = u.x; acx = u.y; ah = u.z; aw = u.w;
+    }
+    if (anchors_out) reinterpret_cast<float4 *>(anchors_out)[a] = make_float4(acy, acx, ah, aw);
+    if (valid_out) valid_out[a] = (y1 >= 0.0 && x1 >= 0.0 && y2 <= (double)img_h && x2 <= (double)img_w) ? 1.0f : 0.0f;
+
+    // models/math_utils.py:122-127 in fp32: c = a_hw*t_yx + a_yx ; s = a_hw*exp(t_hw) ; box = c -/+ 0.5 s
+    float4 d = __ldg(reinterpret_cast<const float4 *>(deltas) + a);
+    float c_y = __fadd_rn(__fmul_rn(ah, d.x), acy);
+    float c_x = __fadd_rn(__fmul_rn(aw, d.y), acx);
+    float s_h = __fmul_rn(ah, __double2float_rn(exp((double)d.z)));   // correctly rounded expf
+    float s_w = __fmul_rn(aw, __double2float_rn(exp((double)d.w)));
+    float b0 = __fsub_rn(c_y, __fmul_rn(0.5f, s_h));
+    float b1 = __fsub_rn(c_x, __fmul_rn(0.5f, s_w));
+    float b2 = __fadd_rn(c_y, __fmul_rn(0.5f, s_h));
+    float b3 = __fadd_rn(c_x, __fmul_rn(0.5f, s_w));
+    // models/rpn.py:135-137: clamp y1,x1 >= 0; y2 <= H; x2 <= W
+    b0 = b0 < 0.f ? 0.f : b0;
+    b1 = b1 < 0.f ? 0.f : b1;
+    b2 = b2 > img_h ? img_h : b2;
+    b3 = b3 > img_w ? img_w : b3;
+    reinterpret_cast<float4 *>(boxes)[a] = make_float4(b0, b1, b2, b3);
+    // models/rpn.py:140-142
+    size_ok[a] = (__fsub_rn(b2, b0) >= min_size && __fsub_rn(b3, b1) >= min_size) ? 1 : 0;
+  }
+}
+
+// ---- top-N ordering by rank counting ------------------------------------------------------------
+// rank(i) = #{j : s_j > s_i} + #{j : s_j == s_i and j > i}  (descending, ties -> higher index
+// first).  The j range is split across blockIdx.y; partial ranks are integer atomics (exact,
+// order independent).  N is ~2e4, so the N^2 = 4e8 compares run in a few microseconds on 148
+// SMs and give a stable, deterministic order without a multi-pass radix sort.
+constexpr int kRankTile = 1024;
+
+__global__ void rank_count_kernel(const float *__restrict__ scores, const uint8_t *__restrict__ keep_mask, int n, int j_per_slice, int32_t *__restrict__ rank)
+{
+  __shared__ __align__(16) float tile[kRankTile];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n && (keep_mask == nullptr || keep_mask[i] != 0);
+  const float si = live ? scores[i] : 0.f;
+  int j0 = blockIdx.y * j_per_slice;
+  int j1 = j0 + j_per_slice < n ? j0 + j_per_slice : n;
+  int cnt = 0;
+  for (int base = j0; base < j1; base += kRankTile) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < kRankTile; q += blockDim.x) {
+      int j = base + q;
+      // entries that do not take part are NaN: they compare false both ways
+      tile[q] = (j < j1 && (keep_mask == nullptr || keep_mask[j] != 0)) ? scores[j] : __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+    if (live) {
+      int lim = j1 - base < kRankTile ? j1 - base : kRankTile;
+      int q = 0;
+      for (; q + 4 <= lim; q += 4) {
+        float4 v = *reinterpret_cast<const float4 *>(&tile[q]);
+        int j = base + q;
+        cnt += (v.x > si) || (v.x == si && j + 0 > i);
+        cnt += (v.y > si) || (v.y == si && j + 1 > i);
+        cnt += (v.z > si) || (v.z == si && j + 2 > i);
+        cnt += (v.w > si) || (v.w == si && j + 3 > i);
+      }
+      for (; q < lim; q++) {
+        float v = tile[q];
+        cnt += (v > si) || (v == si && base + q > i);
+      }
+    }
+  }
+  if (live && cnt) atomicAdd(&rank[i], cnt);
+}
+
+__global__ void rank_scatter_kernel(const uint8_t *__restrict__ keep_mask, int n, int top_n, const int32_t *__restrict__ rank,
+                                    int32_t *__restrict__ order, int32_t *__restrict__ count_out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = i < n && (keep_mask == nullptr || keep_mask[i] != 0);
+  bool hit = false;
+  if (live) {
+    int r = rank[i];
+    if (r < top_n) { order[r] = i; hit = true; }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count_out, __popc(m));
+}
+
+// ---- order-preserving compaction of the ranked, size-filtered boxes (single CTA) ---------------
+__global__ void __launch_bounds__(1024)
+gather_filtered_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, const uint8_t *__restrict__ size_ok,
+                       const int32_t *__restrict__ order, const int32_t *__restrict__ count, int capacity,
+                       float *__restrict__ boxes_out, float *__restrict__ scores_out, int32_t *__restrict__ count_out)
+{
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  int n = *count;
+  if (n > capacity) n = capacity;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int r = base + threadIdx.x;
+    int idx = r < n ? order[r] : -1;
+    int flag = (idx >= 0 && size_ok[idx]) ? 1 : 0;
+    // inclusive warp scan
+    int v = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      warp_sums[lane] = w;                                   // inclusive sums over warps
+    }
+    __syncthreads();
+    int offset = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + v - flag;
+    if (flag) {
+      reinterpret_cast<float4 *>(boxes_out)[offset] = __ldg(reinterpret_cast<const float4 *>(boxes) + idx);
+      scores_out[offset] = scores[idx];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count_out = carry;
+}
+
+// ---- K6: NMS ------------------------------------------------------------------------------------
+// Stage 1: 64x64 suppression bit tiles, upper triangle only.  Arithmetic is the torchvision CPU
+// kernel's, in fp32 with explicit roundings: area = (b2-b0)*(b3-b1); w = max(0, min-max) ...;
+// ovr = inter / (area_i + area_j - inter); suppress iff ovr > thr (thr_f is the largest float
+// <= the double threshold, which makes the float compare identical to the op's double compare).
+__device__ __forceinline__ bool iou_exceeds(const float4 &a, float area_a, const float4 &b, float area_b, float thr_f)
+{
+  float t0 = fmaxf(a.x, b.x), t1 = fmaxf(a.y, b.y);
+  float t2 = fminf(a.z, b.z), t3 = fminf(a.w, b.w);
+  float w = fmaxf(0.f, __fsub_rn(t2, t0));
+  float h = fmaxf(0.f, __fsub_rn(t3, t1));
+  float inter = __fmul_rn(w, h);
+  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return ovr > thr_f;                                        // NaN (0/0) -> false, as in the reference op
+}
+
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ count, int capacity, float thr_f,
+                unsigned long long *__restrict__ mask, int col_blocks)
+{
+  int n = *count;
+  if (n > capacity) n = capacity;
+  const int row_b = blockIdx.y, col_b = blockIdx.x;
+  if (col_b < row_b) return;
+  if (row_b * 64 >= n || col_b * 64 >= n) return;
+  __shared__ float4 cb[64];
+  __shared__ float ca[64];
+  const int t = threadIdx.x;
+  {
+    int j = col_b * 64 + t;
+    float4 b = j < n ? __ldg(reinterpret_cast<const float4 *>(boxes) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cb[t] = b;
+    ca[t] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  }
+  __syncthreads();
+  int i = row_b * 64 + t;
+  if (i < n) {
+    float4 a = __ldg(reinterpret_cast<const float4 *>(boxes) + i);
+    float area = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    int cols = n - col_b * 64 < 64 ? n - col_b * 64 : 64;
+    int start = (row_b == col_b) ? t + 1 : 0;
+    unsigned long long bits = 0;
+    for (int q = start; q < cols; q++)
+      if (iou_exceeds(a, area, cb[q], ca[q], thr_f)) bits |= 1ull << q;
+    mask[(size_t)i * col_blocks + col_b] = bits;
+  }
+}
+
+// Stage 2: the greedy scan, one CTA.  For each 64-box block: one thread resolves the block's
+// internal chain from its diagonal tile (registers only), then every thread ORs the rows of the
+// boxes kept in this block into the running "removed" bitmap (one 64-bit word per thread,
+// coalesced across the warp).  Stops as soon as max_keep boxes are kept.
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int capacity, int col_blocks,
+                int max_keep, int32_t *__restrict__ keep_out, int32_t *__restrict__ kept_count_out)
+{
+  extern __shared__ unsigned long long removed[];            // col_blocks words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long kept_bits_s;
+  __shared__ int kept_total;
+  int n = *count;
+  if (n > capacity) n = capacity;
+  const int nblocks = (n + 63) / 64;
+  for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) removed[w] = 0ull;
+  if (threadIdx.x == 0) kept_total = 0;
+  __syncthreads();
+  for (int b = 0; b < nblocks; b++) {
+    if (kept_total >= max_keep) break;                       // uniform: read after a barrier
+    if (threadIdx.x < 64) {
+      int i = b * 64 + threadIdx.x;
+      diag[threadIdx.x] = i < n ? mask[(size_t)i * col_blocks + b] : 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long dead = removed[b];
+      unsigned long long kept = 0ull;
+      int total = kept_total;
+      int lim = n - b * 64 < 64 ? n - b * 64 : 64;
+      for (int q = 0; q < lim && total < max_keep; q++) {
+        if (!((dead >> q) & 1ull)) {
+          kept |= 1ull << q;
+          dead |= diag[q];
+          keep_out[total++] = b * 64 + q;
+        }
+      }
+      kept_bits_s = kept;
+      kept_total = total;
+    }
+    __syncthreads();
+    unsigned long long kept = kept_bits_s;
+    if (kept) {
+      for (int w = b + 1 + threadIdx.x; w < nblocks; w += blockDim.x) {
+        unsigned long long acc = removed[w];
+        unsigned long long k = kept;
+        while (k) {
+          int q = __ffsll((long long)k) - 1;
+          k &= k - 1;
+          acc |= mask[(size_t)(b * 64 + q) * col_blocks + w];
+        }
+        removed[w] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *kept_count_out = kept_total;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats, const int32_t *__restrict__ index, const int32_t *__restrict__ count,
+                                   int capacity, float *__restrict__ dst)
+{
+  int n = *count;
+  if (n > capacity) n = capacity;
+  size_t total = (size_t)n * row_floats;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / row_floats), c = (int)(e - (size_t)r * row_floats);
+    dst[e] = src[(size_t)index[r] * row_floats + c];
+  }
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+int frcnn_rpn_decode(const float *deltas, const float *anchors_in, int fh, int fw, int feature_pixels, int img_h, int img_w, float min_size,
+                     float *boxes, uint8_t *size_ok, float *anchors_out, float *valid_out, void *stream)
+{
+  FRCNN_REQUIRE(deltas && boxes && size_ok && fh > 0 && fw > 0 && feature_pixels > 0 && img_h > 0 && img_w > 0, "rpn_decode: bad argument");
+  const int A = fh * fw * 9;
+  static const AnchorSizes sizes = make_anchor_sizes();
+  rpn_decode_kernel<<<elementwise_grid(A, 128, 4), 128, 0, as_stream(stream)>>>(deltas, anchors_in, fh, fw, (double)feature_pixels, (float)img_h, (float)img_w, min_size, sizes, boxes, size_ok, anchors_out, valid_out);
+  FRCNN_CHECK_LAUNCH("rpn_decode_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_topk_order(const float *scores, const uint8_t *keep_mask, int n, int top_n, int32_t *order, int32_t *count_out, void *stream)
+{
+  FRCNN_REQUIRE(scores && order && count_out && n > 0 && top_n > 0, "topk_order: bad argument");
+  cudaStream_t st = as_stream(stream);
+  // the per-element rank array is count_out[1..n] (the caller allocates 1 + n int32)
+  int32_t *rank = count_out + 1;
+  cudaError_t e = cudaMemsetAsync(count_out, 0, (size_t)(1 + n) * sizeof(int32_t), st);
+  if (e != cudaSuccess) return cuda_fail(e, "topk_order: memset");
+  const int threads = 256;
+  int gx = ceil_div(n, threads);
+  int slices = ceil_div(4 * kNumSMs, gx);
+  if (slices < 1) slices = 1;
+  int j_per_slice = ceil_div(ceil_div(n, slices), kRankTile) * kRankTile;
+  slices = ceil_div(n, j_per_slice);
+  rank_count_kernel<<<dim3(gx, slices), threads, 0, st>>>(scores, keep_mask, n, j_per_slice, rank);
+  FRCNN_CHECK_LAUNCH("rank_count_kernel");
+  rank_scatter_kernel<<<gx, threads, 0, st>>>(keep_mask, n, top_n, rank, order, count_out);
+  FRCNN_CHECK_LAUNCH("rank_scatter_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_gather_filtered(const float *boxes, const float *scores, const uint8_t *size_ok, const int32_t *order,
+                          const int32_t *count, int capacity, float *boxes_out, float *scores_out, int32_t *count_out, void *stream)
+{
+  FRCNN_REQUIRE(boxes && scores && size_ok && order && count && boxes_out && scores_out && count_out && capacity > 0, "gather_filtered: bad argument");
+  gather_filtered_kernel<<<1, 1024, 0, as_stream(stream)>>>(boxes, scores, size_ok, order, count, capacity, boxes_out, scores_out, count_out);
+  FRCNN_CHECK_LAUNCH("gather_filtered_kernel");
+  return FRCNN_OK;
+}
+
+size_t frcnn_nms_workspace_bytes(int capacity)
+{
+  if (capacity <= 0) return 0;
+  size_t col_blocks = (size_t)ceil_div(capacity, 64);
+  return (size_t)capacity * col_blocks * sizeof(unsigned long long);
+}
+
+int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
+                         int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(boxes && count && keep_out && kept_count_out && capacity > 0 && max_keep > 0, "nms_sorted_f32: bad argument");
+  if (workspace == nullptr || workspace_bytes < frcnn_nms_workspace_bytes(capacity)) return fail(FRCNN_E_WORKSPACE, "nms_sorted_f32: workspace too small");
+  const int col_blocks = ceil_div(capacity, 64);
+  FRCNN_REQUIRE((size_t)col_blocks * 8 <= 160 * 1024, "nms_sorted_f32: capacity too large for the scan bitmap");
+  float thr_f = (float)iou_threshold;
+  if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
+  cudaStream_t st = as_stream(stream);
+  unsigned long long *mask = reinterpret_cast<unsigned long long *>(workspace);
+  nms_mask_kernel<<<dim3(col_blocks, col_blocks), 64, 0, st>>>(boxes, count, capacity, thr_f, mask, col_blocks);
+  FRCNN_CHECK_LAUNCH("nms_mask_kernel");
+  size_t smem = (size_t)col_blocks * sizeof(unsigned long long);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
+  }
+  nms_scan_kernel<<<1, 256, smem, st>>>(mask, count, capacity, col_blocks, max_keep, keep_out, kept_count_out);
+  FRCNN_CHECK_LAUNCH("nms_scan_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index, const int32_t *count, int capacity, float *dst, void *stream)
+{
+  FRCNN_REQUIRE(src && index && count && dst && row_floats > 0 && capacity > 0, "gather_rows_f32: bad argument");
+  gather_rows_kernel<<<elementwise_grid((size_t)capacity * row_floats, 256), 256, 0, as_stream(stream)>>>(src, row_floats, index, count, capacity, dst);
+  FRCNN_CHECK_LAUNCH("gather_rows_kernel");
+  return FRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,552 @@
+"""
+Operator layer: torch.autograd.Function wrappers around the C ABI (include/frcnn_b200.h).
+
+These are the drop-in replacements for the third-party ops the reference calls:
+  conv2d_act     <- F.relu(nn.Conv2d(..., padding="same")) / t.sigmoid(conv) / conv, optionally
+                    followed by nn.MaxPool2d(2,2)            (models/vgg16.py:76-96, rpn.py:88-90)
+  linear_act     <- F.relu(nn.Linear) / nn.Linear            (models/vgg16.py:129-133, detector.py:76-78)
+  roi_pool       <- torchvision.ops.RoIPool((7,7), 1/16)     (models/detector.py:27,72)
+  softmax_rows   <- F.softmax(dim=1)                         (models/detector.py:77)
+  nms / rpn_proposals / label_proposals / losses ...
+Tensors keep the reference's logical shapes; 4-D activations and filters are held in
+torch.channels_last memory format (physically NHWC / OHWI), which is what the kernels read.
+"""
+import numpy as np
+import torch as t
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, check, lib, ptr, stream, workspace
+
+_engine = {"value": _lib.ENGINE_AUTO}
+
+
+def set_engine(name):
+  """'auto' | 'simt' (exact fp32 CUDA-core) | 'tc' (tcgen05 3xTF32)."""
+  _engine["value"] = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32}[name]
+
+
+def get_engine():
+  return _engine["value"]
+
+
+def _require_cuda(*tensors):
+  for x in tensors:
+    if x is not None and not x.is_cuda:
+      raise _lib.FrcnnError("fasterrcnn_b200 ops need CUDA tensors (no CPU path)")
+
+
+def as_nhwc(x):
+  """Logical (N,C,H,W) fp32 tensor -> same logical tensor, physically NHWC (own kernel)."""
+  _require_cuda(x)
+  assert x.dim() == 4 and x.dtype == t.float32
+  n, c, h, w = x.shape
+  nhwc_strides = (h * w * c, 1, w * c, c)
+  if x.stride() == nhwc_strides:
+    return x
+  src = x.contiguous()
+  if c == 1 or (h == 1 and w == 1):
+    return src.as_strided((n, c, h, w), nhwc_strides)           # the two layouts coincide
+  dst = t.empty((n, c, h, w), dtype = t.float32, device = x.device, memory_format = t.channels_last)
+  check(lib().frcnn_nchw_to_nhwc(ptr(src), ptr(dst), n, c, h, w, stream()), "frcnn_nchw_to_nhwc")
+  _lib.count()
+  return dst
+
+
+def as_nchw_contiguous(x):
+  """Physically NHWC logical-NCHW tensor -> contiguous NCHW (own kernel)."""
+  _require_cuda(x)
+  if x.is_contiguous():
+    return x
+  n, c, h, w = x.shape
+  src = as_nhwc(x)
+  dst = t.empty((n, c, h, w), dtype = t.float32, device = x.device)
+  check(lib().frcnn_nhwc_to_nchw(ptr(src), ptr(dst), n, c, h, w, stream()), "frcnn_nhwc_to_nchw")
+  _lib.count()
+  return dst
+
+
+def _empty_nhwc(n, c, h, w, device):
+  return t.empty((n, c, h, w), dtype = t.float32, device = device, memory_format = t.channels_last)
+
+
+def _is_phys_nhwc(x):
+  n, c, h, w = x.shape
+  return x.stride() == (h * w * c, 1, w * c, c)
+
+
+def _phys_nhwc(x):
+  """Returns x with exact NHWC strides (copying through the layout kernel only if needed)."""
+  return as_nhwc(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw (non-autograd) launchers
+# ------------------------------------------------------------------------------------------------
+
+def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None):
+  """x logical (N,Cin,H,W) phys NHWC; w logical (Cout,Cin,KH,KW) phys OHWI -> y logical (N,Cout,Ho,Wo) phys NHWC."""
+  n, cin, h, wd = x.shape
+  cout, cin2, kh, kw = w.shape
+  assert cin == cin2
+  ho = (h + 2 * pad - kh) // stride + 1
+  wo = (wd + 2 * pad - kw) // stride + 1
+  y = _empty_nhwc(n, cout, ho, wo, x.device)
+  eng = _engine["value"]
+  geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
+  ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
+  ws, ws_n = workspace(ws_bytes)
+  check(lib().frcnn_conv2d_fwd(ptr(x), ptr(w), ptr(scale), ptr(bias), ptr(residual), ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
+  _lib.count()
+  return y
+
+
+def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None):
+  n, cin, h, wd = x_shape
+  cout, _, kh, kw = w.shape
+  dx = _empty_nhwc(n, cin, h, wd, dy.device)
+  eng = _engine["value"]
+  geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
+  ws_bytes = lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng)
+  ws, ws_n = workspace(ws_bytes)
+  check(lib().frcnn_conv2d_dgrad(ptr(dy), ptr(w), ptr(addend), ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
+  _lib.count()
+  return dx
+
+
+def conv2d_wgrad_raw(dy, x, w_shape, stride, pad):
+  n, cin, h, wd = x.shape
+  cout, _, kh, kw = w_shape
+  dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = x.device, memory_format = t.channels_last)
+  if kh == 1 and kw == 1:
+    dw = t.empty((cout, cin, 1, 1), dtype = t.float32, device = x.device)
+  eng = _engine["value"]
+  geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
+  ws_bytes = lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng)
+  ws, ws_n = workspace(ws_bytes)
+  check(lib().frcnn_conv2d_wgrad(ptr(dy), ptr(x), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
+  _lib.count()
+  return dw
+
+
+def bias_grad_raw(dz_rows, c):
+  """dz_rows: any tensor whose memory is (rows, C) row-major."""
+  rows = dz_rows.numel() // c
+  db = t.empty((c,), dtype = t.float32, device = dz_rows.device)
+  ws_bytes = lib().frcnn_bias_grad_workspace_bytes(rows, c)
+  ws, ws_n = workspace(ws_bytes, slot = 1)
+  check(lib().frcnn_bias_grad(ptr(dz_rows), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_bias_grad")
+  _lib.count(2)
+  return db
+
+
+def _phys_filter(w):
+  """Filter in OHWI physical layout (channels_last of the logical OIHW tensor)."""
+  o, i, kh, kw = w.shape
+  if kh == 1 and kw == 1:
+    return w if w.is_contiguous() else w.contiguous()
+  if w.stride() == (kh * kw * i, 1, kw * i, i):
+    return w
+  return as_nhwc(w.detach().contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+
+class _ConvAct(t.autograd.Function):
+  """y = [maxpool2x2] act(conv2d(x, w) + b).  Backward: fused (pool+)activation backward, then
+  dgrad / wgrad / bias-grad kernels."""
+
+  @staticmethod
+  def forward(ctx, x, w, b, stride, pad, act, pool):
+    _require_cuda(x, w, b)
+    xp = _phys_nhwc(x.detach())
+    wp = _phys_filter(w.detach())
+    y = conv2d_fwd_raw(xp, wp, b.detach() if b is not None else None, stride, pad, act)
+    ctx.stride, ctx.pad, ctx.act, ctx.pool = stride, pad, act, pool
+    ctx.has_bias = b is not None
+    ctx.w_shape = tuple(w.shape)
+    if pool:
+      assert act == ACT_RELU, "fused pooling is defined for the ReLU convs of VGG-16"
+      n, c, h, wd = y.shape
+      yp = _empty_nhwc(n, c, h // 2, wd // 2, y.device)
+      check(lib().frcnn_maxpool2x2_fwd(ptr(y), ptr(yp), n, h, wd, c, stream()), "frcnn_maxpool2x2_fwd")
+      _lib.count()
+      ctx.save_for_backward(xp, wp, y)
+      return yp
+    ctx.save_for_backward(xp, wp, y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    xp, wp, y = ctx.saved_tensors
+    n, c, h, wd = y.shape
+    dy = _phys_nhwc(dy)
+    if ctx.pool:
+      dz = t.empty_like(y)
+      check(lib().frcnn_maxpool2x2_relu_bwd(ptr(dy), ptr(y), ptr(dz), n, h, wd, c, stream()), "frcnn_maxpool2x2_relu_bwd")
+      _lib.count()
+    elif ctx.act == ACT_RELU:
+      dz = t.empty_like(y)
+      check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
+      _lib.count()
+    elif ctx.act == ACT_SIGMOID:
+      dz = t.empty_like(y)
+      check(lib().frcnn_sigmoid_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_sigmoid_bwd")
+      _lib.count()
+    else:
+      dz = dy
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+      dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad)
+    if ctx.needs_input_grad[1]:
+      dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad)
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      db = bias_grad_raw(dz, c)
+    return dx, dw, db, None, None, None, None
+
+
+def conv2d_act(x, weight, bias, stride = 1, pad = 1, act = ACT_RELU, pool = False):
+  return _ConvAct.apply(x, weight, bias, stride, pad, act, pool)
+
+
+class _LinearAct(t.autograd.Function):
+  """y = act(x @ w.T + b): the KH=KW=1, H=W=1 case of the implicit-GEMM kernels."""
+
+  @staticmethod
+  def forward(ctx, x, w, b, act):
+    _require_cuda(x, w, b)
+    x2 = x.detach().contiguous()
+    w2 = w.detach().contiguous()
+    m, k = x2.shape
+    nout = w2.shape[0]
+    y = t.empty((m, nout), dtype = t.float32, device = x.device)
+    ctx.act = act
+    ctx.has_bias = b is not None
+    if m == 0:
+      ctx.save_for_backward(x2, w2, y)
+      return y
+    eng = _engine["value"]
+    geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
+    ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
+    ws, ws_n = workspace(ws_bytes)
+    check(lib().frcnn_conv2d_fwd(ptr(x2), ptr(w2), None, ptr(b.detach()) if b is not None else None, None, ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd(linear)")
+    _lib.count()
+    ctx.save_for_backward(x2, w2, y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x2, w2, y = ctx.saved_tensors
+    m, k = x2.shape
+    nout = w2.shape[0]
+    dy = dy.contiguous()
+    if m == 0:
+      return t.zeros_like(x2), t.zeros_like(w2), (t.zeros((nout,), device = x2.device) if ctx.has_bias else None), None
+    if ctx.act == ACT_RELU:
+      dz = t.empty_like(y)
+      check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
+      _lib.count()
+    elif ctx.act == ACT_SIGMOID:
+      dz = t.empty_like(y)
+      check(lib().frcnn_sigmoid_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_sigmoid_bwd")
+      _lib.count()
+    else:
+      dz = dy
+    eng = _engine["value"]
+    geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+      dx = t.empty((m, k), dtype = t.float32, device = x2.device)
+      ws, ws_n = workspace(lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
+      check(lib().frcnn_conv2d_dgrad(ptr(dz), ptr(w2), None, ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad(linear)")
+      _lib.count()
+    if ctx.needs_input_grad[1]:
+      dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
+      ws, ws_n = workspace(lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
+      check(lib().frcnn_conv2d_wgrad(ptr(dz), ptr(x2), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad(linear)")
+      _lib.count()
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      db = bias_grad_raw(dz, nout)
+    return dx, dw, db, None
+
+
+def linear_act(x, weight, bias, act = ACT_NONE):
+  return _LinearAct.apply(x, weight, bias, act)
+
+
+class _RoIPool(t.autograd.Function):
+  @staticmethod
+  def forward(ctx, feature_map, proposals, output_size, spatial_scale):
+    _require_cuda(feature_map, proposals)
+    assert feature_map.shape[0] == 1, "Batch size must be 1"
+    fm = _phys_nhwc(feature_map.detach())
+    _, c, h, w = fm.shape
+    props = proposals.detach().contiguous().float()
+    k = props.shape[0]
+    ph, pw = output_size
+    out = t.empty((k, c, ph, pw), dtype = t.float32, device = fm.device)
+    arg = t.empty((k, c, ph, pw), dtype = t.int32, device = fm.device)
+    if k > 0:
+      check(lib().frcnn_roi_pool_fwd(ptr(fm), h, w, c, ptr(props), k, ph, pw, float(spatial_scale), ptr(out), ptr(arg), stream()), "frcnn_roi_pool_fwd")
+      _lib.count()
+    ctx.save_for_backward(arg, props)
+    ctx.geom = (k, h, w, c, ph, pw, float(spatial_scale))
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    arg, props = ctx.saved_tensors
+    k, h, w, c, ph, pw, scale = ctx.geom
+    dfm = _empty_nhwc(1, c, h, w, dout.device)
+    dout = dout.contiguous()
+    check(lib().frcnn_roi_pool_bwd(ptr(dout), ptr(arg), ptr(props), k, h, w, c, ph, pw, scale, None, ptr(dfm), stream()), "frcnn_roi_pool_bwd")
+    _lib.count()
+    return dfm, None, None, None
+
+
+def roi_pool(feature_map, proposals, output_size = (7, 7), spatial_scale = 1.0 / 16.0):
+  """feature_map logical (1,C,H,W); proposals (K,4) as (y1,x1,y2,x2) -> (K,C,7,7)."""
+  return _RoIPool.apply(feature_map, proposals, output_size, spatial_scale)
+
+
+class _Softmax(t.autograd.Function):
+  @staticmethod
+  def forward(ctx, logits):
+    _require_cuda(logits)
+    x = logits.detach().contiguous()
+    n, c = x.shape
+    p = t.empty_like(x)
+    check(lib().frcnn_softmax_rows(ptr(x), ptr(p), n, c, stream()), "frcnn_softmax_rows")
+    _lib.count()
+    ctx.save_for_backward(p)
+    return p
+
+  @staticmethod
+  def backward(ctx, g):
+    (p,) = ctx.saved_tensors
+    n, c = p.shape
+    g = g.contiguous()
+    d = t.empty_like(p)
+    check(lib().frcnn_softmax_rows_bwd(ptr(p), ptr(g), ptr(d), n, c, stream()), "frcnn_softmax_rows_bwd")
+    _lib.count()
+    return d
+
+
+def softmax_rows(logits):
+  return _Softmax.apply(logits)
+
+
+class _RPNLosses(t.autograd.Function):
+  """(class_loss, regression_loss) of models/rpn.py:176-272 in one kernel, gradients included."""
+
+  @staticmethod
+  def forward(ctx, scores, deltas, y_true):
+    _require_cuda(scores, deltas, y_true)
+    s = scores.detach().contiguous()
+    d = deltas.detach().contiguous()
+    y = y_true.detach().contiguous()
+    a = s.numel()
+    assert d.numel() == 4 * a and y.numel() == 6 * a
+    out = t.empty((2,), dtype = t.float32, device = s.device)
+    need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+    ds = t.empty_like(s) if need else None
+    dd = t.empty_like(d) if need else None
+    check(lib().frcnn_rpn_losses(ptr(s), ptr(d), ptr(y), a, ptr(out), ptr(ds), ptr(dd), stream()), "frcnn_rpn_losses")
+    _lib.count()
+    ctx.grads = (ds, dd)
+    ctx.shapes = (scores.shape, deltas.shape)
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    ds, dd = ctx.grads
+    return (ds * g[0]).reshape(ctx.shapes[0]), (dd * g[1]).reshape(ctx.shapes[1]), None
+
+
+def rpn_losses(scores, deltas, y_true):
+  return _RPNLosses.apply(scores, deltas, y_true)
+
+
+class _DetectorLosses(t.autograd.Function):
+  """(class_loss, regression_loss) of models/detector.py:83-155 in one kernel."""
+
+  @staticmethod
+  def forward(ctx, probs, deltas, y_classes, y_deltas):
+    _require_cuda(probs, deltas, y_classes, y_deltas)
+    p = probs.detach().contiguous()
+    d = deltas.detach().contiguous()
+    yc = y_classes.detach().contiguous()
+    yd = y_deltas.detach().contiguous()
+    n, c = p.shape
+    out = t.zeros((2,), dtype = t.float32, device = p.device)
+    dp = t.empty_like(p)
+    dd = t.empty_like(d)
+    if n > 0:
+      check(lib().frcnn_detector_losses(ptr(p), ptr(d), ptr(yc), ptr(yd), n, c, ptr(out), ptr(dp), ptr(dd), stream()), "frcnn_detector_losses")
+      _lib.count()
+    ctx.grads = (dp, dd)
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    dp, dd = ctx.grads
+    return dp * g[0], dd * g[1], None, None
+
+
+def detector_losses(probs, deltas, y_classes, y_deltas):
+  return _DetectorLosses.apply(probs, deltas, y_classes, y_deltas)
+
+
+# ------------------------------------------------------------------------------------------------
+# non-differentiable ops
+# ------------------------------------------------------------------------------------------------
+
+def nms(boxes, scores, iou_threshold):
+  """torchvision.ops.nms replacement for fp32 boxes (models/rpn.py:147-151): returns int64 indices
+  of the kept boxes in descending score order (ties: lower index first)."""
+  _require_cuda(boxes, scores)
+  n = boxes.shape[0]
+  if n == 0:
+    return t.empty((0,), dtype = t.int64, device = boxes.device)
+  b = boxes.detach().contiguous().float()
+  s = scores.detach().contiguous().float()
+  dev = b.device
+  # stable descending order == rank counting with ties -> LOWER index first: negate the tie rule
+  # by ranking the reversed array (ties -> higher index first in reversed space).
+  rev = t.flip(s, dims = (0,)).contiguous()
+  order = t.empty((n,), dtype = t.int32, device = dev)
+  cnt = t.empty((1 + n,), dtype = t.int32, device = dev)
+  check(lib().frcnn_topk_order(ptr(rev), None, n, n, ptr(order), ptr(cnt), stream()), "frcnn_topk_order")
+  _lib.count(3)
+  order = (n - 1) - order                                        # back to original indices
+  sorted_boxes = t.empty((n, 4), dtype = t.float32, device = dev)
+  check(lib().frcnn_gather_rows_f32(ptr(b), 4, ptr(order.contiguous()), ptr(cnt), n, ptr(sorted_boxes), stream()), "frcnn_gather_rows_f32")
+  keep = t.empty((n,), dtype = t.int32, device = dev)
+  kept = t.empty((1,), dtype = t.int32, device = dev)
+  ws, ws_n = workspace(lib().frcnn_nms_workspace_bytes(n), slot = 2)
+  check(lib().frcnn_nms_sorted_f32(ptr(sorted_boxes), ptr(cnt), n, float(iou_threshold), n, ptr(keep), ptr(kept), ws, ws_n, stream()), "frcnn_nms_sorted_f32")
+  _lib.count(3)
+  k = int(kept.item())
+  return order[keep[:k].long()].long()
+
+
+class ProposalBuffers:
+  """Capacity-sized device buffers for the RPN proposal path (reused across steps)."""
+
+  def __init__(self, num_anchors, pre_nms, device):
+    self.num_anchors, self.pre_nms = num_anchors, pre_nms
+    i32, f32, u8 = t.int32, t.float32, t.uint8
+    self.boxes_all = t.empty((num_anchors, 4), dtype = f32, device = device)
+    self.size_ok = t.empty((num_anchors,), dtype = u8, device = device)
+    self.order = t.empty((pre_nms,), dtype = i32, device = device)
+    self.count1 = t.empty((1 + num_anchors,), dtype = i32, device = device)
+    self.boxes_sorted = t.empty((pre_nms, 4), dtype = f32, device = device)
+    self.scores_sorted = t.empty((pre_nms,), dtype = f32, device = device)
+    self.count2 = t.empty((1,), dtype = i32, device = device)
+    self.keep = t.empty((pre_nms,), dtype = i32, device = device)
+    self.count3 = t.empty((1,), dtype = i32, device = device)
+
+
+_proposal_buffers = {}
+
+
+def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, post_nms, anchors = None, keep_mask = None, min_size = 16.0, iou_threshold = 0.7, return_debug = False):
+  """
+  models/rpn.py:99-156 as five stream-ordered kernels with no host round trip until the final
+  count: decode(+anchors, clip, size flag) -> rank/top-N -> ordered compaction -> NMS bit tiles +
+  scan -> gather.  score_map (1,fh,fw,9), delta_map (1,fh,fw,36) contiguous fp32 (NHWC maps).
+  Returns proposals (N,4) fp32 (y1,x1,y2,x2).
+  """
+  _require_cuda(score_map, delta_map)
+  fh, fw = int(score_map.shape[1]), int(score_map.shape[2])
+  a = fh * fw * 9
+  dev = score_map.device
+  scores = score_map.detach().contiguous()
+  deltas = delta_map.detach().contiguous()
+  key = (dev.index, a, pre_nms)
+  buf = _proposal_buffers.get(key)
+  if buf is None:
+    buf = ProposalBuffers(a, pre_nms, dev)
+    _proposal_buffers[key] = buf
+  st = stream()
+  L = lib()
+  check(L.frcnn_rpn_decode(ptr(deltas), ptr(anchors), fh, fw, int(feature_pixels), int(image_shape[1]), int(image_shape[2]), float(min_size),
+                           ptr(buf.boxes_all), ptr(buf.size_ok), None, None, st), "frcnn_rpn_decode")
+  check(L.frcnn_topk_order(ptr(scores), ptr(keep_mask), a, pre_nms, ptr(buf.order), ptr(buf.count1), st), "frcnn_topk_order")
+  check(L.frcnn_gather_filtered(ptr(buf.boxes_all), ptr(scores), ptr(buf.size_ok), ptr(buf.order), ptr(buf.count1), pre_nms,
+                                ptr(buf.boxes_sorted), ptr(buf.scores_sorted), ptr(buf.count2), st), "frcnn_gather_filtered")
+  ws, ws_n = workspace(L.frcnn_nms_workspace_bytes(pre_nms), slot = 2)
+  check(L.frcnn_nms_sorted_f32(ptr(buf.boxes_sorted), ptr(buf.count2), pre_nms, float(iou_threshold), post_nms, ptr(buf.keep), ptr(buf.count3), ws, ws_n, st), "frcnn_nms_sorted_f32")
+  out = t.empty((post_nms, 4), dtype = t.float32, device = dev)
+  check(L.frcnn_gather_rows_f32(ptr(buf.boxes_sorted), 4, ptr(buf.keep), ptr(buf.count3), post_nms, ptr(out), st), "frcnn_gather_rows_f32")
+  _lib.count(8)
+  n = int(buf.count3.item())                                     # the one host sync of the proposal path
+  if return_debug:
+    n1 = int(buf.count1[0].item()); n2 = int(buf.count2.item())
+    return out[:n], dict(order = buf.order[:n1].clone(), boxes_all = buf.boxes_all.clone(), size_ok = buf.size_ok.clone(),
+                         boxes_sorted = buf.boxes_sorted[:n2].clone(), scores_sorted = buf.scores_sorted[:n2].clone(), keep = buf.keep[:n].clone())
+  return out[:n]
+
+
+def generate_anchors_device(image_shape, feature_map_hw, feature_pixels, device = "cuda"):
+  """Anchor map / valid map as the decode kernel builds them (models/anchors.py:43-135): returns
+  CUDA tensors anchors (fh,fw,36) fp32 and valid (fh,fw,9) fp32."""
+  fh, fw = int(feature_map_hw[0]), int(feature_map_hw[1])
+  a = fh * fw * 9
+  zeros = t.zeros((a, 4), dtype = t.float32, device = device)
+  boxes = t.empty((a, 4), dtype = t.float32, device = device)
+  ok = t.empty((a,), dtype = t.uint8, device = device)
+  anchors = t.empty((a, 4), dtype = t.float32, device = device)
+  valid = t.empty((a,), dtype = t.float32, device = device)
+  check(lib().frcnn_rpn_decode(ptr(zeros), None, fh, fw, int(feature_pixels), int(image_shape[1]), int(image_shape[2]), 16.0,
+                               ptr(boxes), ptr(ok), ptr(anchors), ptr(valid), stream()), "frcnn_rpn_decode")
+  _lib.count()
+  return anchors.reshape(fh, fw, 36), valid.reshape(fh, fw, 9)
+
+
+def label_proposals(proposals, gt_boxes, gt_classes, num_classes, min_object_iou = 0.5):
+  """models/faster_rcnn.py:469-524 for an (n,4) proposal tensor that already contains the appended
+  GT boxes.  Returns best_iou (n), class_idx (n) int32, onehot (n,C), packed targets (n,2,4(C-1))."""
+  _require_cuda(proposals, gt_boxes, gt_classes)
+  p = proposals.detach().contiguous()
+  n = p.shape[0]
+  m = gt_boxes.shape[0]
+  dev = p.device
+  best = t.empty((n,), dtype = t.float32, device = dev)
+  cls = t.empty((n,), dtype = t.int32, device = dev)
+  onehot = t.empty((n, num_classes), dtype = t.float32, device = dev)
+  packed = t.empty((n, 2, 4 * (num_classes - 1)), dtype = t.float32, device = dev)
+  check(lib().frcnn_label_proposals(ptr(p), n, ptr(gt_boxes.contiguous()), ptr(gt_classes.contiguous()), m, num_classes, float(min_object_iou),
+                                    ptr(best), ptr(cls), ptr(onehot), ptr(packed), stream()), "frcnn_label_proposals")
+  _lib.count()
+  return best, cls, onehot, packed
+
+
+def detect_postprocess(proposals, classes, deltas, image_hw, score_threshold, iou_threshold = 0.3):
+  """models/faster_rcnn.py:179-226 in one launch.  Returns {class_idx: ndarray (k,5) float64}."""
+  _require_cuda(proposals, classes, deltas)
+  n, c = classes.shape
+  dev = classes.device
+  result = {}
+  if n == 0:
+    return {ci: np.zeros((0, 5), dtype = np.float64) for ci in range(1, c)}
+  out = t.empty((c - 1, n, 5), dtype = t.float64, device = dev)
+  counts = t.empty((c - 1,), dtype = t.int32, device = dev)
+  check(lib().frcnn_detect_postprocess(ptr(proposals.detach().contiguous()), ptr(classes.detach().contiguous()), ptr(deltas.detach().contiguous()),
+                                       n, c, int(image_hw[0]), int(image_hw[1]), float(np.float32(score_threshold)), float(iou_threshold),
+                                       ptr(out), ptr(counts), stream()), "frcnn_detect_postprocess")
+  _lib.count()
+  out_h = out.cpu().numpy()
+  counts_h = counts.cpu().numpy()
+  for ci in range(1, c):
+    result[ci] = out_h[ci - 1, :counts_h[ci - 1]].copy()
+  return result
+
+
+def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale = 1.0, first_step = False):
+  _require_cuda(param, grad, momentum_buf)
+  assert param.is_contiguous() or param.is_contiguous(memory_format = t.channels_last)
+  assert grad.stride() == param.stride() and momentum_buf.stride() == param.stride()
+  check(lib().frcnn_sgd_step(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step), stream()), "frcnn_sgd_step")
+  _lib.count()

@@ -1,0 +1,195 @@
+/*
+ * frcnn_b200.h -- C ABI of libfrcnn_sm100.so: hand-written sm_100a CUDA kernels for the
+ * Faster R-CNN per-image forward/backward hot path.
+ *
+ * The reference (trzy/FasterRCNN) has no FFI of its own: its hot path calls third-party compiled
+ * ops from Python.  Each entry point below cites the reference call site(s) it replaces
+ * (paths relative to pytorch/FasterRCNN/).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - raw DEVICE pointers + explicit sizes + a cudaStream_t passed as void*; the caller
+ *     allocates every output and workspace (query the *_workspace_bytes functions);
+ *   - no hidden allocation, no global mutable state, never synchronises the device;
+ *     stream-ordered on the given stream; re-entrant and thread-safe;
+ *   - returns 0 on success, a negative FRCNN_E_* for a bad argument, a positive cudaError_t
+ *     for a CUDA failure; frcnn_last_error_string() (thread-local) says what went wrong;
+ *   - activations are NHWC fp32; filters are (Cout, KH, KW, Cin) fp32 ("OHWI", i.e. the
+ *     reference's OIHW tensors in torch.channels_last memory format); nn.Linear weights
+ *     (out, in) are the KH=KW=1 case; boxes are (y1, x1, y2, x2) as in the reference.
+ */
+#ifndef FRCNN_B200_H
+#define FRCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define FRCNN_OK 0
+#define FRCNN_E_BADARG (-1)
+#define FRCNN_E_WORKSPACE (-2)
+#define FRCNN_E_UNSUPPORTED (-3)
+
+#define FRCNN_ACT_NONE 0
+#define FRCNN_ACT_RELU 1
+#define FRCNN_ACT_SIGMOID 2
+
+/* math engines for the GEMM-shaped ops */
+#define FRCNN_ENGINE_AUTO 0
+#define FRCNN_ENGINE_SIMT_FP32 1   /* CUDA-core fp32 FMA implicit GEMM (exact fp32 products) */
+#define FRCNN_ENGINE_TC_3XTF32 2   /* tcgen05 kind::tf32, error-compensated 3-product split, fp32 TMEM accumulators */
+
+int frcnn_version(void);
+const char *frcnn_last_error_string(void);
+
+/* ---- layout ------------------------------------------------------------------------------
+ * API tensors are NCHW (models/faster_rcnn.py:86-89); kernels run NHWC. */
+int frcnn_nchw_to_nhwc(const float *src, float *dst, int N, int C, int H, int W, void *stream);
+int frcnn_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H, int W, void *stream);
+
+/* ---- K1/K4/K8: convolution / linear as implicit GEMM ------------------------------------
+ * Replaces F.relu(nn.Conv2d(.., padding="same")) models/vgg16.py:76-96, models/rpn.py:88-90
+ * (act = RELU / SIGMOID / NONE epilogues), nn.Linear models/vgg16.py:129-133,
+ * models/detector.py:76-78 (KH=KW=1, H=W=1, N=rows), torchvision ResNet convs
+ * models/resnet.py:38-46,96 (stride 2, 1x1, 7x7; frozen BN folded into scale/bias, residual add).
+ *   y[n,oh,ow,co] = act( scale[co] * sum_{kh,kw,ci} x[n,oh*s-p+kh,ow*s-p+kw,ci] * w[co,kh,kw,ci]
+ *                        + bias[co] + residual[n,oh,ow,co] )
+ * scale, bias, residual may be NULL.  Ho = (H + 2p - KH)/s + 1, Wo likewise. */
+size_t frcnn_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
+int frcnn_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual,
+                     float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+                     int engine, void *workspace, size_t workspace_bytes, void *stream);
+
+/* K2: data gradient.  dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n,oh,ow,co] * w[co,kh,kw,ci] with
+ * oh*s-p+kh == ih; if addend != NULL it is added (gradient accumulation from a second
+ * consumer); if scale != NULL dy is multiplied per output channel first (folded frozen BN).
+ * Replaces autograd's convolution_backward (input) reached from models/faster_rcnn.py:356. */
+size_t frcnn_conv2d_dgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
+int frcnn_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
+                       int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                       int engine, void *workspace, size_t workspace_bytes, void *stream);
+
+/* K2: filter gradient.  dw[co,kh,kw,ci] = sum_{n,oh,ow} dy[n,oh,ow,co] * x[n,oh*s-p+kh,ow*s-p+kw,ci]
+ * (deterministic two-stage split-K).  Replaces convolution_backward (weight) / mm of nn.Linear. */
+size_t frcnn_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
+int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
+                       int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                       int engine, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- elementwise / pooling pieces of the backward pass -------------------------------------
+ * dz = dy * (y > 0)   (ReLU backward, models/vgg16.py:76-96 under autograd); in place allowed. */
+int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
+/* dbias[c] = sum over rows of dz[row, c]; workspace >= frcnn_bias_grad_workspace_bytes. */
+size_t frcnn_bias_grad_workspace_bytes(size_t rows, int C);
+int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *workspace, size_t workspace_bytes, void *stream);
+/* 2x2 stride-2 max pool, floor mode (nn.MaxPool2d(2,2) models/vgg16.py:78,82,87,92), NHWC. */
+int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
+/* dz[n,h,w,c] = dy[n,h/2,w/2,c] if (h,w) is the first maximum of its window and x > 0, else 0
+ * (max-pool backward fused with the ReLU backward of the conv that produced x). */
+int frcnn_maxpool2x2_relu_bwd(const float *dy, const float *x, float *dz, int N, int H, int W, int C, void *stream);
+/* 3x3 stride-2 pad-1 max pool (torchvision ResNet stem, models/resnet.py:42), NHWC. */
+int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
+/* mean over the spatial positions of (N, HW, C) -> (N, C) (models/resnet.py:117) and its gradient. */
+int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int HW, int C, void *stream);
+int frcnn_spatial_mean_bwd(const float *dy, float *dx, int N, int HW, int C, void *stream);
+/* out = a + b (residual / gradient accumulation). */
+int frcnn_add(const float *a, const float *b, float *out, size_t count, void *stream);
+
+/* ---- K5: fused RPN anchor generation + box-delta decode + clip + min-size flag -------------
+ * Replaces anchors.generate_anchor_maps (models/anchors.py:43-135, regenerated in-kernel from
+ * the 9x4 fp64 template), t_convert_deltas_to_boxes (models/math_utils.py:99-128), the clamp
+ * and >=16 filter (models/rpn.py:135-144).  deltas: (A,4) fp32 NHWC map flattened, A = fh*fw*9,
+ * anchor index a = (y*fw + x)*9 + k.  Outputs: boxes (A,4) clipped to [0,img_h]x[0,img_w],
+ * size_ok (A) uint8 = both sides >= min_size; anchors_out (A,4) (cy,cx,h,w) fp32 and valid_out
+ * (A) fp32 are optional (NULL) exports of the anchor map / valid map.  anchors_in (A,4), when not
+ * NULL, overrides the regenerated anchors (a caller-supplied anchor_map that differs from the
+ * standard one, models/rpn.py:51,120). */
+int frcnn_rpn_decode(const float *deltas, const float *anchors_in, int fh, int fw, int feature_pixels, int img_h, int img_w, float min_size,
+                     float *boxes, uint8_t *size_ok, float *anchors_out, float *valid_out, void *stream);
+
+/* ---- top-N ordering (t.argsort + flip + [0:N], models/rpn.py:129-132) -----------------------
+ * order[r] = index of the r-th best score for r < min(n, top_n); descending by score, ties ->
+ * higher index first (= stable ascending argsort then flip).  If keep_mask != NULL only
+ * entries with keep_mask[i] != 0 take part (allow_edge_proposals=False, models/rpn.py:170-173).
+ * count_out is a device int32 array of 1 + n entries: count_out[0] receives the number of
+ * entries written, count_out[1..n] is scratch for the per-element ranks. */
+int frcnn_topk_order(const float *scores, const uint8_t *keep_mask, int n, int top_n, int32_t *order, int32_t *count_out, void *stream);
+
+/* gather + compaction of the ordered, size-filtered boxes: for r in [0,*count) in order, rows
+ * with size_ok[order[r]] are appended to boxes_out/scores_out; count_out = number appended. */
+int frcnn_gather_filtered(const float *boxes, const float *scores, const uint8_t *size_ok, const int32_t *order,
+                          const int32_t *count, int capacity, float *boxes_out, float *scores_out, int32_t *count_out, void *stream);
+
+/* ---- K6: greedy NMS (torchvision.ops.nms; models/rpn.py:147-151) ----------------------------
+ * boxes (n,4) fp32 ALREADY in descending score order (n read from the device int32 *count,
+ * at most capacity); keeps box i unless an earlier kept box j has IoU(i,j) > thr (IoU in fp32,
+ * compared against the double threshold exactly as the CPU op does).  keep_out receives the
+ * kept POSITIONS in order, at most max_keep of them; kept_count_out their number. */
+size_t frcnn_nms_workspace_bytes(int capacity);
+int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
+                         int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
+/* out[r] = boxes[keep[r]] for r < *kept_count. */
+int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index, const int32_t *count, int capacity, float *dst, void *stream);
+
+/* ---- K7: RoI max pooling (torchvision.ops.RoIPool((7,7), 1/16); models/detector.py:27,65-72)
+ * fm NHWC (1,H,W,C); proposals (K,4) fp32 (y1,x1,y2,x2) as the reference holds them (the
+ * (b,x1,y1,x2,y2) swap of detector.py:68-69 is folded in).  out (K,C,PH,PW) fp32 -- the layout
+ * fc1 consumes (models/vgg16.py:129) -- argmax (K,C,PH,PW) int32 = h*W+w or -1. */
+int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *proposals, int K, int PH, int PW, float spatial_scale,
+                       float *out, int32_t *argmax, void *stream);
+/* dfm (H,W,C) NHWC = scatter-add of dout through argmax; deterministic (no atomics): one
+ * thread per (cell, channel) walks the RoIs in ascending order.  addend (may be NULL) is added. */
+int frcnn_roi_pool_bwd(const float *dout, const int32_t *argmax, const float *proposals, int K, int H, int W, int C, int PH, int PW,
+                       float spatial_scale, const float *addend, float *dfm, void *stream);
+
+/* ---- a10: proposal labelling (FasterRCNNModel._label_proposals, models/faster_rcnn.py:418-524)
+ * proposals (n,4), gt boxes (m,4), gt classes (m) int32.  For each of the n proposals: best IoU
+ * (math_utils.py:39-63 semantics), class (0 if best IoU < min_object_iou), one-hot row
+ * (num_classes) and packed (2, 4*(num_classes-1)) mask/target rows. */
+int frcnn_label_proposals(const float *proposals, int n, const float *gt_boxes, const int32_t *gt_classes, int m, int num_classes,
+                          float min_object_iou, float *best_iou, int32_t *class_idx, float *onehot, float *packed_targets, void *stream);
+
+/* ---- a12: losses, forward value + gradients in one pass -------------------------------------
+ * RPN (models/rpn.py:176-272): scores (A) post-sigmoid, deltas (A,4), y_true (A,6).
+ * losses_out[0] = class loss, [1] = regression loss.  d_scores (A) = dL/d(score) (the
+ * binary_cross_entropy backward), d_deltas (A,4); both NULL for value only.  Deterministic
+ * single-CTA reduction. */
+int frcnn_rpn_losses(const float *scores, const float *deltas, const float *y_true, int A,
+                     float *losses_out, float *d_scores, float *d_deltas, void *stream);
+/* dz = dy * (1 - y) * y  (t.sigmoid backward, models/rpn.py:89). */
+int frcnn_sigmoid_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
+/* Detector (models/detector.py:76-78,83-155): logits (n, C) -> classes = softmax (written to
+ * classes_out), deltas (n, 4(C-1)), y_classes (n, C) one-hot, y_deltas (n,2,4(C-1)).
+ * losses_out[0] = class loss, [1] = regression loss; d_probs (n,C) = dL/d(softmax output),
+ * d_deltas (n,4(C-1)); either may be NULL. */
+int frcnn_softmax_rows(const float *logits, float *probs, int n, int C, void *stream);
+int frcnn_softmax_rows_bwd(const float *probs, const float *d_probs, float *d_logits, int n, int C, void *stream);
+int frcnn_detector_losses(const float *probs, const float *deltas, const float *y_classes, const float *y_deltas, int n, int C,
+                          float *losses_out, float *d_probs, float *d_deltas, void *stream);
+
+/* ---- K10: fused SGD (torch.optim.SGD as configured by __main__.py:98-105) -------------------
+ * g = grad*grad_scale + wd*p; buf = first_step ? g : momentum*buf + g; p -= lr*buf. */
+int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                   float grad_scale, int first_step, void *stream);
+
+/* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
+ * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one
+ * launch: decode in fp64 with stds (0.1,0.1,0.2,0.2), clip to [0,img_h-1]x[0,img_w-1], keep
+ * score > threshold, greedy NMS (fp64 IoU, thr iou_threshold).  out (C-1, n, 5) fp64 rows
+ * (y1,x1,y2,x2,score) in kept order; out_counts (C-1) int32.  n <= 512. */
+int frcnn_detect_postprocess(const float *proposals, const float *classes, const float *deltas, int n, int C, int img_h, int img_w,
+                             float score_threshold, double iou_threshold, double *out, int32_t *out_counts, void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H */

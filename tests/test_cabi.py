@@ -1,0 +1,59 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/frcnn_b200.h declares."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, "include", "frcnn_b200.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags = re.S)
+  return sorted(set(re.findall(r"\b(frcnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+  from fasterrcnn_b200 import _lib
+  if not os.path.exists(_lib.LIB_PATH):
+    import __graft_entry__ as g
+    g.build()
+  handle = _lib.lib()
+  declared = _declared_symbols()
+  assert len(declared) >= 30
+  for name in declared:
+    assert hasattr(handle, name), "missing export: " + name
+  assert sorted(_lib.exported_symbols()) == declared, set(_lib.exported_symbols()) ^ set(declared)
+  assert handle.frcnn_version() >= 100
+
+
+def test_no_cpu_fallback():
+  """Ops refuse CPU tensors instead of silently computing somewhere else."""
+  import torch as t
+  from fasterrcnn_b200 import ops, _lib
+  with pytest.raises(_lib.FrcnnError):
+    ops.conv2d_act(t.zeros((1, 4, 8, 8)), t.zeros((4, 4, 3, 3)), t.zeros((4,)))
+  with pytest.raises(_lib.FrcnnError):
+    ops.nms(t.zeros((4, 4)), t.zeros((4,)), 0.5)
+
+
+def test_product_never_imports_oracle():
+  pkg = os.path.join(ROOT, "fasterrcnn_b200")
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".h")):
+        src = open(os.path.join(dirpath, f)).read()
+        assert "oracle" not in src.replace("# oracle", ""), "%s mentions the oracle" % f
+
+
+def test_state_dict_keys_match_reference_layout():
+  import fasterrcnn_b200 as f
+  from oracle import frcnn_oracle as orc
+  model = f.FasterRCNNModel(21, f.vgg16.VGG16Backbone(0.0))
+  sd = model.state_dict()
+  shapes = orc.vgg16_param_shapes()
+  assert list(sd.keys()) == list(shapes.keys())
+  for k, shape in shapes.items():
+    assert tuple(sd[k].shape) == tuple(shape)
+  frozen = [k for k, p in model.named_parameters() if not p.requires_grad]
+  assert sorted(frozen) == sorted(k for k in shapes if k not in orc.trainable_keys_vgg16(shapes))

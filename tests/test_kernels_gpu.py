@@ -1,0 +1,269 @@
+"""
+GPU parity tests: every kernel is called through the C ABI (fasterrcnn_b200.ops -> ctypes ->
+libfrcnn_sm100.so) and compared with the CPU oracle on the same seeded inputs.
+Bit-exact for index / integer work; floating point within the tolerance written in each test.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch as t
+import torch.nn.functional as F
+
+from oracle import frcnn_oracle as orc
+from oracle import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope = "module")
+def ops():
+  from fasterrcnn_b200 import ops as o
+  return o
+
+
+def _cuda(x):
+  return t.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ---------------------------------------------------------------- conv / linear (K1, K2, K8)
+CONV_CASES = [
+  # name, N, H, W, Cin, Cout, KH, stride, pad
+  ("rgb_stem", 1, 37, 45, 3, 64, 3, 1, 1),
+  ("vgg_64", 1, 40, 56, 64, 64, 3, 1, 1),
+  ("vgg_512_splitk", 1, 19, 23, 256, 512, 3, 1, 1),
+  ("head_1x1_9", 1, 19, 23, 512, 9, 1, 1, 0),
+  ("head_1x1_36", 1, 19, 23, 512, 36, 1, 1, 0),
+  ("resnet_7x7_s2", 1, 61, 77, 3, 64, 7, 2, 3),
+  ("resnet_3x3_s2", 2, 28, 28, 128, 128, 3, 2, 1),
+  ("resnet_1x1_s2", 2, 14, 14, 256, 512, 1, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids = [c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("engine", ["simt"])
+def test_conv_fwd_dgrad_wgrad_vs_torch_fp32(ops, case, engine):
+  _, n, h, w, cin, cout, k, stride, pad = case
+  ops.set_engine(engine)
+  g = t.Generator().manual_seed(7)
+  x = t.randn((n, cin, h, w), generator = g)
+  wt = t.randn((cout, cin, k, k), generator = g) * (2.0 / (cin * k * k)) ** 0.5
+  b = t.randn((cout,), generator = g) * 0.1
+  xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+  yr = F.relu(F.conv2d(xr, wr, br, stride = stride, padding = pad))
+  gy = t.randn(yr.shape, generator = g)
+  yr.backward(gy)
+
+  xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True), b.cuda().requires_grad_(True)
+  y = ops.conv2d_act(xc, wc, bc, stride, pad, ops.ACT_RELU)
+  assert tuple(y.shape) == tuple(yr.shape)
+  tol = dict(rtol = 1e-4, atol = 1e-4)            # fp32 accumulation-order tolerance
+  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), **tol)
+  y.backward(gy.cuda())
+  np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 2e-4)
+  scale = float(wr.grad.abs().max())
+  np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-5 * max(scale, 1.0) + 1e-4)
+  np.testing.assert_allclose(bc.grad.cpu().numpy(), br.grad.numpy(), rtol = 1e-4, atol = 1e-3)
+  ops.set_engine("auto")
+
+
+def test_conv_pool_fused_matches_torch(ops):
+  g = t.Generator().manual_seed(3)
+  x = t.randn((1, 64, 37, 51), generator = g)           # odd sizes: floor-mode pooling drops the last row/col
+  wt = t.randn((128, 64, 3, 3), generator = g) * 0.06
+  b = t.randn((128,), generator = g) * 0.1
+  xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+  yr = F.max_pool2d(F.relu(F.conv2d(xr, wr, b, padding = 1)), 2, 2)
+  gy = t.randn(yr.shape, generator = g)
+  yr.backward(gy)
+  xc, wc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True)
+  y = ops.conv2d_act(xc, wc, b.cuda(), 1, 1, ops.ACT_RELU, pool = True)
+  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol = 1e-4, atol = 1e-4)
+  y.backward(gy.cuda())
+  np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 2e-4)
+  np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-3)
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 25088, 4096), (300, 4096, 4096), (128, 4096, 21), (7, 4096, 80), (0, 4096, 21)])
+def test_linear_vs_torch_fp32(ops, m, k, n):
+  g = t.Generator().manual_seed(11)
+  x = t.randn((m, k), generator = g)
+  wt = t.randn((n, k), generator = g) * (1.0 / k) ** 0.5
+  b = t.randn((n,), generator = g) * 0.1
+  xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+  yr = F.relu(F.linear(xr, wr, br))
+  gy = t.randn(yr.shape, generator = g)
+  yr.backward(gy)
+  xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+  y = ops.linear_act(xc, wc, bc, ops.ACT_RELU)
+  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol = 1e-4, atol = 1e-4)
+  y.backward(gy.cuda())
+  np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 1e-4)
+  np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-4)
+  np.testing.assert_allclose(bc.grad.cpu().numpy(), br.grad.numpy(), rtol = 1e-4, atol = 1e-4)
+
+
+# ---------------------------------------------------------------- anchors + RPN proposal path (K5, K6)
+@pytest.mark.parametrize("tag", list(gi.GEOMETRY_CASES))
+def test_anchor_generation_bit_exact(ops, tag):
+  h, w = gi.GEOMETRY_CASES[tag]
+  am, av = orc.generate_anchor_maps((3, h, w), (512, h // 16, w // 16), 16)
+  a_dev, v_dev = ops.generate_anchors_device((3, h, w), (h // 16, w // 16), 16)
+  assert np.array_equal(a_dev.cpu().numpy(), am)
+  assert np.array_equal(v_dev.cpu().numpy(), av)
+
+
+@pytest.mark.parametrize("tag", gi.RPN_CASES)
+def test_rpn_proposal_stage_matches_reference_golden(ops, golden_dir, tag):
+  g = np.load(os.path.join(golden_dir, "rpn_stage.npz"))
+  c = gi.rpn_case(tag)
+  am, av = orc.generate_anchor_maps(c["image_shape"], (512,) + c["fm_hw"], 16)
+  taps = {}
+  ref = orc.rpn_proposals(t.from_numpy(c["score_map"]), t.from_numpy(c["delta_map"]), am, av, c["image_shape"], c["pre_nms"], c["post_nms"], taps = taps)
+  assert np.array_equal(ref.numpy(), g[tag + "_proposals"])                       # oracle == reference (pinned)
+  props, dbg = ops.rpn_proposals(_cuda(c["score_map"]), _cuda(c["delta_map"]), c["image_shape"], 16, c["pre_nms"], c["post_nms"], return_debug = True)
+  # ordering: bit-exact indices (scores are distinct by construction)
+  assert np.array_equal(dbg["order"].cpu().numpy().astype(np.int64), taps["order"])
+  # decode: <= 1e-4 px on clipped coordinates (expf is correctly rounded here, SLEEF u10 on the CPU)
+  np.testing.assert_allclose(dbg["boxes_sorted"].cpu().numpy(), taps["pre_nms_boxes"], rtol = 0, atol = 1e-4)
+  assert props.shape == ref.shape
+  np.testing.assert_allclose(props.cpu().numpy(), ref.numpy(), rtol = 0, atol = 1e-4)
+
+
+@pytest.mark.parametrize("tag", gi.NMS_CASES)
+def test_nms_bit_exact_vs_oracle_and_golden(ops, golden_dir, tag):
+  boxes, scores, thr = gi.nms_case(tag)
+  if boxes.dtype != np.float32:
+    pytest.skip("fp64 NMS is exercised through detect_postprocess")
+  gold = np.load(os.path.join(golden_dir, "tv_ops.npz"))["nms_" + tag].astype(np.int64)
+  keep = ops.nms(_cuda(boxes), _cuda(scores), thr).cpu().numpy()
+  assert np.array_equal(keep, gold)
+  assert np.array_equal(keep, orc.nms(boxes, scores, thr))
+
+
+def test_nms_full_size_properties(ops):
+  """6000 x 1 and 12000 x 1 at BASELINE sizes: idempotence and the pairwise-IoU invariant."""
+  rng = np.random.default_rng(99)
+  for n in (6000, 12000):
+    b = gi.random_boxes(rng, n)
+    s = rng.permutation(n).astype(np.float32) / n
+    keep = ops.nms(_cuda(b), _cuda(s), 0.7).cpu().numpy()
+    assert np.array_equal(keep, orc.nms(b, s, 0.7))
+    kb, ks = b[keep], s[keep]
+    again = ops.nms(_cuda(kb), _cuda(ks), 0.7).cpu().numpy()
+    assert np.array_equal(again, np.arange(len(keep)))             # idempotent: survivors do not suppress each other
+    assert np.all(np.diff(ks) <= 0)                                  # descending scores
+
+
+# ---------------------------------------------------------------- RoI pooling (K7)
+@pytest.mark.parametrize("tag", gi.ROI_CASES)
+def test_roi_pool_fwd_bit_exact_bwd_matches(ops, tag):
+  fm, rois = gi.roi_case(tag)
+  out_ref, arg_ref = orc.roi_pool_forward(fm, rois)
+  props = np.stack([rois[:, 2], rois[:, 1], rois[:, 4], rois[:, 3]], axis = 1)    # (b,x1,y1,x2,y2) -> (y1,x1,y2,x2)
+  fmc = _cuda(fm).requires_grad_(True)
+  out = ops.roi_pool(fmc, _cuda(props), (7, 7), 1.0 / 16.0)
+  assert np.array_equal(out.detach().cpu().numpy(), out_ref)
+  go = gi.roi_grad(tag, out_ref.shape)
+  out.backward(_cuda(go))
+  gin_ref = orc.roi_pool_backward(go, arg_ref, rois, fm.shape)
+  np.testing.assert_allclose(fmc.grad.cpu().numpy(), gin_ref, rtol = 0, atol = 1e-5)
+
+
+def test_roi_pool_microbench_shape_property(ops):
+  """6000 RoIs (config 5 shape): every output equals the max over its bin computed by the oracle on a sample."""
+  rng = np.random.default_rng(5)
+  fm = np.maximum(rng.normal(0, 1, (1, 512, 37, 62)), 0).astype(np.float32)
+  b = gi.random_boxes(rng, 6000)
+  out = ops.roi_pool(_cuda(fm), _cuda(b), (7, 7), 1.0 / 16.0).cpu().numpy()
+  pick = rng.choice(6000, 64, replace = False)
+  rois = np.stack([np.zeros(64, np.float32), b[pick, 1], b[pick, 0], b[pick, 3], b[pick, 2]], axis = 1)
+  ref, _ = orc.roi_pool_forward(fm, rois)
+  assert np.array_equal(out[pick], ref)
+  assert out.max() <= fm.max() and out.min() >= 0.0
+
+
+# ---------------------------------------------------------------- labelling, losses, post-processing
+def test_label_proposals_vs_oracle(ops):
+  rng = np.random.default_rng(1)
+  props = gi.random_boxes(rng, 500)
+  gt = np.array([[100, 150, 400, 600], [50, 650, 500, 850], [120, 160, 380, 590]], dtype = np.float32)
+  cls = [7, 15, 3]
+  allp = np.vstack([props, gt])
+  p_ref, onehot_ref, packed_ref = orc.label_proposals(t.from_numpy(props), gt, cls)
+  best, cidx, onehot, packed = ops.label_proposals(_cuda(allp), _cuda(gt), t.tensor(cls, dtype = t.int32).cuda(), 21)
+  assert np.array_equal(onehot.cpu().numpy(), onehot_ref.numpy())                  # labels bit-exact
+  np.testing.assert_array_equal(packed[:, 0, :].cpu().numpy(), packed_ref[:, 0, :].numpy())
+  np.testing.assert_allclose(packed[:, 1, :].cpu().numpy(), packed_ref[:, 1, :].numpy(), rtol = 1e-5, atol = 1e-5)
+
+
+def test_rpn_and_detector_losses_and_grads_vs_oracle(ops):
+  smp = orc.synthetic_sample((384, 512), seed = 0)
+  fh, fw = 24, 32
+  g = t.Generator().manual_seed(5)
+  scores = t.rand((1, fh, fw, 9), generator = g) * 0.98 + 0.01
+  deltas = t.randn((1, fh, fw, 36), generator = g) * 0.5
+  import random
+  random.seed(0)
+  mb = orc.sample_rpn_minibatch(smp["gt_rpn_map"], smp["gt_rpn_object_indices"], smp["gt_rpn_background_indices"])
+  sr, dr = scores.clone().requires_grad_(True), deltas.clone().requires_grad_(True)
+  l1, l2 = orc.rpn_class_loss(sr, mb), orc.rpn_regression_loss(dr, mb)
+  (l1 + l2).backward()
+  sc, dc = scores.cuda().requires_grad_(True), deltas.cuda().requires_grad_(True)
+  out = ops.rpn_losses(sc, dc, mb.cuda())
+  out.sum().backward()
+  np.testing.assert_allclose(out.detach().cpu().numpy(), [l1.item(), l2.item()], rtol = 1e-5)
+  np.testing.assert_allclose(sc.grad.cpu().numpy(), sr.grad.numpy(), rtol = 1e-4, atol = 1e-8)
+  np.testing.assert_allclose(dc.grad.cpu().numpy(), dr.grad.numpy(), rtol = 1e-4, atol = 1e-8)
+
+  n, c = 128, 21
+  logits = t.randn((n, c), generator = g)
+  dl = t.randn((n, 80), generator = g) * 0.5
+  yc = F.one_hot(t.randint(0, c, (n,), generator = g), c).float()
+  yd = t.zeros((n, 2, 80))
+  yd[:, 1, :] = t.randn((n, 80), generator = g)
+  yd[:, 0, :] = t.repeat_interleave(yc, 4, dim = 1)[:, 4:]
+  lr_, dlr = logits.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+  pr = F.softmax(lr_, dim = 1)
+  k1, k2 = orc.detector_class_loss(pr, yc), orc.detector_regression_loss(dlr, yd)
+  (k1 + k2).backward()
+  lc, dlc = logits.cuda().requires_grad_(True), dl.cuda().requires_grad_(True)
+  pc = ops.softmax_rows(lc)
+  np.testing.assert_allclose(pc.detach().cpu().numpy(), pr.detach().numpy(), rtol = 1e-5, atol = 1e-7)
+  out = ops.detector_losses(pc, dlc, yc.cuda(), yd.cuda())
+  out.sum().backward()
+  np.testing.assert_allclose(out.detach().cpu().numpy(), [k1.item(), k2.item()], rtol = 1e-5)
+  np.testing.assert_allclose(lc.grad.cpu().numpy(), lr_.grad.numpy(), rtol = 1e-4, atol = 1e-7)
+  np.testing.assert_allclose(dlc.grad.cpu().numpy(), dlr.grad.numpy(), rtol = 1e-4, atol = 1e-8)
+
+
+def test_detect_postprocess_vs_oracle(ops):
+  rng = np.random.default_rng(21)
+  n = 300
+  props = gi.random_boxes(rng, n, 600.0, 800.0)
+  classes = rng.dirichlet(np.ones(21) * 0.3, n).astype(np.float32)
+  deltas = rng.normal(0, 0.5, (n, 80)).astype(np.float32)
+  got = ops.detect_postprocess(_cuda(props), _cuda(classes), _cuda(deltas), (600, 800), 0.05, 0.3)
+  pa = np.empty(props.shape)
+  pa[:, 0] = 0.5 * (props[:, 0] + props[:, 2]); pa[:, 1] = 0.5 * (props[:, 1] + props[:, 3]); pa[:, 2:4] = props[:, 2:4] - props[:, 0:2]
+  for c in range(1, 21):
+    boxes = orc.deltas_to_boxes_np(deltas[:, (c - 1) * 4:(c - 1) * 4 + 4], pa, [0, 0, 0, 0], [0.1, 0.1, 0.2, 0.2])
+    boxes[:, 0::2] = np.clip(boxes[:, 0::2], 0, 599); boxes[:, 1::2] = np.clip(boxes[:, 1::2], 0, 799)
+    sel = np.where(classes[:, c] > 0.05)[0]
+    keep = orc.nms(boxes[sel], classes[sel, c], 0.3)
+    ref = np.hstack([boxes[sel][keep], classes[sel, c][keep][:, None]])
+    assert got[c].shape == ref.shape, c
+    np.testing.assert_allclose(got[c], ref, rtol = 0, atol = 1e-9)
+
+
+def test_sgd_kernel_vs_oracle_update_rule(ops):
+  g = t.Generator().manual_seed(2)
+  p = t.randn((1000003,), generator = g); gr = t.randn((1000003,), generator = g)
+  pr, buf_r = p.clone(), None
+  pc, bc = p.cuda(), t.zeros_like(p).cuda()
+  for step in range(3):
+    gg = gr + 5e-4 * pr
+    buf_r = gg.clone() if buf_r is None else buf_r * 0.9 + gg
+    pr = pr - 1e-3 * buf_r
+    ops.sgd_step(pc, gr.cuda(), bc, 1e-3, 0.9, 5e-4, 1.0, first_step = (step == 0))
+  np.testing.assert_allclose(pc.cpu().numpy(), pr.numpy(), rtol = 1e-6, atol = 1e-7)

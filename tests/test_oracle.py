@@ -62,7 +62,7 @@ def test_roi_pool_matches_torchvision_golden(tvops, tag):
     np.testing.assert_allclose(gin, tvops["roi_small_gin"], rtol = 0, atol = 1e-5)
     assert np.array_equal(out, tvops["roi_small_out"])
   else:
-    assert sha(gin) == str(tvops["roi_%s_gin_sha" % tag]) or True
+    assert sha(gin) == str(tvops["roi_%s_gin_sha" % tag])
 
 
 def test_nms_and_roi_pool_match_live_torchvision():
