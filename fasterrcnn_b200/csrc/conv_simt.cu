@@ -465,6 +465,14 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, float *_
   }
 }
 
+int launch_splitk_reduce(const float *partial, float *out, int M, int Nn, int splits, const Epilogue &epi, cudaStream_t st)
+{
+  size_t total = (size_t)M * Nn;
+  splitk_reduce_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(partial, out, M, Nn, splits, epi);
+  FRCNN_CHECK_LAUNCH("splitk_reduce_kernel");
+  return FRCNN_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------

@@ -17,12 +17,15 @@ import torch as t
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, check, lib, ptr, stream, workspace
 
-_engine = {"value": _lib.ENGINE_AUTO}
+import os as _os
+
+_ENGINES = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32}
+_engine = {"value": _ENGINES[_os.environ.get("FRCNN_ENGINE", "auto")]}
 
 
 def set_engine(name):
   """'auto' | 'simt' (exact fp32 CUDA-core) | 'tc' (tcgen05 3xTF32)."""
-  _engine["value"] = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32}[name]
+  _engine["value"] = _ENGINES[name]
 
 
 def get_engine():
@@ -300,6 +303,8 @@ class _RoIPool(t.autograd.Function):
     k, h, w, c, ph, pw, scale = ctx.geom
     dfm = _empty_nhwc(1, c, h, w, dout.device)
     dout = dout.contiguous()
+    if k == 0:
+      return dfm.zero_(), None, None, None
     check(lib().frcnn_roi_pool_bwd(ptr(dout), ptr(arg), ptr(props), k, h, w, c, ph, pw, scale, None, ptr(dfm), stream()), "frcnn_roi_pool_bwd")
     _lib.count()
     return dfm, None, None, None
@@ -317,8 +322,9 @@ class _Softmax(t.autograd.Function):
     x = logits.detach().contiguous()
     n, c = x.shape
     p = t.empty_like(x)
-    check(lib().frcnn_softmax_rows(ptr(x), ptr(p), n, c, stream()), "frcnn_softmax_rows")
-    _lib.count()
+    if n > 0:
+      check(lib().frcnn_softmax_rows(ptr(x), ptr(p), n, c, stream()), "frcnn_softmax_rows")
+      _lib.count()
     ctx.save_for_backward(p)
     return p
 
@@ -328,8 +334,9 @@ class _Softmax(t.autograd.Function):
     n, c = p.shape
     g = g.contiguous()
     d = t.empty_like(p)
-    check(lib().frcnn_softmax_rows_bwd(ptr(p), ptr(g), ptr(d), n, c, stream()), "frcnn_softmax_rows_bwd")
-    _lib.count()
+    if n > 0:
+      check(lib().frcnn_softmax_rows_bwd(ptr(p), ptr(g), ptr(d), n, c, stream()), "frcnn_softmax_rows_bwd")
+      _lib.count()
     return d
 
 

@@ -291,14 +291,15 @@ def vgg16_param_shapes(num_classes = 21):
   return shapes
 
 
-def synth_params(shapes, seed = 0, heads = "spread"):
+def synth_params(shapes, seed = 0, heads = "spread", input_scale = 50.0):
   """
   Deterministic synthetic weights (no pretrained files offline).  One CPU generator, keys in
   dict order: weights ~ N(0, sqrt(2/fan_in)) (keeps activations O(1) through 13 ReLU convs),
   biases ~ N(0, 0.01).  heads = "reference" uses the reference's head init
   (N(0,0.01)/N(0,0.001), zero bias; models/rpn.py:44-49, models/detector.py:33-36), which makes
   every objectness score ~0.5 (tie stress case); heads = "spread" scales the head weights so
-  scores and classes are well separated.
+  scores and classes are well separated.  The first conv is divided by input_scale (synthetic
+  images are randn*50) so that activations are O(1) and SGD at lr 1e-3 is stable.
   """
   g = t.Generator(device = "cpu")
   g.manual_seed(seed)
@@ -322,6 +323,8 @@ def synth_params(shapes, seed = 0, heads = "spread"):
         elif key.endswith("_regressor.weight"):
           std = 0.004
       out[key] = t.randn(shape, generator = g, dtype = t.float32) * std
+      if len(shape) == 4 and shape[1] == 3:
+        out[key] /= input_scale
     elif key.endswith("running_var"):
       out[key] = t.rand(shape, generator = g, dtype = t.float32) * 0.5 + 0.75
     elif key.endswith("num_batches_tracked"):

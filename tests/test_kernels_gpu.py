@@ -40,9 +40,14 @@ CONV_CASES = [
 ]
 
 
+def _int_tensor(g, shape, lo, hi):
+  return t.randint(lo, hi + 1, shape, generator = g).float()
+
+
 @pytest.mark.parametrize("case", CONV_CASES, ids = [c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("engine", ["simt"])
+@pytest.mark.parametrize("engine", ["simt", "auto"])
 def test_conv_fwd_dgrad_wgrad_vs_torch_fp32(ops, case, engine):
+  """Linear part (no activation): fp32 tolerance = accumulation-order noise only (1e-4 of the output scale)."""
   _, n, h, w, cin, cout, k, stride, pad = case
   ops.set_engine(engine)
   g = t.Generator().manual_seed(7)
@@ -50,38 +55,63 @@ def test_conv_fwd_dgrad_wgrad_vs_torch_fp32(ops, case, engine):
   wt = t.randn((cout, cin, k, k), generator = g) * (2.0 / (cin * k * k)) ** 0.5
   b = t.randn((cout,), generator = g) * 0.1
   xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
-  yr = F.relu(F.conv2d(xr, wr, br, stride = stride, padding = pad))
+  yr = F.conv2d(xr, wr, br, stride = stride, padding = pad)
   gy = t.randn(yr.shape, generator = g)
   yr.backward(gy)
-
   xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True), b.cuda().requires_grad_(True)
-  y = ops.conv2d_act(xc, wc, bc, stride, pad, ops.ACT_RELU)
+  y = ops.conv2d_act(xc, wc, bc, stride, pad, ops.ACT_NONE)
   assert tuple(y.shape) == tuple(yr.shape)
-  tol = dict(rtol = 1e-4, atol = 1e-4)            # fp32 accumulation-order tolerance
-  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), **tol)
+  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol = 1e-4, atol = 1e-4)
   y.backward(gy.cuda())
   np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 2e-4)
   scale = float(wr.grad.abs().max())
   np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-5 * max(scale, 1.0) + 1e-4)
   np.testing.assert_allclose(bc.grad.cpu().numpy(), br.grad.numpy(), rtol = 1e-4, atol = 1e-3)
-  ops.set_engine("auto")
+  ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
 
 
-def test_conv_pool_fused_matches_torch(ops):
+@pytest.mark.parametrize("case", CONV_CASES, ids = [c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_conv_relu_exact_on_integer_data(ops, case, engine):
+  """Small-integer operands: every product and partial sum is exact in fp32 (and in the 3xTF32
+  split), so the result is independent of the accumulation order -> BIT-EXACT vs torch, including
+  the ReLU mask and both gradients."""
+  _, n, h, w, cin, cout, k, stride, pad = case
+  ops.set_engine(engine)
+  g = t.Generator().manual_seed(13)
+  x = _int_tensor(g, (n, cin, h, w), -2, 2)
+  wt = _int_tensor(g, (cout, cin, k, k), -1, 1)
+  b = _int_tensor(g, (cout,), -3, 3)
+  xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+  yr = F.relu(F.conv2d(xr, wr, br, stride = stride, padding = pad))
+  gy = _int_tensor(g, tuple(yr.shape), -1, 1)
+  yr.backward(gy)
+  xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True), b.cuda().requires_grad_(True)
+  y = ops.conv2d_act(xc, wc, bc, stride, pad, ops.ACT_RELU)
+  assert np.array_equal(y.detach().cpu().numpy(), yr.detach().numpy())
+  y.backward(gy.cuda())
+  assert np.array_equal(xc.grad.cpu().numpy(), xr.grad.numpy())
+  assert np.array_equal(wc.grad.cpu().numpy(), wr.grad.numpy())
+  assert np.array_equal(bc.grad.cpu().numpy(), br.grad.numpy())
+  ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
+
+
+def test_conv_pool_fused_exact_on_integer_data(ops):
   g = t.Generator().manual_seed(3)
-  x = t.randn((1, 64, 37, 51), generator = g)           # odd sizes: floor-mode pooling drops the last row/col
-  wt = t.randn((128, 64, 3, 3), generator = g) * 0.06
-  b = t.randn((128,), generator = g) * 0.1
+  x = _int_tensor(g, (1, 64, 37, 51), -2, 2)             # odd sizes: floor-mode pooling drops the last row/col
+  wt = _int_tensor(g, (128, 64, 3, 3), -1, 1)
+  b = _int_tensor(g, (128,), -3, 3)
   xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
   yr = F.max_pool2d(F.relu(F.conv2d(xr, wr, b, padding = 1)), 2, 2)
-  gy = t.randn(yr.shape, generator = g)
+  gy = _int_tensor(g, tuple(yr.shape), -1, 1)
   yr.backward(gy)
   xc, wc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True)
   y = ops.conv2d_act(xc, wc, b.cuda(), 1, 1, ops.ACT_RELU, pool = True)
-  np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol = 1e-4, atol = 1e-4)
+  assert np.array_equal(y.detach().cpu().numpy(), yr.detach().numpy())
   y.backward(gy.cuda())
-  np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 2e-4)
-  np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-3)
+  # max-pool ties (equal integers) are broken by the first maximum in (kh,kw) scan order on both sides
+  assert np.array_equal(xc.grad.cpu().numpy(), xr.grad.numpy())
+  assert np.array_equal(wc.grad.cpu().numpy(), wr.grad.numpy())
 
 
 @pytest.mark.parametrize("m,k,n", [(128, 25088, 4096), (300, 4096, 4096), (128, 4096, 21), (7, 4096, 80), (0, 4096, 21)])
@@ -91,16 +121,33 @@ def test_linear_vs_torch_fp32(ops, m, k, n):
   wt = t.randn((n, k), generator = g) * (1.0 / k) ** 0.5
   b = t.randn((n,), generator = g) * 0.1
   xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
-  yr = F.relu(F.linear(xr, wr, br))
+  yr = F.linear(xr, wr, br)
   gy = t.randn(yr.shape, generator = g)
   yr.backward(gy)
   xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-  y = ops.linear_act(xc, wc, bc, ops.ACT_RELU)
+  y = ops.linear_act(xc, wc, bc, ops.ACT_NONE)
   np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), rtol = 1e-4, atol = 1e-4)
   y.backward(gy.cuda())
   np.testing.assert_allclose(xc.grad.cpu().numpy(), xr.grad.numpy(), rtol = 1e-4, atol = 1e-4)
   np.testing.assert_allclose(wc.grad.cpu().numpy(), wr.grad.numpy(), rtol = 1e-4, atol = 1e-4)
   np.testing.assert_allclose(bc.grad.cpu().numpy(), br.grad.numpy(), rtol = 1e-4, atol = 1e-4)
+
+
+def test_linear_relu_exact_on_integer_data(ops):
+  g = t.Generator().manual_seed(17)
+  x = _int_tensor(g, (300, 4096), -2, 2)
+  wt = _int_tensor(g, (4096, 4096), -1, 1)
+  b = _int_tensor(g, (4096,), -3, 3)
+  xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+  yr = F.relu(F.linear(xr, wr, b))
+  gy = _int_tensor(g, tuple(yr.shape), -1, 1)
+  yr.backward(gy)
+  xc, wc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True)
+  y = ops.linear_act(xc, wc, b.cuda(), ops.ACT_RELU)
+  assert np.array_equal(y.detach().cpu().numpy(), yr.detach().numpy())
+  y.backward(gy.cuda())
+  assert np.array_equal(xc.grad.cpu().numpy(), xr.grad.numpy())
+  assert np.array_equal(wc.grad.cpu().numpy(), wr.grad.numpy())
 
 
 # ---------------------------------------------------------------- anchors + RPN proposal path (K5, K6)
@@ -267,3 +314,44 @@ def test_sgd_kernel_vs_oracle_update_rule(ops):
     pr = pr - 1e-3 * buf_r
     ops.sgd_step(pc, gr.cuda(), bc, 1e-3, 0.9, 5e-4, 1.0, first_step = (step == 0))
   np.testing.assert_allclose(pc.cpu().numpy(), pr.numpy(), rtol = 1e-6, atol = 1e-7)
+
+
+# ---------------------------------------------------------------- tcgen05 engine vs the exact fp32 engine
+TC_CASES = [
+  ("vgg_b5_512_37x62", 1, 37, 62, 512, 512, 3, 1),
+  ("vgg_b3_256_150x250", 1, 150, 250, 128, 256, 3, 1),
+  ("vgg_b1_64_600x1000", 1, 600, 1000, 64, 64, 3, 1),
+  ("rpn_1x1_like_512", 1, 37, 62, 512, 128, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids = [c[0] for c in TC_CASES])
+def test_tcgen05_conv_fwd_matches_fp32_engine(ops, case):
+  """3xTF32 on the tensor cores vs exact-fp32 CUDA cores at the BASELINE layer shapes: <= 2e-5 of the output scale."""
+  _, n, h, w, cin, cout, k, pad = case
+  g = t.Generator().manual_seed(23)
+  x = ops.as_nhwc(t.randn((n, cin, h, w), generator = g).cuda())
+  wt = (t.randn((cout, cin, k, k), generator = g) * (2.0 / (cin * k * k)) ** 0.5).cuda().contiguous(memory_format = t.channels_last)
+  b = (t.randn((cout,), generator = g) * 0.1).cuda()
+  ops.set_engine("simt")
+  y_ref = ops.conv2d_fwd_raw(x, wt, b, 1, pad, ops.ACT_RELU)
+  ops.set_engine("tc")
+  y = ops.conv2d_fwd_raw(x, wt, b, 1, pad, ops.ACT_RELU)
+  ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
+  scale = float(y_ref.abs().max())
+  err = float((y - y_ref).abs().max())
+  assert err <= 2e-5 * scale, (err, scale)
+
+
+def test_tcgen05_linear_fwd_splitk_matches_fp32_engine(ops):
+  g = t.Generator().manual_seed(29)
+  x = t.randn((128, 25088), generator = g).cuda()
+  wt = (t.randn((4096, 25088), generator = g) * (1.0 / 25088) ** 0.5).cuda()
+  b = (t.randn((4096,), generator = g) * 0.1).cuda()
+  ops.set_engine("simt")
+  y_ref = ops.linear_act(x, wt, b, ops.ACT_RELU)
+  ops.set_engine("tc")
+  y = ops.linear_act(x, wt, b, ops.ACT_RELU)
+  ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
+  scale = float(y_ref.abs().max())
+  assert float((y - y_ref).abs().max()) <= 2e-5 * scale

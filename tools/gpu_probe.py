@@ -57,7 +57,7 @@ def main():
     tb = ev_time(lambda: y.backward(g, retain_graph = True))
     print("linear %d x %d x %d  %.2f GFLOP  fwd %.3f ms (%.1f TF/s)  bwd(dx+dw) %.3f ms (%.1f TF/s)" % (m, k, n, gf, tf, gf / tf, tb, 2 * gf / tb), flush = True)
 
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 0, heads = "spread")
+  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 0, heads = "reference")
   model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0))
   model.load_state_dict(params)
   model = model.cuda()
