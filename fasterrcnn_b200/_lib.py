@@ -42,6 +42,7 @@ _SIGNATURES = {
   "frcnn_spatial_mean_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
   "frcnn_add": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_rpn_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+  "frcnn_rpn_targets": (_i, [_vp, _vp, _i, _vp, _i, _d, _d, _vp, _vp, _sz, _vp]),
   "frcnn_topk_order": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
   "frcnn_gather_filtered": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
   "frcnn_nms_workspace_bytes": (_sz, [_i]),

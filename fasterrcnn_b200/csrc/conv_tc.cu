@@ -1,15 +1,21 @@
-// tcgen05 engine (FRCNN_ENGINE_TC_3XTF32): implicit-GEMM convolution on the 5th-gen tensor cores.
+// tcgen05 engine (FRCNN_ENGINE_TC_3XTF32): implicit-GEMM convolution -- forward, data gradient and
+// filter gradient -- on the 5th-gen tensor cores.
 //
 //   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) straight from the NHWC fp32
-//     activation: for filter tap (kh,kw) the A tile of a (tile_h x tile_w) output patch is the
-//     input patch shifted by (kh-pad, kw-pad); the TMA unit zero-fills the out-of-image part, so
-//     im2col and padding are folded into the shared-memory staging and never exist in HBM;
+//     tensors.  For filter tap (kh,kw) the activation tile of an output patch is the input patch
+//     shifted by (kh-pad, kw-pad); the TMA unit zero-fills the part outside the image, so im2col
+//     and padding are folded into the shared-memory staging and never exist in HBM;
 //   * tcgen05.mma kind::tf32 issued by one thread, fp32 accumulators in TMEM (128 lanes x BN cols);
-//   * fp32-grade accuracy through the error-compensated split x = hi + lo (hi = the 11-bit tf32
-//     truncation the tensor core applies itself, lo = x - hi): D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi;
+//   * fp32-grade accuracy through the error-compensated split x = hi + lo (hi = the tf32 truncation
+//     the tensor core applies itself, lo = x - hi): D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-//     epilogue (tcgen05.ld -> scale/bias/residual/activation -> 128-bit stores); a STAGES-deep
-//     mbarrier ring (full/empty) between producer and issuer, tcgen05.commit frees slots.
+//     epilogue (tcgen05.ld -> scale/bias/residual/activation -> 128-bit stores); STAGES-deep
+//     mbarrier ring (full/empty), tcgen05.commit frees slots.
+//
+// GEMM views (M x N x K), all with 128 x BN x 32 tiles:
+//   FWD    pixels x Cout x (tap,ci) : A = x patch   (K-major, 4-D map)   B = w[co][(tap,ci)] (K-major, 2-D map)
+//   DGRAD  pixels x Cin  x (tap,co) : A = dy patch  (K-major, flipped tap) B = w[co][tap][ci] (N-major, 3-D map)
+//   WGRAD  Cout   x Cin  x pixels   : A = dy patch  (M-major)            B = shifted x patch (N-major), one tap per CTA
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -45,17 +51,22 @@ __global__ void split_lo_kernel(const float *__restrict__ x, float *__restrict__
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
+enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+
 struct TcGeom {
   int Cin, Cout, KH, KW, pad;
-  int Ho, Wo;                 // output spatial size (== input size for the stride-1 "same" convs)
-  int tile_w, tile_h;         // output patch of one CTA: tile_w * tile_h == 128
-  int tiles_w, tiles_h;       // patches per image
-  int kb_per_split, total_kb; // k-blocks (32 channels of one tap each)
+  int H, W, nimg;             // spatial size (input == output: stride-1 "same" convs; linear: 1 x rows)
+  int tile_w, tile_h;         // FWD/DGRAD: output patch of one CTA (tile_w * tile_h == 128)
+  int tiles_w, tiles_h;       //            patches per image
+  int pw, ph;                 // WGRAD: pixel patch of one k-block (pw * ph == 32)
+  int patches_w, patches_h;
+  int kb_per_split, total_kb, splits;
 };
 
 constexpr int kTcThreads = 192;
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
-constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128-row A tile
+constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
+constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
 
 __device__ __forceinline__ float tc_act(float v, int act)
 {
@@ -64,14 +75,16 @@ __device__ __forceinline__ float tc_act(float v, int act)
   return v;
 }
 
-template <int BN, int STAGES>
+template <int MODE, int BN, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                   TcGeom g, float *__restrict__ out, float *__restrict__ partial, Epilogue epi)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               TcGeom g, float *__restrict__ out, float *__restrict__ partial, Epilogue epi)
 {
   constexpr int kBBytes = BN * kBK * 4;
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr bool kAMajorMN = (MODE == TC_WGRAD);
+  constexpr bool kBMajorMN = (MODE != TC_FWD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
@@ -80,19 +93,27 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KHW = g.KH * g.KW;
 
-  // tile coordinates
-  const int tiles_per_img = g.tiles_w * g.tiles_h;
-  const int img = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - img * tiles_per_img;
-  const int oh0 = (trem / g.tiles_w) * g.tile_h;
-  const int ow0 = (trem % g.tiles_w) * g.tile_w;
+  // ---- tile coordinates ----
+  int img = 0, oh0 = 0, ow0 = 0, m0 = 0, tap_w = 0, split = 0;
   const int n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * g.kb_per_split;
+  if (MODE == TC_WGRAD) {
+    m0 = blockIdx.x * 128;
+    tap_w = blockIdx.z / g.splits;
+    split = blockIdx.z - tap_w * g.splits;
+  } else {
+    const int tiles_per_img = g.tiles_w * g.tiles_h;
+    img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    oh0 = (trem / g.tiles_w) * g.tile_h;
+    ow0 = (trem % g.tiles_w) * g.tile_w;
+    split = blockIdx.z;
+  }
+  const int kb_begin = split * g.kb_per_split;
   int kb_end = kb_begin + g.kb_per_split;
   if (kb_end > g.total_kb) kb_end = g.total_kb;
   const int nkb = kb_end - kb_begin;
-  const int cblocks = g.Cin / kBK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -113,24 +134,58 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kBK;          // channel blocks per tap (FWD/DGRAD)
+      const int patches_per_img = g.patches_w * g.patches_h;
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         const int kb = kb_begin + i;
-        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
-        const int kh = tap / g.KW, kw = tap - kh * g.KW;
-        uint8_t *st = smem + s * kStageBytes;
+        uint8_t *a_hi = smem + s * kStageBytes;
+        uint8_t *a_lo = a_hi + kABytes;
+        uint8_t *b_hi = a_hi + 2 * kABytes;
+        uint8_t *b_lo = b_hi + kBBytes;
         mbar_expect_tx(&full[s], kStageBytes);
-        tma_load_4d(st, &map_a_hi, &full[s], c0, ow0 + kw - g.pad, oh0 + kh - g.pad, img);
-        tma_load_4d(st + kABytes, &map_a_lo, &full[s], c0, ow0 + kw - g.pad, oh0 + kh - g.pad, img);
-        tma_load_2d(st + 2 * kABytes, &map_b_hi, &full[s], tap * g.Cin + c0, n0);
-        tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, &full[s], tap * g.Cin + c0, n0);
+        if (MODE == TC_WGRAD) {
+          const int im = kb / patches_per_img;
+          const int prem = kb - im * patches_per_img;
+          const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
+          const int kh = tap_w / g.KW, kw = tap_w - kh * g.KW;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {                                        // A: dy, 128 output channels = 4 atoms
+            tma_load_4d(a_hi + j * kAtomBytes, &map_a_hi, &full[s], m0 + 32 * j, px, py, im);
+            tma_load_4d(a_lo + j * kAtomBytes, &map_a_lo, &full[s], m0 + 32 * j, px, py, im);
+          }
+#pragma unroll
+          for (int j = 0; j < BN / 32; j++) {                                  // B: x shifted by the tap
+            tma_load_4d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
+            tma_load_4d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
+          }
+        } else {
+          const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kBK;
+          const int kh = tap / g.KW, kw = tap - kh * g.KW;
+          const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
+          const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
+          tma_load_4d(a_hi, &map_a_hi, &full[s], c0, ow0 + dx, oh0 + dy, img);
+          tma_load_4d(a_lo, &map_a_lo, &full[s], c0, ow0 + dx, oh0 + dy, img);
+          if (MODE == TC_FWD) {
+            tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, n0);
+            tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; j++) {                                // B: w[co0..+32][tap][n0+32j..+32]
+              tma_load_3d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], n0 + 32 * j, tap, c0);
+              tma_load_3d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], n0 + 32 * j, tap, c0);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);
+      constexpr uint32_t a_kstep = kAMajorMN ? 1024 : 32, a_lbo = kAMajorMN ? kAtomBytes : 16;
+      constexpr uint32_t b_kstep = kBMajorMN ? 1024 : 32, b_lbo = kBMajorMN ? kAtomBytes : 16;
       uint32_t accumulate = 0;
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -142,10 +197,10 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const uint32_t b_lo = b_hi + kBBytes;
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
-          const uint64_t da_hi = make_smem_desc(a_hi + k * 32, 16, 1024);
-          const uint64_t da_lo = make_smem_desc(a_lo + k * 32, 16, 1024);
-          const uint64_t db_hi = make_smem_desc(b_hi + k * 32, 16, 1024);
-          const uint64_t db_lo = make_smem_desc(b_lo + k * 32, 16, 1024);
+          const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, 1024);
+          const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, 1024);
+          const uint64_t db_hi = make_smem_desc(b_hi + k * b_kstep, b_lbo, 1024);
+          const uint64_t db_lo = make_smem_desc(b_lo + k * b_kstep, b_lbo, 1024);
           umma_tf32(tmem_base, da_hi, db_lo, idesc, accumulate);     // small terms first
           umma_tf32(tmem_base, da_lo, db_hi, idesc, 1);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
@@ -161,32 +216,42 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     tc_fence_after();
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int oh = oh0 + row / g.tile_w, ow = ow0 + row % g.tile_w;
-    const bool valid = oh < g.Ho && ow < g.Wo;
-    const size_t pix = ((size_t)img * g.Ho + oh) * g.Wo + ow;
-    const bool raw = gridDim.z > 1;
-    // split-K: raw partial sums go to partial[z][pixel][Cout]; the reduce kernel applies the epilogue
-    float *dst = raw ? partial + (size_t)blockIdx.z * ((size_t)(gridDim.x / tiles_per_img) * g.Ho * g.Wo) * g.Cout : out;
+    const bool raw = g.splits > 1;
+    bool valid;
+    size_t row_off;           // element offset of this row's first column (col = n0)
+    size_t res_off = 0;
+    int ntot;
+    if (MODE == TC_WGRAD) {
+      ntot = KHW * g.Cin;
+      valid = (m0 + row) < g.Cout;
+      row_off = ((size_t)(m0 + row) * KHW + tap_w) * g.Cin + n0;
+      if (raw) row_off += (size_t)split * g.Cout * ntot;
+    } else {
+      ntot = (MODE == TC_FWD) ? g.Cout : g.Cin;
+      const int oh = oh0 + row / g.tile_w, ow = ow0 + row % g.tile_w;
+      valid = oh < g.H && ow < g.W;
+      const size_t pix = ((size_t)img * g.H + oh) * g.W + ow;
+      row_off = pix * ntot + n0;
+      res_off = row_off;
+      if (raw) row_off += (size_t)split * ((size_t)g.nimg * g.H * g.W) * ntot;
+    }
+    float *dst = (raw ? partial : out) + row_off;
     for (int c = 0; c < BN / 32; c++) {
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      if (nkb <= 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0.f;
-      }
       if (valid) {
-        const int col0 = n0 + c * 32;
-        float *p = dst + pix * g.Cout + col0;
-        if (!raw) {
+        if (!raw && MODE != TC_WGRAD) {
+          const int col0 = n0 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             float x = v[j];
             if (epi.scale) x *= __ldg(epi.scale + col0 + j);
             if (epi.bias) x += __ldg(epi.bias + col0 + j);
-            if (epi.residual) x += __ldg(epi.residual + pix * g.Cout + col0 + j);
+            if (epi.residual) x += __ldg(epi.residual + res_off + c * 32 + j);
             v[j] = tc_act(x, epi.act);
           }
         }
+        float *p = dst + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
@@ -216,17 +281,22 @@ static EncodeTiledFn encode_fn()
   return fn;
 }
 
+static bool encode(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box)
+{
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn f = encode_fn();
+  if (!f) return false;
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // activation (N,H,W,C) fp32 as a 4-D tensor (C, W, H, N); box {32, box_w, box_h, 1}
 static bool make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h)
 {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  EncodeTiledFn f = encode_fn();
-  if (!f) return false;
-  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return encode(m, base, 4, dims, strides, box);
 }
 
 // matrix (rows, K) fp32 row-major as a 2-D tensor (K, rows); box {32, box_rows}
@@ -235,133 +305,190 @@ static bool make_mat_map(CUtensorMap *m, const float *base, int rows, int K, int
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 4};
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  EncodeTiledFn f = encode_fn();
-  if (!f) return false;
-  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return encode(m, base, 2, dims, strides, box);
+}
+
+// filter (Cout, taps, Cin) fp32 as a 3-D tensor (Cin, taps, Cout); box {32 ci, 1 tap, 32 co}
+static bool make_filter3d_map(CUtensorMap *m, const float *base, int Cout, int taps, int Cin)
+{
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4};
+  cuuint32_t box[3] = {32, 1, 32};
+  return encode(m, base, 3, dims, strides, box);
 }
 
 struct TcPlan {
-  // geometry after folding nn.Linear (H=W=1) into a 1 x rows "image"
-  int N, H, W;
+  int N, H, W;                       // after folding nn.Linear (H=W=1) into a 1 x rows "image"
   int BN, stages;
   int tile_w, tile_h, tiles_w, tiles_h;
+  int pw, ph, patches_w, patches_h;
   int total_kb, splits, kb_per_split;
-  size_t x_lo_off, w_lo_off, partial_off, total_bytes;
+  size_t a_lo_off, b_lo_off, partial_off, total_bytes;
+  size_t a_count, b_count;           // element counts of the two operands that need a lo part
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static bool make_tc_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, TcPlan *p)
+static void best_patch(int total, int H, int W, int *pw, int *ph)
 {
-  if (stride != 1 || (Cin % 32) != 0 || (Cout % 64) != 0) return false;
-  if (KH != KW || 2 * pad != KH - 1) return false;                  // "same" convs and 1x1 / linear
-  if (KH == 1 && H == 1 && W == 1) { p->N = 1; p->H = 1; p->W = N; }  // linear: rows become the W axis
-  else { p->N = N; p->H = H; p->W = W; }
-  if ((long long)p->N * p->H * p->W < 64) return false;             // tiny problems stay on the CUDA-core engine
-  p->BN = (Cout % 128 == 0) ? 128 : 64;
-  p->stages = p->BN == 128 ? 3 : 4;
-  // output patch shape with the least padding waste (ties -> wider)
   long long best = -1;
-  for (int tw = 128; tw >= 8; tw >>= 1) {
-    int th = 128 / tw;
-    long long area = (long long)ceil_div(p->W, tw) * tw * ceil_div(p->H, th) * th;
-    if (best < 0 || area < best) { best = area; p->tile_w = tw; p->tile_h = th; }
+  for (int w = total; w >= 1; w >>= 1) {
+    int h = total / w;
+    if (w > 256 || h > 256) continue;
+    long long area = (long long)ceil_div(W, w) * w * ceil_div(H, h) * h;
+    if (best < 0 || area < best) { best = area; *pw = w; *ph = h; }
   }
-  p->tiles_w = ceil_div(p->W, p->tile_w);
-  p->tiles_h = ceil_div(p->H, p->tile_h);
-  p->total_kb = KH * KW * (Cin / 32);
-  int ctas = p->N * p->tiles_w * p->tiles_h * (Cout / p->BN);
+}
+
+static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, TcPlan *p)
+{
+  if (stride != 1 || KH != KW || 2 * pad != KH - 1) return false;        // stride-1 "same" convs, 1x1, linear
+  if (KH == 1 && H == 1 && W == 1) { p->N = 1; p->H = 1; p->W = N; }      // linear: rows become the W axis
+  else { p->N = N; p->H = H; p->W = W; }
+  const long long pixels = (long long)p->N * p->H * p->W;
+  if (pixels < 64) return false;                                         // tiny problems stay on the CUDA-core engine
+  const int ntot = (mode == TC_FWD) ? Cout : Cin;                         // GEMM N extent
+  if (ntot % 64 != 0) return false;
+  if (mode == TC_FWD && Cin % 32 != 0) return false;
+  if (mode == TC_DGRAD && Cout % 32 != 0) return false;
+  if (mode == TC_WGRAD && (Cout % 128 != 0 || Cin % 64 != 0)) return false;
+  p->BN = (ntot % 128 == 0) ? 128 : 64;
+  p->stages = p->BN == 128 ? 3 : 4;
+  p->tile_w = p->tile_h = p->tiles_w = p->tiles_h = 1;
+  p->pw = p->ph = p->patches_w = p->patches_h = 1;
+  const int taps = KH * KW;
+  int ctas;
+  if (mode == TC_WGRAD) {
+    best_patch(32, p->H, p->W, &p->pw, &p->ph);
+    p->patches_w = ceil_div(p->W, p->pw);
+    p->patches_h = ceil_div(p->H, p->ph);
+    p->total_kb = p->N * p->patches_w * p->patches_h;
+    ctas = (Cout / 128) * (Cin / p->BN) * taps;
+  } else {
+    best_patch(128, p->H, p->W, &p->tile_w, &p->tile_h);
+    p->tiles_w = ceil_div(p->W, p->tile_w);
+    p->tiles_h = ceil_div(p->H, p->tile_h);
+    p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / 32);
+    ctas = p->N * p->tiles_w * p->tiles_h * (ntot / p->BN);
+  }
   int splits = 1;
   if (ctas < kNumSMs) {
     splits = ceil_div(kNumSMs, ctas);
     int max_splits = p->total_kb / 8;
     if (splits > max_splits) splits = max_splits;
-    if (splits > 16) splits = 16;
+    if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
   }
   p->kb_per_split = ceil_div(p->total_kb, splits);
   p->splits = ceil_div(p->total_kb, p->kb_per_split);
-  size_t x_bytes = (size_t)p->N * p->H * p->W * Cin * 4;
-  size_t w_bytes = (size_t)Cout * KH * KW * Cin * 4;
-  p->x_lo_off = 0;
-  p->w_lo_off = align_up(x_bytes, 1024);
-  p->partial_off = p->w_lo_off + align_up(w_bytes, 1024);
-  p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * p->N * p->H * p->W * Cout * 4 : 0);
+  const size_t act_in = (size_t)pixels * Cin, act_out = (size_t)pixels * Cout, filt = (size_t)Cout * taps * Cin;
+  size_t out_elems;
+  if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
+  else if (mode == TC_DGRAD) { p->a_count = act_out; p->b_count = filt; out_elems = act_in; }
+  else { p->a_count = act_out; p->b_count = act_in; out_elems = filt; }
+  p->a_lo_off = 0;
+  p->b_lo_off = align_up(p->a_count * 4, 1024);
+  p->partial_off = p->b_lo_off + align_up(p->b_count * 4, 1024);
+  p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * out_elems * 4 : 0);
   return true;
 }
 
-bool tc_fwd_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad)
-{
-  TcPlan p;
-  return make_tc_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, &p);
-}
-
-size_t tc_fwd_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad)
-{
-  TcPlan p;
-  if (!make_tc_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, &p)) return 0;
-  return p.total_bytes;
-}
-
-template <int BN, int STAGES>
-static int launch_fwd(const CUtensorMap &ma_hi, const CUtensorMap &ma_lo, const CUtensorMap &mb_hi, const CUtensorMap &mb_lo,
-                      const TcGeom &g, const TcPlan &p, float *out, float *partial, const Epilogue &epi, int Cout, cudaStream_t st)
+template <int MODE, int BN, int STAGES>
+static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float *out, float *partial, const Epilogue &epi, cudaStream_t st)
 {
   constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kBK * 4) + 1024 + 256;
-  cudaError_t e = cudaFuncSetAttribute(tc_conv_fwd_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return cuda_fail(e, "tc_conv_fwd_kernel: smem attribute");
-  dim3 grid(p.N * p.tiles_w * p.tiles_h, Cout / BN, p.splits);
-  tc_conv_fwd_kernel<BN, STAGES><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, out, partial, epi);
-  FRCNN_CHECK_LAUNCH("tc_conv_fwd_kernel");
+  cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "tc_conv_kernel: smem attribute");
+  tc_conv_kernel<MODE, BN, STAGES><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;
 }
 
-int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
-                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+// a: the activation-side operand of the mode (x | dy | dy), b: the other one (w | w | x)
+static int run_tc(int mode, const float *a, const float *b, float *out, const Epilogue &epi,
+                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                   void *workspace, size_t workspace_bytes, cudaStream_t st)
 {
   TcPlan p;
-  if (!make_tc_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, &p)) return fail(FRCNN_E_UNSUPPORTED, "tc_conv2d_fwd: unsupported shape");
-  if (workspace == nullptr || workspace_bytes < p.total_bytes) return fail(FRCNN_E_WORKSPACE, "tc_conv2d_fwd: workspace too small");
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
-    return fail(FRCNN_E_BADARG, "tc_conv2d_fwd: operands and workspace must be 16-byte aligned");
+  if (!make_tc_plan(mode, N, H, W, Cin, Cout, KH, KW, stride, pad, &p)) return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: unsupported shape");
+  if (workspace == nullptr || workspace_bytes < p.total_bytes) return fail(FRCNN_E_WORKSPACE, "tcgen05 engine: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return fail(FRCNN_E_BADARG, "tcgen05 engine: operands and workspace must be 16-byte aligned");
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-  float *x_lo = reinterpret_cast<float *>(ws + p.x_lo_off);
-  float *w_lo = reinterpret_cast<float *>(ws + p.w_lo_off);
+  float *a_lo = reinterpret_cast<float *>(ws + p.a_lo_off);
+  float *b_lo = reinterpret_cast<float *>(ws + p.b_lo_off);
   float *partial = reinterpret_cast<float *>(ws + p.partial_off);
-  const size_t x_count = (size_t)p.N * p.H * p.W * Cin, w_count = (size_t)Cout * KH * KW * Cin;
-  split_lo_kernel<<<elementwise_grid(x_count / 4 + 1, 256), 256, 0, st>>>(x, x_lo, x_count);
-  FRCNN_CHECK_LAUNCH("split_lo_kernel(x)");
-  split_lo_kernel<<<elementwise_grid(w_count / 4 + 1, 256), 256, 0, st>>>(w, w_lo, w_count);
-  FRCNN_CHECK_LAUNCH("split_lo_kernel(w)");
+  split_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_lo, p.a_count);
+  FRCNN_CHECK_LAUNCH("split_lo_kernel(a)");
+  split_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_lo, p.b_count);
+  FRCNN_CHECK_LAUNCH("split_lo_kernel(b)");
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const int K = KH * KW * Cin;
-  bool ok = make_act_map(&ma_hi, x, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) && make_act_map(&ma_lo, x_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) &&
-            make_mat_map(&mb_hi, w, Cout, K, p.BN) && make_mat_map(&mb_lo, w_lo, Cout, K, p.BN);
-  if (!ok) return fail(FRCNN_E_BADARG, "tc_conv2d_fwd: cuTensorMapEncodeTiled failed");
+  const int taps = KH * KW;
+  CUtensorMap maps[4];
+  bool ok;
+  dim3 grid;
+  if (mode == TC_FWD) {
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) &&
+         make_mat_map(&maps[2], b, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, Cout, taps * Cin, p.BN);
+    grid = dim3(p.N * p.tiles_w * p.tiles_h, Cout / p.BN, p.splits);
+  } else if (mode == TC_DGRAD) {
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h) &&
+         make_filter3d_map(&maps[2], b, Cout, taps, Cin) && make_filter3d_map(&maps[3], b_lo, Cout, taps, Cin);
+    grid = dim3(p.N * p.tiles_w * p.tiles_h, Cin / p.BN, p.splits);
+  } else {
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph) &&
+         make_act_map(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph) && make_act_map(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph);
+    grid = dim3(Cout / 128, Cin / p.BN, taps * p.splits);
+  }
+  if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 
-  TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.tile_w, p.tile_h, p.tiles_w, p.tiles_h, p.kb_per_split, p.total_kb};
-  Epilogue epi{scale, bias, residual, act};
+  TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tiles_w, p.tiles_h, p.pw, p.ph, p.patches_w, p.patches_h,
+           p.kb_per_split, p.total_kb, p.splits};
   int rc;
-  if (p.BN == 128) rc = launch_fwd<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, g, p, y, partial, epi, Cout, st);
-  else rc = launch_fwd<64, 4>(ma_hi, ma_lo, mb_hi, mb_lo, g, p, y, partial, epi, Cout, st);
+#define TC_LAUNCH(M)                                                                          \
+  (p.BN == 128 ? launch_tc<M, 128, 3>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4>(maps, g, grid, out, partial, epi, st))
+  if (mode == TC_FWD) rc = TC_LAUNCH(TC_FWD);
+  else if (mode == TC_DGRAD) rc = TC_LAUNCH(TC_DGRAD);
+  else rc = TC_LAUNCH(TC_WGRAD);
+#undef TC_LAUNCH
   if (rc != FRCNN_OK) return rc;
-  if (p.splits > 1) return launch_splitk_reduce(partial, y, p.N * p.H * p.W, Cout, p.splits, epi, st);
+  if (p.splits > 1) {
+    const long long pixels = (long long)p.N * p.H * p.W;
+    if (mode == TC_FWD) return launch_splitk_reduce(partial, out, (int)pixels, Cout, p.splits, epi, st);
+    if (mode == TC_DGRAD) return launch_splitk_reduce(partial, out, (int)pixels, Cin, p.splits, epi, st);
+    Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
+    return launch_splitk_reduce(partial, out, Cout, taps * Cin, p.splits, none, st);
+  }
   return FRCNN_OK;
 }
 
-// data / filter gradients on the tensor cores: next increment (MN-major operand variants); until
-// then FRCNN_ENGINE_AUTO routes them to the fp32 CUDA-core engine.
-bool tc_dgrad_supported(int, int, int, int, int, int, int, int, int) { return false; }
-size_t tc_dgrad_workspace(int, int, int, int, int, int, int, int, int) { return 0; }
-int tc_conv2d_dgrad(const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int, void *, size_t, cudaStream_t)
-{ return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: dgrad not built"); }
-bool tc_wgrad_supported(int, int, int, int, int, int, int, int, int) { return false; }
-size_t tc_wgrad_workspace(int, int, int, int, int, int, int, int, int) { return 0; }
-int tc_conv2d_wgrad(const float *, const float *, float *, int, int, int, int, int, int, int, int, int, void *, size_t, cudaStream_t)
-{ return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: wgrad not built"); }
+#define GEOM_PARAMS int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad
+#define GEOM_ARGS N, H, W, Cin, Cout, KH, KW, stride, pad
+
+bool tc_fwd_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_FWD, GEOM_ARGS, &p); }
+bool tc_dgrad_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_DGRAD, GEOM_ARGS, &p); }
+bool tc_wgrad_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_WGRAD, GEOM_ARGS, &p); }
+size_t tc_fwd_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_FWD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
+size_t tc_dgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_DGRAD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
+size_t tc_wgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_WGRAD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
+
+int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
+                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+  Epilogue epi{scale, bias, residual, act};
+  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st);
+}
+
+int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+  Epilogue epi{nullptr, nullptr, addend, FRCNN_ACT_NONE};
+  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st);
+}
+
+int tc_conv2d_wgrad(const float *dy, const float *x, float *dw, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+  Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
+  return run_tc(TC_WGRAD, dy, x, dw, none, GEOM_ARGS, workspace, workspace_bytes, st);
+}
 
 }  // namespace frcnn

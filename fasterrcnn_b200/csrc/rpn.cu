@@ -304,6 +304,82 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats
   }
 }
 
+
+// ---- RPN ground-truth map (models/anchors.py:137-262) ------------------------------------------------
+// IoU in fp64 between the anchor corners (formed in fp32 from the (cy,cx,h,w) map, then widened, as
+// anchors.py:186-187 does) and the fp32 GT boxes; invalid anchors count as IoU -1.  Explicit fp64
+// roundings (no FMA contraction) so that both kernels below reproduce identical IoU bits.
+__device__ __forceinline__ double anchor_gt_iou(float ay1, float ax1, float ay2, float ax2, const float4 &g)
+{
+  double a0 = (double)ay1, a1 = (double)ax1, a2 = (double)ay2, a3 = (double)ax2;
+  double g0 = (double)g.x, g1 = (double)g.y, g2 = (double)g.z, g3 = (double)g.w;
+  double t0 = fmax(a0, g0), t1 = fmax(a1, g1), b0 = fmin(a2, g2), b1 = fmin(a3, g3);
+  double inter = (t0 < b0 && t1 < b1) ? __dmul_rn(__dsub_rn(b0, t0), __dsub_rn(b1, t1)) : 0.0;
+  double area_a = __dmul_rn(__dsub_rn(a2, a0), __dsub_rn(a3, a1));
+  double area_g = __dmul_rn(__dsub_rn(g2, g0), __dsub_rn(g3, g1));
+  double uni = __dsub_rn(__dadd_rn(area_a, area_g), inter);
+  return __ddiv_rn(inter, __dadd_rn(uni, 1e-7));
+}
+
+__device__ __forceinline__ void anchor_corners(const float4 &a, float &y1, float &x1, float &y2, float &x2)
+{
+  y1 = __fsub_rn(a.x, __fmul_rn(0.5f, a.z)); x1 = __fsub_rn(a.y, __fmul_rn(0.5f, a.w));
+  y2 = __fadd_rn(a.x, __fmul_rn(0.5f, a.z)); x2 = __fadd_rn(a.y, __fmul_rn(0.5f, a.w));
+}
+
+// pass 1: per-GT maximum IoU over all anchors (atomicMax on the int64 image of the double: order
+// preserving for values >= 0, and -1 sorts below every non-negative value)
+__global__ void rpn_targets_pass1(const float *__restrict__ anchors, const float *__restrict__ valid, int A, const float *__restrict__ gt, int M,
+                                  long long *__restrict__ gt_max_bits)
+{
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+    float4 an = __ldg(reinterpret_cast<const float4 *>(anchors) + a);
+    float y1, x1, y2, x2;
+    anchor_corners(an, y1, x1, y2, x2);
+    bool ok = valid[a] != 0.f;
+    for (int m = 0; m < M; m++) {
+      double iou = ok ? anchor_gt_iou(y1, x1, y2, x2, __ldg(reinterpret_cast<const float4 *>(gt) + m)) : -1.0;
+      atomicMax(&gt_max_bits[m], __double_as_longlong(iou));
+    }
+  }
+}
+
+__global__ void rpn_targets_pass2(const float *__restrict__ anchors, const float *__restrict__ valid, int A, const float *__restrict__ gt, int M,
+                                  const long long *__restrict__ gt_max_bits, double object_thr, double background_thr, float *__restrict__ rpn_map)
+{
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+    float4 an = __ldg(reinterpret_cast<const float4 *>(anchors) + a);
+    float y1, x1, y2, x2;
+    anchor_corners(an, y1, x1, y2, x2);
+    bool ok = valid[a] != 0.f;
+    double best = -INFINITY;
+    int which = 0;
+    bool top = false;
+    for (int m = 0; m < M; m++) {
+      double iou = ok ? anchor_gt_iou(y1, x1, y2, x2, __ldg(reinterpret_cast<const float4 *>(gt) + m)) : -1.0;
+      if (iou > best) { best = iou; which = m; }                     // np.argmax: first maximum
+      if (__double_as_longlong(iou) == gt_max_bits[m]) top = true;   // ious == max_iou_per_gt_box
+    }
+    int label = -1;
+    if (best < background_thr) label = 0;
+    if (best >= object_thr) label = 1;
+    if (top) label = 1;
+    float enable = label >= 0 ? 1.f : 0.f;
+    if (label < 0) label = 0;
+    // regression targets in fp32 (anchors.py:236-238 operate on float32 arrays)
+    float4 g = __ldg(reinterpret_cast<const float4 *>(gt) + which);
+    float gcy = __fmul_rn(0.5f, __fadd_rn(g.x, g.z)), gcx = __fmul_rn(0.5f, __fadd_rn(g.y, g.w));
+    float gh = __fsub_rn(g.z, g.x), gw = __fsub_rn(g.w, g.y);
+    float *o = rpn_map + (size_t)a * 6;
+    o[0] = __fmul_rn(valid[a], enable);
+    o[1] = (float)label;
+    o[2] = __fdiv_rn(__fsub_rn(gcy, an.x), an.z);
+    o[3] = __fdiv_rn(__fsub_rn(gcx, an.y), an.w);
+    o[4] = __double2float_rn(log((double)__fdiv_rn(gh, an.z)));
+    o[5] = __double2float_rn(log((double)__fdiv_rn(gw, an.w)));
+  }
+}
+
 }  // namespace frcnn
 
 using namespace frcnn;
@@ -386,6 +462,24 @@ int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index
   FRCNN_REQUIRE(src && index && count && dst && row_floats > 0 && capacity > 0, "gather_rows_f32: bad argument");
   gather_rows_kernel<<<elementwise_grid((size_t)capacity * row_floats, 256), 256, 0, as_stream(stream)>>>(src, row_floats, index, count, capacity, dst);
   FRCNN_CHECK_LAUNCH("gather_rows_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_rpn_targets(const float *anchors, const float *valid, int A, const float *gt_boxes, int M, double object_iou_threshold,
+                      double background_iou_threshold, float *rpn_map, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(anchors && valid && gt_boxes && rpn_map && A > 0 && M > 0, "rpn_targets: bad argument");
+  if (workspace == nullptr || workspace_bytes < (size_t)M * sizeof(long long)) return fail(FRCNN_E_WORKSPACE, "rpn_targets: workspace too small (need 8*M bytes)");
+  cudaStream_t st = as_stream(stream);
+  long long *gt_max = reinterpret_cast<long long *>(workspace);
+  // int64 image of -1.0 in every slot: 0xBFF0000000000000 -> byte pattern is not uniform, so fill with a kernel-free trick:
+  // memset to 0x80 gives a large-magnitude negative int64, below the image of -1.0 and of every IoU >= 0
+  cudaError_t e = cudaMemsetAsync(gt_max, 0x80, (size_t)M * sizeof(long long), st);
+  if (e != cudaSuccess) return cuda_fail(e, "rpn_targets: memset");
+  rpn_targets_pass1<<<elementwise_grid(A, 128, 2), 128, 0, st>>>(anchors, valid, A, gt_boxes, M, gt_max);
+  FRCNN_CHECK_LAUNCH("rpn_targets_pass1");
+  rpn_targets_pass2<<<elementwise_grid(A, 128, 2), 128, 0, st>>>(anchors, valid, A, gt_boxes, M, gt_max, object_iou_threshold, background_iou_threshold, rpn_map);
+  FRCNN_CHECK_LAUNCH("rpn_targets_pass2");
   return FRCNN_OK;
 }
 

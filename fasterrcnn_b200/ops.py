@@ -32,6 +32,51 @@ def get_engine():
   return _engine["value"]
 
 
+class _KernelTimer:
+  """CUDA-event timing of the GEMM-shaped launches (bench.py's roofline leg): events are recorded on
+  the launching stream around every conv/linear fwd / dgrad / wgrad call while enabled."""
+
+  def __init__(self):
+    self.enabled = False
+    self.records = []
+
+  def enable(self, on):
+    self.enabled = bool(on)
+    if on:
+      self.records = []
+
+  def begin(self):
+    if not self.enabled:
+      return None
+    e = t.cuda.Event(enable_timing = True)
+    e.record()
+    return e
+
+  def end(self, start, kind, gflop):
+    if start is None:
+      return
+    e = t.cuda.Event(enable_timing = True)
+    e.record()
+    self.records.append((kind, gflop, start, e))
+
+  def collect(self):
+    t.cuda.synchronize()
+    out = {}
+    for kind, gflop, a, b in self.records:
+      d = out.setdefault(kind, dict(ms = 0.0, gflop = 0.0, launches = 0))
+      d["ms"] += a.elapsed_time(b); d["gflop"] += gflop; d["launches"] += 1
+    self.records = []
+    return out
+
+
+kernel_timer = _KernelTimer()
+
+
+def _engine_name(supported_tc):
+  e = _engine["value"]
+  return "tcgen05_3xtf32" if (e != _lib.ENGINE_SIMT_FP32 and supported_tc) else "simt_fp32"
+
+
 def _require_cuda(*tensors):
   for x in tensors:
     if x is not None and not x.is_cuda:
@@ -98,7 +143,9 @@ def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None):
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
   ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
   ws, ws_n = workspace(ws_bytes)
+  t0 = kernel_timer.begin()
   check(lib().frcnn_conv2d_fwd(ptr(x), ptr(w), ptr(scale), ptr(bias), ptr(residual), ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
+  kernel_timer.end(t0, "conv_fwd", 2e-9 * n * ho * wo * cout * kh * kw * cin)
   _lib.count()
   return y
 
@@ -111,7 +158,9 @@ def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None):
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
   ws_bytes = lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng)
   ws, ws_n = workspace(ws_bytes)
+  t0 = kernel_timer.begin()
   check(lib().frcnn_conv2d_dgrad(ptr(dy), ptr(w), ptr(addend), ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
+  kernel_timer.end(t0, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin)
   _lib.count()
   return dx
 
@@ -126,7 +175,9 @@ def conv2d_wgrad_raw(dy, x, w_shape, stride, pad):
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
   ws_bytes = lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng)
   ws, ws_n = workspace(ws_bytes)
+  t0 = kernel_timer.begin()
   check(lib().frcnn_conv2d_wgrad(ptr(dy), ptr(x), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
+  kernel_timer.end(t0, "conv_wgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin)
   _lib.count()
   return dw
 
@@ -233,7 +284,9 @@ class _LinearAct(t.autograd.Function):
     geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
     ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
     ws, ws_n = workspace(ws_bytes)
+    t0 = kernel_timer.begin()
     check(lib().frcnn_conv2d_fwd(ptr(x2), ptr(w2), None, ptr(b.detach()) if b is not None else None, None, ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd(linear)")
+    kernel_timer.end(t0, "linear_fwd", 2e-9 * m * k * nout)
     _lib.count()
     ctx.save_for_backward(x2, w2, y)
     return y
@@ -262,12 +315,16 @@ class _LinearAct(t.autograd.Function):
     if ctx.needs_input_grad[0]:
       dx = t.empty((m, k), dtype = t.float32, device = x2.device)
       ws, ws_n = workspace(lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
+      t0 = kernel_timer.begin()
       check(lib().frcnn_conv2d_dgrad(ptr(dz), ptr(w2), None, ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad(linear)")
+      kernel_timer.end(t0, "linear_dgrad", 2e-9 * m * k * nout)
       _lib.count()
     if ctx.needs_input_grad[1]:
       dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
       ws, ws_n = workspace(lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
+      t0 = kernel_timer.begin()
       check(lib().frcnn_conv2d_wgrad(ptr(dz), ptr(x2), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad(linear)")
+      kernel_timer.end(t0, "linear_wgrad", 2e-9 * m * k * nout)
       _lib.count()
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = bias_grad_raw(dz, nout)

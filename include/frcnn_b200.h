@@ -113,6 +113,13 @@ int frcnn_add(const float *a, const float *b, float *out, size_t count, void *st
 int frcnn_rpn_decode(const float *deltas, const float *anchors_in, int fh, int fw, int feature_pixels, int img_h, int img_w, float min_size,
                      float *boxes, uint8_t *size_ok, float *anchors_out, float *valid_out, void *stream);
 
+/* ---- (f)1: RPN ground truth (anchors.generate_rpn_map, models/anchors.py:137-262) -------------------
+ * anchors (A,4) fp32 (cy,cx,h,w), valid (A) fp32, gt_boxes (M,4) fp32 -> rpn_map (A,6) fp32 =
+ * [trainable, object, ty, tx, th, tw]: IoU in fp64, anchor positive if IoU >= object threshold or
+ * it is a best anchor of some GT box, negative if < background threshold.  workspace >= 8*M bytes. */
+int frcnn_rpn_targets(const float *anchors, const float *valid, int A, const float *gt_boxes, int M, double object_iou_threshold,
+                      double background_iou_threshold, float *rpn_map, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- top-N ordering (t.argsort + flip + [0:N], models/rpn.py:129-132) -----------------------
  * order[r] = index of the r-th best score for r < min(n, top_n); descending by score, ties ->
  * higher index first (= stable ascending argsort then flip).  If keep_mask != NULL only

@@ -1,0 +1,20 @@
+#!/bin/bash
+# third GPU round: TC fwd+bwd bring-up (isolated), full suite, probe, bench, ncu launch list + full capture
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -k "tcgen05" --timeout 300 -p no:cacheprovider > gpurun_out/pytest_tc.log 2>&1
+TC_RC=$?
+echo "pytest tc exit $TC_RC" >> gpurun_out/pytest_tc.log
+tail -30 gpurun_out/pytest_tc.log
+if [ $TC_RC -ne 0 ]; then export FRCNN_ENGINE=simt; echo "TC engine failed -> running the rest on FRCNN_ENGINE=simt"; fi
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "not tcgen05" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
+timeout 600 python tools/gpu_probe.py ${FRCNN_ENGINE:-auto} > gpurun_out/probe_auto.log 2>&1
+echo "probe exit $?" >> gpurun_out/probe_auto.log
+grep -v "^-\|Self C" gpurun_out/probe_auto.log | tail -60
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+echo "bench exit $?"; tail -3 gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 30 -c 4 -o gpurun_out/prof_tc -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"; ls -la gpurun_out/
