@@ -427,11 +427,15 @@ wgrad_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *_
   }
 }
 
-// naive filter gradient for shapes the vector kernel does not take (Cin or Cout not a multiple
-// of 4, e.g. the RGB stem): one thread per filter element, fixed summation order.
-__global__ void wgrad_naive_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dw, ConvGeom g)
+// scalar filter gradient for shapes the vector kernel does not take (Cin or Cout not a multiple of
+// 4: the RGB stem, the 9/21-wide heads): one thread per filter element and K slice (blockIdx.y),
+// fixed summation order inside a slice, slices combined by the deterministic split-K reduce.
+__global__ void wgrad_scalar_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dst, ConvGeom g, int pix_per_slice)
 {
-  size_t total = (size_t)g.Cout * g.KH * g.KW * g.Cin;
+  const size_t total = (size_t)g.Cout * g.KH * g.KW * g.Cin;
+  const int npix = g.N * g.Ho * g.Wo;
+  const int p0 = blockIdx.y * pix_per_slice;
+  const int p1 = p0 + pix_per_slice < npix ? p0 + pix_per_slice : npix;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     int ci = (int)(e % g.Cin);
     size_t r = e / g.Cin;
@@ -439,18 +443,24 @@ __global__ void wgrad_naive_kernel(const float *__restrict__ dy, const float *__
     int kh = (int)(r % g.KH);
     int co = (int)(r / g.KH);
     float s = 0.f;
-    for (int n = 0; n < g.N; n++)
-      for (int oh = 0; oh < g.Ho; oh++) {
-        int ih = oh * g.stride - g.pad + kh;
-        if (ih < 0 || ih >= g.H) continue;
-        for (int ow = 0; ow < g.Wo; ow++) {
-          int iw = ow * g.stride - g.pad + kw;
-          if (iw < 0 || iw >= g.W) continue;
-          s = fmaf(dy[((size_t)(n * g.Ho + oh) * g.Wo + ow) * g.Cout + co], x[((size_t)(n * g.H + ih) * g.W + iw) * g.Cin + ci], s);
-        }
-      }
-    dw[e] = s;
+    for (int p = p0; p < p1; p++) {
+      int n = p / (g.Ho * g.Wo), rem = p - n * g.Ho * g.Wo;
+      int oh = rem / g.Wo, ow = rem - oh * g.Wo;
+      int ih = oh * g.stride - g.pad + kh, iw = ow * g.stride - g.pad + kw;
+      if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+      s = fmaf(__ldg(dy + (size_t)p * g.Cout + co), __ldg(x + ((size_t)(n * g.H + ih) * g.W + iw) * g.Cin + ci), s);
+    }
+    dst[(size_t)blockIdx.y * total + e] = s;
   }
+}
+
+static int scalar_wgrad_slices(const ConvGeom &g)
+{
+  int npix = g.N * g.Ho * g.Wo;
+  int slices = npix / 64;
+  if (slices > 64) slices = 64;
+  if (slices < 1) slices = 1;
+  return slices;
 }
 
 // split-K second stage: out = epilogue(sum_z partial[z]) in fixed z order (deterministic)
@@ -574,6 +584,10 @@ size_t simt_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int 
 {
   ConvGeom g = make_geom(N, H, W, Cin, Cout, KH, KW, stride, pad);
   if (!geom_ok(g)) return 0;
+  if ((Cin % 4) != 0 || (Cout % 4) != 0) {
+    int slices = scalar_wgrad_slices(g);
+    return slices > 1 ? (size_t)slices * Cout * KH * KW * Cin * sizeof(float) : 0;
+  }
   Plan p = make_wgrad_plan(g);
   return p.splits > 1 ? (size_t)p.splits * Cout * KH * KW * Cin * sizeof(float) : 0;
 }
@@ -606,8 +620,21 @@ int simt_conv2d_wgrad(const float *dy, const float *x, float *dw,
   if (!geom_ok(g)) return fail(FRCNN_E_BADARG, "conv2d_wgrad: bad geometry");
   if ((Cin % 4) != 0 || (Cout % 4) != 0) {
     size_t total = (size_t)Cout * KH * KW * Cin;
-    wgrad_naive_kernel<<<elementwise_grid(total, 128), 128, 0, st>>>(dy, x, dw, g);
-    FRCNN_CHECK_LAUNCH("wgrad_naive_kernel");
+    int slices = scalar_wgrad_slices(g);
+    int npix = N * g.Ho * g.Wo;
+    int per = ceil_div(npix, slices);
+    slices = ceil_div(npix, per);
+    float *target = dw;
+    if (slices > 1) {
+      if (workspace == nullptr || workspace_bytes < (size_t)slices * total * sizeof(float)) return fail(FRCNN_E_WORKSPACE, "conv2d_wgrad: workspace too small for the K slices");
+      target = reinterpret_cast<float *>(workspace);
+    }
+    wgrad_scalar_kernel<<<dim3(elementwise_grid(total, 128, 2), slices), 128, 0, st>>>(dy, x, target, g, per);
+    FRCNN_CHECK_LAUNCH("wgrad_scalar_kernel");
+    if (slices > 1) {
+      Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
+      return launch_splitk_reduce(target, dw, Cout, KH * KW * Cin, slices, none, st);
+    }
     return FRCNN_OK;
   }
   const int M = Cout, Nn = KH * KW * Cin, Kpix = N * g.Ho * g.Wo;

@@ -16,6 +16,7 @@
 //   FWD    pixels x Cout x (tap,ci) : A = x patch   (K-major, 4-D map)   B = w[co][(tap,ci)] (K-major, 2-D map)
 //   DGRAD  pixels x Cin  x (tap,co) : A = dy patch  (K-major, flipped tap) B = w[co][tap][ci] (N-major, 3-D map)
 //   WGRAD  Cout   x Cin  x pixels   : A = dy patch  (M-major)            B = shifted x patch (N-major), one tap per CTA
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,22 +33,32 @@ struct Epilogue {
 };
 int launch_splitk_reduce(const float *partial, float *out, int M, int Nn, int splits, const Epilogue &epi, cudaStream_t st);
 
-// ---- lo = x - tf32_trunc(x) ----------------------------------------------------------------------
-__global__ void split_lo_kernel(const float *__restrict__ x, float *__restrict__ lo, size_t count)
+// ---- x = hi + lo: hi = x rounded to tf32 (exactly representable, so the tensor core's own fp32->tf32
+// conversion -- whatever its rounding -- is the identity), lo = x - hi (exact in fp32, <= 13 bits) ----
+__device__ __forceinline__ float tf32_rna(float x)
+{
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void split_hi_lo_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, size_t count)
 {
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
-    float4 r;
-    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    float4 h, r;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+    reinterpret_cast<float4 *>(hi)[i] = h;
     reinterpret_cast<float4 *>(lo)[i] = r;
   }
-  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride)
-    lo[i] = x[i] - __uint_as_float(__float_as_uint(x[i]) & 0xffffe000u);
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
+    float h = tf32_rna(x[i]);
+    hi[i] = h;
+    lo[i] = x[i] - h;
+  }
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
@@ -56,11 +67,12 @@ enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 struct TcGeom {
   int Cin, Cout, KH, KW, pad;
   int H, W, nimg;             // spatial size (input == output: stride-1 "same" convs; linear: 1 x rows)
-  int tile_w, tile_h;         // FWD/DGRAD: output patch of one CTA (tile_w * tile_h == 128)
-  int tiles_w, tiles_h;       //            patches per image
-  int pw, ph;                 // WGRAD: pixel patch of one k-block (pw * ph == 32)
+  int tile_w, tile_h, tile_n; // FWD/DGRAD: output patch of one CTA (tile_w * tile_h * tile_n == 128; tile_n images)
+  int tiles_w, tiles_h;       //            patches per image group
+  int pw, ph, pn;             // WGRAD: pixel patch of one k-block (pw * ph * pn == 32)
   int patches_w, patches_h;
   int kb_per_split, total_kb, splits;
+  int mn_lbo, mn_sbo, mn_kstep;   // MN-major operand descriptor strides in bytes (4096 / 512 / 1024)
 };
 
 constexpr int kTcThreads = 192;
@@ -104,8 +116,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     split = blockIdx.z - tap_w * g.splits;
   } else {
     const int tiles_per_img = g.tiles_w * g.tiles_h;
-    img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
+    img = (blockIdx.x / tiles_per_img) * g.tile_n;                 // first image of this CTA's image group
+    const int trem = blockIdx.x % tiles_per_img;
     oh0 = (trem / g.tiles_w) * g.tile_h;
     ow0 = (trem % g.tiles_w) * g.tile_w;
     split = blockIdx.z;
@@ -146,8 +158,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint8_t *b_lo = b_hi + kBBytes;
         mbar_expect_tx(&full[s], kStageBytes);
         if (MODE == TC_WGRAD) {
-          const int im = kb / patches_per_img;
-          const int prem = kb - im * patches_per_img;
+          const int im = (kb / patches_per_img) * g.pn;              // first image of the patch's image group
+          const int prem = kb % patches_per_img;
           const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
           const int kh = tap_w / g.KW, kw = tap_w - kh * g.KW;
 #pragma unroll
@@ -184,8 +196,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);
-      constexpr uint32_t a_kstep = kAMajorMN ? 1024 : 32, a_lbo = kAMajorMN ? kAtomBytes : 16;
-      constexpr uint32_t b_kstep = kBMajorMN ? 1024 : 32, b_lbo = kBMajorMN ? kAtomBytes : 16;
+      const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
+      const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
       uint32_t accumulate = 0;
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -197,10 +209,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t b_lo = b_hi + kBBytes;
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
-          const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, 1024);
-          const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, 1024);
-          const uint64_t db_hi = make_smem_desc(b_hi + k * b_kstep, b_lbo, 1024);
-          const uint64_t db_lo = make_smem_desc(b_lo + k * b_kstep, b_lbo, 1024);
+          constexpr uint32_t a_lt = kAMajorMN ? kLayoutSW128Base32B : kLayoutSW128, b_lt = kBMajorMN ? kLayoutSW128Base32B : kLayoutSW128;
+          const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t db_hi = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
+          const uint64_t db_lo = make_smem_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, da_hi, db_lo, idesc, accumulate);     // small terms first
           umma_tf32(tmem_base, da_lo, db_hi, idesc, 1);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
@@ -228,9 +241,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (raw) row_off += (size_t)split * g.Cout * ntot;
     } else {
       ntot = (MODE == TC_FWD) ? g.Cout : g.Cin;
-      const int oh = oh0 + row / g.tile_w, ow = ow0 + row % g.tile_w;
-      valid = oh < g.H && ow < g.W;
-      const size_t pix = ((size_t)img * g.H + oh) * g.W + ow;
+      const int per_img = g.tile_w * g.tile_h;
+      const int nn = row / per_img, rrem = row - nn * per_img;
+      const int oh = oh0 + rrem / g.tile_w, ow = ow0 + rrem % g.tile_w;
+      valid = (img + nn) < g.nimg && oh < g.H && ow < g.W;
+      const size_t pix = ((size_t)(img + nn) * g.H + oh) * g.W + ow;
       row_off = pix * ntot + n0;
       res_off = row_off;
       if (raw) row_off += (size_t)split * ((size_t)g.nimg * g.H * g.W) * ntot;
@@ -281,22 +296,24 @@ static EncodeTiledFn encode_fn()
   return fn;
 }
 
-static bool encode(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box)
+// mn_major: the tile feeds an MN-major (transposed) tf32 operand -> 32-byte-atom swizzle
+static bool encode(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box, bool mn_major)
 {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn f = encode_fn();
   if (!f) return false;
   return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// activation (N,H,W,C) fp32 as a 4-D tensor (C, W, H, N); box {32, box_w, box_h, 1}
-static bool make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h)
+// activation (N,H,W,C) fp32 as a 4-D tensor (C, W, H, N); box {32, box_w, box_h, box_n}
+static bool make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h, int box_n, bool mn_major = false)
 {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  return encode(m, base, 4, dims, strides, box);
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  return encode(m, base, 4, dims, strides, box, mn_major);
 }
 
 // matrix (rows, K) fp32 row-major as a 2-D tensor (K, rows); box {32, box_rows}
@@ -305,7 +322,7 @@ static bool make_mat_map(CUtensorMap *m, const float *base, int rows, int K, int
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 4};
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  return encode(m, base, 2, dims, strides, box);
+  return encode(m, base, 2, dims, strides, box, false);
 }
 
 // filter (Cout, taps, Cin) fp32 as a 3-D tensor (Cin, taps, Cout); box {32 ci, 1 tap, 32 co}
@@ -314,30 +331,32 @@ static bool make_filter3d_map(CUtensorMap *m, const float *base, int Cout, int t
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4};
   cuuint32_t box[3] = {32, 1, 32};
-  return encode(m, base, 3, dims, strides, box);
+  return encode(m, base, 3, dims, strides, box, true);
 }
 
 struct TcPlan {
   int N, H, W;                       // after folding nn.Linear (H=W=1) into a 1 x rows "image"
   int BN, stages;
-  int tile_w, tile_h, tiles_w, tiles_h;
-  int pw, ph, patches_w, patches_h;
+  int tile_w, tile_h, tile_n, tiles_w, tiles_h, groups;
+  int pw, ph, pn, patches_w, patches_h, pgroups;
   int total_kb, splits, kb_per_split;
-  size_t a_lo_off, b_lo_off, partial_off, total_bytes;
+  size_t a_hi_off, a_lo_off, b_hi_off, b_lo_off, partial_off, total_bytes;
   size_t a_count, b_count;           // element counts of the two operands that need a lo part
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static void best_patch(int total, int H, int W, int *pw, int *ph)
+// patch (pw x ph x pn, product == total, powers of two) with the least padded volume; ties -> wider, then taller
+static void best_patch(int total, int N, int H, int W, int *pw, int *ph, int *pn)
 {
   long long best = -1;
-  for (int w = total; w >= 1; w >>= 1) {
-    int h = total / w;
-    if (w > 256 || h > 256) continue;
-    long long area = (long long)ceil_div(W, w) * w * ceil_div(H, h) * h;
-    if (best < 0 || area < best) { best = area; *pw = w; *ph = h; }
-  }
+  for (int w = total; w >= 1; w >>= 1)
+    for (int h = total / w; h >= 1; h >>= 1) {
+      int n = total / (w * h);
+      if (w > 256 || h > 256 || n > 256) continue;
+      long long vol = (long long)ceil_div(W, w) * w * ceil_div(H, h) * h * ceil_div(N, n) * n;
+      if (best < 0 || vol < best) { best = vol; *pw = w; *ph = h; *pn = n; }
+    }
 }
 
 static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, TcPlan *p)
@@ -354,22 +373,24 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   if (mode == TC_WGRAD && (Cout % 128 != 0 || Cin % 64 != 0)) return false;
   p->BN = (ntot % 128 == 0) ? 128 : 64;
   p->stages = p->BN == 128 ? 3 : 4;
-  p->tile_w = p->tile_h = p->tiles_w = p->tiles_h = 1;
-  p->pw = p->ph = p->patches_w = p->patches_h = 1;
+  p->tile_w = p->tile_h = p->tile_n = p->tiles_w = p->tiles_h = p->groups = 1;
+  p->pw = p->ph = p->pn = p->patches_w = p->patches_h = p->pgroups = 1;
   const int taps = KH * KW;
   int ctas;
   if (mode == TC_WGRAD) {
-    best_patch(32, p->H, p->W, &p->pw, &p->ph);
+    best_patch(32, p->N, p->H, p->W, &p->pw, &p->ph, &p->pn);
     p->patches_w = ceil_div(p->W, p->pw);
     p->patches_h = ceil_div(p->H, p->ph);
-    p->total_kb = p->N * p->patches_w * p->patches_h;
+    p->pgroups = ceil_div(p->N, p->pn);
+    p->total_kb = p->pgroups * p->patches_w * p->patches_h;
     ctas = (Cout / 128) * (Cin / p->BN) * taps;
   } else {
-    best_patch(128, p->H, p->W, &p->tile_w, &p->tile_h);
+    best_patch(128, p->N, p->H, p->W, &p->tile_w, &p->tile_h, &p->tile_n);
     p->tiles_w = ceil_div(p->W, p->tile_w);
     p->tiles_h = ceil_div(p->H, p->tile_h);
+    p->groups = ceil_div(p->N, p->tile_n);
     p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / 32);
-    ctas = p->N * p->tiles_w * p->tiles_h * (ntot / p->BN);
+    ctas = p->groups * p->tiles_w * p->tiles_h * (ntot / p->BN);
   }
   int splits = 1;
   if (ctas < kNumSMs) {
@@ -386,8 +407,10 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
   else if (mode == TC_DGRAD) { p->a_count = act_out; p->b_count = filt; out_elems = act_in; }
   else { p->a_count = act_out; p->b_count = act_in; out_elems = filt; }
-  p->a_lo_off = 0;
-  p->b_lo_off = align_up(p->a_count * 4, 1024);
+  p->a_hi_off = 0;
+  p->a_lo_off = align_up(p->a_count * 4, 1024);
+  p->b_hi_off = 2 * p->a_lo_off;
+  p->b_lo_off = p->b_hi_off + align_up(p->b_count * 4, 1024);
   p->partial_off = p->b_lo_off + align_up(p->b_count * 4, 1024);
   p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * out_elems * 4 : 0);
   return true;
@@ -415,35 +438,42 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return fail(FRCNN_E_BADARG, "tcgen05 engine: operands and workspace must be 16-byte aligned");
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  float *a_hi = reinterpret_cast<float *>(ws + p.a_hi_off);
   float *a_lo = reinterpret_cast<float *>(ws + p.a_lo_off);
+  float *b_hi = reinterpret_cast<float *>(ws + p.b_hi_off);
   float *b_lo = reinterpret_cast<float *>(ws + p.b_lo_off);
   float *partial = reinterpret_cast<float *>(ws + p.partial_off);
-  split_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_lo, p.a_count);
-  FRCNN_CHECK_LAUNCH("split_lo_kernel(a)");
-  split_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_lo, p.b_count);
-  FRCNN_CHECK_LAUNCH("split_lo_kernel(b)");
+  split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_hi, a_lo, p.a_count);
+  FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(a)");
+  split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_hi, b_lo, p.b_count);
+  FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(b)");
+  a = a_hi;
+  b = b_hi;
 
   const int taps = KH * KW;
   CUtensorMap maps[4];
   bool ok;
   dim3 grid;
   if (mode == TC_FWD) {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h) &&
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) &&
          make_mat_map(&maps[2], b, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, Cout, taps * Cin, p.BN);
-    grid = dim3(p.N * p.tiles_w * p.tiles_h, Cout / p.BN, p.splits);
+    grid = dim3(p.groups * p.tiles_w * p.tiles_h, Cout / p.BN, p.splits);
   } else if (mode == TC_DGRAD) {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h) &&
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
          make_filter3d_map(&maps[2], b, Cout, taps, Cin) && make_filter3d_map(&maps[3], b_lo, Cout, taps, Cin);
-    grid = dim3(p.N * p.tiles_w * p.tiles_h, Cin / p.BN, p.splits);
+    grid = dim3(p.groups * p.tiles_w * p.tiles_h, Cin / p.BN, p.splits);
   } else {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph) &&
-         make_act_map(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph) && make_act_map(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph);
+    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) &&
+         make_act_map(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true) && make_act_map(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true);
     grid = dim3(Cout / 128, Cin / p.BN, taps * p.splits);
   }
   if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 
-  TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tiles_w, p.tiles_h, p.pw, p.ph, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits};
+  static const int dbg_lbo = getenv("FRCNN_TC_MN_LBO") ? atoi(getenv("FRCNN_TC_MN_LBO")) : kAtomBytes;
+  static const int dbg_sbo = getenv("FRCNN_TC_MN_SBO") ? atoi(getenv("FRCNN_TC_MN_SBO")) : 512;
+  static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 1024;
+  TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
+           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep};
   int rc;
 #define TC_LAUNCH(M)                                                                          \
   (p.BN == 128 ? launch_tc<M, 128, 3>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4>(maps, g, grid, out, partial, epi, st))

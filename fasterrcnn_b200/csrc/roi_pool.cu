@@ -96,25 +96,42 @@ roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const flo
   }
 }
 
-// grid (C/32, ceil(H/8)); block (32 lanes = channels, 8 warps = rows)
+// grid (C/32, ceil(H/8)); block (32 lanes = channels, 8 warps = rows).  A per-CTA table of the
+// clipped row range [hs,he) of every (RoI, ph) lets a thread visit only the bins that can hold an
+// argmax on its row (typically 7-14 of the 49), in ascending (RoI, bin) order.
 __global__ void __launch_bounds__(256)
-roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ argmax, int K, int H, int W, int C, int bins,
-                    const float *__restrict__ addend, float *__restrict__ dfm)
+roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ argmax, const float *__restrict__ proposals, float scale,
+                    int K, int H, int W, int C, int PH, int PW, const float *__restrict__ addend, float *__restrict__ dfm)
 {
-  extern __shared__ float line[];                 // [W][256]
+  extern __shared__ float line[];                 // [W][256] floats, then the (K x PH) row-range table
+  int32_t *rows = reinterpret_cast<int32_t *>(line + (size_t)W * 256);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int h = blockIdx.y * 8 + warp;
   const bool live = c < C && h < H;
+  const int bins = PH * PW;
+  for (int e = threadIdx.x; e < K * PH; e += blockDim.x) {
+    int n = e / PH, ph = e - n * PH;
+    const RoiBins r = roi_bins(proposals + 4 * (size_t)n, scale, PH, PW);
+    int hs = (int)floorf(__fmul_rn((float)ph, r.bh)) + r.ys;
+    int he = (int)ceilf(__fmul_rn((float)(ph + 1), r.bh)) + r.ys;
+    hs = min(max(hs, 0), H); he = min(max(he, 0), H);
+    rows[e] = (hs << 16) | he;
+  }
   for (int w = 0; w < W; w++) line[w * 256 + threadIdx.x] = 0.f;
+  __syncthreads();
   if (live) {
     const int lo = h * W, hi = lo + W;
     for (int n = 0; n < K; n++) {
       const int32_t *a = argmax + ((size_t)n * C + c) * bins;
       const float *g = dout + ((size_t)n * C + c) * bins;
-      for (int b = 0; b < bins; b++) {
-        int idx = __ldg(a + b);
-        if (idx >= lo && idx < hi) line[(idx - lo) * 256 + threadIdx.x] += __ldg(g + b);
+      for (int ph = 0; ph < PH; ph++) {
+        const int packed = rows[n * PH + ph];
+        if (h < (packed >> 16) || h >= (packed & 0xffff)) continue;
+        for (int pw = 0; pw < PW; pw++) {
+          int idx = __ldg(a + ph * PW + pw);
+          if (idx >= lo && idx < hi) line[(idx - lo) * 256 + threadIdx.x] += __ldg(g + ph * PW + pw);
+        }
       }
     }
     for (int w = 0; w < W; w++) {
@@ -151,15 +168,15 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
 int frcnn_roi_pool_bwd(const float *dout, const int32_t *argmax, const float *proposals, int K, int H, int W, int C, int PH, int PW,
                        float spatial_scale, const float *addend, float *dfm, void *stream)
 {
-  (void)proposals; (void)spatial_scale;
-  FRCNN_REQUIRE(dout && argmax && dfm && K >= 0 && H > 0 && W > 0 && C > 0 && PH > 0 && PW > 0, "roi_pool_bwd: bad argument");
-  size_t smem = (size_t)W * 256 * sizeof(float);
-  FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_bwd: feature map too wide for the shared-memory line buffer");
+  FRCNN_REQUIRE(dout && argmax && proposals && dfm && K >= 0 && H > 0 && W > 0 && C > 0 && PH > 0 && PW > 0, "roi_pool_bwd: bad argument");
+  FRCNN_REQUIRE(H < 32768, "roi_pool_bwd: feature map too tall");
+  size_t smem = (size_t)W * 256 * sizeof(float) + (size_t)K * PH * sizeof(int32_t);
+  FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_bwd: feature map too wide / too many RoIs for the shared-memory buffers");
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roi_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_pool_bwd: smem attribute");
   }
-  roi_pool_bwd_kernel<<<dim3(ceil_div(C, 32), ceil_div(H, 8)), 256, smem, as_stream(stream)>>>(dout, argmax, K, H, W, C, PH * PW, addend, dfm);
+  roi_pool_bwd_kernel<<<dim3(ceil_div(C, 32), ceil_div(H, 8)), 256, smem, as_stream(stream)>>>(dout, argmax, proposals, spatial_scale, K, H, W, C, PH, PW, addend, dfm);
   FRCNN_CHECK_LAUNCH("roi_pool_bwd_kernel");
   return FRCNN_OK;
 }

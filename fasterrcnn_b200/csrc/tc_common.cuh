@@ -43,9 +43,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-  uint32_t polls = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
+    if (clock64() - t0 > 4000000000ll) __trap();        // ~2 s at 2 GHz: far beyond any legitimate wait
   }
 }
 
@@ -129,15 +130,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v)
 // K-major operand  (rows = M/N index, 128-B rows of 32 fp32 along K): LBO unused (1), SBO = 1024 B
 //   (8 rows x 128 B per swizzle atom); advancing K by 8 fp32 = +32 B on the start address.
 // MN-major operand (rows = K index, 128-B rows of 32 fp32 along M/N): LBO = byte distance between
-//   32-column atoms, SBO = 1024 B between 8-row K atoms; advancing K by 8 = +1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+//   32-column atoms, SBO = byte distance between K atoms; advancing K by 8 rows = +1024 B.
+//
+// 32-bit MN-major operands (tf32 "transposed") must use layout type 1 = SWIZZLE_128B_BASE32B: 32-byte
+// chunks swizzled within the 128-byte row over a 4-row period (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+// the K atom is then 4 rows (512 B): SBO = 512, LBO = distance between 32-column atoms.
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
 
