@@ -38,7 +38,8 @@ _SIGNATURES = {
   "frcnn_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-  "frcnn_spatial_mean_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+  "frcnn_spatial_mean_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+  "frcnn_scale_rows": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
   "frcnn_spatial_mean_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
   "frcnn_add": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_rpn_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -8,9 +8,14 @@
 //   * tcgen05.mma kind::tf32 issued by one thread, fp32 accumulators in TMEM (128 lanes x BN cols);
 //   * fp32-grade accuracy through the error-compensated split x = hi + lo (hi = the tf32 truncation
 //     the tensor core applies itself, lo = x - hi): D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi;
+//   * the tensor core's own fp32 accumulation is the remaining error source on long K chains, so
+//     chains are kept short: every kChunkKB k-blocks (48 MMAs) the accumulator -- double-buffered in
+//     TMEM -- is drained by the epilogue warps into fp32 registers (round-to-nearest adds on the CUDA
+//     cores) while the issuer already fills the other buffer;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-//     epilogue (tcgen05.ld -> scale/bias/residual/activation -> 128-bit stores); STAGES-deep
-//     mbarrier ring (full/empty), tcgen05.commit frees slots.
+//     accumulate/epilogue (tcgen05.ld -> register sums -> scale/bias/residual/activation -> 128-bit
+//     stores); STAGES-deep mbarrier ring (full/empty) for operands, 2-deep ring (acc_full/acc_empty)
+//     for accumulators, tcgen05.commit signals both.
 //
 // GEMM views (M x N x K), all with 128 x BN x 32 tiles:
 //   FWD    pixels x Cout x (tap,ci) : A = x patch   (K-major, 4-D map)   B = w[co][(tap,ci)] (K-major, 2-D map)
@@ -79,6 +84,7 @@ constexpr int kTcThreads = 192;
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
 constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
+constexpr int kChunkKB = 4;                   // k-blocks accumulated inside the tensor core before a register drain
 
 __device__ __forceinline__ float tc_act(float v, int act)
 {
@@ -101,8 +107,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
   uint64_t *empty = full + STAGES;
-  uint64_t *tmem_full = empty + STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  uint64_t *acc_full = empty + STAGES;        // [2]
+  uint64_t *acc_empty = acc_full + 2;         // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KHW = g.KH * g.KW;
@@ -129,14 +136,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
   }
   tc_fence_before();
   __syncthreads();
@@ -199,7 +206,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
       const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
       uint32_t accumulate = 0;
+      int chunk = 0;
+      uint32_t tmem_acc = tmem_base;
       for (int i = 0; i < nkb; i++) {
+        if (i % kChunkKB == 0) {                                     // new accumulation chain in the other TMEM buffer
+          const int b = chunk & 1;
+          mbar_wait(&acc_empty[b], ((chunk >> 1) & 1) ^ 1);          // drained by the epilogue warps (first use passes)
+          tc_fence_after();
+          tmem_acc = tmem_base + b * BN;
+          accumulate = 0;
+        }
         const int s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -214,21 +230,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
           const uint64_t db_hi = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
           const uint64_t db_lo = make_smem_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_base, da_hi, db_lo, idesc, accumulate);     // small terms first
-          umma_tf32(tmem_base, da_lo, db_hi, idesc, 1);
-          umma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
+          umma_tf32(tmem_acc, da_hi, db_lo, idesc, accumulate);      // small terms first
+          umma_tf32(tmem_acc, da_lo, db_hi, idesc, 1);
+          umma_tf32(tmem_acc, da_hi, db_hi, idesc, 1);
           accumulate = 1;
         }
-        umma_commit(&empty[s]);                                      // frees the slot when these MMAs retire
+        umma_commit(&empty[s]);                                      // frees the operand slot when these MMAs retire
+        if (i % kChunkKB == kChunkKB - 1 || i == nkb - 1) {
+          umma_commit(&acc_full[chunk & 1]);                         // chain complete -> epilogue warps may drain it
+          chunk++;
+        }
       }
-      umma_commit(tmem_full);
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    // ===== accumulate + epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; j++) acc[j] = 0.f;
+    const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
+    for (int c = 0; c < nchunks; c++) {
+      const int b = c & 1;
+      mbar_wait(&acc_full[b], (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; cc++) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + cc * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];       // fp32 round-to-nearest, outside the tensor core
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
     const bool raw = g.splits > 1;
     bool valid;
     size_t row_off;           // element offset of this row's first column (col = n0)
@@ -250,33 +286,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       res_off = row_off;
       if (raw) row_off += (size_t)split * ((size_t)g.nimg * g.H * g.W) * ntot;
     }
-    float *dst = (raw ? partial : out) + row_off;
-    for (int c = 0; c < BN / 32; c++) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      if (valid) {
-        if (!raw && MODE != TC_WGRAD) {
-          const int col0 = n0 + c * 32;
+    if (valid) {
+      float *dst = (raw ? partial : out) + row_off;
+      if (!raw && MODE != TC_WGRAD) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float x = v[j];
-            if (epi.scale) x *= __ldg(epi.scale + col0 + j);
-            if (epi.bias) x += __ldg(epi.bias + col0 + j);
-            if (epi.residual) x += __ldg(epi.residual + res_off + c * 32 + j);
-            v[j] = tc_act(x, epi.act);
-          }
+        for (int j = 0; j < BN; j++) {
+          float x = acc[j];
+          if (epi.scale) x *= __ldg(epi.scale + n0 + j);
+          if (epi.bias) x += __ldg(epi.bias + n0 + j);
+          if (epi.residual) x += __ldg(epi.residual + res_off + j);
+          acc[j] = tc_act(x, epi.act);
         }
-        float *p = dst + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+#pragma unroll
+      for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

@@ -103,6 +103,15 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
   }
 }
 
+// out[r][c] = x[r][c] * scale[r]  (per-row scale: folds a frozen BatchNorm's gamma/sqrt(var+eps) into the
+// filter rows, and un-folds it from the filter gradient)
+__global__ void scale_rows_kernel(const float *__restrict__ x, const float *__restrict__ scale, float *__restrict__ out, size_t rows, size_t row_len)
+{
+  size_t total = rows * row_len;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = x[e] * __ldg(scale + e / row_len);
+}
+
 // ---- bias gradient: column sums of (rows, C), two deterministic stages ----------------------
 constexpr int kBiasRowsPerBlock = 256;
 
@@ -225,18 +234,20 @@ __global__ void maxpool3x3s2_fwd_kernel(const float *__restrict__ x, float *__re
   }
 }
 
-__global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int HW, int C)
+__global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
 {
-  // torch: y.mean(-1).mean(-1) on (N,C,4,4) == mean over W then over H; HW is laid out (h, w)
-  // here we reproduce mean-of-row-means only for square maps handled by the caller; generic
-  // path: plain mean in (h,w) order.
+  // y.mean(-1).mean(-1) (models/resnet.py:117): mean over W for every row, then mean of the row means
   size_t total = (size_t)N * C;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
     int n = (int)(e / C);
-    float s = 0.f;
-    for (int p = 0; p < HW; p++) s += __ldg(x + ((size_t)n * HW + p) * C + c);
-    y[e] = s / (float)HW;
+    float acc = 0.f;
+    for (int h = 0; h < H; h++) {
+      float s = 0.f;
+      for (int w = 0; w < W; w++) s += __ldg(x + (((size_t)n * H + h) * W + w) * C + c);
+      acc += s / (float)W;
+    }
+    y[e] = acc / (float)H;
   }
 }
 
@@ -297,6 +308,15 @@ int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t 
   return FRCNN_OK;
 }
 
+int frcnn_scale_rows(const float *x, const float *scale, float *out, size_t rows, size_t row_len, void *stream)
+{
+  FRCNN_REQUIRE(x && scale && out, "scale_rows: null pointer");
+  if (rows * row_len == 0) return FRCNN_OK;
+  scale_rows_kernel<<<elementwise_grid(rows * row_len, 256), 256, 0, as_stream(stream)>>>(x, scale, out, rows, row_len);
+  FRCNN_CHECK_LAUNCH("scale_rows_kernel");
+  return FRCNN_OK;
+}
+
 size_t frcnn_bias_grad_workspace_bytes(size_t rows, int C)
 {
   size_t blocks = ceil_div<size_t>(rows, kBiasRowsPerBlock);
@@ -345,10 +365,10 @@ int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C,
   return FRCNN_OK;
 }
 
-int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int HW, int C, void *stream)
+int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)
 {
-  FRCNN_REQUIRE(x && y && N > 0 && HW > 0 && C > 0, "spatial_mean_fwd: bad argument");
-  spatial_mean_fwd_kernel<<<elementwise_grid((size_t)N * C, 256), 256, 0, as_stream(stream)>>>(x, y, N, HW, C);
+  FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "spatial_mean_fwd: bad argument");
+  spatial_mean_fwd_kernel<<<elementwise_grid((size_t)N * C, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
   FRCNN_CHECK_LAUNCH("spatial_mean_fwd_kernel");
   return FRCNN_OK;
 }

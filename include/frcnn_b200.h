@@ -95,9 +95,12 @@ int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, v
 int frcnn_maxpool2x2_relu_bwd(const float *dy, const float *x, float *dz, int N, int H, int W, int C, void *stream);
 /* 3x3 stride-2 pad-1 max pool (torchvision ResNet stem, models/resnet.py:42), NHWC. */
 int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
-/* mean over the spatial positions of (N, HW, C) -> (N, C) (models/resnet.py:117) and its gradient. */
-int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int HW, int C, void *stream);
+/* y.mean(-1).mean(-1) of (N, H, W, C) -> (N, C) (models/resnet.py:117) and its gradient (HW = H*W). */
+int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
 int frcnn_spatial_mean_bwd(const float *dy, float *dx, int N, int HW, int C, void *stream);
+/* out[r][:] = x[r][:] * scale[r]: folds a frozen BatchNorm (gamma/sqrt(var+eps), models/resnet.py:56-77) into
+ * the filter rows before the conv kernels, and un-folds the filter gradient afterwards. */
+int frcnn_scale_rows(const float *x, const float *scale, float *out, size_t rows, size_t row_len, void *stream);
 /* out = a + b (residual / gradient accumulation). */
 int frcnn_add(const float *a, const float *b, float *out, size_t count, void *stream);
 

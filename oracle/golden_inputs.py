@@ -120,5 +120,6 @@ def rpn_case(tag):
 
 # ---- end-to-end -----------------------------------------------------------------------------
 E2E_CASES = {
-  "small": dict(hw = (384, 512), weight_seed = 0, sample_seed = 0, heads = "spread", score_threshold = 0.05),
+  "small": dict(hw = (384, 512), weight_seed = 0, sample_seed = 0, heads = "spread", score_threshold = 0.05, backbone = "vgg16"),
+  "resnet50_small": dict(hw = (384, 512), weight_seed = 1, sample_seed = 0, heads = "spread", score_threshold = 0.05, backbone = "resnet50"),
 }

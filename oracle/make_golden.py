@@ -84,15 +84,21 @@ def main():
   np.savez_compressed(os.path.join(OUT, "rpn_stage.npz"), **rp)
 
   # ---- 4. end-to-end on a small image: forward / predict / train_step --------------------
-  e2e = {}
+  from oracle import resnet_oracle
+  ref_shim.patch_resnet_offline()
   for tag in gi.E2E_CASES:
+    e2e = {}
     cfg = gi.E2E_CASES[tag]
     h, w = cfg["hw"]
-    params = orc.synth_params(orc.vgg16_param_shapes(), seed = cfg["weight_seed"], heads = cfg["heads"])
-    backbone = ref.vgg16.VGG16Backbone(dropout_probability = 0.0)
+    if cfg["backbone"] == "vgg16":
+      params = orc.synth_params(orc.vgg16_param_shapes(), seed = cfg["weight_seed"], heads = cfg["heads"])
+      backbone = ref.vgg16.VGG16Backbone(dropout_probability = 0.0)
+    else:
+      params = orc.synth_params(resnet_oracle.param_shapes(cfg["backbone"]), seed = cfg["weight_seed"], heads = cfg["heads"])
+      backbone = ref.resnet.ResNetBackbone(architecture = {"resnet50": ref.resnet.Architecture.ResNet50, "resnet101": ref.resnet.Architecture.ResNet101}[cfg["backbone"]])
     model = ref.faster_rcnn.FasterRCNNModel(num_classes = 21, backbone = backbone, allow_edge_proposals = True)
     model.load_state_dict(params)
-    smp = orc.synthetic_sample((h, w), seed = cfg["sample_seed"])
+    smp = orc.synthetic_sample((h, w), seed = cfg["sample_seed"], backbone = cfg["backbone"])
     image = smp["image"]
 
     model.eval()
@@ -131,7 +137,7 @@ def main():
     for key in sd:
       e2e["%s_w2_head/%s" % (tag, key)] = sd[key].reshape(-1)[:64].numpy().copy()
       e2e["%s_w2_norm/%s" % (tag, key)] = np.float64(sd[key].double().norm().item())
-  np.savez_compressed(os.path.join(OUT, "e2e_vgg16.npz"), **e2e)
+    np.savez_compressed(os.path.join(OUT, "e2e_%s.npz" % cfg["backbone"]), **e2e)
   print("golden vectors written to", OUT)
   for f in sorted(os.listdir(OUT)):
     print("  %-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -358,8 +358,8 @@ def test_tcgen05_linear_fwd_splitk_matches_fp32_engine(ops):
   scale = float(y64.abs().max())
   err_tc = float((y.double().cpu() - y64).abs().max())
   err_simt = float((y_simt.double().cpu() - y64).abs().max())
-  assert err_tc <= 1e-4 * scale, (err_tc, scale)
-  assert err_tc <= 4 * err_simt + 1e-6, (err_tc, err_simt)         # 3xTF32 is as accurate as plain fp32 FMA accumulation
+  assert err_simt <= 1e-5 * scale, (err_simt, scale)
+  assert err_tc <= 1e-5 * scale, (err_tc, err_simt, scale)          # 3xTF32 + out-of-core accumulation: fp32-grade
 
 
 TC_BWD_CASES = [

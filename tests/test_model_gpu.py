@@ -22,20 +22,30 @@ class Box:
     self.corners, self.class_index, self.class_name = corners, class_index, str(class_index)
 
 
-def _build(hw, heads = "spread", seed = 0):
+def _build(cfg):
   import fasterrcnn_b200 as f
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = seed, heads = heads)
-  model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
+  from fasterrcnn_b200 import resnet
+  from oracle import resnet_oracle
+  kind = cfg["backbone"]
+  if kind == "vgg16":
+    shapes = orc.vgg16_param_shapes()
+    backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  else:
+    shapes = resnet_oracle.param_shapes(kind)
+    backbone = resnet.ResNetBackbone({"resnet50": resnet.Architecture.ResNet50, "resnet101": resnet.Architecture.ResNet101}[kind])
+  params = orc.synth_params(shapes, seed = cfg["weight_seed"], heads = cfg["heads"])
+  model = f.FasterRCNNModel(num_classes = 21, backbone = backbone, allow_edge_proposals = True)
   model.load_state_dict(params)
   model = model.cuda()
-  oracle = orc.OracleModel(params)
-  smp = orc.synthetic_sample(hw, seed = seed)
+  oracle = orc.OracleModel(params, backbone = kind)
+  smp = orc.synthetic_sample(cfg["hw"], seed = cfg["sample_seed"], backbone = kind)
   return model, oracle, smp
 
 
-def test_forward_and_predict_match_oracle(golden_dir):
-  cfg = gi.E2E_CASES["small"]
-  model, oracle, smp = _build(cfg["hw"])
+@pytest.mark.parametrize("tag", list(gi.E2E_CASES))
+def test_forward_and_predict_match_oracle(golden_dir, tag):
+  cfg = gi.E2E_CASES[tag]
+  model, oracle, smp = _build(cfg)
   t.set_num_threads(os.cpu_count() or 8)
   taps = {}
   with t.no_grad():
@@ -54,26 +64,27 @@ def test_forward_and_predict_match_oracle(golden_dir):
   np.testing.assert_allclose(classes.cpu().numpy(), c_ref.numpy(), rtol = 0, atol = 1e-4)      # class scores within 1e-4
   np.testing.assert_allclose(deltas.cpu().numpy(), d_ref.numpy(), rtol = 0, atol = 1e-4)
   # golden (the unmodified reference's own outputs)
-  g = np.load(os.path.join(golden_dir, "e2e_vgg16.npz"))
-  np.testing.assert_allclose(classes.cpu().numpy(), g["small_fwd_classes"], rtol = 0, atol = 1e-4)
+  g = np.load(os.path.join(golden_dir, "e2e_%s.npz" % cfg["backbone"]))
+  np.testing.assert_allclose(classes.cpu().numpy(), g[tag + "_fwd_classes"], rtol = 0, atol = 1e-4)
 
   pred = model.predict(image_data = smp["image"].cuda(), score_threshold = cfg["score_threshold"])
   ref = oracle.predict(smp["image"], cfg["score_threshold"])
   counts = np.array([pred[c].shape[0] for c in range(1, 21)])
   assert np.array_equal(counts, np.array([ref[c].shape[0] for c in range(1, 21)]))
-  assert np.array_equal(counts, g["small_pred_counts"])
+  assert np.array_equal(counts, g[tag + "_pred_counts"])
   for c in range(1, 21):
     np.testing.assert_allclose(pred[c], ref[c], rtol = 0, atol = 5e-2)
 
 
-def test_train_step_matches_oracle(golden_dir):
-  cfg = gi.E2E_CASES["small"]
-  model, oracle, smp = _build(cfg["hw"])
+@pytest.mark.parametrize("tag", list(gi.E2E_CASES))
+def test_train_step_matches_oracle(golden_dir, tag):
+  cfg = gi.E2E_CASES[tag]
+  model, oracle, smp = _build(cfg)
   t.set_num_threads(os.cpu_count() or 8)
   params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
   optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)                     # __main__.py:98-105
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
-  g = np.load(os.path.join(golden_dir, "e2e_vgg16.npz"))
+  g = np.load(os.path.join(golden_dir, "e2e_%s.npz" % cfg["backbone"]))
 
   losses, ref_losses = [], []
   for who in ("ref", "gpu"):
@@ -92,7 +103,7 @@ def test_train_step_matches_oracle(golden_dir):
         losses.append([l.rpn_class, l.rpn_regression, l.detector_class, l.detector_regression, l.total])
         if step == 0:
           grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
-  np.testing.assert_allclose(np.array(ref_losses), g["small_losses"], rtol = 1e-5, atol = 1e-6)   # oracle == reference
+  np.testing.assert_allclose(np.array(ref_losses), g[tag + "_losses"], rtol = 1e-5, atol = 1e-6)   # oracle == reference
   np.testing.assert_allclose(np.array(losses[0]), np.array(ref_losses[0]), rtol = 2e-4, atol = 1e-5)   # step 1: within 2e-4 relative
   np.testing.assert_allclose(np.array(losses[1]), np.array(ref_losses[1]), rtol = 5e-3, atol = 1e-4)   # step 2 (after an SGD update, re-sampled RoIs)
   assert set(grads) == set(ref_grads)

@@ -89,14 +89,16 @@ def test_rpn_proposal_stage_bit_exact(golden_dir, tag):
   assert np.array_equal(props.numpy(), g[tag + "_proposals"])
 
 
-def test_e2e_vgg16_forward_predict_train_match_reference(golden_dir):
-  g = np.load(os.path.join(golden_dir, "e2e_vgg16.npz"))
-  tag = "small"
+@pytest.mark.parametrize("tag", list(gi.E2E_CASES))
+def test_e2e_forward_predict_train_match_reference(golden_dir, tag):
+  from oracle import resnet_oracle
   cfg = gi.E2E_CASES[tag]
+  g = np.load(os.path.join(golden_dir, "e2e_%s.npz" % cfg["backbone"]))
   t.set_num_threads(8)
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = cfg["weight_seed"], heads = cfg["heads"])
-  model = orc.OracleModel(params)
-  smp = orc.synthetic_sample(cfg["hw"], seed = cfg["sample_seed"])
+  shapes = orc.vgg16_param_shapes() if cfg["backbone"] == "vgg16" else resnet_oracle.param_shapes(cfg["backbone"])
+  params = orc.synth_params(shapes, seed = cfg["weight_seed"], heads = cfg["heads"])
+  model = orc.OracleModel(params, backbone = cfg["backbone"])
+  smp = orc.synthetic_sample(cfg["hw"], seed = cfg["sample_seed"], backbone = cfg["backbone"])
   with t.no_grad():
     props, classes, deltas = model.forward(smp["image"])
   np.testing.assert_allclose(props.numpy(), g[tag + "_fwd_proposals"], rtol = 0, atol = 1e-4)
