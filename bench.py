@@ -116,9 +116,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU oracle port (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+  """Threads the CPU arm may really use: min(logical CPUs, affinity mask, cgroup CPU quota)."""
+  n = os.cpu_count() or 1
+  try:
+    n = min(n, len(os.sched_getaffinity(0)))
+  except Exception:
+    pass
+  try:
+    with open("/sys/fs/cgroup/cpu.max") as f:
+      quota, period = f.read().split()
+    if quota != "max":
+      n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+  except Exception:
+    pass
+  env = os.environ.get("FRCNN_CPU_THREADS")
+  return int(env) if env else n
+
+
 def cpu_port_times(steps, warmup):
   from oracle import frcnn_oracle as orc
-  cores = os.cpu_count() or 1
+  cores = host_threads()
   t.set_num_threads(cores)
   params = orc.synth_params(orc.vgg16_param_shapes(), seed = 0, heads = "reference")
   model = orc.OracleModel(params)

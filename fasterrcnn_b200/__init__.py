@@ -6,7 +6,7 @@ with the model / training-loop API of trzy/FasterRCNN's pytorch/FasterRCNN packa
     model = FasterRCNNModel(num_classes = 21, backbone = vgg16.VGG16Backbone(dropout_probability = 0.0)).cuda()
 """
 from . import _lib, ops                                             # noqa: F401
-from . import anchors, math_utils, backbone, vgg16, rpn, detector   # noqa: F401
+from . import anchors, math_utils, backbone, vgg16, vgg16_torch, resnet, rpn, detector, optim   # noqa: F401
 from .faster_rcnn import FasterRCNNModel                            # noqa: F401
 
-__all__ = ["FasterRCNNModel", "vgg16", "rpn", "detector", "anchors", "math_utils", "backbone", "ops"]
+__all__ = ["FasterRCNNModel", "vgg16", "vgg16_torch", "resnet", "rpn", "detector", "anchors", "math_utils", "backbone", "ops", "optim"]

@@ -233,63 +233,75 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cou
   }
 }
 
-// Stage 2: the greedy scan, one CTA.  For each 64-box block: one thread resolves the block's
-// internal chain from its diagonal tile (registers only), then every thread ORs the rows of the
-// boxes kept in this block into the running "removed" bitmap (one 64-bit word per thread,
-// coalesced across the warp).  Stops as soon as max_keep boxes are kept.
-__global__ void __launch_bounds__(256)
+// Stage 2: the greedy scan, one CTA, software-pipelined over the 64-box blocks.  While lane 0 of
+// warp 0 resolves block b's internal chain from its diagonal tile (64 dependent steps, registers /
+// shared memory only), the other 31 warps already build block b+1's "removed" word: a column
+// gather over the rows of every box kept so far (one 8-byte load per kept box, all independent ->
+// one L2 round trip), plus preloads of block b's rows for column b+1 and of the next diagonal.
+// After the barrier the rows of the boxes just kept are OR-ed in.  Stops at max_keep.
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int capacity, int col_blocks,
                 int max_keep, int32_t *__restrict__ keep_out, int32_t *__restrict__ kept_count_out)
 {
-  extern __shared__ unsigned long long removed[];            // col_blocks words
-  __shared__ unsigned long long diag[64];
+  extern __shared__ int32_t kept_idx[];                      // max_keep entries: positions of the kept boxes
+  __shared__ unsigned long long diag[2][64];
+  __shared__ unsigned long long next_rows[64];
+  __shared__ unsigned long long removed[2];
   __shared__ unsigned long long kept_bits_s;
   __shared__ int kept_total;
   int n = *count;
   if (n > capacity) n = capacity;
   const int nblocks = (n + 63) / 64;
-  for (int w = threadIdx.x; w < col_blocks; w += blockDim.x) removed[w] = 0ull;
-  if (threadIdx.x == 0) kept_total = 0;
+  const int t = threadIdx.x;
+  if (t == 0) { kept_total = 0; removed[0] = 0ull; removed[1] = 0ull; kept_bits_s = 0ull; }
+  if (t < 64) diag[0][t] = (t < n) ? mask[(size_t)t * col_blocks] : 0ull;
   __syncthreads();
   for (int b = 0; b < nblocks; b++) {
-    if (kept_total >= max_keep) break;                       // uniform: read after a barrier
-    if (threadIdx.x < 64) {
-      int i = b * 64 + threadIdx.x;
-      diag[threadIdx.x] = i < n ? mask[(size_t)i * col_blocks + b] : 0ull;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long dead = removed[b];
+    const int cur = b & 1, nxt = cur ^ 1;
+    const int kept_before = kept_total;
+    if (kept_before >= max_keep) break;                      // uniform (read after a barrier)
+    const bool has_next = b + 1 < nblocks;
+    if (t == 0) {
+      unsigned long long dead = removed[cur];
       unsigned long long kept = 0ull;
-      int total = kept_total;
-      int lim = n - b * 64 < 64 ? n - b * 64 : 64;
+      int total = kept_before;
+      const int lim = n - b * 64 < 64 ? n - b * 64 : 64;
       for (int q = 0; q < lim && total < max_keep; q++) {
         if (!((dead >> q) & 1ull)) {
           kept |= 1ull << q;
-          dead |= diag[q];
-          keep_out[total++] = b * 64 + q;
+          dead |= diag[cur][q];
+          kept_idx[total] = b * 64 + q;
+          keep_out[total] = b * 64 + q;
+          total++;
         }
       }
       kept_bits_s = kept;
       kept_total = total;
-    }
-    __syncthreads();
-    unsigned long long kept = kept_bits_s;
-    if (kept) {
-      for (int w = b + 1 + threadIdx.x; w < nblocks; w += blockDim.x) {
-        unsigned long long acc = removed[w];
-        unsigned long long k = kept;
-        while (k) {
-          int q = __ffsll((long long)k) - 1;
-          k &= k - 1;
-          acc |= mask[(size_t)(b * 64 + q) * col_blocks + w];
-        }
-        removed[w] = acc;
+      removed[cur] = 0ull;                                   // becomes the "next" word two blocks from now
+    } else if (t >= 32 && has_next) {
+      unsigned long long acc = 0ull;
+      for (int k = t - 32; k < kept_before; k += kScanThreads - 32) acc |= mask[(size_t)kept_idx[k] * col_blocks + (b + 1)];
+      unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)acc);
+      unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(acc >> 32));
+      if ((t & 31) == 0) {
+        unsigned long long w = ((unsigned long long)hi << 32) | lo;
+        if (w) atomicOr(&removed[nxt], w);
+      }
+      if (t >= 64 && t < 128) {
+        int i = b * 64 + (t - 64);
+        next_rows[t - 64] = i < n ? mask[(size_t)i * col_blocks + (b + 1)] : 0ull;
+      } else if (t >= 128 && t < 192) {
+        int i = (b + 1) * 64 + (t - 128);
+        diag[nxt][t - 128] = i < n ? mask[(size_t)i * col_blocks + (b + 1)] : 0ull;
       }
     }
     __syncthreads();
+    if (has_next && t < 64 && ((kept_bits_s >> t) & 1ull) && next_rows[t]) atomicOr(&removed[nxt], next_rows[t]);
+    __syncthreads();
   }
-  if (threadIdx.x == 0) *kept_count_out = kept_total;
+  if (t == 0) *kept_count_out = kept_total;
 }
 
 __global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats, const int32_t *__restrict__ index, const int32_t *__restrict__ count,
@@ -440,19 +452,20 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
   FRCNN_REQUIRE(boxes && count && keep_out && kept_count_out && capacity > 0 && max_keep > 0, "nms_sorted_f32: bad argument");
   if (workspace == nullptr || workspace_bytes < frcnn_nms_workspace_bytes(capacity)) return fail(FRCNN_E_WORKSPACE, "nms_sorted_f32: workspace too small");
   const int col_blocks = ceil_div(capacity, 64);
-  FRCNN_REQUIRE((size_t)col_blocks * 8 <= 160 * 1024, "nms_sorted_f32: capacity too large for the scan bitmap");
   float thr_f = (float)iou_threshold;
   if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
   cudaStream_t st = as_stream(stream);
   unsigned long long *mask = reinterpret_cast<unsigned long long *>(workspace);
   nms_mask_kernel<<<dim3(col_blocks, col_blocks), 64, 0, st>>>(boxes, count, capacity, thr_f, mask, col_blocks);
   FRCNN_CHECK_LAUNCH("nms_mask_kernel");
-  size_t smem = (size_t)col_blocks * sizeof(unsigned long long);
-  if (smem > 48 * 1024) {
+  const int keep_cap = max_keep < capacity ? max_keep : capacity;
+  size_t smem = (size_t)keep_cap * sizeof(int32_t);
+  FRCNN_REQUIRE(smem <= 200 * 1024, "nms_sorted_f32: max_keep too large for the scan's kept list");
+  if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
   }
-  nms_scan_kernel<<<1, 256, smem, st>>>(mask, count, capacity, col_blocks, max_keep, keep_out, kept_count_out);
+  nms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, count, capacity, col_blocks, keep_cap, keep_out, kept_count_out);
   FRCNN_CHECK_LAUNCH("nms_scan_kernel");
   return FRCNN_OK;
 }
