@@ -46,7 +46,7 @@ def _build(cfg):
 def test_forward_and_predict_match_oracle(golden_dir, tag):
   cfg = gi.E2E_CASES[tag]
   model, oracle, smp = _build(cfg)
-  t.set_num_threads(os.cpu_count() or 8)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
   taps = {}
   with t.no_grad():
     p_ref, c_ref, d_ref = oracle.forward(smp["image"], taps = taps)
@@ -80,7 +80,7 @@ def test_forward_and_predict_match_oracle(golden_dir, tag):
 def test_train_step_matches_oracle(golden_dir, tag):
   cfg = gi.E2E_CASES[tag]
   model, oracle, smp = _build(cfg)
-  t.set_num_threads(os.cpu_count() or 8)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
   params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
   optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)                     # __main__.py:98-105
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
