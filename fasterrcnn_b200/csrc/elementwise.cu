@@ -113,26 +113,44 @@ __global__ void scale_rows_kernel(const float *__restrict__ x, const float *__re
 }
 
 // ---- bias gradient: column sums of (rows, C), two deterministic stages ----------------------
-constexpr int kBiasRowsPerBlock = 256;
+constexpr int kBiasRowsPerBlock = 64;
 
 __global__ void bias_grad_stage1(const float *__restrict__ dz, float *__restrict__ partial, size_t rows, int C)
 {
-  // block b sums rows [b*256, b*256+256) for every channel; threads stride over channels
+  // block b sums rows [b*64, b*64+64) for every channel; 4 independent row streams per thread keep
+  // enough loads in flight, combined in a fixed order (deterministic)
   size_t r0 = (size_t)blockIdx.x * kBiasRowsPerBlock;
   size_t r1 = r0 + kBiasRowsPerBlock < rows ? r0 + kBiasRowsPerBlock : rows;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (size_t r = r0; r < r1; r++) s += __ldg(dz + r * C + c);
-    partial[(size_t)blockIdx.x * C + c] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    size_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      s0 += __ldg(dz + r * C + c);
+      s1 += __ldg(dz + (r + 1) * C + c);
+      s2 += __ldg(dz + (r + 2) * C + c);
+      s3 += __ldg(dz + (r + 3) * C + c);
+    }
+    for (; r < r1; r++) s0 += __ldg(dz + r * C + c);
+    partial[(size_t)blockIdx.x * C + c] = (s0 + s1) + (s2 + s3);
   }
 }
 
 __global__ void bias_grad_stage2(const float *__restrict__ partial, float *__restrict__ dbias, int blocks, int C)
 {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < blocks; b++) s += partial[(size_t)b * C + c];
-    dbias[c] = s;
+  // one warp per channel group of 32: lanes = channels (coalesced), 8 row-slices per CTA combined through shared memory
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < C)
+    for (int b = slice; b < blocks; b += 8) s += partial[(size_t)b * C + c];
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += red[k][lane];
+    dbias[c] = tot;
   }
 }
 
@@ -331,7 +349,7 @@ int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *wor
   float *partial = reinterpret_cast<float *>(workspace);
   bias_grad_stage1<<<blocks, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream)>>>(dz, partial, rows, C);
   FRCNN_CHECK_LAUNCH("bias_grad_stage1");
-  bias_grad_stage2<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partial, dbias, blocks, C);
+  bias_grad_stage2<<<ceil_div(C, 32), 256, 0, as_stream(stream)>>>(partial, dbias, blocks, C);
   FRCNN_CHECK_LAUNCH("bias_grad_stage2");
   return FRCNN_OK;
 }
