@@ -7,7 +7,9 @@
 //     and padding are folded into the shared-memory staging and never exist in HBM;
 //   * tcgen05.mma kind::tf32 issued by one thread, fp32 accumulators in TMEM (128 lanes x BN cols);
 //   * fp32-grade accuracy through the error-compensated split x = hi + lo (hi = the tf32 truncation
-//     the tensor core applies itself, lo = x - hi): D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi;
+//     the tensor core applies itself, lo = x - hi): D += A_hi*B_hi + (A_hi*B_lo + A_lo*B_hi).  The B_hi and
+//     B_lo tiles sit back to back in shared memory, so A_hi * [B_hi | B_lo] is ONE N = 2*BN instruction (A_hi
+//     is read once) into accumulator columns [main | corr]; A_lo * B_hi accumulates into the corr columns;
 //   * the tensor core's own fp32 accumulation is the remaining error source on long K chains, so
 //     chains are kept short: every kChunkKB k-blocks (48 MMAs) the accumulator -- double-buffered in
 //     TMEM -- is drained by the epilogue warps into fp32 registers (round-to-nearest adds on the CUDA
@@ -84,7 +86,7 @@ constexpr int kTcThreads = 192;
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
 constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
-constexpr int kChunkKB = 4;                   // k-blocks accumulated inside the tensor core before a register drain
+constexpr int kChunkKB = 8;                   // k-blocks (32 accumulations per column) inside the tensor core before a register drain
 
 __device__ __forceinline__ float tc_act(float v, int act)
 {
@@ -143,7 +145,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, 4 * BN);                                   // 2 accumulator buffers x [main | corr] columns
   }
   tc_fence_before();
   __syncthreads();
@@ -202,7 +204,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);
+      constexpr uint32_t idesc_main = make_idesc_tf32(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);   // A_hi x [B_hi | B_lo]
+      constexpr uint32_t idesc_corr = make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);       // A_lo x B_hi
       const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
       const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
       uint32_t accumulate = 0;
@@ -213,7 +216,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int b = chunk & 1;
           mbar_wait(&acc_empty[b], ((chunk >> 1) & 1) ^ 1);          // drained by the epilogue warps (first use passes)
           tc_fence_after();
-          tmem_acc = tmem_base + b * BN;
+          tmem_acc = tmem_base + b * 2 * BN;
           accumulate = 0;
         }
         const int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -221,18 +224,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * kStageBytes);
         const uint32_t a_lo = a_hi + kABytes;
-        const uint32_t b_hi = a_hi + 2 * kABytes;
-        const uint32_t b_lo = b_hi + kBBytes;
+        const uint32_t b_hi = a_hi + 2 * kABytes;                    // b_lo follows at + kBBytes
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
           constexpr uint32_t a_lt = kAMajorMN ? kLayoutSW128Base32B : kLayoutSW128, b_lt = kBMajorMN ? kLayoutSW128Base32B : kLayoutSW128;
           const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
           const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t db_hi = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
-          const uint64_t db_lo = make_smem_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_acc, da_hi, db_lo, idesc, accumulate);      // small terms first
-          umma_tf32(tmem_acc, da_lo, db_hi, idesc, 1);
-          umma_tf32(tmem_acc, da_hi, db_hi, idesc, 1);
+          const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);     // covers b_hi then b_lo (contiguous)
+          umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate);     // [main | corr] (+)= A_hi * [B_hi | B_lo]
+          umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);         // corr += A_lo * B_hi
           accumulate = 1;
         }
         umma_commit(&empty[s]);                                      // frees the operand slot when these MMAs retire
@@ -257,9 +257,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
       for (int cc = 0; cc < BN / 32; cc++) {
         float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + cc * 32, v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + BN + cc * 32, v);    // corr: A_hi*B_lo + A_lo*B_hi
 #pragma unroll
-        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];       // fp32 round-to-nearest, outside the tensor core
+        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];          // fp32 round-to-nearest, outside the tensor core
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + cc * 32, v);         // main: A_hi*B_hi
+#pragma unroll
+        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];
       }
       tc_fence_before();
       __syncwarp();
@@ -306,7 +309,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, 4 * BN);
   }
 }
 

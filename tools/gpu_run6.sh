@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 600 -p no:cacheprovider -x -k "tcgen05 or conv or linear" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+grep -v "^E  \|^    \|^$" gpurun_out/pytest_gpu.log | tail -15
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+echo "bench exit $?"; tail -3 gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
+timeout 300 python tools/gpu_probe.py auto 2>&1 | grep -v "^-\|Self C" | tail -45 > gpurun_out/probe_auto.log; head -16 gpurun_out/probe_auto.log
