@@ -31,6 +31,12 @@ _SIGNATURES = {
   "frcnn_conv2d_dgrad": (_i, [_vp] * 4 + _GEOM + [_i, _vp, _sz, _vp]),
   "frcnn_conv2d_wgrad_workspace_bytes": (_sz, _GEOM + [_i]),
   "frcnn_conv2d_wgrad": (_i, [_vp] * 3 + _GEOM + [_i, _vp, _sz, _vp]),
+  "frcnn_conv2d_uses_tensor_cores": (_i, [_i] + _GEOM + [_i]),
+  "frcnn_tf32_split_bytes": (_sz, [_sz]),
+  "frcnn_tf32_split": (_i, [_vp, _sz, _vp, _vp]),
+  "frcnn_conv2d_fwd_presplit": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),
+  "frcnn_conv2d_dgrad_presplit": (_i, [_vp] * 6 + _GEOM + [_vp, _sz, _vp]),
+  "frcnn_conv2d_wgrad_presplit": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_sigmoid_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_bias_grad_workspace_bytes": (_sz, [_sz, _i]),

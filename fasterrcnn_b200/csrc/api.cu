@@ -24,17 +24,19 @@ bool tc_fwd_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, in
 size_t tc_fwd_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st);
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split);
+size_t tf32_split_bytes(size_t count);
+int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
 bool tc_dgrad_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 size_t tc_dgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st);
+                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split);
 bool tc_wgrad_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 size_t tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int tc_conv2d_wgrad(const float *dy, const float *x, float *dw,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st);
+                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *x_split);
 
 }  // namespace frcnn
 
@@ -66,7 +68,7 @@ int frcnn_conv2d_fwd(const float *x, const float *w, const float *scale, const f
   FRCNN_REQUIRE(act >= FRCNN_ACT_NONE && act <= FRCNN_ACT_SIGMOID, "conv2d_fwd: unknown activation");
   if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_fwd_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd: shape not supported by the tcgen05 engine");
   if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_fwd_supported(GEOM_ARGS))
-    return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream));
+    return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
   return simt_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream));
 }
 
@@ -87,7 +89,7 @@ int frcnn_conv2d_dgrad(const float *dy, const float *w, const float *addend, flo
   FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad: null pointer");
   if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_dgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tcgen05 engine");
   if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_dgrad_supported(GEOM_ARGS))
-    return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
+    return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
   return simt_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
 }
 
@@ -108,8 +110,52 @@ int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
   FRCNN_REQUIRE(dy && x && dw, "conv2d_wgrad: null pointer");
   if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_wgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tcgen05 engine");
   if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_wgrad_supported(GEOM_ARGS))
-    return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
+    return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
   return simt_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
+}
+
+/* ---- tf32 hi/lo operand splits shared between the passes of one step -------------------------------- */
+int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
+{
+  if (engine == FRCNN_ENGINE_SIMT_FP32) return 0;
+  if (pass == 0) return tc_fwd_supported(GEOM_ARGS) ? 1 : 0;
+  if (pass == 1) return tc_dgrad_supported(GEOM_ARGS) ? 1 : 0;
+  return tc_wgrad_supported(GEOM_ARGS) ? 1 : 0;
+}
+
+size_t frcnn_tf32_split_bytes(size_t count) { return tf32_split_bytes(count); }
+
+int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream)
+{
+  FRCNN_REQUIRE(x && out && count > 0, "tf32_split: bad argument");
+  return tf32_split(x, count, out, as_stream(stream));
+}
+
+int frcnn_conv2d_fwd_presplit(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
+                              const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+                              void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(x && w && y, "conv2d_fwd_presplit: null pointer");
+  if (!tc_fwd_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split);
+}
+
+int frcnn_conv2d_dgrad_presplit(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
+                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad_presplit: null pointer");
+  if (!tc_dgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split);
+}
+
+int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
+                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && x && dw, "conv2d_wgrad_presplit: null pointer");
+  if (!tc_wgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, x_split);
 }
 
 }  // extern "C"

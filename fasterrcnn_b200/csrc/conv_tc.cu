@@ -461,9 +461,21 @@ static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float 
 }
 
 // a: the activation-side operand of the mode (x | dy | dy), b: the other one (w | w | x)
+size_t tf32_split_bytes(size_t count) { return 2 * align_up(count * 4, 1024); }
+
+int tf32_split(const float *x, size_t count, void *out, cudaStream_t st)
+{
+  float *hi = reinterpret_cast<float *>(out);
+  float *lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(out) + align_up(count * 4, 1024));
+  split_hi_lo_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, hi, lo, count);
+  FRCNN_CHECK_LAUNCH("split_hi_lo_kernel");
+  return FRCNN_OK;
+}
+
+// a_split / b_split: optional buffers produced by tf32_split for the two operands (NULL = split here)
 static int run_tc(int mode, const float *a, const float *b, float *out, const Epilogue &epi,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st)
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *a_split = nullptr, const void *b_split = nullptr)
 {
   TcPlan p;
   if (!make_tc_plan(mode, N, H, W, Cin, Cout, KH, KW, stride, pad, &p)) return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: unsupported shape");
@@ -476,10 +488,20 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   float *b_hi = reinterpret_cast<float *>(ws + p.b_hi_off);
   float *b_lo = reinterpret_cast<float *>(ws + p.b_lo_off);
   float *partial = reinterpret_cast<float *>(ws + p.partial_off);
-  split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_hi, a_lo, p.a_count);
-  FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(a)");
-  split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_hi, b_lo, p.b_count);
-  FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(b)");
+  if (a_split) {
+    a_hi = const_cast<float *>(reinterpret_cast<const float *>(a_split));
+    a_lo = const_cast<float *>(reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(a_split) + align_up(p.a_count * 4, 1024)));
+  } else {
+    split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_hi, a_lo, p.a_count);
+    FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(a)");
+  }
+  if (b_split) {
+    b_hi = const_cast<float *>(reinterpret_cast<const float *>(b_split));
+    b_lo = const_cast<float *>(reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(b_split) + align_up(p.b_count * 4, 1024)));
+  } else {
+    split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_hi, b_lo, p.b_count);
+    FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(b)");
+  }
   a = a_hi;
   b = b_hi;
 
@@ -536,22 +558,24 @@ size_t tc_dgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_DGRAD,
 size_t tc_wgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_WGRAD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
 
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
-                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st)
+                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split)
 {
   Epilogue epi{scale, bias, residual, act};
-  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st);
+  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st, x_split, w_split);
 }
 
-int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st)
+int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                    const void *dy_split, const void *w_split)
 {
   Epilogue epi{nullptr, nullptr, addend, FRCNN_ACT_NONE};
-  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st);
+  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, w_split);
 }
 
-int tc_conv2d_wgrad(const float *dy, const float *x, float *dw, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st)
+int tc_conv2d_wgrad(const float *dy, const float *x, float *dw, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                    const void *dy_split, const void *x_split)
 {
   Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
-  return run_tc(TC_WGRAD, dy, x, dw, none, GEOM_ARGS, workspace, workspace_bytes, st);
+  return run_tc(TC_WGRAD, dy, x, dw, none, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, x_split);
 }
 
 }  // namespace frcnn

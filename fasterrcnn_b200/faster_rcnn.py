@@ -42,6 +42,7 @@ class FasterRCNNModel(nn.Module):
   def forward(self, image_data, anchor_map = None, anchor_valid_map = None):
     assert image_data.shape[0] == 1, "Batch size must be 1"
     image_shape = image_data.shape[1:]
+    ops.begin_step()
     feature_map = self._stage1_feature_extractor(image_data = image_data)
     objectness_score_map, box_deltas_map, proposals = self._stage2_region_proposal_network(
       feature_map = feature_map, image_shape = image_shape, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map,
@@ -68,6 +69,7 @@ class FasterRCNNModel(nn.Module):
     assert len(gt_rpn_background_indices) == 1, "Batch size must be 1"
     assert len(gt_boxes) == 1, "Batch size must be 1"
     image_shape = image_data.shape[1:]
+    ops.begin_step()
 
     feature_map = self._stage1_feature_extractor(image_data = image_data)
     rpn_score_map, rpn_box_deltas_map, proposals = self._stage2_region_proposal_network(
@@ -86,6 +88,7 @@ class FasterRCNNModel(nn.Module):
     all_l = t.cat([rpn_l, det_l])
     total_loss = all_l.sum()
     total_loss.backward()
+    ops.begin_step()                       # operand splits of this step's weights are stale after the update
     optimizer.step()
 
     host = t.cat([all_l.detach(), total_loss.detach().reshape(1)]).cpu().numpy()                   # one D2H for the five numbers

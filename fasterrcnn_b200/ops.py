@@ -131,37 +131,104 @@ def _phys_nhwc(x):
 # raw (non-autograd) launchers
 # ------------------------------------------------------------------------------------------------
 
-def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None):
-  """x logical (N,Cin,H,W) phys NHWC; w logical (Cout,Cin,KH,KW) phys OHWI -> y logical (N,Cout,Ho,Wo) phys NHWC."""
+# ---- tf32 hi/lo operand splits shared between the passes of one step (tcgen05 engine) ---------------
+_split_cache = {}
+_uses_tc_cache = {}
+
+
+def begin_step():
+  """Drops the cached operand splits (called at the start of every forward / train_step)."""
+  _split_cache.clear()
+
+
+def _uses_tc(pass_, geom):
+  key = (pass_, geom, _engine["value"])
+  r = _uses_tc_cache.get(key)
+  if r is None:
+    r = bool(lib().frcnn_conv2d_uses_tensor_cores(pass_, *geom, _engine["value"]))
+    _uses_tc_cache[key] = r
+  return r
+
+
+def tf32_split(x, cache = True):
+  """Returns the [hi | lo] split buffer of x (frcnn_tf32_split), computing it at most once per tensor version."""
+  key = (x.data_ptr(), x.numel(), x._version)
+  hit = _split_cache.get(key)
+  if hit is not None:
+    return hit[0]
+  buf = t.empty((lib().frcnn_tf32_split_bytes(x.numel()),), dtype = t.uint8, device = x.device)
+  check(lib().frcnn_tf32_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_tf32_split")
+  _lib.count()
+  if cache:
+    _split_cache[key] = (buf, x)                 # holding x keeps its address from being recycled while cached
+  return buf
+
+
+def drop_split(x):
+  _split_cache.pop((x.data_ptr(), x.numel(), x._version), None)
+
+
+def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, scale = None, bias = None, residual = None, act = ACT_NONE, addend = None):
+  """One implicit-GEMM launch.  pass 0: a=x, b=w, out=y | pass 1: a=dy, b=w, out=dx | pass 2: a=dy, b=x, out=dw."""
+  eng = _engine["value"]
+  L = lib()
+  presplit = (a_split is not None or b_split is not None)
+  if pass_ == 0:
+    ws, ws_n = workspace(L.frcnn_conv2d_fwd_workspace_bytes(*geom, eng))
+    t0 = kernel_timer.begin()
+    if presplit:
+      check(L.frcnn_conv2d_fwd_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ws, ws_n, stream()), "frcnn_conv2d_fwd_presplit")
+    else:
+      check(L.frcnn_conv2d_fwd(ptr(a), ptr(b), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
+  elif pass_ == 1:
+    ws, ws_n = workspace(L.frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
+    t0 = kernel_timer.begin()
+    if presplit:
+      check(L.frcnn_conv2d_dgrad_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_dgrad_presplit")
+    else:
+      check(L.frcnn_conv2d_dgrad(ptr(a), ptr(b), ptr(addend), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
+  else:
+    ws, ws_n = workspace(L.frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
+    t0 = kernel_timer.begin()
+    if presplit:
+      check(L.frcnn_conv2d_wgrad_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_wgrad_presplit")
+    else:
+      check(L.frcnn_conv2d_wgrad(ptr(a), ptr(b), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
+  kernel_timer.end(t0, kind, gflop)
+  _lib.count()
+
+
+def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None, reuse_x = False, reuse_w = True):
+  """x logical (N,Cin,H,W) phys NHWC; w logical (Cout,Cin,KH,KW) phys OHWI -> y logical (N,Cout,Ho,Wo) phys NHWC.
+  reuse_x / reuse_w: the operand will be used by another pass of this step -> its tf32 split is cached."""
   n, cin, h, wd = x.shape
   cout, cin2, kh, kw = w.shape
   assert cin == cin2
   ho = (h + 2 * pad - kh) // stride + 1
   wo = (wd + 2 * pad - kw) // stride + 1
   y = _empty_nhwc(n, cout, ho, wo, x.device)
-  eng = _engine["value"]
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
-  ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
-  ws, ws_n = workspace(ws_bytes)
-  t0 = kernel_timer.begin()
-  check(lib().frcnn_conv2d_fwd(ptr(x), ptr(w), ptr(scale), ptr(bias), ptr(residual), ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
-  kernel_timer.end(t0, "conv_fwd", 2e-9 * n * ho * wo * cout * kh * kw * cin)
-  _lib.count()
+  xs = ws_ = None
+  if _uses_tc(0, geom):
+    if reuse_x:
+      xs = tf32_split(x)
+    if reuse_w:
+      ws_ = tf32_split(w)
+  _gemm(0, x, w, y, geom, "conv_fwd", 2e-9 * n * ho * wo * cout * kh * kw * cin, xs, ws_, scale = scale, bias = bias, residual = residual, act = act)
   return y
 
 
-def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None):
+def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = False):
   n, cin, h, wd = x_shape
   cout, _, kh, kw = w.shape
   dx = _empty_nhwc(n, cin, h, wd, dy.device)
-  eng = _engine["value"]
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
-  ws_bytes = lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng)
-  ws, ws_n = workspace(ws_bytes)
-  t0 = kernel_timer.begin()
-  check(lib().frcnn_conv2d_dgrad(ptr(dy), ptr(w), ptr(addend), ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
-  kernel_timer.end(t0, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin)
-  _lib.count()
+  ds = ws_ = None
+  if _uses_tc(1, geom):
+    ws_ = tf32_split(w)
+    if reuse_dy:
+      ds = tf32_split(dy)
+  _gemm(1, dy, w, dx, geom, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, ws_, addend = addend)
   return dx
 
 
@@ -171,14 +238,16 @@ def conv2d_wgrad_raw(dy, x, w_shape, stride, pad):
   dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = x.device, memory_format = t.channels_last)
   if kh == 1 and kw == 1:
     dw = t.empty((cout, cin, 1, 1), dtype = t.float32, device = x.device)
-  eng = _engine["value"]
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
-  ws_bytes = lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng)
-  ws, ws_n = workspace(ws_bytes)
-  t0 = kernel_timer.begin()
-  check(lib().frcnn_conv2d_wgrad(ptr(dy), ptr(x), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
-  kernel_timer.end(t0, "conv_wgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin)
-  _lib.count()
+  ds = xs = None
+  if _uses_tc(2, geom):
+    key_dy = (dy.data_ptr(), dy.numel(), dy._version)
+    key_x = (x.data_ptr(), x.numel(), x._version)
+    ds = _split_cache[key_dy][0] if key_dy in _split_cache else None
+    xs = _split_cache[key_x][0] if key_x in _split_cache else None
+  _gemm(2, dy, x, dw, geom, "conv_wgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, xs)
+  drop_split(dy)
+  drop_split(x)
   return dw
 
 
@@ -216,7 +285,7 @@ class _ConvAct(t.autograd.Function):
     _require_cuda(x, w, b)
     xp = _phys_nhwc(x.detach())
     wp = _phys_filter(w.detach())
-    y = conv2d_fwd_raw(xp, wp, b.detach() if b is not None else None, stride, pad, act)
+    y = conv2d_fwd_raw(xp, wp, b.detach() if b is not None else None, stride, pad, act, reuse_x = bool(ctx.needs_input_grad[1]))
     ctx.stride, ctx.pad, ctx.act, ctx.pool = stride, pad, act, pool
     ctx.has_bias = b is not None
     ctx.w_shape = tuple(w.shape)
@@ -252,7 +321,7 @@ class _ConvAct(t.autograd.Function):
       dz = dy
     dx = dw = db = None
     if ctx.needs_input_grad[0]:
-      dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad)
+      dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = ctx.needs_input_grad[1])
     if ctx.needs_input_grad[1]:
       dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad)
     if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -277,17 +346,14 @@ class _LinearAct(t.autograd.Function):
     y = t.empty((m, nout), dtype = t.float32, device = x.device)
     ctx.act = act
     ctx.has_bias = b is not None
-    if m == 0:
-      ctx.save_for_backward(x2, w2, y)
-      return y
-    eng = _engine["value"]
-    geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
-    ws_bytes = lib().frcnn_conv2d_fwd_workspace_bytes(*geom, eng)
-    ws, ws_n = workspace(ws_bytes)
-    t0 = kernel_timer.begin()
-    check(lib().frcnn_conv2d_fwd(ptr(x2), ptr(w2), None, ptr(b.detach()) if b is not None else None, None, ptr(y), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd(linear)")
-    kernel_timer.end(t0, "linear_fwd", 2e-9 * m * k * nout)
-    _lib.count()
+    if m > 0:
+      geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
+      xs = ws_ = None
+      if _uses_tc(0, geom):
+        ws_ = tf32_split(w2)
+        if ctx.needs_input_grad[1]:
+          xs = tf32_split(x2)
+      _gemm(0, x2, w2, y, geom, "linear_fwd", 2e-9 * m * k * nout, xs, ws_, bias = b.detach() if b is not None else None, act = act)
     ctx.save_for_backward(x2, w2, y)
     return y
 
@@ -309,23 +375,26 @@ class _LinearAct(t.autograd.Function):
       _lib.count()
     else:
       dz = dy
-    eng = _engine["value"]
     geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
     dx = dw = db = None
     if ctx.needs_input_grad[0]:
       dx = t.empty((m, k), dtype = t.float32, device = x2.device)
-      ws, ws_n = workspace(lib().frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
-      t0 = kernel_timer.begin()
-      check(lib().frcnn_conv2d_dgrad(ptr(dz), ptr(w2), None, ptr(dx), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad(linear)")
-      kernel_timer.end(t0, "linear_dgrad", 2e-9 * m * k * nout)
-      _lib.count()
+      ds = ws_ = None
+      if _uses_tc(1, geom):
+        ws_ = tf32_split(w2)
+        if ctx.needs_input_grad[1]:
+          ds = tf32_split(dz)
+      _gemm(1, dz, w2, dx, geom, "linear_dgrad", 2e-9 * m * k * nout, ds, ws_)
     if ctx.needs_input_grad[1]:
       dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
-      ws, ws_n = workspace(lib().frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
-      t0 = kernel_timer.begin()
-      check(lib().frcnn_conv2d_wgrad(ptr(dz), ptr(x2), ptr(dw), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad(linear)")
-      kernel_timer.end(t0, "linear_wgrad", 2e-9 * m * k * nout)
-      _lib.count()
+      ds = xs = None
+      if _uses_tc(2, geom):
+        kd, kx = (dz.data_ptr(), dz.numel(), dz._version), (x2.data_ptr(), x2.numel(), x2._version)
+        ds = _split_cache[kd][0] if kd in _split_cache else None
+        xs = _split_cache[kx][0] if kx in _split_cache else None
+      _gemm(2, dz, x2, dw, geom, "linear_wgrad", 2e-9 * m * k * nout, ds, xs)
+      drop_split(dz)
+      drop_split(x2)
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = bias_grad_raw(dz, nout)
     return dx, dw, db, None

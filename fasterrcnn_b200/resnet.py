@@ -69,7 +69,7 @@ class _ConvBNAct(t.autograd.Function):
     wp = ops._phys_filter(w.detach())
     w_eff = _scale_rows(wp, scale)
     res = ops.as_nhwc(residual.detach()) if residual is not None else None
-    y = ops.conv2d_fwd_raw(xp, w_eff, shift, stride, pad, act, residual = res)
+    y = ops.conv2d_fwd_raw(xp, w_eff, shift, stride, pad, act, residual = res, reuse_x = bool(ctx.needs_input_grad[1]))
     ctx.stride, ctx.pad, ctx.act = stride, pad, act
     ctx.w_shape = tuple(w.shape)
     ctx.has_residual = residual is not None
@@ -88,7 +88,7 @@ class _ConvBNAct(t.autograd.Function):
       dz = dy
     dx = dw = dres = None
     if ctx.needs_input_grad[0]:
-      dx = ops.conv2d_dgrad_raw(dz, w_eff, tuple(xp.shape), ctx.stride, ctx.pad)
+      dx = ops.conv2d_dgrad_raw(dz, w_eff, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = ctx.needs_input_grad[1])
     if ctx.needs_input_grad[1]:
       dw = _scale_rows(ops.conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad), scale)
     if ctx.has_residual and ctx.needs_input_grad[4]:

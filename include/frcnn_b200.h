@@ -82,6 +82,24 @@ int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
                        int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                        int engine, void *workspace, size_t workspace_bytes, void *stream);
 
+/* tcgen05 engine, operand splits shared between passes: the 3xTF32 scheme needs x = hi + lo for both operands of a
+ * GEMM.  A tensor used by several passes of one step (x: forward + filter gradient; dy: data + filter gradient; w:
+ * forward + data gradient) can be split ONCE with frcnn_tf32_split into a caller-owned buffer of
+ * frcnn_tf32_split_bytes(count) bytes and handed to the *_presplit variants (either split pointer may be NULL = split
+ * internally).  frcnn_conv2d_uses_tensor_cores(pass, geometry, engine): pass 0 = fwd, 1 = dgrad, 2 = wgrad. */
+int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
+size_t frcnn_tf32_split_bytes(size_t count);
+int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream);
+int frcnn_conv2d_fwd_presplit(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
+                              const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+                              void *workspace, size_t workspace_bytes, void *stream);
+int frcnn_conv2d_dgrad_presplit(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
+                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                void *workspace, size_t workspace_bytes, void *stream);
+int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
+                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- elementwise / pooling pieces of the backward pass -------------------------------------
  * dz = dy * (y > 0)   (ReLU backward, models/vgg16.py:76-96 under autograd); in place allowed. */
 int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
