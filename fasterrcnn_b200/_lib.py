@@ -57,6 +57,8 @@ _SIGNATURES = {
   "frcnn_gather_rows_f32": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp]),
   "frcnn_roi_pool_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
   "frcnn_roi_pool_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+  "frcnn_roi_align_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp]),
+  "frcnn_roi_align_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp]),
   "frcnn_label_proposals": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
   "frcnn_rpn_losses": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
   "frcnn_softmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),

@@ -441,6 +441,43 @@ def roi_pool(feature_map, proposals, output_size = (7, 7), spatial_scale = 1.0 /
   return _RoIPool.apply(feature_map, proposals, output_size, spatial_scale)
 
 
+class _RoIAlign(t.autograd.Function):
+  """EXTENSION: torchvision.ops.roi_align semantics (fixed sampling_ratio, aligned flag); the reference has RoIPool only."""
+
+  @staticmethod
+  def forward(ctx, feature_map, proposals, output_size, spatial_scale, sampling_ratio, aligned):
+    _require_cuda(feature_map, proposals)
+    assert feature_map.shape[0] == 1, "Batch size must be 1"
+    fm = as_nhwc(feature_map.detach())
+    _, c, h, w = fm.shape
+    props = proposals.detach().contiguous().float()
+    k = props.shape[0]
+    ph, pw = output_size
+    out = t.empty((k, c, ph, pw), dtype = t.float32, device = fm.device)
+    if k > 0:
+      check(lib().frcnn_roi_align_fwd(ptr(fm), h, w, c, ptr(props), k, ph, pw, float(spatial_scale), int(sampling_ratio), int(bool(aligned)), ptr(out), stream()), "frcnn_roi_align_fwd")
+      _lib.count()
+    ctx.save_for_backward(props)
+    ctx.geom = (k, h, w, c, ph, pw, float(spatial_scale), int(sampling_ratio), int(bool(aligned)))
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    (props,) = ctx.saved_tensors
+    k, h, w, c, ph, pw, scale, s, al = ctx.geom
+    dfm = _empty_nhwc(1, c, h, w, dout.device)
+    if k == 0:
+      return dfm.zero_(), None, None, None, None, None
+    check(lib().frcnn_roi_align_bwd(ptr(dout.contiguous()), ptr(props), k, h, w, c, ph, pw, scale, s, al, None, ptr(dfm), stream()), "frcnn_roi_align_bwd")
+    _lib.count()
+    return dfm, None, None, None, None, None
+
+
+def roi_align(feature_map, proposals, output_size = (7, 7), spatial_scale = 1.0 / 16.0, sampling_ratio = 2, aligned = False):
+  """feature_map logical (1,C,H,W); proposals (K,4) as (y1,x1,y2,x2) -> (K,C,7,7).  Extension (no reference counterpart)."""
+  return _RoIAlign.apply(feature_map, proposals, output_size, spatial_scale, sampling_ratio, aligned)
+
+
 class _Softmax(t.autograd.Function):
   @staticmethod
   def forward(ctx, logits):

@@ -176,6 +176,14 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
 int frcnn_roi_pool_bwd(const float *dout, const int32_t *argmax, const float *proposals, int K, int H, int W, int C, int PH, int PW,
                        float spatial_scale, const float *addend, float *dfm, void *stream);
 
+/* ---- EXTENSION (BASELINE configs 3, 5): RoIAlign.  The reference has RoIPool only; semantics are
+ * torchvision.ops.roi_align's (fixed sampling_ratio in 1..4, `aligned` flag), fp32, same layouts as roi_pool.
+ * Backward is deterministic (no atomics); addend (may be NULL) is added to the result. */
+int frcnn_roi_align_fwd(const float *fm, int H, int W, int C, const float *proposals, int K, int PH, int PW, float spatial_scale,
+                        int sampling_ratio, int aligned, float *out, void *stream);
+int frcnn_roi_align_bwd(const float *dout, const float *proposals, int K, int H, int W, int C, int PH, int PW, float spatial_scale,
+                        int sampling_ratio, int aligned, const float *addend, float *dfm, void *stream);
+
 /* ---- a10: proposal labelling (FasterRCNNModel._label_proposals, models/faster_rcnn.py:418-524)
  * proposals (n,4), gt boxes (m,4), gt classes (m) int32.  For each of the n proposals: best IoU
  * (math_utils.py:39-63 semantics), class (0 if best IoU < min_object_iou), one-hot row

@@ -161,3 +161,87 @@ void oracle_roi_pool_bwd(const float *grad_output, const int32_t *argmax, const 
     }
   }
 }
+
+/*
+ * RoIAlign (EXTENSION -- the reference has no RoIAlign; SURVEY.md 8c/8f: the only available oracle is
+ * torchvision.ops.roi_align, restated here for fixed sampling_ratio > 0).  input NCHW, rois (K,5) =
+ * [batch, x1, y1, x2, y2], output (K,C,PH,PW).  Pinned bit-for-bit against torchvision's CPU op in tests/test_oracle.py.
+ */
+static void oracle_bilinear(int H, int W, float y, float x, int *yl, int *xl, int *yh, int *xh, float *w1, float *w2, float *w3, float *w4)
+{
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) { *yl = -1; *w1 = *w2 = *w3 = *w4 = 0.f; *xl = *yh = *xh = 0; return; }
+  if (y <= 0) y = 0;
+  if (x <= 0) x = 0;
+  int y_low = (int)y, x_low = (int)x, y_high, x_high;
+  if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else y_high = y_low + 1;
+  if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else x_high = x_low + 1;
+  float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+  *yl = y_low; *xl = x_low; *yh = y_high; *xh = x_high;
+  *w1 = hy * hx; *w2 = hy * lx; *w3 = ly * hx; *w4 = ly * lx;
+}
+
+void oracle_roi_align_fwd(const float *input, int C, int H, int W, const float *rois, int K, int PH, int PW, float scale,
+                          int S, int aligned, float *output)
+{
+  float offset = aligned ? 0.5f : 0.0f;
+  for (int n = 0; n < K; n++) {
+    const float *r = rois + 5 * n;
+    int b = (int)r[0];
+    float sw = r[1] * scale - offset, sh = r[2] * scale - offset, ew = r[3] * scale - offset, eh = r[4] * scale - offset;
+    float rw = ew - sw, rh = eh - sh;
+    if (!aligned) { rw = rw > 1.f ? rw : 1.f; rh = rh > 1.f ? rh : 1.f; }
+    float bh = rh / (float)PH, bw = rw / (float)PW;
+    float count = (float)(S * S > 0 ? S * S : 1);
+    for (int c = 0; c < C; c++) {
+      const float *plane = input + ((size_t)b * C + c) * H * W;
+      for (int ph = 0; ph < PH; ph++)
+        for (int pw = 0; pw < PW; pw++) {
+          float acc = 0.f;
+          for (int iy = 0; iy < S; iy++) {
+            float yy = sh + ph * bh + (iy + .5f) * bh / (float)S;
+            for (int ix = 0; ix < S; ix++) {
+              float xx = sw + pw * bw + (ix + .5f) * bw / (float)S;
+              int yl, xl, yh, xh; float w1, w2, w3, w4;
+              oracle_bilinear(H, W, yy, xx, &yl, &xl, &yh, &xh, &w1, &w2, &w3, &w4);
+              if (yl < 0) continue;
+              acc += w1 * plane[yl * W + xl] + w2 * plane[yl * W + xh] + w3 * plane[yh * W + xl] + w4 * plane[yh * W + xh];
+            }
+          }
+          output[(((size_t)n * C + c) * PH + ph) * PW + pw] = acc / count;
+        }
+    }
+  }
+}
+
+void oracle_roi_align_bwd(const float *grad_output, const float *rois, int K, int C, int H, int W, int PH, int PW, float scale,
+                          int S, int aligned, int n_img, float *grad_input)
+{
+  memset(grad_input, 0, (size_t)n_img * C * H * W * sizeof(float));
+  float offset = aligned ? 0.5f : 0.0f;
+  for (int n = 0; n < K; n++) {
+    const float *r = rois + 5 * n;
+    int b = (int)r[0];
+    float sw = r[1] * scale - offset, sh = r[2] * scale - offset, ew = r[3] * scale - offset, eh = r[4] * scale - offset;
+    float rw = ew - sw, rh = eh - sh;
+    if (!aligned) { rw = rw > 1.f ? rw : 1.f; rh = rh > 1.f ? rh : 1.f; }
+    float bh = rh / (float)PH, bw = rw / (float)PW;
+    float count = (float)(S * S);
+    for (int c = 0; c < C; c++) {
+      float *plane = grad_input + ((size_t)b * C + c) * H * W;
+      for (int ph = 0; ph < PH; ph++)
+        for (int pw = 0; pw < PW; pw++) {
+          float g = grad_output[(((size_t)n * C + c) * PH + ph) * PW + pw] / count;
+          for (int iy = 0; iy < S; iy++) {
+            float yy = sh + ph * bh + (iy + .5f) * bh / (float)S;
+            for (int ix = 0; ix < S; ix++) {
+              float xx = sw + pw * bw + (ix + .5f) * bw / (float)S;
+              int yl, xl, yh, xh; float w1, w2, w3, w4;
+              oracle_bilinear(H, W, yy, xx, &yl, &xl, &yh, &xh, &w1, &w2, &w3, &w4);
+              if (yl < 0) continue;
+              plane[yl * W + xl] += g * w1; plane[yl * W + xh] += g * w2; plane[yh * W + xl] += g * w3; plane[yh * W + xh] += g * w4;
+            }
+          }
+        }
+    }
+  }
+}

@@ -55,6 +55,10 @@ def _clib():
     lib.oracle_roi_pool_fwd.argtypes = [vp] + [ctypes.c_int] * 4 + [vp] + [ctypes.c_int] * 3 + [ctypes.c_float, vp, vp]
     lib.oracle_roi_pool_bwd.restype = None
     lib.oracle_roi_pool_bwd.argtypes = [vp, vp, vp] + [ctypes.c_int] * 7 + [vp]
+    lib.oracle_roi_align_fwd.restype = None
+    lib.oracle_roi_align_fwd.argtypes = [vp] + [ctypes.c_int] * 3 + [vp] + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
+    lib.oracle_roi_align_bwd.restype = None
+    lib.oracle_roi_align_bwd.argtypes = [vp, vp] + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     _lib = lib
   return _lib
 
@@ -108,6 +112,27 @@ def roi_pool_backward(grad_output, argmax, rois, input_shape):
   K, _, PH, PW = go.shape
   gi = np.empty((B, C, H, W), dtype = np.float32)
   _clib().oracle_roi_pool_bwd(go.ctypes.data, arg.ctypes.data, r.ctypes.data, K, C, H, W, PH, PW, B, gi.ctypes.data)
+  return gi
+
+
+def roi_align_forward(feature_map, rois, output_size = (7, 7), spatial_scale = 1.0 / 16.0, sampling_ratio = 2, aligned = False):
+  """EXTENSION oracle: torchvision.ops.roi_align (fixed sampling_ratio) restated in C; feature_map (1,C,H,W), rois (K,5)."""
+  fm = np.ascontiguousarray(feature_map, dtype = np.float32)
+  r = np.ascontiguousarray(rois, dtype = np.float32)
+  _, C, H, W = fm.shape
+  PH, PW = output_size
+  out = np.empty((r.shape[0], C, PH, PW), dtype = np.float32)
+  _clib().oracle_roi_align_fwd(fm.ctypes.data, C, H, W, r.ctypes.data, r.shape[0], PH, PW, np.float32(spatial_scale), int(sampling_ratio), int(aligned), out.ctypes.data)
+  return out
+
+
+def roi_align_backward(grad_output, rois, input_shape, spatial_scale = 1.0 / 16.0, sampling_ratio = 2, aligned = False):
+  go = np.ascontiguousarray(grad_output, dtype = np.float32)
+  r = np.ascontiguousarray(rois, dtype = np.float32)
+  B, C, H, W = input_shape
+  K, _, PH, PW = go.shape
+  gi = np.empty((B, C, H, W), dtype = np.float32)
+  _clib().oracle_roi_align_bwd(go.ctypes.data, r.ctypes.data, K, C, H, W, PH, PW, np.float32(spatial_scale), int(sampling_ratio), int(aligned), B, gi.ctypes.data)
   return gi
 
 

@@ -230,6 +230,22 @@ def test_roi_pool_microbench_shape_property(ops):
   assert out.max() <= fm.max() and out.min() >= 0.0
 
 
+@pytest.mark.parametrize("aligned", [False, True])
+def test_roi_align_extension_vs_oracle(ops, aligned):
+  """EXTENSION (no reference counterpart): RoIAlign forward / deterministic backward vs the torchvision-pinned oracle."""
+  for tag, s_ratio in (("small", 2), ("small", 3), ("vgg_b128", 2)):
+    fm, rois = gi.roi_case(tag)
+    props = np.stack([rois[:, 2], rois[:, 1], rois[:, 4], rois[:, 3]], axis = 1)
+    ref = orc.roi_align_forward(fm, rois, (7, 7), 1.0 / 16.0, s_ratio, aligned)
+    fmc = _cuda(fm).requires_grad_(True)
+    out = ops.roi_align(fmc, _cuda(props), (7, 7), 1.0 / 16.0, s_ratio, aligned)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol = 1e-6, atol = 1e-6)
+    go = gi.roi_grad(tag, ref.shape)
+    out.backward(_cuda(go))
+    gin = orc.roi_align_backward(go, rois, fm.shape, 1.0 / 16.0, s_ratio, aligned)
+    np.testing.assert_allclose(fmc.grad.cpu().numpy(), gin, rtol = 1e-5, atol = 2e-5)
+
+
 # ---------------------------------------------------------------- labelling, losses, post-processing
 def test_label_proposals_vs_oracle(ops):
   rng = np.random.default_rng(1)

@@ -148,3 +148,51 @@ def test_empty_and_ragged_inputs():
   model = f.FasterRCNNModel(21, f.vgg16.VGG16Backbone(0.0)).cuda()
   with pytest.raises(AssertionError):
     model(image_data = t.zeros((2, 3, 64, 64), device = dev))
+
+
+def test_config1_full_size_forward_600x800():
+  """BASELINE config 1: single 600x800 image, VGG-16, forward-only (RPN -> RoI -> NMS correctness) vs the CPU oracle."""
+  cfg = dict(backbone = "vgg16", weight_seed = 3, heads = "spread", hw = (600, 800), sample_seed = 3)
+  model, oracle, smp = _build(cfg)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  with t.no_grad():
+    p_ref, c_ref, d_ref = oracle.forward(smp["image"])
+  model.eval()
+  with t.no_grad():
+    props, classes, deltas = model(image_data = smp["image"].cuda())
+  assert abs(props.shape[0] - p_ref.shape[0]) <= 3
+  pg, pr = props.cpu().numpy(), p_ref.numpy()
+  dist = np.abs(pg[:, None, :] - pr[None, :, :]).max(axis = 2)
+  partner = dist.argmin(axis = 1)
+  ok = dist[np.arange(pg.shape[0]), partner] <= 5e-2
+  assert ok.mean() >= 0.97, ok.mean()
+  np.testing.assert_allclose(classes.cpu().numpy()[ok], c_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)
+  np.testing.assert_allclose(deltas.cpu().numpy()[ok], d_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)
+
+
+def test_config2_full_size_train_step_600x1000():
+  """BASELINE config 2: VGG-16 fwd+bwd at 1000x600, batch 1: losses and every parameter gradient vs the CPU oracle."""
+  cfg = dict(backbone = "vgg16", weight_seed = 5, heads = "reference", hw = (600, 1000), sample_seed = 5)
+  model, oracle, smp = _build(cfg)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
+  optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)
+  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
+  random.seed(1); np.random.seed(1); t.manual_seed(1)
+  ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = False)
+  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
+  random.seed(1); np.random.seed(1); t.manual_seed(1)
+  got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
+                         gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
+                         gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
+  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
+  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
+  np.testing.assert_allclose(a, b, rtol = 1e-3, atol = 1e-5)
+  assert model.last_step_info["num_rois"] == 128
+  for k, p in model.named_parameters():
+    if p.grad is None:
+      continue
+    ga, gb = p.grad.detach().cpu().double(), ref_grads[k].double()
+    rel = float((ga - gb).norm() / (gb.norm() + 1e-12))
+    assert rel < 2e-2, (k, rel)

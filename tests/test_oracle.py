@@ -80,6 +80,22 @@ def test_nms_and_roi_pool_match_live_torchvision():
   assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("aligned", [False, True])
+@pytest.mark.parametrize("sampling_ratio", [1, 2, 3])
+def test_roi_align_extension_matches_live_torchvision(aligned, sampling_ratio):
+  """RoIAlign is an extension (the reference has none): its oracle is pinned on torchvision.ops.roi_align's CPU op."""
+  tv = pytest.importorskip("torchvision")
+  fm, rois = gi.roi_case("small")
+  out = orc.roi_align_forward(fm, rois, (7, 7), 1.0 / 16.0, sampling_ratio, aligned)
+  x = t.from_numpy(fm).requires_grad_(True)
+  ref = tv.ops.roi_align(x, t.from_numpy(rois), (7, 7), 1.0 / 16.0, sampling_ratio, aligned)
+  np.testing.assert_allclose(out, ref.detach().numpy(), rtol = 1e-6, atol = 1e-6)
+  go = gi.roi_grad("small", out.shape)
+  ref.backward(t.from_numpy(go))
+  gin = orc.roi_align_backward(go, rois, fm.shape, 1.0 / 16.0, sampling_ratio, aligned)
+  np.testing.assert_allclose(gin, x.grad.numpy(), rtol = 1e-5, atol = 1e-5)
+
+
 @pytest.mark.parametrize("tag", gi.RPN_CASES)
 def test_rpn_proposal_stage_bit_exact(golden_dir, tag):
   g = np.load(os.path.join(golden_dir, "rpn_stage.npz"))
