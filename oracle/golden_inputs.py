@@ -123,3 +123,43 @@ E2E_CASES = {
   "small": dict(hw = (384, 512), weight_seed = 0, sample_seed = 0, heads = "spread", score_threshold = 0.05, backbone = "vgg16"),
   "resnet50_small": dict(hw = (384, 512), weight_seed = 1, sample_seed = 0, heads = "spread", score_threshold = 0.05, backbone = "resnet50"),
 }
+
+
+# ---- evaluation statistics (statistics.py:65-214) ---------------------------------------------
+STATS_CASES = {"voc_like": (11, 40), "sparse": (12, 6), "crowded": (13, 25)}     # tag -> (seed, images)
+
+
+def stats_case(tag):
+  """
+  Seeded detections: per image a list of ground-truth boxes [(corners f32 (4,), class)] and a dict class -> (k,5) f32 array of
+  (y1,x1,y2,x2,score) rows.  Predictions are jittered copies of ground truths (so IoUs straddle 0.5, several predictions compete
+  for one object and one prediction can overlap two objects) plus random false positives.
+  """
+  seed, n_images = STATS_CASES[tag]
+  rng = np.random.RandomState(seed)
+  images = []
+  for _ in range(n_images):
+    n_gt = int(rng.randint(0, 7)) if tag != "crowded" else int(rng.randint(6, 14))
+    gts = []
+    for _ in range(n_gt):
+      cy, cx = rng.uniform(80, 520), rng.uniform(80, 920)
+      hh, ww = rng.uniform(20, 160), rng.uniform(20, 200)
+      if tag == "crowded" and len(gts) > 0 and rng.rand() < 0.6:          # overlapping same-class neighbours
+        base = gts[rng.randint(len(gts))]
+        corners = base[0] + rng.uniform(-25, 25, size = 4).astype(np.float32)
+        gts.append((corners.astype(np.float32), base[1]))
+        continue
+      gts.append((np.array([cy - hh, cx - ww, cy + hh, cx + ww], dtype = np.float32), int(rng.randint(1, 6 if tag != "voc_like" else 21))))
+    preds = {}
+    for corners, cls in gts:
+      for _ in range(int(rng.randint(0, 4))):
+        jitter = rng.normal(0, 0.18, size = 4) * np.array([corners[2] - corners[0], corners[3] - corners[1]] * 2)
+        row = np.concatenate([corners + jitter, [rng.uniform(0.05, 1.0)]]).astype(np.float32)
+        preds.setdefault(cls, []).append(row)
+    for _ in range(int(rng.randint(0, 5))):
+      cls = int(rng.randint(1, 6 if tag != "voc_like" else 21))
+      cy, cx = rng.uniform(80, 520), rng.uniform(80, 920)
+      hh, ww = rng.uniform(20, 160), rng.uniform(20, 200)
+      preds.setdefault(cls, []).append(np.array([cy - hh, cx - ww, cy + hh, cx + ww, rng.uniform(0.05, 0.9)], dtype = np.float32))
+    images.append((gts, {c: np.stack(r, axis = 0) for c, r in preds.items()}))
+  return images

@@ -26,9 +26,31 @@ def sha(a):
   return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def statistics_golden(ref):
+  """statistics.PrecisionRecallCurveCalculator of the reference on seeded detections (golden_inputs.stats_case)."""
+  import importlib
+  stats_mod = importlib.import_module("pytorch.FasterRCNN.statistics")
+  out = {}
+  for tag in gi.STATS_CASES:
+    calc = stats_mod.PrecisionRecallCurveCalculator()
+    for gts, preds in gi.stats_case(tag):
+      boxes = [ref.Box(class_index = c, class_name = str(c), corners = b) for b, c in gts]
+      calc.add_image_results(scored_boxes_by_class_index = preds, gt_boxes = boxes)
+    classes = sorted(calc._object_count_by_class_index.keys())
+    out[tag + "_classes"] = np.array(classes, dtype = np.int32)
+    out[tag + "_ap"] = np.array([calc._compute_average_precision(class_index = c)[0] for c in classes], dtype = np.float64)
+    out[tag + "_map"] = np.float64(calc.compute_mean_average_precision())
+    out[tag + "_tp"] = np.array([sum(1 for p in calc._unsorted_predictions_by_class_index[c] if p[1]) for c in classes], dtype = np.int32)
+    out[tag + "_npred"] = np.array([len(calc._unsorted_predictions_by_class_index[c]) for c in classes], dtype = np.int32)
+  np.savez_compressed(os.path.join(OUT, "statistics.npz"), **out)
+
+
 def main():
   os.makedirs(OUT, exist_ok = True)
   ref = ref_shim.load()
+  if "--only-statistics" in sys.argv:
+    statistics_golden(ref)
+    return
   tv = ref.torchvision
   t.set_num_threads(8)
 
@@ -138,6 +160,7 @@ def main():
       e2e["%s_w2_head/%s" % (tag, key)] = sd[key].reshape(-1)[:64].numpy().copy()
       e2e["%s_w2_norm/%s" % (tag, key)] = np.float64(sd[key].double().norm().item())
     np.savez_compressed(os.path.join(OUT, "e2e_%s.npz" % cfg["backbone"]), **e2e)
+  statistics_golden(ref)
   print("golden vectors written to", OUT)
   for f in sorted(os.listdir(OUT)):
     print("  %-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

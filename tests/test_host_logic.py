@@ -1,0 +1,120 @@
+"""
+CPU tests of the host-side mirrors that sit either side of the hot path:
+  * fasterrcnn_b200.statistics vs outputs of the reference's statistics.py (tests/golden/statistics.npz, made by
+    oracle/make_golden.py running the unmodified reference on the seeded detections of oracle/golden_inputs.stats_case);
+  * fasterrcnn_b200.state key/layout conversions vs the model's state-dict keys.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch as t
+
+from oracle import golden_inputs as gi
+from oracle import frcnn_oracle as orc
+from fasterrcnn_b200 import statistics, state
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _box(corners, cls):
+  return types.SimpleNamespace(class_index = cls, class_name = str(cls), corners = corners)
+
+
+@pytest.mark.parametrize("tag", list(gi.STATS_CASES))
+def test_precision_recall_matches_reference(tag):
+  g = np.load(os.path.join(GOLDEN, "statistics.npz"))
+  calc = statistics.PrecisionRecallCurveCalculator()
+  for gts, preds in gi.stats_case(tag):
+    calc.add_image_results(scored_boxes_by_class_index = preds, gt_boxes = [_box(b, c) for b, c in gts])
+  classes = sorted(calc._object_count_by_class_index.keys())
+  assert classes == list(g[tag + "_classes"])
+  tp = [sum(1 for p in calc._unsorted_predictions_by_class_index[c] if p[1]) for c in classes]
+  npred = [len(calc._unsorted_predictions_by_class_index[c]) for c in classes]
+  assert tp == list(g[tag + "_tp"])                        # the greedy matching visits pairs in the reference's order
+  assert npred == list(g[tag + "_npred"])
+  aps = calc.compute_class_average_precisions()
+  np.testing.assert_array_equal(np.array([aps[c] for c in classes]), g[tag + "_ap"])       # same arithmetic -> same doubles
+  assert calc.compute_mean_average_precision() == g[tag + "_map"]
+
+
+def test_precision_recall_edge_cases():
+  calc = statistics.PrecisionRecallCurveCalculator()
+  # objects but no predictions at all: AP 0 for that class, counted in the mean
+  calc.add_image_results(scored_boxes_by_class_index = {}, gt_boxes = [_box(np.array([0, 0, 10, 10], dtype = np.float32), 3)])
+  # predictions for a class with no objects in the image: all false positives, class not counted in the mean
+  calc.add_image_results(scored_boxes_by_class_index = {5: np.array([[0, 0, 10, 10, 0.9]], dtype = np.float32)}, gt_boxes = [])
+  assert calc.compute_mean_average_precision() == 0.0
+  assert list(calc._object_count_by_class_index.keys()) == [3]
+  # a perfect detection
+  calc = statistics.PrecisionRecallCurveCalculator()
+  b = np.array([10, 10, 50, 60], dtype = np.float32)
+  calc.add_image_results(scored_boxes_by_class_index = {1: np.concatenate([b, [0.8]])[None, :].astype(np.float32)}, gt_boxes = [_box(b, 1)])
+  assert calc.compute_mean_average_precision() == 1.0
+
+
+def test_training_statistics_running_means():
+  st = statistics.TrainingStatistics()
+  for i in range(3):
+    st.on_training_step(types.SimpleNamespace(rpn_class = 1.0 + i, rpn_regression = 0.5, detector_class = 2.0 * i, detector_regression = 0.25))
+  assert st.rpn_class_loss == 2.0 and st.detector_class_loss == 2.0
+  assert st.get_progbar_postfix()["total_loss"] == "4.75"
+
+
+def test_caffe_vgg16_key_map_targets_live_keys():
+  shapes = orc.vgg16_param_shapes()
+  caffe = {}
+  for layer, ours in state._CAFFE_LAYERS.items():
+    caffe[layer + ".weight"] = t.zeros(shapes[ours + ".weight"])
+    caffe[layer + ".bias"] = t.zeros(shapes[ours + ".bias"])
+  caffe["classifier.6.weight"] = t.zeros((1000, 4096))      # ImageNet head: ignored
+  converted, missing = state.caffe_vgg16_to_state(caffe)
+  assert missing == []
+  assert set(converted.keys()) <= set(shapes.keys())         # every key exists in the model (the reference's fc keys do not)
+  assert "_stage3_detector_network._pool_to_feature_vector._fc1.weight" in converted
+  del caffe["features.28.weight"]
+  _, missing = state.caffe_vgg16_to_state(caffe)
+  assert missing == ["features.28"]
+  with pytest.raises(ValueError):
+    state.caffe_vgg16_to_state({"something.else": t.zeros(1)})
+
+
+class _FakeH5(dict):
+  """Just enough of h5py.File: nested groups addressed by '/'-joined paths."""
+  def __contains__(self, path):
+    try:
+      self[path]
+      return True
+    except KeyError:
+      return False
+
+  def __getitem__(self, path):
+    node = dict(self)
+    for part in path.split("/"):
+      node = node[part]
+    return node
+
+
+def test_keras_vgg16_layout_conversion():
+  rng = np.random.RandomState(0)
+  layers = {}
+  shapes = orc.vgg16_param_shapes()
+  for name in state._KERAS_CONV_LAYERS:
+    co, ci, kh, kw = shapes["_stage1_feature_extractor._%s.weight" % name]
+    layers[name] = {"conv2d": {"kernel:0": rng.randn(kh, kw, ci, co).astype(np.float32), "bias:0": rng.randn(co).astype(np.float32)}}
+  fc1 = rng.randn(25088, 8).astype(np.float32)
+  # a narrow fc1 keeps the test light; the conversion only relies on the (7,7,512,out) factorisation of the rows
+  layers["fc2"] = {"dense": {"kernel:0": rng.randn(16, 8).astype(np.float32), "bias:0": rng.randn(8).astype(np.float32)}}
+  f = _FakeH5({"model_weights": layers})
+  converted, missing = state.keras_vgg16_to_state(f)
+  assert missing == ["fc1"]
+  k = layers["block3_conv2"]["conv2d"]["kernel:0"]
+  w = converted["_stage1_feature_extractor._block3_conv2.weight"].numpy()
+  assert w.shape == (256, 256, 3, 3)
+  assert w[5, 7, 1, 2] == k[1, 2, 7, 5]
+  assert converted["_stage3_detector_network._pool_to_feature_vector._fc2.weight"].shape == (8, 16)
+  # fc1 row permutation: Keras row (y,x,c) -> reference column c*49 + y*7 + x   (state.py:146-157)
+  kernel = t.from_numpy(fc1).reshape(7, 7, 512, 8).permute(2, 0, 1, 3).reshape(-1, 8).permute(1, 0)
+  y, x, c, o = 3, 5, 100, 2
+  assert kernel[o, c * 49 + y * 7 + x] == fc1[(y * 7 + x) * 512 + c, o]

@@ -196,3 +196,42 @@ def test_config2_full_size_train_step_600x1000():
     ga, gb = p.grad.detach().cpu().double(), ref_grads[k].double()
     rel = float((ga - gb).norm() / (gb.norm() + 1e-12))
     assert rel < 2e-2, (k, rel)
+
+
+def test_checkpoint_round_trip_and_caffe_partial_load(tmp_path):
+  """state.save / state.load (reference state.py:221-288): own-format round trip is bit-exact; a Caffe VGG-16 file initialises
+  the 13 convs AND fc1/fc2 (the reference loses the fc layers to a key mismatch) and leaves the heads untouched."""
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import state
+  cfg = gi.E2E_CASES["small"]
+  model, _, _ = _build(cfg)
+  path = str(tmp_path / "ckpt.pth")
+  state.save(model, path, epoch = 3)
+  fresh = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0)).cuda()
+  state.load(fresh, path)
+  a, b = model.state_dict(), fresh.state_dict()
+  assert list(a.keys()) == list(b.keys())
+  for k in a:
+    assert t.equal(a[k], b[k]), k
+  assert t.load(path)["epoch"] == 3
+
+  caffe = {}
+  rng = t.Generator().manual_seed(5)
+  for layer, ours in state._CAFFE_LAYERS.items():
+    caffe[layer + ".weight"] = t.randn(a[ours + ".weight"].shape, generator = rng)
+    caffe[layer + ".bias"] = t.randn(a[ours + ".bias"].shape, generator = rng)
+  cpath = str(tmp_path / "vgg16_caffe.pth")
+  t.save(caffe, cpath)
+  head_before = fresh.state_dict()["_stage2_region_proposal_network._rpn_class.weight"].clone()
+  state.load(fresh, cpath)
+  sd = fresh.state_dict()
+  for layer, ours in state._CAFFE_LAYERS.items():
+    assert t.equal(sd[ours + ".weight"].cpu(), caffe[layer + ".weight"]), ours
+  assert t.equal(sd["_stage2_region_proposal_network._rpn_class.weight"], head_before)
+
+  tracker = state.BestWeightsTracker(str(tmp_path / "best.pth"))
+  tracker.on_epoch_end(model = model, epoch = 1, mAP = 10.0)
+  tracker.on_epoch_end(model = fresh, epoch = 2, mAP = 5.0)          # worse: ignored
+  tracker.save_best_weights(model)
+  best = t.load(str(tmp_path / "best.pth"))
+  assert best["epoch"] == 1 and t.equal(best["model_state_dict"]["_stage1_feature_extractor._block1_conv1.weight"], a["_stage1_feature_extractor._block1_conv1.weight"].cpu())
