@@ -53,6 +53,18 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # synthetic weights: Kaiming backbone (first layer /50 for the randn*50 image), reference head init
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(family):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed `ncu --set full` summary
+  (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None when there is no capture for it."""
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+  try:
+    with open(path) as fp:
+      entry = json.load(fp).get(family)
+    return None if entry is None else (entry["dram_bytes_per_launch"], "%s (%d launches)" % (entry["source"], entry["launches"]))
+  except (OSError, ValueError, KeyError):
+    return None
+
+
 def init_weights(model, seed):
   g = t.Generator(device = "cpu").manual_seed(seed)
   with t.no_grad():
@@ -167,18 +179,10 @@ def run_reference(args, rank):
   print(json.dumps(line), flush = True)
 
 
-# ------------------------------------------------------------------------------------------------
-# ours
-# ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
-  import torch.distributed as dist
+def make_train_step(dev, rank = 0):
+  """Builds the benchmark workload on `dev`: model + fused optimizer + one synthetic sample.  Returns step(from_host) -> Loss."""
   import fasterrcnn_b200 as f
-  from fasterrcnn_b200 import anchors as fanchors, ops, optim, _lib
-
-  t.cuda.set_device(local_rank)
-  dev = t.device("cuda", local_rank)
-  if world > 1:
-    dist.init_process_group("nccl", device_id = dev)
+  from fasterrcnn_b200 import anchors as fanchors, optim
 
   model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
   init_weights(model, seed = 0)                                   # identical replicas
@@ -196,7 +200,7 @@ def run_ours(args, rank, local_rank, world):
   image_dev, gt_map_dev = image_host.cuda(), gt_map_host.cuda()
   random.seed(rank); t.manual_seed(rank)
 
-  def step(from_host):
+  def step(from_host = False):
     if from_host:
       img = image_host.to(dev, non_blocking = True)
       gmap = gt_map_host.to(dev, non_blocking = True)
@@ -204,6 +208,26 @@ def run_ours(args, rank, local_rank, world):
       img, gmap = image_dev, gt_map_dev
     return model.train_step(optimizer = optimizer, image_data = img, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map, gt_rpn_map = gmap,
                             gt_rpn_object_indices = [obj_idx], gt_rpn_background_indices = [bg_idx], gt_boxes = [boxes])
+
+  step.h2d_bytes = image_host.numel() * 4 + gt_map_host.numel() * 4
+  step.model = model
+  return step
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+  import torch.distributed as dist
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import anchors as fanchors, ops, optim, _lib
+
+  t.cuda.set_device(local_rank)
+  dev = t.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id = dev)
+
+  step = make_train_step(dev, rank)
 
   def barrier():
     if world > 1:
@@ -237,7 +261,7 @@ def run_ours(args, rank, local_rank, world):
   gemm_stats = ops.kernel_timer.collect()
   ops.kernel_timer.enable(False)
   clocks = sampler.stop() if rank == 0 else None
-  rois = model.last_step_info.get("num_rois")
+  rois = step.model.last_step_info.get("num_rois")
   # end-to-end leg: host buffers in, loss out (the loss read-back is part of train_step's return value)
   for _ in range(2):
     step(True)
@@ -250,7 +274,7 @@ def run_ours(args, rank, local_rank, world):
   peaks = measured_peaks()
   value = world * args.steps / (ms_dev / 1e3)
   e2e_value = world * args.steps / (ms_e2e / 1e3)
-  h2d = image_host.numel() * 4 + gt_map_host.numel() * 4
+  h2d = step.h2d_bytes
   d2h = 5 * 4 + 4 + 4 * 2100                                     # losses (5 fp32) + proposal count + class indices for the sampler
   # dominant kernel family = implicit-GEMM convolution / linear
   top = max(gemm_stats.items(), key = lambda kv: kv[1]["ms"]) if gemm_stats else (None, None)
@@ -258,7 +282,8 @@ def run_ours(args, rank, local_rank, world):
   if top[0] is not None:
     st = top[1]
     achieved = st["gflop"] / st["ms"]                              # GFLOP / ms = TFLOP/s
-    roofline = dict(bound = "tensor", kernel = top[0], achieved = achieved, peak = peaks["tflops"], unit = "TFLOP/s", frac = achieved / peaks["tflops"], traffic = None,
+    traffic, traffic_source = ncu_traffic(top[0]) or (None, None)
+    roofline = dict(bound = "tensor", kernel = top[0], achieved = achieved, peak = peaks["tflops"], unit = "TFLOP/s", frac = achieved / peaks["tflops"], traffic = traffic, traffic_unit = "bytes per launch (dram read + write, ncu --set full)", traffic_source = traffic_source,
                     peak_source = peaks["source"], launches = st["launches"], ms_per_step = st["ms"] / args.steps,
                     note = "algorithmic FLOPs (2*M*N*K) per launch / CUDA-event time; tcgen05 kernels execute 3 TF32 products per algorithmic MAC (3xTF32, fp32-grade), TF32 dense peak is 1/2 of the bf16 figure used as denominator",
                     families = {k: dict(tflops = v["gflop"] / v["ms"], ms_per_step = v["ms"] / args.steps, launches = v["launches"]) for k, v in gemm_stats.items()})
@@ -271,7 +296,7 @@ def run_ours(args, rank, local_rank, world):
               higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = "f32", data = "synthetic",
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
                             parallelism = "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)" % world,
-                            engine = "auto: tcgen05 3xTF32 forward convs/linears, fp32 CUDA-core dgrad/wgrad",
+                            engine = "auto: tcgen05 3xTF32 (fp32-grade) implicit GEMM for conv/linear fwd, dgrad and wgrad; exact-fp32 CUDA-core kernels for the RGB stem and the 9/21/36/80-wide heads",
                             l2 = "per-step working set (~1.7 GB of weights, activations, gradients) exceeds the 126 MB L2; no explicit flush"),
               e2e = dict(value = e2e_value, unit = "images/s", h2d_bytes_per_step = h2d, d2h_bytes_per_step = d2h, ms_per_step = ms_e2e / args.steps),
               gpu_launches = launches, clocks = clocks, roofline = roofline, cpu_baseline = cpu,

@@ -32,6 +32,7 @@ _SIGNATURES = {
   "frcnn_conv2d_wgrad_workspace_bytes": (_sz, _GEOM + [_i]),
   "frcnn_conv2d_wgrad": (_i, [_vp] * 3 + _GEOM + [_i, _vp, _sz, _vp]),
   "frcnn_conv2d_uses_tensor_cores": (_i, [_i] + _GEOM + [_i]),
+  "frcnn_debug_tc_trace": (None, [_vp]),
   "frcnn_tf32_split_bytes": (_sz, [_sz]),
   "frcnn_tf32_split": (_i, [_vp, _sz, _vp, _vp]),
   "frcnn_conv2d_fwd_presplit": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),
@@ -55,6 +56,7 @@ _SIGNATURES = {
   "frcnn_nms_workspace_bytes": (_sz, [_i]),
   "frcnn_nms_sorted_f32": (_i, [_vp, _vp, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
   "frcnn_gather_rows_f32": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp]),
+  "frcnn_append_rows_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
   "frcnn_roi_pool_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
   "frcnn_roi_pool_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
   "frcnn_roi_align_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp]),

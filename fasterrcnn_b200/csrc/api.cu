@@ -26,6 +26,7 @@ int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const floa
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
                   void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split);
 size_t tf32_split_bytes(size_t count);
+void tc_set_trace(void *buf);
 int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
 bool tc_dgrad_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 size_t tc_dgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
@@ -124,6 +125,8 @@ int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int C
 }
 
 size_t frcnn_tf32_split_bytes(size_t count) { return tf32_split_bytes(count); }
+
+void frcnn_debug_tc_trace(void *buf) { tc_set_trace(buf); }
 
 int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream)
 {

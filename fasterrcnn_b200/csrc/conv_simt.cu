@@ -592,6 +592,80 @@ size_t simt_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int 
   return p.splits > 1 ? (size_t)p.splits * Cout * KH * KW * Cin * sizeof(float) : 0;
 }
 
+
+// ---- RGB stem: 3x3 stride-1 "same" convolution with Cin = 3 (vgg16.py:32 block1_conv1) ----------------------------------
+// K = 27 is too short for either GEMM engine (one or two k-steps per tile, all prologue/epilogue), so the stem gets a direct
+// kernel: a CTA owns a 16 x 8 pixel patch and 64 output channels; the haloed input patch (10 x 18 x 3 floats) and the 27 x 64
+// filter slice sit in shared memory.  A half-warp owns 8 consecutive pixels of one row, lane = channel quad, so every thread
+// carries 8 x 4 accumulators, reads its input values as shared-memory broadcasts and its weights as conflict-free 128-bit
+// loads (39 loads per 288 FMAs), and a pixel's 64 channels leave as one 256-byte row (full 128-bit coalescing).
+constexpr int kStemTW = 16, kStemTH = 8;
+
+__global__ void __launch_bounds__(256, 2)
+stem3x3_kernel(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ y, Epilogue epi, int N, int H, int W, int Cout)
+{
+  __shared__ float xs[kStemTH + 2][(kStemTW + 2) * 3];
+  __shared__ __align__(16) float ws[27][64];
+  const int tiles_w = (W + kStemTW - 1) / kStemTW, tiles_h = (H + kStemTH - 1) / kStemTH;
+  int tile = blockIdx.x;
+  const int n = tile / (tiles_w * tiles_h);
+  tile -= n * tiles_w * tiles_h;
+  const int oh0 = (tile / tiles_w) * kStemTH, ow0 = (tile % tiles_w) * kStemTW;
+  const int co0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  for (int e = t; e < (kStemTH + 2) * (kStemTW + 2) * 3; e += 256) {
+    const int r = e / ((kStemTW + 2) * 3), q = e - r * (kStemTW + 2) * 3;
+    const int ih = oh0 + r - 1, iw = ow0 + q / 3 - 1;
+    xs[r][q] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((size_t)n * H + ih) * W + iw) * 3 + q % 3) : 0.f;
+  }
+  for (int e = t; e < 27 * 64; e += 256) {
+    const int co = e / 27, k = e - co * 27;                           // OHWI: 27 contiguous taps per output channel
+    ws[k][co] = __ldg(w + (size_t)(co0 + co) * 27 + k);
+  }
+  __syncthreads();
+  const int half = t >> 4, cq = t & 15;                               // 16 half-warps: row = half / 2, 8-pixel segment = half % 2
+  const int row = half >> 1, px0 = (half & 1) * 8;
+  float acc[8][4];
+#pragma unroll
+  for (int p = 0; p < 8; p++) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+    float xv[30];
+#pragma unroll
+    for (int i = 0; i < 30; i++) xv[i] = xs[row + kh][px0 * 3 + i];   // 10 pixels x 3 channels, broadcast within the half-warp
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 wv = *reinterpret_cast<const float4 *>(&ws[(kh * 3 + kw) * 3 + c][cq * 4]);
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+          const float v = xv[(p + kw) * 3 + c];
+          acc[p][0] = fmaf(v, wv.x, acc[p][0]);
+          acc[p][1] = fmaf(v, wv.y, acc[p][1]);
+          acc[p][2] = fmaf(v, wv.z, acc[p][2]);
+          acc[p][3] = fmaf(v, wv.w, acc[p][3]);
+        }
+      }
+  }
+  const int oh = oh0 + row;
+  if (oh >= H) return;
+  const int c = co0 + cq * 4;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (epi.scale) sc = __ldg(reinterpret_cast<const float4 *>(epi.scale + c));
+  if (epi.bias) bi = __ldg(reinterpret_cast<const float4 *>(epi.bias + c));
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int ow = ow0 + px0 + p;
+    if (ow >= W) break;
+    float4 o = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+    if (epi.scale) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+    o.x = apply_act(o.x + bi.x, epi.act); o.y = apply_act(o.y + bi.y, epi.act);
+    o.z = apply_act(o.z + bi.z, epi.act); o.w = apply_act(o.w + bi.w, epi.act);
+    *reinterpret_cast<float4 *>(y + (((size_t)n * H + oh) * W + ow) * Cout + c) = o;
+  }
+}
+
 int simt_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
                     void *workspace, size_t workspace_bytes, cudaStream_t st)
@@ -599,6 +673,12 @@ int simt_conv2d_fwd(const float *x, const float *w, const float *scale, const fl
   ConvGeom g = make_geom(N, H, W, Cin, Cout, KH, KW, stride, pad);
   if (!geom_ok(g)) return fail(FRCNN_E_BADARG, "conv2d_fwd: bad geometry");
   Epilogue epi{scale, bias, residual, act};
+  if (Cin == 3 && KH == 3 && KW == 3 && stride == 1 && pad == 1 && Cout % 64 == 0 && residual == nullptr) {
+    const int tiles = N * ceil_div(H, kStemTH) * ceil_div(W, kStemTW);
+    stem3x3_kernel<<<dim3(tiles, Cout / 64), 256, 0, st>>>(x, w, y, epi, N, H, W, Cout);
+    FRCNN_CHECK_LAUNCH("stem3x3_kernel");
+    return FRCNN_OK;
+  }
   return launch_igemm<MODE_FWD>(x, w, y, epi, g, N * g.Ho * g.Wo, Cout, KH * KW * Cin, Cin, workspace, workspace_bytes, st);
 }
 

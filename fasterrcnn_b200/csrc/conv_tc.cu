@@ -80,7 +80,51 @@ struct TcGeom {
   int patches_w, patches_h;
   int kb_per_split, total_kb, splits;
   int mn_lbo, mn_sbo, mn_kstep;   // MN-major operand descriptor strides in bytes (4096 / 512 / 1024)
+  int m_tiles, n_tiles, items;    // work items = m_tiles * n_tiles * (taps for WGRAD) * splits; CTAs loop over them (persistent grid)
+  unsigned long long *trace;      // debug: per-CTA %globaltimer stamps (frcnn_debug_tc_trace), NULL in production
 };
+
+// one work item of the persistent loop: an output tile (or one split-K slice of it)
+struct TcItem {
+  int img, oh0, ow0, m0, n0, tap_w, split, kb_begin, nkb;
+};
+
+template <int MODE, int BN>
+__device__ __forceinline__ TcItem tc_decode_item(const TcGeom &g, int w)
+{
+  TcItem it;
+  const int mt = w % g.m_tiles;
+  int r = w / g.m_tiles;
+  const int nt = r % g.n_tiles;
+  r /= g.n_tiles;                                    // FWD/DGRAD: split; WGRAD: tap * splits + split
+  it.n0 = nt * BN;
+  it.img = it.oh0 = it.ow0 = it.m0 = it.tap_w = 0;
+  if (MODE == TC_WGRAD) {
+    it.m0 = mt * 128;
+    it.tap_w = r / g.splits;
+    it.split = r - it.tap_w * g.splits;
+  } else {
+    const int tiles_per_img = g.tiles_w * g.tiles_h;
+    it.img = (mt / tiles_per_img) * g.tile_n;        // first image of this tile's image group
+    const int trem = mt % tiles_per_img;
+    it.oh0 = (trem / g.tiles_w) * g.tile_h;
+    it.ow0 = (trem % g.tiles_w) * g.tile_w;
+    it.split = r;
+  }
+  it.kb_begin = it.split * g.kb_per_split;
+  int kb_end = it.kb_begin + g.kb_per_split;
+  if (kb_end > g.total_kb) kb_end = g.total_kb;
+  it.nkb = kb_end - it.kb_begin;
+  return it;
+}
+
+__device__ __forceinline__ unsigned long long tc_globaltimer()
+{
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+#define TC_TRACE(slot) do { if (g.trace) g.trace[(size_t)blockIdx.x * 16 + (slot)] = tc_globaltimer(); } while (0)
 
 constexpr int kTcThreads = 192;
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
@@ -116,26 +160,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KHW = g.KH * g.KW;
 
-  // ---- tile coordinates ----
-  int img = 0, oh0 = 0, ow0 = 0, m0 = 0, tap_w = 0, split = 0;
-  const int n0 = blockIdx.y * BN;
-  if (MODE == TC_WGRAD) {
-    m0 = blockIdx.x * 128;
-    tap_w = blockIdx.z / g.splits;
-    split = blockIdx.z - tap_w * g.splits;
-  } else {
-    const int tiles_per_img = g.tiles_w * g.tiles_h;
-    img = (blockIdx.x / tiles_per_img) * g.tile_n;                 // first image of this CTA's image group
-    const int trem = blockIdx.x % tiles_per_img;
-    oh0 = (trem / g.tiles_w) * g.tile_h;
-    ow0 = (trem % g.tiles_w) * g.tile_w;
-    split = blockIdx.z;
-  }
-  const int kb_begin = split * g.kb_per_split;
-  int kb_end = kb_begin + g.kb_per_split;
-  if (kb_end > g.total_kb) kb_end = g.total_kb;
-  const int nkb = kb_end - kb_begin;
-
+  if (threadIdx.x == 0) TC_TRACE(0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
@@ -152,52 +177,58 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (threadIdx.x == 0) TC_TRACE(1);
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer: runs ahead across work items (the smem ring never drains between tiles) =====
       const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kBK;          // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int kb = kb_begin + i;
-        uint8_t *a_hi = smem + s * kStageBytes;
-        uint8_t *a_lo = a_hi + kABytes;
-        uint8_t *b_hi = a_hi + 2 * kABytes;
-        uint8_t *b_lo = b_hi + kBBytes;
-        mbar_expect_tx(&full[s], kStageBytes);
-        if (MODE == TC_WGRAD) {
-          const int im = (kb / patches_per_img) * g.pn;              // first image of the patch's image group
-          const int prem = kb % patches_per_img;
-          const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
-          const int kh = tap_w / g.KW, kw = tap_w - kh * g.KW;
+      int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
+      for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
+        const TcItem t = tc_decode_item<MODE, BN>(g, w);
+        for (int i = 0; i < t.nkb; i++, it++) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const int kb = t.kb_begin + i;
+          uint8_t *a_hi = smem + s * kStageBytes;
+          uint8_t *a_lo = a_hi + kABytes;
+          uint8_t *b_hi = a_hi + 2 * kABytes;
+          uint8_t *b_lo = b_hi + kBBytes;
+          mbar_expect_tx(&full[s], kStageBytes);
+          if (MODE == TC_WGRAD) {
+            const int im = (kb / patches_per_img) * g.pn;            // first image of the patch's image group
+            const int prem = kb % patches_per_img;
+            const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
+            const int kh = t.tap_w / g.KW, kw = t.tap_w - kh * g.KW;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {                                        // A: dy, 128 output channels = 4 atoms
-            tma_load_4d(a_hi + j * kAtomBytes, &map_a_hi, &full[s], m0 + 32 * j, px, py, im);
-            tma_load_4d(a_lo + j * kAtomBytes, &map_a_lo, &full[s], m0 + 32 * j, px, py, im);
-          }
+            for (int j = 0; j < 4; j++) {                                      // A: dy, 128 output channels = 4 atoms
+              tma_load_4d(a_hi + j * kAtomBytes, &map_a_hi, &full[s], t.m0 + 32 * j, px, py, im);
+              tma_load_4d(a_lo + j * kAtomBytes, &map_a_lo, &full[s], t.m0 + 32 * j, px, py, im);
+            }
 #pragma unroll
-          for (int j = 0; j < BN / 32; j++) {                                  // B: x shifted by the tap
-            tma_load_4d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
-            tma_load_4d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
-          }
-        } else {
-          const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kBK;
-          const int kh = tap / g.KW, kw = tap - kh * g.KW;
-          const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
-          const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
-          tma_load_4d(a_hi, &map_a_hi, &full[s], c0, ow0 + dx, oh0 + dy, img);
-          tma_load_4d(a_lo, &map_a_lo, &full[s], c0, ow0 + dx, oh0 + dy, img);
-          if (MODE == TC_FWD) {
-            tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, n0);
-            tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, n0);
+            for (int j = 0; j < BN / 32; j++) {                                // B: x shifted by the tap
+              tma_load_4d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], t.n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
+              tma_load_4d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], t.n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
+            }
           } else {
+            const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kBK;
+            const int kh = tap / g.KW, kw = tap - kh * g.KW;
+            const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
+            const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
+            tma_load_4d(a_hi, &map_a_hi, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+            tma_load_4d(a_lo, &map_a_lo, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+            if (MODE == TC_FWD) {
+              tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, t.n0);
+              tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, t.n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; j++) {                                // B: w[co0..+32][tap][n0+32j..+32]
-              tma_load_3d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], n0 + 32 * j, tap, c0);
-              tma_load_3d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], n0 + 32 * j, tap, c0);
+              for (int j = 0; j < BN / 32; j++) {                              // B: w[co0..+32][tap][n0+32j..+32]
+                tma_load_3d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], t.n0 + 32 * j, tap, c0);
+                tma_load_3d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], t.n0 + 32 * j, tap, c0);
+              }
             }
           }
+          if (it == 0) TC_TRACE(2);
         }
       }
     }
@@ -209,107 +240,127 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
       const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
       uint32_t accumulate = 0;
-      int chunk = 0;
+      int it = 0, chunk = 0;                                         // ring position / accumulation chains started, across all items
       uint32_t tmem_acc = tmem_base;
-      for (int i = 0; i < nkb; i++) {
-        if (i % kChunkKB == 0) {                                     // new accumulation chain in the other TMEM buffer
-          const int b = chunk & 1;
-          mbar_wait(&acc_empty[b], ((chunk >> 1) & 1) ^ 1);          // drained by the epilogue warps (first use passes)
+      for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
+        const TcItem t = tc_decode_item<MODE, BN>(g, w);
+        for (int i = 0; i < t.nkb; i++, it++) {
+          if (i % kChunkKB == 0) {                                   // new accumulation chain in the other TMEM buffer
+            const int b = chunk & 1;
+            mbar_wait(&acc_empty[b], ((chunk >> 1) & 1) ^ 1);        // drained by the epilogue warps (first use passes)
+            tc_fence_after();
+            tmem_acc = tmem_base + b * 2 * BN;
+            accumulate = 0;
+          }
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
           tc_fence_after();
-          tmem_acc = tmem_base + b * 2 * BN;
-          accumulate = 0;
-        }
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * kStageBytes);
-        const uint32_t a_lo = a_hi + kABytes;
-        const uint32_t b_hi = a_hi + 2 * kABytes;                    // b_lo follows at + kBBytes
+          if (it == 0) TC_TRACE(3);
+          const uint32_t a_hi = smem_u32(smem + s * kStageBytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + 2 * kABytes;                  // b_lo follows at + kBBytes
 #pragma unroll
-        for (int k = 0; k < kBK / 8; k++) {
-          constexpr uint32_t a_lt = kAMajorMN ? kLayoutSW128Base32B : kLayoutSW128, b_lt = kBMajorMN ? kLayoutSW128Base32B : kLayoutSW128;
-          const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);     // covers b_hi then b_lo (contiguous)
-          umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate);     // [main | corr] (+)= A_hi * [B_hi | B_lo]
-          umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);         // corr += A_lo * B_hi
-          accumulate = 1;
+          for (int k = 0; k < kBK / 8; k++) {
+            constexpr uint32_t a_lt = kAMajorMN ? kLayoutSW128Base32B : kLayoutSW128, b_lt = kBMajorMN ? kLayoutSW128Base32B : kLayoutSW128;
+            const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);   // covers b_hi then b_lo (contiguous)
+            umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate);   // [main | corr] (+)= A_hi * [B_hi | B_lo]
+            umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);       // corr += A_lo * B_hi
+            accumulate = 1;
+          }
+          umma_commit(&empty[s]);                                    // frees the operand slot when these MMAs retire
+          if (i % kChunkKB == kChunkKB - 1 || i == t.nkb - 1) {
+            umma_commit(&acc_full[chunk & 1]);                       // chain complete -> epilogue warps may drain it
+            chunk++;
+          }
         }
-        umma_commit(&empty[s]);                                      // frees the operand slot when these MMAs retire
-        if (i % kChunkKB == kChunkKB - 1 || i == nkb - 1) {
-          umma_commit(&acc_full[chunk & 1]);                         // chain complete -> epilogue warps may drain it
-          chunk++;
-        }
+        if (w == blockIdx.x) TC_TRACE(4);
       }
+      TC_TRACE(5);
     }
   } else {
     // ===== accumulate + epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // While these warps finish and store item i, the MMA warp is already up to two chains into item i+1.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    float acc[BN];
-#pragma unroll
-    for (int j = 0; j < BN; j++) acc[j] = 0.f;
-    const int nchunks = (nkb + kChunkKB - 1) / kChunkKB;
-    for (int c = 0; c < nchunks; c++) {
-      const int b = c & 1;
-      mbar_wait(&acc_full[b], (c >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < BN / 32; cc++) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + BN + cc * 32, v);    // corr: A_hi*B_lo + A_lo*B_hi
-#pragma unroll
-        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];          // fp32 round-to-nearest, outside the tensor core
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + cc * 32, v);         // main: A_hi*B_hi
-#pragma unroll
-        for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[b]);
-    }
     const bool raw = g.splits > 1;
-    bool valid;
-    size_t row_off;           // element offset of this row's first column (col = n0)
-    size_t res_off = 0;
-    int ntot;
-    if (MODE == TC_WGRAD) {
-      ntot = KHW * g.Cin;
-      valid = (m0 + row) < g.Cout;
-      row_off = ((size_t)(m0 + row) * KHW + tap_w) * g.Cin + n0;
-      if (raw) row_off += (size_t)split * g.Cout * ntot;
-    } else {
-      ntot = (MODE == TC_FWD) ? g.Cout : g.Cin;
-      const int per_img = g.tile_w * g.tile_h;
-      const int nn = row / per_img, rrem = row - nn * per_img;
-      const int oh = oh0 + rrem / g.tile_w, ow = ow0 + rrem % g.tile_w;
-      valid = (img + nn) < g.nimg && oh < g.H && ow < g.W;
-      const size_t pix = ((size_t)(img + nn) * g.H + oh) * g.W + ow;
-      row_off = pix * ntot + n0;
-      res_off = row_off;
-      if (raw) row_off += (size_t)split * ((size_t)g.nimg * g.H * g.W) * ntot;
-    }
-    if (valid) {
-      float *dst = (raw ? partial : out) + row_off;
-      if (!raw && MODE != TC_WGRAD) {
+    int cg = 0;                                                      // accumulation chains drained so far, across all items
+    for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
+      const TcItem t = tc_decode_item<MODE, BN>(g, w);
+      float acc[BN];
 #pragma unroll
-        for (int j = 0; j < BN; j++) {
-          float x = acc[j];
-          if (epi.scale) x *= __ldg(epi.scale + n0 + j);
-          if (epi.bias) x += __ldg(epi.bias + n0 + j);
-          if (epi.residual) x += __ldg(epi.residual + res_off + j);
-          acc[j] = tc_act(x, epi.act);
+      for (int j = 0; j < BN; j++) acc[j] = 0.f;
+      const int nchunks = (t.nkb + kChunkKB - 1) / kChunkKB;
+      for (int c = 0; c < nchunks; c++, cg++) {
+        const int b = cg & 1;
+        mbar_wait(&acc_full[b], (cg >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; cc++) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + BN + cc * 32, v);    // corr: A_hi*B_lo + A_lo*B_hi
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];          // fp32 round-to-nearest, outside the tensor core
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + cc * 32, v);         // main: A_hi*B_hi
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
       }
+      if (w == blockIdx.x && threadIdx.x == 64) TC_TRACE(6);
+      bool valid;
+      size_t row_off;           // element offset of this row's first column (col = n0)
+      size_t res_off = 0;
+      int ntot;
+      if (MODE == TC_WGRAD) {
+        ntot = KHW * g.Cin;
+        valid = (t.m0 + row) < g.Cout;
+        row_off = ((size_t)(t.m0 + row) * KHW + t.tap_w) * g.Cin + t.n0;
+        if (raw) row_off += (size_t)t.split * g.Cout * ntot;
+      } else {
+        ntot = (MODE == TC_FWD) ? g.Cout : g.Cin;
+        const int per_img = g.tile_w * g.tile_h;
+        const int nn = row / per_img, rrem = row - nn * per_img;
+        const int oh = t.oh0 + rrem / g.tile_w, ow = t.ow0 + rrem % g.tile_w;
+        valid = (t.img + nn) < g.nimg && oh < g.H && ow < g.W;
+        const size_t pix = ((size_t)(t.img + nn) * g.H + oh) * g.W + ow;
+        row_off = pix * ntot + t.n0;
+        res_off = row_off;
+        if (raw) row_off += (size_t)t.split * ((size_t)g.nimg * g.H * g.W) * ntot;
+      }
+      if (valid) {
+        float *dst = (raw ? partial : out) + row_off;
+        if (!raw && MODE != TC_WGRAD) {
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < BN; j++) {
+            float x = acc[j];
+            if (epi.scale) x *= __ldg(epi.scale + t.n0 + j);
+            if (epi.bias) x += __ldg(epi.bias + t.n0 + j);
+            if (epi.residual) x += __ldg(epi.residual + res_off + j);
+            acc[j] = tc_act(x, epi.act);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+      if (w == blockIdx.x && threadIdx.x == 64) TC_TRACE(7);
     }
+    if (threadIdx.x == 64) TC_TRACE(8);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 4 * BN);
+  }
+  if (threadIdx.x == 0 && g.trace) {
+    TC_TRACE(9);
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g.trace[(size_t)blockIdx.x * 16 + 10] = smid;
   }
 }
 
@@ -373,6 +424,7 @@ struct TcPlan {
   int tile_w, tile_h, tile_n, tiles_w, tiles_h, groups;
   int pw, ph, pn, patches_w, patches_h, pgroups;
   int total_kb, splits, kb_per_split;
+  int m_tiles, n_tiles, items;       // persistent-loop work items (see TcGeom)
   size_t a_hi_off, a_lo_off, b_hi_off, b_lo_off, partial_off, total_bytes;
   size_t a_count, b_count;           // element counts of the two operands that need a lo part
 };
@@ -416,25 +468,49 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->patches_h = ceil_div(p->H, p->ph);
     p->pgroups = ceil_div(p->N, p->pn);
     p->total_kb = p->pgroups * p->patches_w * p->patches_h;
-    ctas = (Cout / 128) * (Cin / p->BN) * taps;
+    p->m_tiles = Cout / 128;
+    p->n_tiles = Cin / p->BN;
+    ctas = p->m_tiles * p->n_tiles * taps;
   } else {
     best_patch(128, p->N, p->H, p->W, &p->tile_w, &p->tile_h, &p->tile_n);
     p->tiles_w = ceil_div(p->W, p->tile_w);
     p->tiles_h = ceil_div(p->H, p->tile_h);
     p->groups = ceil_div(p->N, p->tile_n);
     p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / 32);
-    ctas = p->groups * p->tiles_w * p->tiles_h * (ntot / p->BN);
+    p->m_tiles = p->groups * p->tiles_w * p->tiles_h;
+    p->n_tiles = ntot / p->BN;
+    ctas = p->m_tiles * p->n_tiles;
   }
+  // Split-K by a wave-quantisation cost model.  CTAs are persistent (grid = min(items, SMs)), every item of a launch costs the
+  // same, so the launch takes ceil(items / SMs) rounds of (k-blocks * t_kb + t_item); splitting K shortens the rounds at the
+  // price of a partial-sum pass (write s partials, read them back, write the result) -- taken only when it pays.
+  const size_t out_elems_plan = (mode == TC_WGRAD) ? (size_t)Cout * taps * Cin : (size_t)pixels * ntot;
+  const double t_kb = (p->BN == 128) ? 0.56 : 0.42;                 // us per k-block (measured, smem-bandwidth bound mainloop)
+  const double t_item = 2.5;                                         // us of per-item pipeline refill / final drain not overlapped
   int splits = 1;
-  if (ctas < kNumSMs) {
+  double best_t = -1.0;
+  const int max_splits = p->total_kb / kChunkKB > 32 ? 32 : p->total_kb / kChunkKB;
+  for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); sp++) {
+    const int kbs = ceil_div(p->total_kb, sp);
+    const int real = ceil_div(p->total_kb, kbs);                     // splits actually produced with this slice length
+    if (real != sp) continue;
+    const long long items = (long long)ctas * sp;
+    const long long rounds = (items + kNumSMs - 1) / kNumSMs;
+    double tt = rounds * (kbs * t_kb + t_item);
+    if (sp > 1) tt += 4.0 + (double)(sp + 2) * out_elems_plan * 4.0 / 4.0e6;   // reduce pass at ~4 TB/s effective + launch
+    if (best_t < 0 || tt < best_t) { best_t = tt; splits = sp; }
+  }
+  static const int force_splits = getenv("FRCNN_TC_SPLITS") ? atoi(getenv("FRCNN_TC_SPLITS")) : 0;    // debug / A-B knob
+  if (force_splits > 0) splits = force_splits > max_splits ? (max_splits < 1 ? 1 : max_splits) : force_splits;
+  if (force_splits < 0 && ctas < kNumSMs) {                                                           // -1: the pre-cost-model rule
     splits = ceil_div(kNumSMs, ctas);
-    int max_splits = p->total_kb / 8;
-    if (splits > max_splits) splits = max_splits;
+    if (splits > p->total_kb / 8) splits = p->total_kb / 8;
     if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
-  }
+  } else if (force_splits < 0) splits = 1;
   p->kb_per_split = ceil_div(p->total_kb, splits);
   p->splits = ceil_div(p->total_kb, p->kb_per_split);
+  p->items = ctas * p->splits;
   const size_t act_in = (size_t)pixels * Cin, act_out = (size_t)pixels * Cout, filt = (size_t)Cout * taps * Cin;
   size_t out_elems;
   if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
@@ -453,12 +529,15 @@ template <int MODE, int BN, int STAGES>
 static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float *out, float *partial, const Epilogue &epi, cudaStream_t st)
 {
   constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kBK * 4) + 1024 + 256;
-  cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return cuda_fail(e, "tc_conv_kernel: smem attribute");
+  static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
   tc_conv_kernel<MODE, BN, STAGES><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;
 }
+
+static unsigned long long *g_tc_trace = nullptr;      // debug only (frcnn_debug_tc_trace); never set on the product path
+void tc_set_trace(void *buf) { g_tc_trace = reinterpret_cast<unsigned long long *>(buf); }
 
 // a: the activation-side operand of the mode (x | dy | dy), b: the other one (w | w | x)
 size_t tf32_split_bytes(size_t count) { return 2 * align_up(count * 4, 1024); }
@@ -512,23 +591,22 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   if (mode == TC_FWD) {
     ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) &&
          make_mat_map(&maps[2], b, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, Cout, taps * Cin, p.BN);
-    grid = dim3(p.groups * p.tiles_w * p.tiles_h, Cout / p.BN, p.splits);
   } else if (mode == TC_DGRAD) {
     ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
          make_filter3d_map(&maps[2], b, Cout, taps, Cin) && make_filter3d_map(&maps[3], b_lo, Cout, taps, Cin);
-    grid = dim3(p.groups * p.tiles_w * p.tiles_h, Cin / p.BN, p.splits);
   } else {
     ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) &&
          make_act_map(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true) && make_act_map(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true);
-    grid = dim3(Cout / 128, Cin / p.BN, taps * p.splits);
   }
   if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 
   static const int dbg_lbo = getenv("FRCNN_TC_MN_LBO") ? atoi(getenv("FRCNN_TC_MN_LBO")) : kAtomBytes;
   static const int dbg_sbo = getenv("FRCNN_TC_MN_SBO") ? atoi(getenv("FRCNN_TC_MN_SBO")) : 512;
   static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 1024;
+  static const bool persistent = !(getenv("FRCNN_TC_PERSISTENT") && atoi(getenv("FRCNN_TC_PERSISTENT")) == 0);   // 0: one CTA per item (A-B knob)
+  grid = dim3(persistent && p.items > kNumSMs ? kNumSMs : p.items, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep};
+           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace};
   int rc;
 #define TC_LAUNCH(M)                                                                          \
   (p.BN == 128 ? launch_tc<M, 128, 3>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4>(maps, g, grid, out, partial, epi, st))

@@ -233,75 +233,131 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cou
   }
 }
 
-// Stage 2: the greedy scan, one CTA, software-pipelined over the 64-box blocks.  While lane 0 of
-// warp 0 resolves block b's internal chain from its diagonal tile (64 dependent steps, registers /
-// shared memory only), the other 31 warps already build block b+1's "removed" word: a column
-// gather over the rows of every box kept so far (one 8-byte load per kept box, all independent ->
-// one L2 round trip), plus preloads of block b's rows for column b+1 and of the next diagonal.
-// After the barrier the rows of the boxes just kept are OR-ed in.  Stops at max_keep.
+// Stage 2: the greedy scan, one CTA, software-pipelined over the 64-box blocks so that no global-memory round trip sits on
+// the serial chain.  Block c may be resolved once its "removed" word holds the rows of every box kept in blocks < c:
+//   * kept boxes of blocks < c-2: a column gather (one 8-byte load per kept box) ISSUED at iteration c-2 into registers and
+//     folded at iteration c-1 -- a full iteration of slack for the L2 latency;
+//   * kept boxes of blocks c-2 and c-1: their rows at columns +2 / +1, OR-ed in right after those blocks are resolved;
+//   * the diagonal tile and those two row slices of every block depend on nothing and stream in three blocks ahead
+//     (cp.async, 4-slot ring).
+// Per iteration the chain is: lane 0 walks the surviving boxes of the block (ffs + one shared-memory load per KEPT box),
+// barrier, <=64 shared-memory atomics, barrier.  Stops at max_keep.
 constexpr int kScanThreads = 1024;
+constexpr int kScanGather = kScanThreads - 32;               // threads of warps 1..31 do the gathers
+constexpr int kScanDefer = 3;                                // gather loads kept in flight per thread (covers max_keep <= 2976)
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid)
+{
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 8 : 0;                                    // src-size 0 -> the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int capacity, int col_blocks,
                 int max_keep, int32_t *__restrict__ keep_out, int32_t *__restrict__ kept_count_out)
 {
   extern __shared__ int32_t kept_idx[];                      // max_keep entries: positions of the kept boxes
-  __shared__ unsigned long long diag[2][64];
-  __shared__ unsigned long long next_rows[64];
-  __shared__ unsigned long long removed[2];
+  __shared__ unsigned long long ring[4][3][64];              // per block slot: [0] diagonal tile, [1] rows at column +1, [2] at column +2
+  __shared__ unsigned long long removed[4];                  // removed[c & 3]: suppression word of block c, accumulated ahead of time
   __shared__ unsigned long long kept_bits_s;
   __shared__ int kept_total;
   int n = *count;
   if (n > capacity) n = capacity;
   const int nblocks = (n + 63) / 64;
   const int t = threadIdx.x;
-  if (t == 0) { kept_total = 0; removed[0] = 0ull; removed[1] = 0ull; kept_bits_s = 0ull; }
-  if (t < 64) diag[0][t] = (t < n) ? mask[(size_t)t * col_blocks] : 0ull;
+  if (t == 0) { kept_total = 0; kept_bits_s = 0ull; removed[0] = removed[1] = removed[2] = removed[3] = 0ull; }
+
+  // stream block `blk`'s three 64-word slices into ring slot blk & 3 (threads 64..255); one cp.async group per block
+  auto prefetch_block = [&](int blk) {
+    if (t >= 64 && t < 256 && blk < nblocks) {
+      const int which = (t - 64) >> 6, j = (t - 64) & 63;
+      const int i = blk * 64 + j, col = blk + which;
+      const bool ok = i < n && col < nblocks;
+      cp_async8(&ring[blk & 3][which][j], mask + (ok ? (size_t)i * col_blocks + col : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch_block(0);
+  prefetch_block(1);
+  prefetch_block(2);
+  asm volatile("cp.async.wait_group 2;" ::: "memory");        // block 0 landed
   __syncthreads();
+
+  unsigned long long pend[kScanDefer] = {0ull, 0ull, 0ull};  // gather issued last iteration, not yet folded
+  unsigned long long pend_sync = 0ull;
+  int pend_col = -1;
   for (int b = 0; b < nblocks; b++) {
-    const int cur = b & 1, nxt = cur ^ 1;
     const int kept_before = kept_total;
     if (kept_before >= max_keep) break;                      // uniform (read after a barrier)
-    const bool has_next = b + 1 < nblocks;
     if (t == 0) {
-      unsigned long long dead = removed[cur];
+      const int lim = n - b * 64 < 64 ? n - b * 64 : 64;
+      const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+      unsigned long long alive = ~removed[b & 3] & valid;
       unsigned long long kept = 0ull;
       int total = kept_before;
-      const int lim = n - b * 64 < 64 ? n - b * 64 : 64;
-      for (int q = 0; q < lim && total < max_keep; q++) {
-        if (!((dead >> q) & 1ull)) {
-          kept |= 1ull << q;
-          dead |= diag[cur][q];
-          kept_idx[total] = b * 64 + q;
-          keep_out[total] = b * 64 + q;
-          total++;
-        }
+      const unsigned long long *diag = ring[b & 3][0];
+      while (alive && total < max_keep) {                    // ascending position = descending score: the greedy order
+        const int q = __ffsll((long long)alive) - 1;
+        kept |= 1ull << q;
+        kept_idx[total] = b * 64 + q;
+        keep_out[total] = b * 64 + q;
+        total++;
+        alive &= ~(diag[q] | (1ull << q));
       }
       kept_bits_s = kept;
       kept_total = total;
-      removed[cur] = 0ull;                                   // becomes the "next" word two blocks from now
-    } else if (t >= 32 && has_next) {
-      unsigned long long acc = 0ull;
-      for (int k = t - 32; k < kept_before; k += kScanThreads - 32) acc |= mask[(size_t)kept_idx[k] * col_blocks + (b + 1)];
-      unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)acc);
-      unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(acc >> 32));
-      if ((t & 31) == 0) {
-        unsigned long long w = ((unsigned long long)hi << 32) | lo;
-        if (w) atomicOr(&removed[nxt], w);
+      removed[b & 3] = 0ull;                                 // slot is reused by block b + 4 (first written at iteration b + 2)
+    } else if (t >= 32) {
+      if (pend_col >= 0) {                                   // fold the gather issued one iteration ago (column b + 1)
+        unsigned long long acc = pend[0] | pend[1] | pend[2] | pend_sync;
+        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)acc);
+        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(acc >> 32));
+        if ((t & 31) == 0) {
+          unsigned long long w = ((unsigned long long)hi << 32) | lo;
+          if (w) atomicOr(&removed[pend_col & 3], w);
+        }
       }
-      if (t >= 64 && t < 128) {
-        int i = b * 64 + (t - 64);
-        next_rows[t - 64] = i < n ? mask[(size_t)i * col_blocks + (b + 1)] : 0ull;
-      } else if (t >= 128 && t < 192) {
-        int i = (b + 1) * 64 + (t - 128);
-        diag[nxt][t - 128] = i < n ? mask[(size_t)i * col_blocks + (b + 1)] : 0ull;
+      if (b + 2 < nblocks) {                                 // issue the gather for column b + 2 over the boxes kept in blocks < b
+        const int g = t - 32;
+#pragma unroll
+        for (int u = 0; u < kScanDefer; u++) {
+          const int k = g + u * kScanGather;
+          pend[u] = k < kept_before ? mask[(size_t)kept_idx[k] * col_blocks + (b + 2)] : 0ull;
+        }
+        pend_sync = 0ull;
+        for (int k = g + kScanDefer * kScanGather; k < kept_before; k += kScanGather) pend_sync |= mask[(size_t)kept_idx[k] * col_blocks + (b + 2)];
+        pend_col = b + 2;
+      } else {
+        pend_col = -1;
       }
     }
+    prefetch_block(b + 3);                                   // slot (b + 3) & 3 was last used by block b - 1
+    asm volatile("cp.async.wait_group 2;" ::: "memory");      // groups up to block b + 1 complete (own copies; barrier publishes)
     __syncthreads();
-    if (has_next && t < 64 && ((kept_bits_s >> t) & 1ull) && next_rows[t]) atomicOr(&removed[nxt], next_rows[t]);
+    if (t < 64 && ((kept_bits_s >> t) & 1ull)) {
+      const unsigned long long r1 = ring[b & 3][1][t], r2 = ring[b & 3][2][t];
+      if (r1) atomicOr(&removed[(b + 1) & 3], r1);
+      if (r2) atomicOr(&removed[(b + 2) & 3], r2);
+    }
     __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (t == 0) *kept_count_out = kept_total;
+}
+
+// dst rows [*dst_count, *dst_count + m) <- src rows: appends the ground-truth boxes behind the device-counted proposals
+// (faster_rcnn.py:467) without bringing the count to the host
+__global__ void append_rows_kernel(float *__restrict__ dst, const int32_t *__restrict__ dst_count, int dst_capacity_rows, int row_floats,
+                                   const float *__restrict__ src, int m)
+{
+  int n = *dst_count;
+  if (n < 0) n = 0;
+  const int total = m * row_floats;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int r = e / row_floats;
+    if (n + r < dst_capacity_rows) dst[(size_t)(n + r) * row_floats + (e - r * row_floats)] = src[e];
+  }
 }
 
 __global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats, const int32_t *__restrict__ index, const int32_t *__restrict__ count,
@@ -475,6 +531,14 @@ int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index
   FRCNN_REQUIRE(src && index && count && dst && row_floats > 0 && capacity > 0, "gather_rows_f32: bad argument");
   gather_rows_kernel<<<elementwise_grid((size_t)capacity * row_floats, 256), 256, 0, as_stream(stream)>>>(src, row_floats, index, count, capacity, dst);
   FRCNN_CHECK_LAUNCH("gather_rows_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_append_rows_f32(float *dst, const int32_t *dst_count, int dst_capacity_rows, int row_floats, const float *src, int m, void *stream)
+{
+  FRCNN_REQUIRE(dst && dst_count && src && dst_capacity_rows > 0 && row_floats > 0 && m > 0, "append_rows_f32: bad argument");
+  append_rows_kernel<<<ceil_div(m * row_floats, 128), 128, 0, as_stream(stream)>>>(dst, dst_count, dst_capacity_rows, row_floats, src, m);
+  FRCNN_CHECK_LAUNCH("append_rows_kernel");
   return FRCNN_OK;
 }
 

@@ -70,30 +70,70 @@ class FasterRCNNModel(nn.Module):
     assert len(gt_boxes) == 1, "Batch size must be 1"
     image_shape = image_data.shape[1:]
     ops.begin_step()
+    dev = image_data.device
+    gt = gt_boxes[0]
 
+    # Everything up to the proposal labels is enqueued without a host round trip: the proposal count stays on the device, the
+    # GT boxes are appended behind it there (faster_rcnn.py:467), labels are computed for every row of the padded buffer.
     feature_map = self._stage1_feature_extractor(image_data = image_data)
-    rpn_score_map, rpn_box_deltas_map, proposals = self._stage2_region_proposal_network(
+    rpn_score_map, rpn_box_deltas_map, (padded, count) = self._stage2_region_proposal_network(
       feature_map = feature_map, image_shape = image_shape, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map,
-      max_proposals_pre_nms = 12000, max_proposals_post_nms = 2000)
+      max_proposals_pre_nms = 12000, max_proposals_post_nms = 2000, deferred_extra_rows = len(gt))
 
+    # host work that needs nothing from the device overlaps the backbone / RPN kernels queued above
     gt_rpn_minibatch_map = self._sample_rpn_minibatch(rpn_map = gt_rpn_map, object_indices = gt_rpn_object_indices, background_indices = gt_rpn_background_indices)
-    proposals, gt_classes, gt_box_deltas = self._label_proposals(proposals = proposals, gt_boxes = gt_boxes[0], min_background_iou_threshold = 0.0, min_object_iou_threshold = 0.5)
-    proposals, gt_classes, gt_box_deltas = self._sample_proposals(proposals = proposals, gt_classes = gt_classes, gt_box_deltas = gt_box_deltas, max_proposals = self._proposal_batch_size, positive_fraction = 0.25)
-    proposals, gt_classes, gt_box_deltas = proposals.detach(), gt_classes.detach(), gt_box_deltas.detach()
+    gt_box_corners = t.from_numpy(np.array([box.corners for box in gt], dtype = np.float32).reshape(-1, 4)).to(dev)
+    gt_box_class_idxs = t.tensor([box.class_index for box in gt], dtype = t.int32, device = dev)
+    ops.append_rows(padded, count, gt_box_corners)
+    _, class_idx, gt_classes, gt_box_deltas = ops.label_proposals(padded, gt_box_corners, gt_box_class_idxs, self._num_classes, 0.5)
+
+    # the step's one mid-step synchronisation: proposal count + class labels in a single pinned read-back; the RPN losses are
+    # queued behind it so the device has work while the host draws the samples
+    fetch = self._pinned("fetch", (1 + padded.shape[0],), t.int32)
+    fetch[0:1].copy_(count, non_blocking = True)
+    fetch[1:].copy_(class_idx, non_blocking = True)
+    fetched = t.cuda.Event()
+    fetched.record()
+    rpn_l = ops.rpn_losses(rpn_score_map, rpn_box_deltas_map, gt_rpn_minibatch_map)                # (class, regression)
+    fetched.synchronize()
+    n = int(fetch[0]) + len(gt)                                                                    # proposals + appended GT boxes
+    indices = self._sample_proposal_indices(fetch[1:1 + n].numpy(), self._proposal_batch_size, 0.25)
+    if indices is None:
+      proposals, gt_classes, gt_box_deltas = padded[:n], gt_classes[:n], gt_box_deltas[:n]
+    else:
+      index_dev = t.from_numpy(indices).to(dev, non_blocking = True)
+      proposals, gt_classes, gt_box_deltas = padded[index_dev], gt_classes[index_dev], gt_box_deltas[index_dev]
 
     detector_classes, detector_box_deltas = self._stage3_detector_network(feature_map = feature_map, proposals = proposals)
 
-    rpn_l = ops.rpn_losses(rpn_score_map, rpn_box_deltas_map, gt_rpn_minibatch_map)                # (class, regression)
     det_l = ops.detector_losses(detector_classes, detector_box_deltas, gt_classes, gt_box_deltas)    # (class, regression)
     all_l = t.cat([rpn_l, det_l])
     total_loss = all_l.sum()
+    # The five numbers are final once the forward kernels have run: their read-back is queued NOW, in front of the backward and
+    # optimizer kernels, and only its event is awaited at the end -- train_step returns with the backward still in flight, so the
+    # next step's launches queue up behind it and the device never drains between steps.
+    loss_host = self._pinned("loss", (5,), t.float32)
+    loss_host.copy_(t.cat([all_l.detach(), total_loss.detach().reshape(1)]), non_blocking = True)
+    loss_ready = t.cuda.Event()
+    loss_ready.record()
     total_loss.backward()
     ops.begin_step()                       # operand splits of this step's weights are stale after the update
     optimizer.step()
 
-    host = t.cat([all_l.detach(), total_loss.detach().reshape(1)]).cpu().numpy()                   # one D2H for the five numbers
+    loss_ready.synchronize()
+    host = loss_host.numpy()
     self.last_step_info = dict(num_rois = int(proposals.shape[0]))
     return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host[4]))
+
+  def _pinned(self, name, shape, dtype):
+    """Reusable page-locked host buffer for the small device-to-host reads of train_step."""
+    buffers = self.__dict__.setdefault("_pinned_buffers", {})
+    key = (name, tuple(shape), dtype)
+    buf = buffers.get(key)
+    if buf is None:
+      buf = t.empty(shape, dtype = dtype).pin_memory()
+      buffers[key] = buf
+    return buf
 
   # ---- faster_rcnn.py:364-416 --------------------------------------------------------------------
   def _sample_rpn_minibatch(self, rpn_map, object_indices, background_indices):
@@ -134,21 +174,28 @@ class FasterRCNNModel(nn.Module):
     return proposals, gt_classes, gt_box_deltas
 
   # ---- faster_rcnn.py:526-561 --------------------------------------------------------------------
-  def _sample_proposals(self, proposals, gt_classes, gt_box_deltas, max_proposals, positive_fraction):
+  def _sample_proposal_indices(self, cls_host, max_proposals, positive_fraction):
+    """Host half of faster_rcnn.py:526-561 on the class labels (numpy int): row indices to keep (int64), an empty array when the
+    image yields no positive or no negative sample, None when sampling is off (max_proposals <= 0: keep every row)."""
     if max_proposals <= 0:
-      return proposals, gt_classes, gt_box_deltas
-    class_indices = getattr(self, "_last_class_idx", None)
-    if class_indices is None or class_indices.shape[0] != gt_classes.shape[0]:
-      class_indices = t.argmax(gt_classes, dim = 1)
-    cls_host = class_indices.cpu().numpy()                     # the one D2H the sampling needs (counts decide the CPU-generator draws)
+      return None
     positive_indices = np.where(cls_host > 0)[0]
     negative_indices = np.where(cls_host <= 0)[0]
     num_samples = min(max_proposals, len(cls_host))
     num_positive_samples = min(round(num_samples * positive_fraction), len(positive_indices))
     num_negative_samples = min(num_samples - num_positive_samples, len(negative_indices))
     if num_positive_samples <= 0 or num_negative_samples <= 0:
-      return proposals[[]], gt_classes[[]], gt_box_deltas[[]]
+      return np.zeros((0,), dtype = np.int64)
     positive_sample_indices = positive_indices[t.randperm(len(positive_indices))[0:num_positive_samples].numpy()]   # CPU generator, as the reference
     negative_sample_indices = negative_indices[t.randperm(len(negative_indices))[0:num_negative_samples].numpy()]
-    indices = t.from_numpy(np.concatenate([positive_sample_indices, negative_sample_indices]).astype(np.int64)).to(proposals.device)
+    return np.concatenate([positive_sample_indices, negative_sample_indices]).astype(np.int64)
+
+  def _sample_proposals(self, proposals, gt_classes, gt_box_deltas, max_proposals, positive_fraction):
+    class_indices = getattr(self, "_last_class_idx", None)
+    if class_indices is None or class_indices.shape[0] != gt_classes.shape[0]:
+      class_indices = t.argmax(gt_classes, dim = 1)
+    indices = self._sample_proposal_indices(class_indices.cpu().numpy(), max_proposals, positive_fraction)
+    if indices is None:
+      return proposals, gt_classes, gt_box_deltas
+    indices = t.from_numpy(indices).to(proposals.device)
     return proposals[indices], gt_classes[indices], gt_box_deltas[indices]

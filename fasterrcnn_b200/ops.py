@@ -71,6 +71,10 @@ class _KernelTimer:
 
 kernel_timer = _KernelTimer()
 
+# profiling aid: FRCNN_LAUNCH_LOG=<file> appends one line per tcgen05 GEMM launch (family, pass, GFLOP) in launch order, so an ncu
+# capture filtered on tc_conv_kernel can be attributed to kernel families (tools/summarize_ncu.py)
+_launch_log = open(_os.environ["FRCNN_LAUNCH_LOG"], "w") if _os.environ.get("FRCNN_LAUNCH_LOG") else None
+
 
 def _engine_name(supported_tc):
   e = _engine["value"]
@@ -195,6 +199,9 @@ def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, s
     else:
       check(L.frcnn_conv2d_wgrad(ptr(a), ptr(b), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
   kernel_timer.end(t0, kind, gflop)
+  if _launch_log is not None and presplit:                         # presplit <=> the tcgen05 engine took this launch
+    _launch_log.write("%s %d %.6f\n" % (kind, pass_, gflop))
+    _launch_log.flush()
   _lib.count()
 
 
@@ -621,12 +628,15 @@ class ProposalBuffers:
 _proposal_buffers = {}
 
 
-def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, post_nms, anchors = None, keep_mask = None, min_size = 16.0, iou_threshold = 0.7, return_debug = False):
+def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, post_nms, anchors = None, keep_mask = None, min_size = 16.0, iou_threshold = 0.7, return_debug = False,
+                  defer_count = False, extra_rows = 0):
   """
   models/rpn.py:99-156 as five stream-ordered kernels with no host round trip until the final
   count: decode(+anchors, clip, size flag) -> rank/top-N -> ordered compaction -> NMS bit tiles +
   scan -> gather.  score_map (1,fh,fw,9), delta_map (1,fh,fw,36) contiguous fp32 (NHWC maps).
-  Returns proposals (N,4) fp32 (y1,x1,y2,x2).
+  Returns proposals (N,4) fp32 (y1,x1,y2,x2).  defer_count = True (training): no host sync at all -- returns the
+  capacity-padded (post_nms + extra_rows, 4) buffer (rows past the count are zero) and the device-side count tensor, so the
+  caller can append the GT boxes, label, and fetch count + labels in ONE device-to-host copy.
   """
   _require_cuda(score_map, delta_map)
   fh, fw = int(score_map.shape[1]), int(score_map.shape[2])
@@ -648,15 +658,25 @@ def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, po
                                 ptr(buf.boxes_sorted), ptr(buf.scores_sorted), ptr(buf.count2), st), "frcnn_gather_filtered")
   ws, ws_n = workspace(L.frcnn_nms_workspace_bytes(pre_nms), slot = 2)
   check(L.frcnn_nms_sorted_f32(ptr(buf.boxes_sorted), ptr(buf.count2), pre_nms, float(iou_threshold), post_nms, ptr(buf.keep), ptr(buf.count3), ws, ws_n, st), "frcnn_nms_sorted_f32")
-  out = t.empty((post_nms, 4), dtype = t.float32, device = dev)
+  out = (t.zeros if defer_count else t.empty)((post_nms + extra_rows, 4), dtype = t.float32, device = dev)
   check(L.frcnn_gather_rows_f32(ptr(buf.boxes_sorted), 4, ptr(buf.keep), ptr(buf.count3), post_nms, ptr(out), st), "frcnn_gather_rows_f32")
   _lib.count(8)
+  if defer_count:
+    return out, buf.count3
   n = int(buf.count3.item())                                     # the one host sync of the proposal path
   if return_debug:
     n1 = int(buf.count1[0].item()); n2 = int(buf.count2.item())
     return out[:n], dict(order = buf.order[:n1].clone(), boxes_all = buf.boxes_all.clone(), size_ok = buf.size_ok.clone(),
                          boxes_sorted = buf.boxes_sorted[:n2].clone(), scores_sorted = buf.scores_sorted[:n2].clone(), keep = buf.keep[:n].clone())
   return out[:n]
+
+
+def append_rows(dst, dst_count, src):
+  """dst[count + r] = src[r] on the device (count stays a device value): faster_rcnn.py:467 without a host round trip."""
+  _require_cuda(dst, dst_count, src)
+  src = src.contiguous()
+  check(lib().frcnn_append_rows_f32(ptr(dst), ptr(dst_count), int(dst.shape[0]), int(dst.shape[1]), ptr(src), int(src.shape[0]), stream()), "frcnn_append_rows_f32")
+  _lib.count()
 
 
 def generate_anchors_device(image_shape, feature_map_hw, feature_pixels, device = "cuda"):

@@ -26,8 +26,10 @@ class RegionProposalNetwork(nn.Module):
       layer.bias.data.zero_()
     self._anchor_cache = {}
 
-  def forward(self, feature_map, image_shape, anchor_map, anchor_valid_map, max_proposals_pre_nms, max_proposals_post_nms):
-    """-> objectness (1,H,W,9), box deltas (1,H,W,36), proposals (N,4) (y1,x1,y2,x2)."""
+  def forward(self, feature_map, image_shape, anchor_map, anchor_valid_map, max_proposals_pre_nms, max_proposals_post_nms, deferred_extra_rows = None):
+    """-> objectness (1,H,W,9), box deltas (1,H,W,36), proposals (N,4) (y1,x1,y2,x2).
+    deferred_extra_rows (not in the reference; used by FasterRCNNModel.train_step): when an int, the third result is the pair
+    (capacity-padded proposals with that many spare rows, device-side count) and no host synchronisation happens here."""
     assert feature_map.shape[0] == 1                                      # rpn.py:159
     y = ops.conv2d_act(feature_map, self._rpn_conv1.weight, self._rpn_conv1.bias, 1, 1, ops.ACT_RELU)
     scores = ops.conv2d_act(y, self._rpn_class.weight, self._rpn_class.bias, 1, 0, ops.ACT_SIGMOID)
@@ -38,7 +40,8 @@ class RegionProposalNetwork(nn.Module):
     anchors_dev, keep_mask = self._resolve_anchors(anchor_map, anchor_valid_map, image_shape, objectness_score_map.shape[1:3], feature_map.device)
     proposals = ops.rpn_proposals(
       objectness_score_map, box_deltas_map, image_shape, 16,
-      max_proposals_pre_nms, max_proposals_post_nms, anchors = anchors_dev, keep_mask = keep_mask)
+      max_proposals_pre_nms, max_proposals_post_nms, anchors = anchors_dev, keep_mask = keep_mask,
+      defer_count = deferred_extra_rows is not None, extra_rows = deferred_extra_rows or 0)
     return objectness_score_map, box_deltas_map, proposals
 
   def _resolve_anchors(self, anchor_map, anchor_valid_map, image_shape, fm_hw, device):
@@ -55,7 +58,11 @@ class RegionProposalNetwork(nn.Module):
     anchors_dev = None
     if anchor_map is not None:
       am = anchor_map if isinstance(anchor_map, np.ndarray) else anchor_map.detach().cpu().numpy()
-      if am.shape != entry["std_anchors"].shape or not np.array_equal(am, entry["std_anchors"]):
+      if am is entry.get("verified_standard"):
+        pass                                                              # same array object as last time: already compared equal
+      elif am.shape == entry["std_anchors"].shape and np.array_equal(am, entry["std_anchors"]):
+        entry["verified_standard"] = am                                   # holding the reference keeps the identity test sound
+      else:
         ck = (am.shape, am.tobytes()[:4096])
         anchors_dev = entry["custom"].get(ck)
         if anchors_dev is None:

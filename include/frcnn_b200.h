@@ -87,6 +87,10 @@ int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
  * forward + data gradient) can be split ONCE with frcnn_tf32_split into a caller-owned buffer of
  * frcnn_tf32_split_bytes(count) bytes and handed to the *_presplit variants (either split pointer may be NULL = split
  * internally).  frcnn_conv2d_uses_tensor_cores(pass, geometry, engine): pass 0 = fwd, 1 = dgrad, 2 = wgrad. */
+/* Debug/profiling hook (not used by the product path): when buf != NULL every tcgen05 conv CTA writes 16 x u64 %globaltimer
+ * stamps (entry, setup done, first TMA, first MMA, first item issued, all MMAs issued, first item drained / stored, epilogue
+ * done, exit, SM id) to buf[blockIdx * 16 ...]; buf must hold 148 * 16 * 8 bytes.  Pass NULL to switch it off again. */
+void frcnn_debug_tc_trace(void *buf);
 int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
 size_t frcnn_tf32_split_bytes(size_t count);
 int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream);
@@ -164,6 +168,10 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
                          int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
 /* out[r] = boxes[keep[r]] for r < *kept_count. */
 int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index, const int32_t *count, int capacity, float *dst, void *stream);
+/* dst[*dst_count + r][:] = src[r][:] for r < m (rows past dst_capacity_rows are dropped): appends the ground-truth boxes to the
+ * proposal list (reference faster_rcnn.py:467 `t.vstack([proposals, gt_box_corners])`) while the proposal count is still a
+ * device-side value, so labelling can be enqueued without a host round trip.  dst_count is NOT updated. */
+int frcnn_append_rows_f32(float *dst, const int32_t *dst_count, int dst_capacity_rows, int row_floats, const float *src, int m, void *stream);
 
 /* ---- K7: RoI max pooling (torchvision.ops.RoIPool((7,7), 1/16); models/detector.py:27,65-72)
  * fm NHWC (1,H,W,C); proposals (K,4) fp32 (y1,x1,y2,x2) as the reference holds them (the
