@@ -24,6 +24,7 @@
 //   DGRAD  pixels x Cin  x (tap,co) : A = dy patch  (K-major, flipped tap) B = w[co][tap][ci] (N-major, 3-D map)
 //   WGRAD  Cout   x Cin  x pixels   : A = dy patch  (M-major)            B = shifted x patch (N-major), one tap per CTA
 #include <stdlib.h>
+#include <atomic>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -82,11 +83,23 @@ struct TcGeom {
   int mn_lbo, mn_sbo, mn_kstep;   // MN-major operand descriptor strides in bytes (4096 / 512 / 1024)
   int m_tiles, n_tiles, items;    // work items = m_tiles * n_tiles * (taps for WGRAD) * splits; CTAs loop over them (persistent grid)
   unsigned long long *trace;      // debug: per-CTA %globaltimer stamps (frcnn_debug_tc_trace), NULL in production
+  // stream-K (streamk != 0): the launch's (tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per CTA, so
+  // every SM gets the same number of k-blocks whatever the tile count.  A CTA whose range starts inside a tile parks its raw
+  // partial sums in sk_slots[cta] and publishes sk_flags[cta] = sk_tag; the CTA that owns the tile's first k-block adds them.
+  int streamk;
+  long long units;                // tiles * total_kb
+  float *sk_slots;                // gridDim.x x (128 x BN) fp32
+  unsigned long long *sk_flags;   // gridDim.x
+  unsigned long long sk_tag;      // unique per launch (stale workspace contents can never match)
 };
 
 // one work item of the persistent loop: an output tile (or one split-K slice of it)
+enum { TC_ITEM_FULL = 0, TC_ITEM_HEAD = 1, TC_ITEM_PART = 2 };
+
 struct TcItem {
   int img, oh0, ow0, m0, n0, tap_w, split, kb_begin, nkb;
+  int kind;                       // FULL: whole K range here | HEAD: first k-blocks, finishes the tile | PART: later k-blocks, parked
+  long long tile_end;             // stream-K: first unit after this tile
 };
 
 template <int MODE, int BN>
@@ -115,7 +128,44 @@ __device__ __forceinline__ TcItem tc_decode_item(const TcGeom &g, int w)
   int kb_end = it.kb_begin + g.kb_per_split;
   if (kb_end > g.total_kb) kb_end = g.total_kb;
   it.nkb = kb_end - it.kb_begin;
+  it.kind = TC_ITEM_FULL;
+  it.tile_end = 0;
   return it;
+}
+
+// walks the work of one CTA: split-K mode -> items blockIdx.x, +gridDim.x, ...; stream-K mode -> units [cta*U/G, (cta+1)*U/G)
+struct TcCursor {
+  long long pos, end;
+};
+
+__device__ __forceinline__ long long tc_sk_start(const TcGeom &g, int cta) { return (long long)cta * g.units / (long long)gridDim.x; }
+
+__device__ __forceinline__ TcCursor tc_cursor(const TcGeom &g)
+{
+  TcCursor c;
+  if (g.streamk) { c.pos = tc_sk_start(g, blockIdx.x); c.end = tc_sk_start(g, blockIdx.x + 1); }
+  else { c.pos = blockIdx.x; c.end = g.items; }
+  return c;
+}
+
+template <int MODE, int BN>
+__device__ __forceinline__ bool tc_next(const TcGeom &g, TcCursor &c, TcItem &t)
+{
+  if (c.pos >= c.end) return false;
+  if (!g.streamk) {
+    t = tc_decode_item<MODE, BN>(g, (int)c.pos);
+    c.pos += gridDim.x;
+    return true;
+  }
+  const int tile = (int)(c.pos / g.total_kb);
+  t = tc_decode_item<MODE, BN>(g, tile);               // splits == 1 in this mode: the tile's coordinates (and tap)
+  t.kb_begin = (int)(c.pos - (long long)tile * g.total_kb);
+  t.tile_end = (long long)(tile + 1) * g.total_kb;
+  const long long stop = t.tile_end < c.end ? t.tile_end : c.end;
+  t.nkb = (int)(stop - c.pos);
+  t.kind = t.kb_begin > 0 ? TC_ITEM_PART : (t.nkb == g.total_kb ? TC_ITEM_FULL : TC_ITEM_HEAD);
+  c.pos = stop;
+  return true;
 }
 
 __device__ __forceinline__ unsigned long long tc_globaltimer()
@@ -184,8 +234,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kBK;          // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
       int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
-      for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
-        const TcItem t = tc_decode_item<MODE, BN>(g, w);
+      TcCursor cur = tc_cursor(g);
+      TcItem t;
+      while (tc_next<MODE, BN>(g, cur, t)) {
         for (int i = 0; i < t.nkb; i++, it++) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -242,8 +293,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t accumulate = 0;
       int it = 0, chunk = 0;                                         // ring position / accumulation chains started, across all items
       uint32_t tmem_acc = tmem_base;
-      for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
-        const TcItem t = tc_decode_item<MODE, BN>(g, w);
+      TcCursor cur = tc_cursor(g);
+      TcItem t;
+      bool first_item = true;
+      while (tc_next<MODE, BN>(g, cur, t)) {
         for (int i = 0; i < t.nkb; i++, it++) {
           if (i % kChunkKB == 0) {                                   // new accumulation chain in the other TMEM buffer
             const int b = chunk & 1;
@@ -275,7 +328,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             chunk++;
           }
         }
-        if (w == blockIdx.x) TC_TRACE(4);
+        if (first_item) TC_TRACE(4);
+        first_item = false;
       }
       TC_TRACE(5);
     }
@@ -286,8 +340,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int row = q * 32 + lane;
     const bool raw = g.splits > 1;
     int cg = 0;                                                      // accumulation chains drained so far, across all items
-    for (int w = blockIdx.x; w < g.items; w += gridDim.x) {
-      const TcItem t = tc_decode_item<MODE, BN>(g, w);
+    TcCursor cur = tc_cursor(g);
+    TcItem t;
+    bool first_item = true;
+    while (tc_next<MODE, BN>(g, cur, t)) {
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; j++) acc[j] = 0.f;
@@ -310,7 +366,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[b]);
       }
-      if (w == blockIdx.x && threadIdx.x == 64) TC_TRACE(6);
+      if (first_item && threadIdx.x == 64) TC_TRACE(6);
+      if (t.kind == TC_ITEM_PART) {
+        // park the raw partial sums of this (tile, k-range) and publish them; the tile's HEAD owner folds them in
+        float *slot = g.sk_slots + ((size_t)blockIdx.x * 128 + row) * BN;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4) __stcg(reinterpret_cast<float4 *>(slot + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
+        if (threadIdx.x == 64) {
+          asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(g.sk_flags + blockIdx.x), "l"(g.sk_tag) : "memory");
+          if (first_item) TC_TRACE(7);
+        }
+        first_item = false;
+        continue;
+      }
+      if (t.kind == TC_ITEM_HEAD) {
+        // the CTAs after this one hold the rest of the tile's K range as the FIRST item of their ranges: long done, or about to be
+        for (int j = blockIdx.x + 1; j < (int)gridDim.x && tc_sk_start(g, j) < t.tile_end; j++) {
+          if (threadIdx.x == 64) {
+            const long long t0 = clock64();
+            unsigned long long seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(g.sk_flags + j) : "memory");
+              if (seen != g.sk_tag && clock64() - t0 > 20000000000ll) __trap();    // ~10 s: a partner that never ran
+            } while (seen != g.sk_tag);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const float *slot = g.sk_slots + ((size_t)j * 128 + row) * BN;
+#pragma unroll
+          for (int q = 0; q < BN; q += 4) {
+            const float4 p = __ldcg(reinterpret_cast<const float4 *>(slot + q));
+            acc[q] += p.x; acc[q + 1] += p.y; acc[q + 2] += p.z; acc[q + 3] += p.w;
+          }
+        }
+      }
       bool valid;
       size_t row_off;           // element offset of this row's first column (col = n0)
       size_t res_off = 0;
@@ -334,19 +424,37 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (valid) {
         float *dst = (raw ? partial : out) + row_off;
         if (!raw && MODE != TC_WGRAD) {
+          // scale / bias / residual as 128-bit loads with no control flow between them (the loads of a whole row batch up), the
+          // activation dispatched ONCE outside the element loop: a per-element `switch (act)` serialises every load behind a branch
+          const bool has_scale = epi.scale != nullptr, has_bias = epi.bias != nullptr, has_res = epi.residual != nullptr;
 #pragma unroll
-          for (int j = 0; j < BN; j++) {
-            float x = acc[j];
-            if (epi.scale) x *= __ldg(epi.scale + t.n0 + j);
-            if (epi.bias) x += __ldg(epi.bias + t.n0 + j);
-            if (epi.residual) x += __ldg(epi.residual + res_off + j);
-            acc[j] = tc_act(x, epi.act);
+          for (int j = 0; j < BN; j += 4) {
+            if (has_scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4 *>(epi.scale + t.n0 + j));
+              acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
+            }
+            if (has_bias) {
+              const float4 bi = __ldg(reinterpret_cast<const float4 *>(epi.bias + t.n0 + j));
+              acc[j] += bi.x; acc[j + 1] += bi.y; acc[j + 2] += bi.z; acc[j + 3] += bi.w;
+            }
+            if (has_res) {
+              const float4 re = __ldg(reinterpret_cast<const float4 *>(epi.residual + res_off + j));
+              acc[j] += re.x; acc[j + 1] += re.y; acc[j + 2] += re.z; acc[j + 3] += re.w;
+            }
+          }
+          if (epi.act == FRCNN_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < BN; j++) acc[j] = acc[j] > 0.0f ? acc[j] : 0.0f;
+          } else if (epi.act == FRCNN_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < BN; j++) acc[j] = 1.0f / (1.0f + expf(-acc[j]));
           }
         }
 #pragma unroll
         for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
-      if (w == blockIdx.x && threadIdx.x == 64) TC_TRACE(7);
+      if (first_item && threadIdx.x == 64) TC_TRACE(7);
+      first_item = false;
     }
     if (threadIdx.x == 64) TC_TRACE(8);
   }
@@ -425,6 +533,9 @@ struct TcPlan {
   int pw, ph, pn, patches_w, patches_h, pgroups;
   int total_kb, splits, kb_per_split;
   int m_tiles, n_tiles, items;       // persistent-loop work items (see TcGeom)
+  int streamk, grid;                 // stream-K decomposition (default) and its CTA count
+  long long units;
+  size_t flags_off;
   size_t a_hi_off, a_lo_off, b_hi_off, b_lo_off, partial_off, total_bytes;
   size_t a_count, b_count;           // element counts of the two operands that need a lo part
 };
@@ -481,36 +592,39 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->n_tiles = ntot / p->BN;
     ctas = p->m_tiles * p->n_tiles;
   }
-  // Split-K by a wave-quantisation cost model.  CTAs are persistent (grid = min(items, SMs)), every item of a launch costs the
-  // same, so the launch takes ceil(items / SMs) rounds of (k-blocks * t_kb + t_item); splitting K shortens the rounds at the
-  // price of a partial-sum pass (write s partials, read them back, write the result) -- taken only when it pays.
+  // Work decomposition.  Default = stream-K: the tiles * total_kb k-block units of the launch are cut into one equal contiguous
+  // range per CTA (persistent grid <= one CTA per SM), so the SMs finish together whatever the tile count; a tile that straddles
+  // two ranges is summed through a per-CTA slot in the workspace by the CTA owning its first k-block (no reduce kernel).
+  // FRCNN_TC_STREAMK=0 selects the older scheme: whole-tile items, optional split-K chosen by a wave-quantisation cost model,
+  // partial sums reduced by a second kernel.
+  static const bool use_streamk = !(getenv("FRCNN_TC_STREAMK") && atoi(getenv("FRCNN_TC_STREAMK")) == 0);
   const size_t out_elems_plan = (mode == TC_WGRAD) ? (size_t)Cout * taps * Cin : (size_t)pixels * ntot;
-  const double t_kb = (p->BN == 128) ? 0.56 : 0.42;                 // us per k-block (measured, smem-bandwidth bound mainloop)
-  const double t_item = 2.5;                                         // us of per-item pipeline refill / final drain not overlapped
   int splits = 1;
-  double best_t = -1.0;
-  const int max_splits = p->total_kb / kChunkKB > 32 ? 32 : p->total_kb / kChunkKB;
-  for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); sp++) {
-    const int kbs = ceil_div(p->total_kb, sp);
-    const int real = ceil_div(p->total_kb, kbs);                     // splits actually produced with this slice length
-    if (real != sp) continue;
-    const long long items = (long long)ctas * sp;
-    const long long rounds = (items + kNumSMs - 1) / kNumSMs;
-    double tt = rounds * (kbs * t_kb + t_item);
-    if (sp > 1) tt += 4.0 + (double)(sp + 2) * out_elems_plan * 4.0 / 4.0e6;   // reduce pass at ~4 TB/s effective + launch
-    if (best_t < 0 || tt < best_t) { best_t = tt; splits = sp; }
+  p->streamk = use_streamk ? 1 : 0;
+  p->units = (long long)ctas * p->total_kb;
+  if (use_streamk) {
+    long long gsz = p->units / kChunkKB;                             // at least one accumulation chain per CTA
+    if (gsz > kNumSMs) gsz = kNumSMs;
+    if (gsz < 1) gsz = 1;
+    p->grid = (int)gsz;
+  } else {
+    const double t_kb = (p->BN == 128) ? 0.56 : 0.42;               // us per k-block (measured, smem-bandwidth bound mainloop)
+    const double t_item = 2.5;                                       // us of per-item pipeline refill / final drain not overlapped
+    double best_t = -1.0;
+    const int max_splits = p->total_kb / kChunkKB > 32 ? 32 : p->total_kb / kChunkKB;
+    for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); sp++) {
+      const int kbs = ceil_div(p->total_kb, sp);
+      if (ceil_div(p->total_kb, kbs) != sp) continue;                // slice lengths that do not produce exactly sp splits
+      const long long rounds = ((long long)ctas * sp + kNumSMs - 1) / kNumSMs;
+      double tt = rounds * (kbs * t_kb + t_item);
+      if (sp > 1) tt += 4.0 + (double)(sp + 2) * out_elems_plan * 4.0 / 4.0e6;   // reduce pass at ~4 TB/s effective + launch
+      if (best_t < 0 || tt < best_t) { best_t = tt; splits = sp; }
+    }
   }
-  static const int force_splits = getenv("FRCNN_TC_SPLITS") ? atoi(getenv("FRCNN_TC_SPLITS")) : 0;    // debug / A-B knob
-  if (force_splits > 0) splits = force_splits > max_splits ? (max_splits < 1 ? 1 : max_splits) : force_splits;
-  if (force_splits < 0 && ctas < kNumSMs) {                                                           // -1: the pre-cost-model rule
-    splits = ceil_div(kNumSMs, ctas);
-    if (splits > p->total_kb / 8) splits = p->total_kb / 8;
-    if (splits > 32) splits = 32;
-    if (splits < 1) splits = 1;
-  } else if (force_splits < 0) splits = 1;
   p->kb_per_split = ceil_div(p->total_kb, splits);
   p->splits = ceil_div(p->total_kb, p->kb_per_split);
   p->items = ctas * p->splits;
+  if (!p->streamk) p->grid = p->items > kNumSMs ? kNumSMs : p->items;
   const size_t act_in = (size_t)pixels * Cin, act_out = (size_t)pixels * Cout, filt = (size_t)Cout * taps * Cin;
   size_t out_elems;
   if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
@@ -521,7 +635,13 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->b_hi_off = 2 * p->a_lo_off;
   p->b_lo_off = p->b_hi_off + align_up(p->b_count * 4, 1024);
   p->partial_off = p->b_lo_off + align_up(p->b_count * 4, 1024);
-  p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * out_elems * 4 : 0);
+  if (p->streamk) {
+    p->flags_off = p->partial_off + align_up((size_t)p->grid * 128 * p->BN * 4, 1024);
+    p->total_bytes = p->flags_off + align_up((size_t)p->grid * 8, 1024);
+  } else {
+    p->flags_off = 0;
+    p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * out_elems * 4 : 0);
+  }
   return true;
 }
 
@@ -561,6 +681,9 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   if (workspace == nullptr || workspace_bytes < p.total_bytes) return fail(FRCNN_E_WORKSPACE, "tcgen05 engine: workspace too small");
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return fail(FRCNN_E_BADARG, "tcgen05 engine: operands and workspace must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(epi.scale) & 15) || (reinterpret_cast<uintptr_t>(epi.bias) & 15) ||
+      (reinterpret_cast<uintptr_t>(epi.residual) & 15))
+    return fail(FRCNN_E_BADARG, "tcgen05 engine: output, scale, bias and residual must be 16-byte aligned");
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
   float *a_hi = reinterpret_cast<float *>(ws + p.a_hi_off);
   float *a_lo = reinterpret_cast<float *>(ws + p.a_lo_off);
@@ -603,10 +726,12 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   static const int dbg_lbo = getenv("FRCNN_TC_MN_LBO") ? atoi(getenv("FRCNN_TC_MN_LBO")) : kAtomBytes;
   static const int dbg_sbo = getenv("FRCNN_TC_MN_SBO") ? atoi(getenv("FRCNN_TC_MN_SBO")) : 512;
   static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 1024;
-  static const bool persistent = !(getenv("FRCNN_TC_PERSISTENT") && atoi(getenv("FRCNN_TC_PERSISTENT")) == 0);   // 0: one CTA per item (A-B knob)
-  grid = dim3(persistent && p.items > kNumSMs ? kNumSMs : p.items, 1, 1);
+  static std::atomic<unsigned long long> launch_serial{0};
+  grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace};
+           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
+           p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
+           0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull)};
   int rc;
 #define TC_LAUNCH(M)                                                                          \
   (p.BN == 128 ? launch_tc<M, 128, 3>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4>(maps, g, grid, out, partial, epi, st))

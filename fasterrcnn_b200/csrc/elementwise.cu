@@ -154,6 +154,83 @@ __global__ void bias_grad_stage2(const float *__restrict__ partial, float *__res
   }
 }
 
+
+// ---- fused activation backward: dz (+ its tf32 hi/lo split) (+ per-channel sums for the bias gradient) in one pass -------
+// Replaces relu_bwd -> split_hi_lo -> bias_grad_stage1 (three passes over dz) for the layers whose gradient GEMMs run on the
+// tcgen05 engine.  A CTA owns a slab of <= 1024 channels (blockIdx.y) and a block of rows (blockIdx.x); threads are laid out
+// [row lane][float4 channel group] so every access is a full 128-bit coalesced row segment; column sums are kept per thread
+// and combined over the row lanes through shared memory in a fixed order (deterministic), then reduced by bias_grad_stage2.
+__device__ __forceinline__ float fused_tf32_rna(float x)
+{
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int MODE>     // 0: dz = dy   1: dz = y > 0 ? dy : 0
+__global__ void __launch_bounds__(256)
+act_bwd_fused_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, float *__restrict__ hi, float *__restrict__ lo,
+                     float *__restrict__ partial, size_t rows, int C, int slab_c, int rows_per_block)
+{
+  __shared__ float4 red[256];
+  const int groups = slab_c / 4;                       // float4 groups per row inside this CTA's channel slab (divides 256)
+  const int lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const size_t row_f4 = (size_t)C / 4;
+  const size_t col_f4 = (size_t)blockIdx.y * groups + cg;
+  const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+  const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t r = r0 + rl; r < r1; r += lanes) {
+    const size_t e = r * row_f4 + col_f4;
+    float4 g = __ldg(reinterpret_cast<const float4 *>(dy) + e);
+    if (MODE == 1) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(y) + e);
+      g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f;
+      g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    }
+    if (dz) reinterpret_cast<float4 *>(dz)[e] = g;
+    if (hi) {
+      float4 h, l;
+      h.x = fused_tf32_rna(g.x); h.y = fused_tf32_rna(g.y); h.z = fused_tf32_rna(g.z); h.w = fused_tf32_rna(g.w);
+      l.x = g.x - h.x; l.y = g.y - h.y; l.z = g.z - h.z; l.w = g.w - h.w;
+      reinterpret_cast<float4 *>(hi)[e] = h;
+      reinterpret_cast<float4 *>(lo)[e] = l;
+    }
+    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+  }
+  if (partial) {
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0) {
+      float4 tot = red[cg];
+      for (int k = 1; k < lanes; k++) {
+        const float4 o = red[k * groups + cg];
+        tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
+      }
+      reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * C)[col_f4] = tot;
+    }
+  }
+}
+
+static bool act_bwd_fused_plan(size_t rows, int C, int *slab_c, int *blocks_x, int *rows_per_block)
+{
+  if (C < 64 || rows == 0) return false;
+  int sc = C >= 1024 ? 1024 : C;
+  if (C % sc != 0 || (sc & (sc - 1)) != 0) return false;          // slabs of 64..1024 channels, power of two (4 * divisor of 256)
+  const int lanes = 256 / (sc / 4);
+  const int slabs = C / sc;
+  size_t want = ceil_div<size_t>(rows, (size_t)lanes);
+  size_t cap = (size_t)(4 * kNumSMs / slabs > 1 ? 4 * kNumSMs / slabs : 1);
+  if (want > cap) want = cap;
+  size_t per = ceil_div<size_t>(rows, want);
+  per = ceil_div<size_t>(per, (size_t)lanes) * lanes;
+  *slab_c = sc;
+  *rows_per_block = (int)per;
+  *blocks_x = (int)ceil_div<size_t>(rows, per);
+  return true;
+}
+
 // ---- pooling ---------------------------------------------------------------------------------
 template <int VEC>
 __global__ void maxpool2x2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
@@ -351,6 +428,50 @@ int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *wor
   FRCNN_CHECK_LAUNCH("bias_grad_stage1");
   bias_grad_stage2<<<ceil_div(C, 32), 256, 0, as_stream(stream)>>>(partial, dbias, blocks, C);
   FRCNN_CHECK_LAUNCH("bias_grad_stage2");
+  return FRCNN_OK;
+}
+
+int frcnn_act_bwd_fused_supported(size_t rows, int C)
+{
+  int a, b, c;
+  return act_bwd_fused_plan(rows, C, &a, &b, &c) ? 1 : 0;
+}
+
+size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C)
+{
+  int sc, bx, per;
+  if (!act_bwd_fused_plan(rows, C, &sc, &bx, &per)) return 0;
+  return (size_t)bx * C * sizeof(float);
+}
+
+int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && rows > 0 && C > 0, "act_bwd_fused: bad argument");
+  FRCNN_REQUIRE(act == FRCNN_ACT_NONE || (act == FRCNN_ACT_RELU && y), "act_bwd_fused: activation must be NONE or RELU (with y)");
+  FRCNN_REQUIRE(dz || dz_split || dbias, "act_bwd_fused: nothing to produce");
+  int sc, bx, per;
+  if (!act_bwd_fused_plan(rows, C, &sc, &bx, &per)) return fail(FRCNN_E_UNSUPPORTED, "act_bwd_fused: channel count not a multiple of a 64..1024 power-of-two slab");
+  float *partial = nullptr;
+  if (dbias) {
+    if (workspace == nullptr || workspace_bytes < (size_t)bx * C * sizeof(float)) return fail(FRCNN_E_WORKSPACE, "act_bwd_fused: workspace too small");
+    partial = reinterpret_cast<float *>(workspace);
+  }
+  float *hi = nullptr, *lo = nullptr;
+  if (dz_split) {
+    const size_t count = rows * (size_t)C;
+    hi = reinterpret_cast<float *>(dz_split);
+    lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(dz_split) + (count * 4 + 1023) / 1024 * 1024);     // frcnn_tf32_split layout
+  }
+  dim3 grid(bx, C / sc);
+  cudaStream_t st = as_stream(stream);
+  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per);
+  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per);
+  FRCNN_CHECK_LAUNCH("act_bwd_fused_kernel");
+  if (dbias) {
+    bias_grad_stage2<<<ceil_div(C, 32), 256, 0, st>>>(partial, dbias, bx, C);
+    FRCNN_CHECK_LAUNCH("bias_grad_stage2");
+  }
   return FRCNN_OK;
 }
 

@@ -98,13 +98,22 @@ class FasterRCNNModel(nn.Module):
     fetched.synchronize()
     n = int(fetch[0]) + len(gt)                                                                    # proposals + appended GT boxes
     indices = self._sample_proposal_indices(fetch[1:1 + n].numpy(), self._proposal_batch_size, 0.25)
-    if indices is None:
-      proposals, gt_classes, gt_box_deltas = padded[:n], gt_classes[:n], gt_box_deltas[:n]
+    if indices is None or len(indices) == 0:
+      keep = n if indices is None else 0                                                           # no sampling | no usable sample
+      proposals, gt_classes, gt_box_deltas = padded[:keep], gt_classes[:keep], gt_box_deltas[:keep]
+      detector_classes, detector_box_deltas = self._stage3_detector_network(feature_map = feature_map, proposals = proposals)
     else:
-      index_dev = t.from_numpy(indices).to(dev, non_blocking = True)
-      proposals, gt_classes, gt_box_deltas = padded[index_dev], gt_classes[index_dev], gt_box_deltas[index_dev]
-
-    detector_classes, detector_box_deltas = self._stage3_detector_network(feature_map = feature_map, proposals = proposals)
+      # sampled row indices go up in one pinned copy ([count | indices]); the proposal rows are gathered first so that RoI pooling
+      # -- the first sizeable kernel after the synchronisation -- is in flight before the label rows are gathered
+      k = len(indices)
+      upload = self._pinned("sample", (1 + self._proposal_batch_size if self._proposal_batch_size > 0 else 1 + padded.shape[0],), t.int32)
+      upload[0] = k
+      upload[1:1 + k] = t.from_numpy(indices.astype(np.int32))
+      sample_dev = upload[:1 + k].to(dev, non_blocking = True)
+      proposals = ops.gather_rows(padded, sample_dev[1:], sample_dev[0:1], k)
+      detector_classes, detector_box_deltas = self._stage3_detector_network(feature_map = feature_map, proposals = proposals)
+      gt_classes = ops.gather_rows(gt_classes, sample_dev[1:], sample_dev[0:1], k)
+      gt_box_deltas = ops.gather_rows(gt_box_deltas, sample_dev[1:], sample_dev[0:1], k)
 
     det_l = ops.detector_losses(detector_classes, detector_box_deltas, gt_classes, gt_box_deltas)    # (class, regression)
     all_l = t.cat([rpn_l, det_l])

@@ -225,7 +225,7 @@ def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None, 
   return y
 
 
-def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = False):
+def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = False, dy_split = None):
   n, cin, h, wd = x_shape
   cout, _, kh, kw = w.shape
   dx = _empty_nhwc(n, cin, h, wd, dy.device)
@@ -233,13 +233,15 @@ def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = Fals
   ds = ws_ = None
   if _uses_tc(1, geom):
     ws_ = tf32_split(w)
-    if reuse_dy:
+    if dy_split is not None:
+      ds = dy_split
+    elif reuse_dy:
       ds = tf32_split(dy)
   _gemm(1, dy, w, dx, geom, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, ws_, addend = addend)
   return dx
 
 
-def conv2d_wgrad_raw(dy, x, w_shape, stride, pad):
+def conv2d_wgrad_raw(dy, x, w_shape, stride, pad, dy_split = None):
   n, cin, h, wd = x.shape
   cout, _, kh, kw = w_shape
   dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = x.device, memory_format = t.channels_last)
@@ -250,7 +252,7 @@ def conv2d_wgrad_raw(dy, x, w_shape, stride, pad):
   if _uses_tc(2, geom):
     key_dy = (dy.data_ptr(), dy.numel(), dy._version)
     key_x = (x.data_ptr(), x.numel(), x._version)
-    ds = _split_cache[key_dy][0] if key_dy in _split_cache else None
+    ds = dy_split if dy_split is not None else (_split_cache[key_dy][0] if key_dy in _split_cache else None)
     xs = _split_cache[key_x][0] if key_x in _split_cache else None
   _gemm(2, dy, x, dw, geom, "conv_wgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, xs)
   drop_split(dy)
@@ -267,6 +269,41 @@ def bias_grad_raw(dz_rows, c):
   check(lib().frcnn_bias_grad(ptr(dz_rows), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_bias_grad")
   _lib.count(2)
   return db
+
+
+def _act_bwd(dy, y, act, c, want_split, want_bias, need_fp32):
+  """Backward of the fused epilogue y = act(z + b) over a (rows, c) row-major gradient.  Returns (dz, dz_split, db):
+  dz fp32 tensor (when need_fp32 is False and the fused kernel runs it is only a placeholder carrying shape and a valid address:
+  the tcgen05 GEMMs read dz_split), dz_split = [hi | lo] operand buffer or None, db = bias gradient or None.
+  One frcnn_act_bwd_fused launch when the channel count allows it, else the separate kernels."""
+  rows = dy.numel() // c
+  L = lib()
+  if act in (ACT_NONE, ACT_RELU) and rows > 0 and (want_split or want_bias) and L.frcnn_act_bwd_fused_supported(rows, c):
+    write_dz = act == ACT_RELU and (need_fp32 or not want_split)
+    dz = t.empty_like(y) if write_dz else None
+    split = t.empty((L.frcnn_tf32_split_bytes(dy.numel()),), dtype = t.uint8, device = dy.device) if want_split else None
+    db = t.empty((c,), dtype = t.float32, device = dy.device) if want_bias else None
+    ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1) if want_bias else (None, 0)
+    check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
+    _lib.count(2 if want_bias else 1)
+    if dz is None and act == ACT_NONE:
+      dz = dy
+    elif dz is None:                                             # placeholder over the hi half, in y's physical (channels-last) layout
+      flat = split[:dy.numel() * 4].view(t.float32)
+      dz = flat.view(y.shape[0], y.shape[2], y.shape[3], y.shape[1]).permute(0, 3, 1, 2) if y.dim() == 4 else flat.view(y.shape)
+    return dz, split, db
+  if act == ACT_RELU:
+    dz = t.empty_like(y)
+    check(L.frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
+    _lib.count()
+  elif act == ACT_SIGMOID:
+    dz = t.empty_like(y)
+    check(L.frcnn_sigmoid_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_sigmoid_bwd")
+    _lib.count()
+  else:
+    dz = dy
+  db = bias_grad_raw(dz, c) if want_bias and rows > 0 else None
+  return dz, None, db
 
 
 def _phys_filter(w):
@@ -312,27 +349,23 @@ class _ConvAct(t.autograd.Function):
     xp, wp, y = ctx.saved_tensors
     n, c, h, wd = y.shape
     dy = _phys_nhwc(dy)
+    geom = (xp.shape[0], xp.shape[2], xp.shape[3], xp.shape[1], c, ctx.w_shape[2], ctx.w_shape[3], ctx.stride, ctx.pad)
+    want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    tc_dx, tc_dw = want_dx and _uses_tc(1, geom), want_dw and _uses_tc(2, geom)
+    need_fp32 = (want_dx and not tc_dx) or (want_dw and not tc_dw)          # a CUDA-core GEMM reads dz itself
+    want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+    act = ctx.act
     if ctx.pool:
       dz = t.empty_like(y)
       check(lib().frcnn_maxpool2x2_relu_bwd(ptr(dy), ptr(y), ptr(dz), n, h, wd, c, stream()), "frcnn_maxpool2x2_relu_bwd")
       _lib.count()
-    elif ctx.act == ACT_RELU:
-      dz = t.empty_like(y)
-      check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
-      _lib.count()
-    elif ctx.act == ACT_SIGMOID:
-      dz = t.empty_like(y)
-      check(lib().frcnn_sigmoid_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_sigmoid_bwd")
-      _lib.count()
-    else:
-      dz = dy
-    dx = dw = db = None
-    if ctx.needs_input_grad[0]:
-      dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = ctx.needs_input_grad[1])
-    if ctx.needs_input_grad[1]:
-      dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
-      db = bias_grad_raw(dz, c)
+      dy, act = dz, ACT_NONE                                                # ReLU mask already applied by the pooling backward
+    dz, dz_split, db = _act_bwd(dy, y, act, c, tc_dx or tc_dw, want_bias, need_fp32)
+    dx = dw = None
+    if want_dx:
+      dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = want_dw, dy_split = dz_split if tc_dx else None)
+    if want_dw:
+      dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad, dy_split = dz_split if tc_dw else None)
     return dx, dw, db, None, None, None, None
 
 
@@ -372,38 +405,29 @@ class _LinearAct(t.autograd.Function):
     dy = dy.contiguous()
     if m == 0:
       return t.zeros_like(x2), t.zeros_like(w2), (t.zeros((nout,), device = x2.device) if ctx.has_bias else None), None
-    if ctx.act == ACT_RELU:
-      dz = t.empty_like(y)
-      check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
-      _lib.count()
-    elif ctx.act == ACT_SIGMOID:
-      dz = t.empty_like(y)
-      check(lib().frcnn_sigmoid_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_sigmoid_bwd")
-      _lib.count()
-    else:
-      dz = dy
     geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
-    dx = dw = db = None
-    if ctx.needs_input_grad[0]:
+    want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    tc_dx, tc_dw = want_dx and _uses_tc(1, geom), want_dw and _uses_tc(2, geom)
+    need_fp32 = (want_dx and not tc_dx) or (want_dw and not tc_dw)
+    dz, dz_split, db = _act_bwd(dy, y, ctx.act, nout, tc_dx or tc_dw, ctx.has_bias and ctx.needs_input_grad[2], need_fp32)
+    dx = dw = None
+    if want_dx:
       dx = t.empty((m, k), dtype = t.float32, device = x2.device)
       ds = ws_ = None
-      if _uses_tc(1, geom):
+      if tc_dx:
         ws_ = tf32_split(w2)
-        if ctx.needs_input_grad[1]:
-          ds = tf32_split(dz)
+        ds = dz_split if dz_split is not None else (tf32_split(dz) if want_dw else None)
       _gemm(1, dz, w2, dx, geom, "linear_dgrad", 2e-9 * m * k * nout, ds, ws_)
-    if ctx.needs_input_grad[1]:
+    if want_dw:
       dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
       ds = xs = None
-      if _uses_tc(2, geom):
+      if tc_dw:
         kd, kx = (dz.data_ptr(), dz.numel(), dz._version), (x2.data_ptr(), x2.numel(), x2._version)
-        ds = _split_cache[kd][0] if kd in _split_cache else None
+        ds = dz_split if dz_split is not None else (_split_cache[kd][0] if kd in _split_cache else None)
         xs = _split_cache[kx][0] if kx in _split_cache else None
       _gemm(2, dz, x2, dw, geom, "linear_wgrad", 2e-9 * m * k * nout, ds, xs)
       drop_split(dz)
       drop_split(x2)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
-      db = bias_grad_raw(dz, nout)
     return dx, dw, db, None
 
 
@@ -669,6 +693,17 @@ def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, po
     return out[:n], dict(order = buf.order[:n1].clone(), boxes_all = buf.boxes_all.clone(), size_ok = buf.size_ok.clone(),
                          boxes_sorted = buf.boxes_sorted[:n2].clone(), scores_sorted = buf.scores_sorted[:n2].clone(), keep = buf.keep[:n].clone())
   return out[:n]
+
+
+def gather_rows(src, index_i32, count_i32, capacity):
+  """dst[r] = src[index[r]] for r < *count (rows past the count are left untouched); index / count are device int32."""
+  _require_cuda(src, index_i32, count_i32)
+  src = src.contiguous()
+  row_floats = src.numel() // src.shape[0]
+  dst = t.empty((capacity,) + tuple(src.shape[1:]), dtype = t.float32, device = src.device)
+  check(lib().frcnn_gather_rows_f32(ptr(src), row_floats, ptr(index_i32), ptr(count_i32), capacity, ptr(dst), stream()), "frcnn_gather_rows_f32")
+  _lib.count()
+  return dst
 
 
 def append_rows(dst, dst_count, src):

@@ -110,6 +110,15 @@ int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, voi
 /* dbias[c] = sum over rows of dz[row, c]; workspace >= frcnn_bias_grad_workspace_bytes. */
 size_t frcnn_bias_grad_workspace_bytes(size_t rows, int C);
 int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *workspace, size_t workspace_bytes, void *stream);
+/* One pass for the backward of `y = act(conv/linear(x) + b)` over the (rows, C) row-major gradient: dz = dy (act NONE) or
+ * y > 0 ? dy : 0 (act RELU), written as fp32 (dz, may be NULL), as the tcgen05 engine's [hi | lo] operand split (dz_split, layout of
+ * frcnn_tf32_split, may be NULL) and reduced over rows into dbias (may be NULL; needs the workspace).  Replaces the autograd
+ * chain relu-backward -> (operand split) -> bias.sum(0) of F.relu(nn.Conv2d) / F.relu(nn.Linear) (vgg16.py:76-96,129-133).
+ * C must be a multiple of a power-of-two slab of 64..1024 channels (frcnn_act_bwd_fused_supported), else FRCNN_E_UNSUPPORTED. */
+int frcnn_act_bwd_fused_supported(size_t rows, int C);
+size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C);
+int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                        void *workspace, size_t workspace_bytes, void *stream);
 /* 2x2 stride-2 max pool, floor mode (nn.MaxPool2d(2,2) models/vgg16.py:78,82,87,92), NHWC. */
 int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
 /* dz[n,h,w,c] = dy[n,h/2,w/2,c] if (h,w) is the first maximum of its window and x > 0, else 0

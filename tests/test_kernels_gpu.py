@@ -419,3 +419,39 @@ def test_tcgen05_linear_backward_matches_fp64(ops):
   ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
   assert float((xc.grad.double().cpu() - dx64).abs().max()) <= 1e-4 * float(dx64.abs().max())
   assert float((wc.grad.double().cpu() - dw64).abs().max()) <= 1e-4 * float(dw64.abs().max())
+
+
+@pytest.mark.parametrize("rows,c,act", [(37 * 45, 256, "relu"), (2294, 512, "relu"), (128, 4096, "relu"), (1000, 64, "none"), (77, 2048, "none")])
+def test_act_bwd_fused_matches_separate_passes(ops, rows, c, act):
+  """frcnn_act_bwd_fused = relu-backward + tf32 operand split + bias row-sum in one pass: dz bit-exact, hi + lo == dz exactly with
+  hi tf32-representable (10 explicit mantissa bits), bias gradient within fp32 summation-order noise; bit-exact on integers."""
+  from fasterrcnn_b200._lib import lib, ptr, check, stream, workspace
+  L = lib()
+  assert L.frcnn_act_bwd_fused_supported(rows, c) == 1
+  assert L.frcnn_act_bwd_fused_supported(rows, 21) == 0 and L.frcnn_act_bwd_fused_supported(rows, 96) == 0
+  g = t.Generator().manual_seed(rows + c)
+  for integer in (False, True):
+    dy = (_int_tensor(g, (rows, c), -3, 3) if integer else t.randn((rows, c), generator = g)).cuda()
+    y = t.randn((rows, c), generator = g).cuda()
+    code = ops.ACT_RELU if act == "relu" else ops.ACT_NONE
+    dz = t.empty_like(dy)
+    split = t.empty((L.frcnn_tf32_split_bytes(dy.numel()),), dtype = t.uint8, device = "cuda")
+    db = t.empty((c,), dtype = t.float32, device = "cuda")
+    ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1)
+    check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y), code, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
+    want = t.where(y > 0, dy, t.zeros_like(dy)) if act == "relu" else dy
+    assert t.equal(dz, want)
+    lo_off = (dy.numel() * 4 + 1023) // 1024 * 1024
+    hi = split[:dy.numel() * 4].view(t.float32).view(rows, c)
+    lo = split[lo_off:lo_off + dy.numel() * 4].view(t.float32).view(rows, c)
+    assert t.equal(hi + lo, want)
+    assert int((hi.view(t.int32) & 0x1FFF).abs().max()) == 0              # low 13 mantissa bits clear: exactly a tf32 value
+    ref = want.double().sum(0)
+    if integer:
+      assert t.equal(db.double(), ref)
+    else:
+      assert float((db.double() - ref).abs().max()) <= 1e-5 * float(want.abs().sum(0).max())
+    # split-only and bias-only variants leave the other outputs untouched
+    db2 = t.full((c,), 7.0, device = "cuda")
+    check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y), code, None, ptr(split), None, rows, c, None, 0, stream()), "frcnn_act_bwd_fused")
+    assert t.equal(split[:dy.numel() * 4].view(t.float32).view(rows, c), hi) and float(db2[0]) == 7.0
