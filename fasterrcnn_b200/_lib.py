@@ -70,6 +70,7 @@ _SIGNATURES = {
   "frcnn_softmax_rows_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
   "frcnn_detector_losses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
   "frcnn_sgd_step": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp]),
+  "frcnn_sgd_step_split": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp, _vp]),
   "frcnn_detect_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _vp, _vp, _vp]),
 }
 

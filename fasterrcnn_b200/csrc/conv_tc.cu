@@ -176,7 +176,7 @@ __device__ __forceinline__ unsigned long long tc_globaltimer()
 }
 #define TC_TRACE(slot) do { if (g.trace) g.trace[(size_t)blockIdx.x * 16 + (slot)] = tc_globaltimer(); } while (0)
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 224;                  // warp 0: TMA producer (A operand), 1: MMA issuer, 2-5: accumulate/epilogue, 6: TMA producer (B operand)
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
 constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
@@ -212,7 +212,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   if (threadIdx.x == 0) TC_TRACE(0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }      // full: one arrive.expect_tx per producer
     for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
@@ -228,9 +228,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) TC_TRACE(1);
-  if (warp == 0) {
+  if (warp == 0 || warp == 6) {
     if (lane == 0) {
-      // ===== TMA producer: runs ahead across work items (the smem ring never drains between tiles) =====
+      // ===== TMA producers: warp 0 feeds the A operand, warp 6 the B operand (up to 8 box loads each per k-block: issuing them
+      // from one thread was the limit of the filter-gradient mainloop).  Both run ahead across work items. =====
+      const bool feed_a = (warp == 0);
       const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kBK;          // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
       int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
@@ -245,41 +247,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint8_t *a_lo = a_hi + kABytes;
           uint8_t *b_hi = a_hi + 2 * kABytes;
           uint8_t *b_lo = b_hi + kBBytes;
-          mbar_expect_tx(&full[s], kStageBytes);
+          mbar_expect_tx(&full[s], feed_a ? 2 * kABytes : 2 * kBBytes);
           if (MODE == TC_WGRAD) {
             const int im = (kb / patches_per_img) * g.pn;            // first image of the patch's image group
             const int prem = kb % patches_per_img;
             const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
             const int kh = t.tap_w / g.KW, kw = t.tap_w - kh * g.KW;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {                                      // A: dy, 128 output channels = 4 atoms
-              tma_load_4d(a_hi + j * kAtomBytes, &map_a_hi, &full[s], t.m0 + 32 * j, px, py, im);
-              tma_load_4d(a_lo + j * kAtomBytes, &map_a_lo, &full[s], t.m0 + 32 * j, px, py, im);
-            }
-#pragma unroll
-            for (int j = 0; j < BN / 32; j++) {                                // B: x shifted by the tap
-              tma_load_4d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], t.n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
-              tma_load_4d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], t.n0 + 32 * j, px + kw - g.pad, py + kh - g.pad, im);
+            if (feed_a) {                                                      // A: dy, 128 output channels = 4 atoms in one box
+              tma_load_5d(a_hi, &map_a_hi, &full[s], 0, px, py, im, t.m0 / 32);
+              tma_load_5d(a_lo, &map_a_lo, &full[s], 0, px, py, im, t.m0 / 32);
+            } else {                                                           // B: x shifted by the tap, BN / 32 atoms in one box
+              tma_load_5d(b_hi, &map_b_hi, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / 32);
+              tma_load_5d(b_lo, &map_b_lo, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / 32);
             }
           } else {
             const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kBK;
             const int kh = tap / g.KW, kw = tap - kh * g.KW;
             const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
             const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
-            tma_load_4d(a_hi, &map_a_hi, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
-            tma_load_4d(a_lo, &map_a_lo, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
-            if (MODE == TC_FWD) {
+            if (feed_a) {
+              tma_load_4d(a_hi, &map_a_hi, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+              tma_load_4d(a_lo, &map_a_lo, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+            } else if (MODE == TC_FWD) {
               tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, t.n0);
               tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, t.n0);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 32; j++) {                              // B: w[co0..+32][tap][n0+32j..+32]
-                tma_load_3d(b_hi + j * kAtomBytes, &map_b_hi, &full[s], t.n0 + 32 * j, tap, c0);
-                tma_load_3d(b_lo + j * kAtomBytes, &map_b_lo, &full[s], t.n0 + 32 * j, tap, c0);
-              }
+            } else {                                                           // B: w[co0..+32][tap][n0 .. n0+BN) as BN / 32 atoms in one box
+              tma_load_4d(b_hi, &map_b_hi, &full[s], 0, tap, c0, t.n0 / 32);
+              tma_load_4d(b_lo, &map_b_lo, &full[s], 0, tap, c0, t.n0 / 32);
             }
           }
-          if (it == 0) TC_TRACE(2);
+          if (it == 0 && feed_a) TC_TRACE(2);
         }
       }
     }
@@ -517,13 +514,25 @@ static bool make_mat_map(CUtensorMap *m, const float *base, int rows, int K, int
   return encode(m, base, 2, dims, strides, box, false);
 }
 
-// filter (Cout, taps, Cin) fp32 as a 3-D tensor (Cin, taps, Cout); box {32 ci, 1 tap, 32 co}
-static bool make_filter3d_map(CUtensorMap *m, const float *base, int Cout, int taps, int Cin)
+// MN-major operand tiles are stacks of 32-channel atoms ([atom][32 k-rows][32 channels], 4 KB each).  Splitting the channel axis
+// into (32, C/32) and putting the atom index LAST in the tensor map lets ONE box load deliver the whole stack in exactly that
+// order (the producer thread's issue rate of small boxes was the limit of the filter-gradient mainloop):
+// activation (N,H,W,C) as the 5-D tensor (32, W, H, N, C/32); box {32, box_w, box_h, box_n, atoms}
+static bool make_act_map_atoms(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h, int box_n, int atoms)
 {
-  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
-  cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4};
-  cuuint32_t box[3] = {32, 1, 32};
-  return encode(m, base, 3, dims, strides, box, true);
+  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 32)};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 128};
+  cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n, (cuuint32_t)atoms};
+  return encode(m, base, 5, dims, strides, box, true);
+}
+
+// filter (Cout, taps, Cin) as the 4-D tensor (32, taps, Cout, Cin/32); box {32 ci, 1 tap, 32 co, atoms}
+static bool make_filter_map_atoms(CUtensorMap *m, const float *base, int Cout, int taps, int Cin, int atoms)
+{
+  cuuint64_t dims[4] = {32, (cuuint64_t)taps, (cuuint64_t)Cout, (cuuint64_t)(Cin / 32)};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4, 128};
+  cuuint32_t box[4] = {32, 1, 32, (cuuint32_t)atoms};
+  return encode(m, base, 4, dims, strides, box, true);
 }
 
 struct TcPlan {
@@ -600,9 +609,12 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   static const bool use_streamk = !(getenv("FRCNN_TC_STREAMK") && atoi(getenv("FRCNN_TC_STREAMK")) == 0);
   const size_t out_elems_plan = (mode == TC_WGRAD) ? (size_t)Cout * taps * Cin : (size_t)pixels * ntot;
   int splits = 1;
-  p->streamk = use_streamk ? 1 : 0;
+  // stream-K pays when a launch has between ~half a wave and a few waves of tiles: fewer tiles mean many CTAs share one tile and
+  // the owner's serial fix-up (64 KB per partner) outweighs the balance -- the split-K + parallel reduce path is better there --
+  // and with many waves of tiles the quantisation loss is below 1/8 of a tile per SM anyway.
+  p->streamk = (use_streamk && ctas >= kNumSMs / 2 && ctas < 8 * kNumSMs) ? 1 : 0;
   p->units = (long long)ctas * p->total_kb;
-  if (use_streamk) {
+  if (p->streamk) {
     long long gsz = p->units / kChunkKB;                             // at least one accumulation chain per CTA
     if (gsz > kNumSMs) gsz = kNumSMs;
     if (gsz < 1) gsz = 1;
@@ -716,10 +728,10 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
          make_mat_map(&maps[2], b, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, Cout, taps * Cin, p.BN);
   } else if (mode == TC_DGRAD) {
     ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
-         make_filter3d_map(&maps[2], b, Cout, taps, Cin) && make_filter3d_map(&maps[3], b_lo, Cout, taps, Cin);
+         make_filter_map_atoms(&maps[2], b, Cout, taps, Cin, p.BN / 32) && make_filter_map_atoms(&maps[3], b_lo, Cout, taps, Cin, p.BN / 32);
   } else {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, true) &&
-         make_act_map(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true) && make_act_map(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, true);
+    ok = make_act_map_atoms(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 4) && make_act_map_atoms(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 4) &&
+         make_act_map_atoms(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / 32) && make_act_map_atoms(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / 32);
   }
   if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 

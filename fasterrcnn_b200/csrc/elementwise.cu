@@ -69,6 +69,13 @@ __global__ void add_kernel(const float *__restrict__ a, const float *__restrict_
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) out[i] = a[i] + b[i];
 }
 
+__device__ __forceinline__ float fused_tf32_rna(float x)
+{
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // torch.optim.SGD (momentum, dampening 0, no nesterov, L2 weight decay folded into the gradient):
 // separate mul/add roundings as torch's foreach kernels produce them (no FMA contraction).
 __device__ __forceinline__ float sgd_one(float p, float g, float &buf, float lr, float mom, float wd, float gs, int first)
@@ -80,8 +87,9 @@ __device__ __forceinline__ float sgd_one(float p, float g, float &buf, float lr,
   return __fadd_rn(p, __fmul_rn(-lr, b));
 }
 
+// hi / lo (optional): the updated weights' tf32 operand split for the next step's tcgen05 GEMMs, written in the same pass
 __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, size_t count,
-                           float lr, float mom, float wd, float gs, int first)
+                           float lr, float mom, float wd, float gs, int first, float *__restrict__ hi, float *__restrict__ lo)
 {
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -95,11 +103,20 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
     pv.w = sgd_one(pv.w, gv.w, bv.w, lr, mom, wd, gs, first);
     reinterpret_cast<float4 *>(p)[i] = pv;
     reinterpret_cast<float4 *>(buf)[i] = bv;
+    if (hi) {
+      float4 h, l;
+      h.x = fused_tf32_rna(pv.x); h.y = fused_tf32_rna(pv.y); h.z = fused_tf32_rna(pv.z); h.w = fused_tf32_rna(pv.w);
+      l.x = pv.x - h.x; l.y = pv.y - h.y; l.z = pv.z - h.z; l.w = pv.w - h.w;
+      reinterpret_cast<float4 *>(hi)[i] = h;
+      reinterpret_cast<float4 *>(lo)[i] = l;
+    }
   }
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
     float b = first ? 0.f : buf[i];
-    p[i] = sgd_one(p[i], g[i], b, lr, mom, wd, gs, first);
+    const float v = sgd_one(p[i], g[i], b, lr, mom, wd, gs, first);
+    p[i] = v;
     buf[i] = b;
+    if (hi) { const float h = fused_tf32_rna(v); hi[i] = h; lo[i] = v - h; }
   }
 }
 
@@ -160,12 +177,6 @@ __global__ void bias_grad_stage2(const float *__restrict__ partial, float *__res
 // tcgen05 engine.  A CTA owns a slab of <= 1024 channels (blockIdx.y) and a block of rows (blockIdx.x); threads are laid out
 // [row lane][float4 channel group] so every access is a full 128-bit coalesced row segment; column sums are kept per thread
 // and combined over the row lanes through shared memory in a fixed order (deterministic), then reduced by bias_grad_stage2.
-__device__ __forceinline__ float fused_tf32_rna(float x)
-{
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 template <int MODE>     // 0: dz = dy   1: dz = y > 0 ? dy : 0
 __global__ void __launch_bounds__(256)
@@ -393,14 +404,25 @@ int frcnn_add(const float *a, const float *b, float *out, size_t count, void *st
   return FRCNN_OK;
 }
 
-int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
-                   float grad_scale, int first_step, void *stream)
+int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                         float grad_scale, int first_step, void *param_split, void *stream)
 {
   FRCNN_REQUIRE(param && grad && momentum_buf, "sgd_step: null pointer");
   if (count == 0) return FRCNN_OK;
-  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step);
+  float *hi = nullptr, *lo = nullptr;
+  if (param_split) {
+    hi = reinterpret_cast<float *>(param_split);
+    lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(param_split) + (count * 4 + 1023) / 1024 * 1024);   // frcnn_tf32_split layout
+  }
+  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo);
   FRCNN_CHECK_LAUNCH("sgd_kernel");
   return FRCNN_OK;
+}
+
+int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                   float grad_scale, int first_step, void *stream)
+{
+  return frcnn_sgd_step_split(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, stream);
 }
 
 int frcnn_scale_rows(const float *x, const float *scale, float *out, size_t rows, size_t row_len, void *stream)

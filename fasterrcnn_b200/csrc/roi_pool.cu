@@ -1,22 +1,23 @@
 // K7: RoI max pooling forward/backward (torchvision.ops.RoIPool semantics).
 //
-// Forward: one CTA per (RoI, 128-channel slab); the feature map is NHWC so the 32 lanes of a warp
-// read 32 consecutive channels of one cell (128 B, fully coalesced).  Each thread scans its
-// channel's 49 bins in the reference's row-major order with a strict '>' so that the argmax is
-// the reference's; results are staged in shared memory as [channel][49] and written out as one
-// contiguous (128 x 49) fp32 run per slab -- i.e. directly in the (K, C, 7, 7) order that fc1
-// (models/vgg16.py:129) consumes, with 128-bit stores.
+// Forward: one CTA per (RoI, 32-channel group), 8 warps; a warp takes every 8th bin, its 32 lanes are 32 consecutive channels
+// of one NHWC cell (128 B, fully coalesced), so a RoI's cells are scanned by 16 x 8 warps in parallel instead of one thread per
+// channel walking the whole RoI.  Each bin is scanned in the reference's row-major order with a strict '>' so that the argmax
+// is the reference's; results are staged in shared memory as [channel][49] and written out as one contiguous (32 x 49) fp32
+// run -- i.e. directly in the (K, C, 7, 7) order that fc1 (models/vgg16.py:129) consumes, with 128-bit stores.
 //
-// Backward: deterministic, atomics-free.  A thread owns one (feature row h, channel c) line of
-// the gradient map in shared memory, walks every (RoI, bin) of its channel in ascending order and
-// accumulates the entries whose argmax falls on its line; the summation order per cell is
-// therefore fixed (RoI ascending, bin ascending), unlike the atomicAdd scatter of the library op.
+// Backward: deterministic, atomics-free.  A CTA owns one feature-map row h and 32 channels; its 8 warps split the RoIs into 8
+// contiguous chunks, each warp accumulating into its own [W][32] line buffer in shared memory the gradient entries of its RoIs
+// whose argmax falls on row h (a per-CTA table of clipped row ranges skips the bins that cannot), walking (RoI, bin) in
+// ascending order; the 8 buffers are then combined in chunk order.  The summation order per cell is therefore fixed, unlike
+// the atomicAdd scatter of the library op.
 #include <float.h>
 #include "common.cuh"
 
 namespace frcnn {
 
-constexpr int kSlab = 128;       // channels per CTA (forward)
+constexpr int kRoiChannels = 32;  // channels per CTA (one warp-wide NHWC segment)
+constexpr int kRoiWarps = 8;
 
 struct RoiBins {
   int ys, xs, rh, rw;
@@ -38,47 +39,47 @@ __device__ __forceinline__ RoiBins roi_bins(const float *__restrict__ p, float s
   return r;
 }
 
-__global__ void __launch_bounds__(kSlab)
+__global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
                     float *__restrict__ out, int32_t *__restrict__ argmax)
 {
-  extern __shared__ float smem[];                 // [kSlab][PH*PW] values then [kSlab][PH*PW] argmax
+  extern __shared__ float smem[];                 // [32][PH*PW] values then [32][PH*PW] argmax
   const int bins = PH * PW;
   float *s_val = smem;
-  int32_t *s_arg = reinterpret_cast<int32_t *>(smem + (size_t)kSlab * bins);
+  int32_t *s_arg = reinterpret_cast<int32_t *>(smem + (size_t)kRoiChannels * bins);
   const int n = blockIdx.x;
-  const int c0 = blockIdx.y * kSlab;
-  const int c = c0 + threadIdx.x;
+  const int c0 = blockIdx.y * kRoiChannels;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
   const RoiBins r = roi_bins(proposals + 4 * (size_t)n, scale, PH, PW);
   if (c < C) {
-    for (int ph = 0; ph < PH; ph++) {
+    for (int b = warp; b < bins; b += kRoiWarps) {
+      const int ph = b / PW, pw = b - ph * PW;
       int hs = (int)floorf(__fmul_rn((float)ph, r.bh)) + r.ys;
       int he = (int)ceilf(__fmul_rn((float)(ph + 1), r.bh)) + r.ys;
       hs = min(max(hs, 0), H); he = min(max(he, 0), H);
-      for (int pw = 0; pw < PW; pw++) {
-        int ws = (int)floorf(__fmul_rn((float)pw, r.bw)) + r.xs;
-        int we = (int)ceilf(__fmul_rn((float)(pw + 1), r.bw)) + r.xs;
-        ws = min(max(ws, 0), W); we = min(max(we, 0), W);
-        bool empty = (he <= hs) || (we <= ws);
-        float best = empty ? 0.f : -FLT_MAX;
-        int besti = -1;
-        for (int h = hs; h < he; h++) {
-          const float *row = fm + ((size_t)h * W) * C + c;
-          for (int w = ws; w < we; w++) {
-            float v = __ldg(row + (size_t)w * C);
-            if (v > best) { best = v; besti = h * W + w; }
-          }
+      int ws = (int)floorf(__fmul_rn((float)pw, r.bw)) + r.xs;
+      int we = (int)ceilf(__fmul_rn((float)(pw + 1), r.bw)) + r.xs;
+      ws = min(max(ws, 0), W); we = min(max(we, 0), W);
+      const bool empty = (he <= hs) || (we <= ws);
+      float best = empty ? 0.f : -FLT_MAX;
+      int besti = -1;
+      for (int h = hs; h < he; h++) {
+        const float *row = fm + ((size_t)h * W) * C + c;
+        for (int w = ws; w < we; w++) {
+          const float v = __ldg(row + (size_t)w * C);
+          if (v > best) { best = v; besti = h * W + w; }
         }
-        s_val[threadIdx.x * bins + ph * PW + pw] = best;
-        s_arg[threadIdx.x * bins + ph * PW + pw] = besti;
       }
+      s_val[lane * bins + b] = best;
+      s_arg[lane * bins + b] = besti;
     }
   }
   __syncthreads();
-  // contiguous write-out of the slab: out[(n*C + c0) * bins ...]
-  int live = min(kSlab, C - c0);
-  size_t base = ((size_t)n * C + c0) * bins;
-  int total = live * bins;
+  // contiguous write-out of the group: out[(n*C + c0) * bins ...]
+  const int live = min(kRoiChannels, C - c0);
+  const size_t base = ((size_t)n * C + c0) * bins;
+  const int total = live * bins;
   if (((base | (size_t)total) & 3) == 0) {
     float4 *o4 = reinterpret_cast<float4 *>(out + base);
     int4 *a4 = reinterpret_cast<int4 *>(argmax + base);
@@ -96,19 +97,17 @@ roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const flo
   }
 }
 
-// grid (C/32, ceil(H/8)); block (32 lanes = channels, 8 warps = rows).  A per-CTA table of the
-// clipped row range [hs,he) of every (RoI, ph) lets a thread visit only the bins that can hold an
-// argmax on its row (typically 7-14 of the 49), in ascending (RoI, bin) order.
-__global__ void __launch_bounds__(256)
+// grid (ceil(C/32), H); block = 8 warps x 32 channel lanes.
+__global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ argmax, const float *__restrict__ proposals, float scale,
                     int K, int H, int W, int C, int PH, int PW, const float *__restrict__ addend, float *__restrict__ dfm)
 {
-  extern __shared__ float line[];                 // [W][256] floats, then the (K x PH) row-range table
-  int32_t *rows = reinterpret_cast<int32_t *>(line + (size_t)W * 256);
+  extern __shared__ float line[];                 // [8 chunks][W][32] floats, then the (K x PH) row-range table
+  int32_t *rows = reinterpret_cast<int32_t *>(line + (size_t)kRoiWarps * W * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const int h = blockIdx.y * 8 + warp;
-  const bool live = c < C && h < H;
+  const int c0 = blockIdx.x * 32;
+  const int c = c0 + lane;
+  const int h = blockIdx.y;
   const int bins = PH * PW;
   for (int e = threadIdx.x; e < K * PH; e += blockDim.x) {
     int n = e / PH, ph = e - n * PH;
@@ -118,11 +117,14 @@ roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ 
     hs = min(max(hs, 0), H); he = min(max(he, 0), H);
     rows[e] = (hs << 16) | he;
   }
-  for (int w = 0; w < W; w++) line[w * 256 + threadIdx.x] = 0.f;
+  float *mine = line + (size_t)warp * W * 32;
+  for (int w = 0; w < W; w++) mine[w * 32 + lane] = 0.f;
   __syncthreads();
-  if (live) {
+  if (c < C) {
     const int lo = h * W, hi = lo + W;
-    for (int n = 0; n < K; n++) {
+    const int per = (K + kRoiWarps - 1) / kRoiWarps;
+    const int n_end = min(K, (warp + 1) * per);
+    for (int n = warp * per; n < n_end; n++) {
       const int32_t *a = argmax + ((size_t)n * C + c) * bins;
       const float *g = dout + ((size_t)n * C + c) * bins;
       for (int ph = 0; ph < PH; ph++) {
@@ -130,16 +132,21 @@ roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ 
         if (h < (packed >> 16) || h >= (packed & 0xffff)) continue;
         for (int pw = 0; pw < PW; pw++) {
           int idx = __ldg(a + ph * PW + pw);
-          if (idx >= lo && idx < hi) line[(idx - lo) * 256 + threadIdx.x] += __ldg(g + ph * PW + pw);
+          if (idx >= lo && idx < hi) mine[(idx - lo) * 32 + lane] += __ldg(g + ph * PW + pw);
         }
       }
     }
-    for (int w = 0; w < W; w++) {
-      size_t o = ((size_t)h * W + w) * C + c;
-      float v = line[w * 256 + threadIdx.x];
-      if (addend) v += __ldg(addend + o);
-      dfm[o] = v;
-    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < W * 32; e += blockDim.x) {
+    const int w = e >> 5, l = e & 31;
+    if (c0 + l >= C) continue;
+    float v = line[e];
+#pragma unroll
+    for (int k = 1; k < kRoiWarps; k++) v += line[(size_t)k * W * 32 + e];          // chunk order: RoIs ascending
+    const size_t o = ((size_t)h * W + w) * C + c0 + l;
+    if (addend) v += __ldg(addend + o);
+    dfm[o] = v;
   }
 }
 
@@ -154,13 +161,13 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
 {
   FRCNN_REQUIRE(fm && proposals && out && H > 0 && W > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0, "roi_pool_fwd: bad argument");
   if (K == 0) return FRCNN_OK;
-  size_t smem = (size_t)kSlab * PH * PW * (sizeof(float) + sizeof(int32_t));
+  size_t smem = (size_t)kRoiChannels * PH * PW * (sizeof(float) + sizeof(int32_t));
   FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_fwd: pooled size too large");
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_pool_fwd: smem attribute");
   }
-  roi_pool_fwd_kernel<<<dim3(K, ceil_div(C, kSlab)), kSlab, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
+  roi_pool_fwd_kernel<<<dim3(K, ceil_div(C, kRoiChannels)), kRoiWarps * 32, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
   FRCNN_CHECK_LAUNCH("roi_pool_fwd_kernel");
   return FRCNN_OK;
 }
@@ -170,13 +177,13 @@ int frcnn_roi_pool_bwd(const float *dout, const int32_t *argmax, const float *pr
 {
   FRCNN_REQUIRE(dout && argmax && proposals && dfm && K >= 0 && H > 0 && W > 0 && C > 0 && PH > 0 && PW > 0, "roi_pool_bwd: bad argument");
   FRCNN_REQUIRE(H < 32768, "roi_pool_bwd: feature map too tall");
-  size_t smem = (size_t)W * 256 * sizeof(float) + (size_t)K * PH * sizeof(int32_t);
+  size_t smem = (size_t)kRoiWarps * W * 32 * sizeof(float) + (size_t)K * PH * sizeof(int32_t);
   FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_bwd: feature map too wide / too many RoIs for the shared-memory buffers");
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roi_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_pool_bwd: smem attribute");
   }
-  roi_pool_bwd_kernel<<<dim3(ceil_div(C, 32), ceil_div(H, 8)), 256, smem, as_stream(stream)>>>(dout, argmax, proposals, spatial_scale, K, H, W, C, PH, PW, addend, dfm);
+  roi_pool_bwd_kernel<<<dim3(ceil_div(C, 32), H), kRoiWarps * 32, smem, as_stream(stream)>>>(dout, argmax, proposals, spatial_scale, K, H, W, C, PH, PW, addend, dfm);
   FRCNN_CHECK_LAUNCH("roi_pool_bwd_kernel");
   return FRCNN_OK;
 }

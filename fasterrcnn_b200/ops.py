@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, check, lib, ptr, stream, workspace
 
 import os as _os
+import weakref
 
 _ENGINES = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32}
 _engine = {"value": _ENGINES[_os.environ.get("FRCNN_ENGINE", "auto")]}
@@ -154,8 +155,32 @@ def _uses_tc(pass_, geom):
   return r
 
 
+# Weights updated by the fused optimizer carry their operand split with them: frcnn_sgd_step_split writes the updated weights'
+# [hi | lo] into a per-parameter buffer in the same pass, so the next step's GEMMs need no split pass over (for VGG-16) 547 MB of
+# weights.  Entries are keyed by storage address and validated against the parameter's address / version, so a weight that was
+# changed any other way (load_state_dict, .cuda(), a torch optimizer) simply falls back to the per-step split below.
+_weight_splits = {}            # (data_ptr, numel) -> dict(ref = weakref(param), buf, version)
+
+
+def weight_split_buffer(param):
+  """Per-parameter [hi | lo] buffer for sgd_step(..., split_out =); (re)allocated when the parameter's storage moved."""
+  key = (param.data_ptr(), param.numel())
+  e = _weight_splits.get(key)
+  if e is None or e["ref"]() is not param:
+    for k in [k for k, v in _weight_splits.items() if v["ref"]() is None or v["ref"]() is param]:
+      del _weight_splits[k]                                        # dead parameters and this parameter's old address
+    e = dict(ref = weakref.ref(param), buf = t.empty((lib().frcnn_tf32_split_bytes(param.numel()),), dtype = t.uint8, device = param.device), version = -1)
+    _weight_splits[key] = e
+  return e
+
+
 def tf32_split(x, cache = True):
   """Returns the [hi | lo] split buffer of x (frcnn_tf32_split), computing it at most once per tensor version."""
+  e = _weight_splits.get((x.data_ptr(), x.numel()))
+  if e is not None:
+    p = e["ref"]()
+    if p is not None and p.data_ptr() == x.data_ptr() and p._version == e["version"]:
+      return e["buf"]
   key = (x.data_ptr(), x.numel(), x._version)
   hit = _split_cache.get(key)
   if hit is not None:
@@ -769,9 +794,15 @@ def detect_postprocess(proposals, classes, deltas, image_hw, score_threshold, io
   return result
 
 
-def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale = 1.0, first_step = False):
+def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale = 1.0, first_step = False, carry_split = False):
+  """torch.optim.SGD's update (momentum, L2 weight decay) in one kernel, in place.  carry_split: also write the updated weights'
+  tf32 operand split into the parameter's persistent buffer (see _weight_splits)."""
   _require_cuda(param, grad, momentum_buf)
   assert param.is_contiguous() or param.is_contiguous(memory_format = t.channels_last)
   assert grad.stride() == param.stride() and momentum_buf.stride() == param.stride()
-  check(lib().frcnn_sgd_step(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step), stream()), "frcnn_sgd_step")
+  e = weight_split_buffer(param) if carry_split else None
+  check(lib().frcnn_sgd_step_split(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step),
+                                   ptr(e["buf"]) if e is not None else None, stream()), "frcnn_sgd_step_split")
+  if e is not None:
+    e["version"] = param._version                                  # the raw-pointer update does not bump torch's version counter
   _lib.count()

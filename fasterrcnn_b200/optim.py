@@ -37,7 +37,8 @@ class FusedSGD(t.optim.Optimizer):
         g = p.grad
         if g.stride() != p.stride():
           g = g.contiguous(memory_format = t.channels_last) if p.dim() == 4 and not p.is_contiguous() else g.contiguous()
-        ops.sgd_step(p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], self.grad_scale, first)
+        # matrices / filters feed the tcgen05 GEMMs next step: their operand split is produced by the same kernel
+        ops.sgd_step(p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], self.grad_scale, first, carry_split = p.dim() >= 2 and p.numel() >= 4096)
 
 
 class DataParallel:

@@ -230,6 +230,10 @@ int frcnn_detector_losses(const float *probs, const float *deltas, const float *
  * g = grad*grad_scale + wd*p; buf = first_step ? g : momentum*buf + g; p -= lr*buf. */
 int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
                    float grad_scale, int first_step, void *stream);
+/* Same update; additionally writes the UPDATED weights' tf32 [hi | lo] operand split (layout of frcnn_tf32_split, param_split
+ * may be NULL) so the next step's tcgen05 GEMMs do not need a separate split pass over the weights. */
+int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                         float grad_scale, int first_step, void *param_split, void *stream);
 
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one

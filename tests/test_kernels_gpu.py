@@ -172,7 +172,9 @@ def test_rpn_proposal_stage_matches_reference_golden(ops, golden_dir, tag):
   # ordering: bit-exact indices (scores are distinct by construction)
   assert np.array_equal(dbg["order"].cpu().numpy().astype(np.int64), taps["order"])
   # decode: <= 1e-4 px on clipped coordinates (expf is correctly rounded here, SLEEF u10 on the CPU)
-  np.testing.assert_allclose(dbg["boxes_sorted"].cpu().numpy(), taps["pre_nms_boxes"], rtol = 0, atol = 1e-4)
+  got, want = dbg["boxes_sorted"].cpu().numpy(), taps["pre_nms_boxes"]
+  bad = np.argwhere(np.abs(got - want) > 1e-4)
+  assert bad.shape[0] == 0, "decode mismatch at (row, col) %s: got %s want %s" % (bad[:4].tolist(), got[bad[:4, 0]].tolist(), want[bad[:4, 0]].tolist())
   assert props.shape == ref.shape
   np.testing.assert_allclose(props.cpu().numpy(), ref.numpy(), rtol = 0, atol = 1e-4)
 
