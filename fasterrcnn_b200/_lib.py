@@ -106,7 +106,13 @@ def check(status, what):
     raise FrcnnError("%s failed with status %d: %s" % (what, status, msg.decode() if msg else "?"))
 
 
+_raw_stream = getattr(t._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+  """cudaStream_t of torch's current stream on the current device (the C ABI launches on it)."""
+  if _raw_stream is not None:
+    return _raw_stream(t.cuda.current_device())          # one C call instead of building a torch.cuda.Stream object per launch
   return t.cuda.current_stream().cuda_stream
 
 

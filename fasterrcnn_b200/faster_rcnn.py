@@ -61,7 +61,8 @@ class FasterRCNNModel(nn.Module):
 
   # ---- faster_rcnn.py:228-362 --------------------------------------------------------------------
   def train_step(self, optimizer, image_data, anchor_map, anchor_valid_map, gt_rpn_map, gt_rpn_object_indices, gt_rpn_background_indices, gt_boxes):
-    self.train()
+    if not self.training:
+      self.train()
     optimizer.zero_grad()
     assert image_data.shape[0] == 1, "Batch size must be 1"
     assert len(gt_rpn_map.shape) == 5 and gt_rpn_map.shape[0] == 1, "Batch size must be 1"
@@ -75,26 +76,34 @@ class FasterRCNNModel(nn.Module):
 
     # Everything up to the proposal labels is enqueued without a host round trip: the proposal count stays on the device, the
     # GT boxes are appended behind it there (faster_rcnn.py:467), labels are computed for every row of the padded buffer.
-    feature_map = self._stage1_feature_extractor(image_data = image_data)
+    backbone_map = self._stage1_feature_extractor(image_data = image_data)
+    # The two consumers of the shared feature map are back-propagated separately (the RPN branch early, see below), each leaving
+    # its gradient on this detached leaf; the backbone then gets their sum -- the same two-term sum autograd would form.
+    feature_map = backbone_map.detach().requires_grad_(True) if backbone_map.requires_grad else backbone_map
     rpn_score_map, rpn_box_deltas_map, (padded, count) = self._stage2_region_proposal_network(
       feature_map = feature_map, image_shape = image_shape, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map,
       max_proposals_pre_nms = 12000, max_proposals_post_nms = 2000, deferred_extra_rows = len(gt))
 
     # host work that needs nothing from the device overlaps the backbone / RPN kernels queued above
     gt_rpn_minibatch_map = self._sample_rpn_minibatch(rpn_map = gt_rpn_map, object_indices = gt_rpn_object_indices, background_indices = gt_rpn_background_indices)
-    gt_box_corners = t.from_numpy(np.array([box.corners for box in gt], dtype = np.float32).reshape(-1, 4)).to(dev)
-    gt_box_class_idxs = t.tensor([box.class_index for box in gt], dtype = t.int32, device = dev)
+    # small host arrays go up through page-locked staging buffers: a cudaMemcpyAsync from PAGEABLE memory first synchronises the
+    # stream, which would stall the host here until the previous step's backward has drained
+    gt_box_corners = self._upload("gt_corners", np.array([box.corners for box in gt], dtype = np.float32).reshape(-1, 4), dev)
+    gt_box_class_idxs = self._upload("gt_classes", np.array([box.class_index for box in gt], dtype = np.int32), dev)
     ops.append_rows(padded, count, gt_box_corners)
     _, class_idx, gt_classes, gt_box_deltas = ops.label_proposals(padded, gt_box_corners, gt_box_class_idxs, self._num_classes, 0.5)
 
-    # the step's one mid-step synchronisation: proposal count + class labels in a single pinned read-back; the RPN losses are
-    # queued behind it so the device has work while the host draws the samples
+    # the step's one mid-step synchronisation: proposal count + class labels in a single pinned read-back.  The RPN losses AND the
+    # whole backward of the RPN branch (which needs nothing from the detector) are queued behind it, so the device has ~0.4 ms of
+    # work while the host draws the samples and launches the detector
     fetch = self._pinned("fetch", (1 + padded.shape[0],), t.int32)
     fetch[0:1].copy_(count, non_blocking = True)
     fetch[1:].copy_(class_idx, non_blocking = True)
     fetched = t.cuda.Event()
     fetched.record()
     rpn_l = ops.rpn_losses(rpn_score_map, rpn_box_deltas_map, gt_rpn_minibatch_map)                # (class, regression)
+    ones = self._ones2(dev)
+    t.autograd.backward([rpn_l], [ones])                                                           # d(total)/d(loss) = 1 for every term
     fetched.synchronize()
     n = int(fetch[0]) + len(gt)                                                                    # proposals + appended GT boxes
     indices = self._sample_proposal_indices(fetch[1:1 + n].numpy(), self._proposal_batch_size, 0.25)
@@ -116,16 +125,18 @@ class FasterRCNNModel(nn.Module):
       gt_box_deltas = ops.gather_rows(gt_box_deltas, sample_dev[1:], sample_dev[0:1], k)
 
     det_l = ops.detector_losses(detector_classes, detector_box_deltas, gt_classes, gt_box_deltas)    # (class, regression)
-    all_l = t.cat([rpn_l, det_l])
-    total_loss = all_l.sum()
+    all_l = t.cat([rpn_l.detach(), det_l.detach()])
     # The five numbers are final once the forward kernels have run: their read-back is queued NOW, in front of the backward and
     # optimizer kernels, and only its event is awaited at the end -- train_step returns with the backward still in flight, so the
     # next step's launches queue up behind it and the device never drains between steps.
     loss_host = self._pinned("loss", (5,), t.float32)
-    loss_host.copy_(t.cat([all_l.detach(), total_loss.detach().reshape(1)]), non_blocking = True)
+    loss_host.copy_(t.cat([all_l, all_l.sum().reshape(1)]), non_blocking = True)
     loss_ready = t.cuda.Event()
     loss_ready.record()
-    total_loss.backward()
+    if det_l.requires_grad:
+      t.autograd.backward([det_l], [ones])                                                         # detector branch -> its params, feature_map.grad
+    if feature_map is not backbone_map and feature_map.grad is not None:
+      backbone_map.backward(feature_map.grad)                                                      # both branches' gradient into the backbone
     ops.begin_step()                       # operand splits of this step's weights are stale after the update
     optimizer.step()
 
@@ -133,6 +144,28 @@ class FasterRCNNModel(nn.Module):
     host = loss_host.numpy()
     self.last_step_info = dict(num_rois = int(proposals.shape[0]))
     return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host[4]))
+
+  def _ones2(self, device):
+    cache = self.__dict__.setdefault("_ones2_cache", {})
+    key = str(device)
+    if key not in cache:
+      cache[key] = t.ones((2,), dtype = t.float32, device = device)
+    return cache[key]
+
+  def _upload(self, name, array, device):
+    """Asynchronous host-to-device copy of a small numpy array through a reusable page-locked buffer.  Two buffers per name,
+    alternated per call: the previous call's copy is ordered before this step's mid-step synchronisation, so a buffer is never
+    rewritten while its copy is still pending."""
+    flip = self.__dict__.setdefault("_upload_flip", {})
+    flip[name] = 1 - flip.get(name, 0)
+    src = t.from_numpy(np.ascontiguousarray(array))
+    capacity = 64
+    while capacity < src.numel():
+      capacity *= 2                                                   # size classes keep the set of pinned allocations small
+    staging = self._pinned((name, flip[name]), (capacity,), src.dtype)
+    view = staging[:src.numel()].view(src.shape)
+    view.copy_(src)
+    return view.to(device, non_blocking = True)
 
   def _pinned(self, name, shape, dtype):
     """Reusable page-locked host buffer for the small device-to-host reads of train_step."""
@@ -161,11 +194,11 @@ class FasterRCNNModel(nn.Module):
     trainable = np.concatenate([np.asarray(positive_anchors)[positive_anchor_idxs], np.asarray(negative_anchors)[negative_anchor_idxs]])
     _, fh, fw, k, _ = rpn_map.shape
     flat = (trainable[:, 0] * fw + trainable[:, 1]) * k + trainable[:, 2]
-    flat_dev = t.from_numpy(flat.astype(np.int64)).to(rpn_map.device, non_blocking = True)
+    flat_dev = self._upload("rpn_minibatch", flat.astype(np.int64), rpn_map.device)
     minibatch = rpn_map.clone()
     mask = minibatch.view(-1, 6)[:, 0]
     mask.zero_()
-    mask[flat_dev] = 1.0
+    mask.index_fill_(0, flat_dev, 1.0)          # (mask[idx] = 1.0 would upload the scalar from pageable memory: a hidden stream sync)
     return minibatch
 
   # ---- faster_rcnn.py:418-524 --------------------------------------------------------------------
