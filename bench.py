@@ -96,7 +96,7 @@ class ClockSampler:
 
   def start(self):
     try:
-      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                                    stdout = subprocess.PIPE, stderr = subprocess.DEVNULL, text = True)
     except Exception:
       self.proc = None

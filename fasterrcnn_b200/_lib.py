@@ -69,6 +69,9 @@ _SIGNATURES = {
   "frcnn_softmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),
   "frcnn_softmax_rows_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
   "frcnn_detector_losses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+  "frcnn_heads_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+  "frcnn_heads_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+  "frcnn_heads_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
   "frcnn_sgd_step": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp]),
   "frcnn_sgd_step_split": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp, _vp]),
   "frcnn_detect_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _vp, _vp, _vp]),

@@ -28,9 +28,9 @@ class DetectorNetwork(nn.Module):
     assert feature_map.shape[0] == 1, "Batch size must be 1"
     rois = ops.roi_pool(feature_map, proposals, (7, 7), self._spatial_scale)
     y = self._pool_to_feature_vector(rois = rois)
-    classes_raw = ops.linear_act(y, self._classifier.weight, self._classifier.bias, ops.ACT_NONE)
+    # class logits (21) and box deltas (80) are one narrow GEMM over the feature vectors
+    classes_raw, box_deltas = ops.two_heads(y, self._classifier.weight, self._classifier.bias, ops.ACT_NONE, self._regressor.weight, self._regressor.bias, ops.ACT_NONE)
     classes = ops.softmax_rows(classes_raw)
-    box_deltas = ops.linear_act(y, self._regressor.weight, self._regressor.bias, ops.ACT_NONE)
     return classes, box_deltas
 
 

@@ -460,6 +460,61 @@ def linear_act(x, weight, bias, act = ACT_NONE):
   return _LinearAct.apply(x, weight, bias, act)
 
 
+class _TwoHeads(t.autograd.Function):
+  """(y1, y2) = (act1(x w1^T + b1), act2(x w2^T + b2)) for two narrow heads sharing the input rows x (M, K): frcnn_heads_fwd / _bwd.
+  x may be a 4-D NHWC-physical activation (rows = pixels) or a 2-D matrix; outputs are (M, N1) / (M, N2) row-major."""
+
+  @staticmethod
+  def forward(ctx, x, w1, b1, act1, w2, b2, act2):
+    _require_cuda(x, w1, w2)
+    xp = _phys_nhwc(x.detach()) if x.dim() == 4 else x.detach().contiguous()
+    k = xp.shape[1]
+    m = xp.numel() // k
+    n1, n2 = w1.shape[0], w2.shape[0]
+    y1 = t.empty((m, n1), dtype = t.float32, device = x.device)
+    y2 = t.empty((m, n2), dtype = t.float32, device = x.device)
+    L = lib()
+    if m > 0:
+      ws, ws_n = workspace(L.frcnn_heads_workspace_bytes(m, k, n1, n2), slot = 1)
+      check(L.frcnn_heads_fwd(ptr(xp), m, k, ptr(w1.detach()), ptr(b1.detach()) if b1 is not None else None, n1, act1,
+                              ptr(w2.detach()), ptr(b2.detach()) if b2 is not None else None, n2, act2, ptr(y1), ptr(y2), ws, ws_n, stream()), "frcnn_heads_fwd")
+      _lib.count(2)
+    ctx.acts = (act1, act2)
+    ctx.has_bias = (b1 is not None, b2 is not None)
+    ctx.x_is_map = x.dim() == 4
+    ctx.save_for_backward(xp, w1.detach(), w2.detach(), y1, y2)
+    return y1, y2
+
+  @staticmethod
+  def backward(ctx, dy1, dy2):
+    xp, w1, w2, y1, y2 = ctx.saved_tensors
+    k = xp.shape[1]
+    m = xp.numel() // k
+    n1, n2 = w1.shape[0], w2.shape[0]
+    dev = xp.device
+    dw1 = t.empty_strided(w1.shape, w1.stride(), dtype = t.float32, device = dev)
+    dw2 = t.empty_strided(w2.shape, w2.stride(), dtype = t.float32, device = dev)
+    db1 = t.empty((n1,), dtype = t.float32, device = dev) if ctx.has_bias[0] else None
+    db2 = t.empty((n2,), dtype = t.float32, device = dev) if ctx.has_bias[1] else None
+    dx = None
+    if m == 0:
+      return (t.zeros_like(xp) if ctx.needs_input_grad[0] else None), dw1.zero_(), (db1.zero_() if db1 is not None else None), None, dw2.zero_(), (db2.zero_() if db2 is not None else None), None
+    if ctx.needs_input_grad[0]:
+      dx = t.empty_like(xp)                                   # same physical layout as x (NHWC rows / matrix)
+    dy1 = dy1.contiguous() if dy1 is not None else t.zeros_like(y1)
+    dy2 = dy2.contiguous() if dy2 is not None else t.zeros_like(y2)
+    L = lib()
+    ws, ws_n = workspace(L.frcnn_heads_workspace_bytes(m, k, n1, n2), slot = 1)
+    check(L.frcnn_heads_bwd(ptr(xp), m, k, ptr(w1), n1, ctx.acts[0], ptr(y1), ptr(dy1), ptr(w2), n2, ctx.acts[1], ptr(y2), ptr(dy2),
+                            ptr(dx), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ws, ws_n, stream()), "frcnn_heads_bwd")
+    _lib.count(4)
+    return dx, dw1, db1, None, dw2, db2, None
+
+
+def two_heads(x, w1, b1, act1, w2, b2, act2):
+  return _TwoHeads.apply(x, w1, b1, act1, w2, b2, act2)
+
+
 class _RoIPool(t.autograd.Function):
   @staticmethod
   def forward(ctx, feature_map, proposals, output_size, spatial_scale):

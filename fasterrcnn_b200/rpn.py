@@ -32,10 +32,12 @@ class RegionProposalNetwork(nn.Module):
     (capacity-padded proposals with that many spare rows, device-side count) and no host synchronisation happens here."""
     assert feature_map.shape[0] == 1                                      # rpn.py:159
     y = ops.conv2d_act(feature_map, self._rpn_conv1.weight, self._rpn_conv1.bias, 1, 1, ops.ACT_RELU)
-    scores = ops.conv2d_act(y, self._rpn_class.weight, self._rpn_class.bias, 1, 0, ops.ACT_SIGMOID)
-    deltas = ops.conv2d_act(y, self._rpn_boxes.weight, self._rpn_boxes.bias, 1, 0, ops.ACT_NONE)
-    objectness_score_map = scores.permute(0, 2, 3, 1).contiguous()         # already NHWC in memory: no copy
-    box_deltas_map = deltas.permute(0, 2, 3, 1).contiguous()
+    # the two 1x1 heads (9 sigmoid scores, 36 deltas) are one narrow GEMM over the pixels' 512-channel rows; its row-major
+    # outputs ARE the (1,H,W,9) / (1,H,W,36) maps the reference permutes into (rpn.py:95-96)
+    scores, deltas = ops.two_heads(y, self._rpn_class.weight, self._rpn_class.bias, ops.ACT_SIGMOID, self._rpn_boxes.weight, self._rpn_boxes.bias, ops.ACT_NONE)
+    fh, fw = int(y.shape[2]), int(y.shape[3])
+    objectness_score_map = scores.view(1, fh, fw, scores.shape[1])
+    box_deltas_map = deltas.view(1, fh, fw, deltas.shape[1])
 
     anchors_dev, keep_mask = self._resolve_anchors(anchor_map, anchor_valid_map, image_shape, objectness_score_map.shape[1:3], feature_map.device)
     proposals = ops.rpn_proposals(

@@ -217,6 +217,19 @@ int frcnn_rpn_losses(const float *scores, const float *deltas, const float *y_tr
                      float *losses_out, float *d_scores, float *d_deltas, void *stream);
 /* dz = dy * (1 - y) * y  (t.sigmoid backward, models/rpn.py:89). */
 int frcnn_sigmoid_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
+/* ---- two narrow heads on one shared input: y1 = act1(x w1^T + b1), y2 = act2(x w2^T + b2) ------------------------------
+ * Replaces the pairs of third-party calls `t.sigmoid(conv1x1(y))` + `conv1x1(y)` of the RPN (models/rpn.py:89-90; x = the (H*W, 512)
+ * NHWC rows of the 3x3 conv's output, outputs = the (1,H,W,9) / (1,H,W,36) maps) and `Linear` + `Linear` of the detector
+ * (models/detector.py:76-78; x (N, 4096), outputs (N, 21) logits / (N, 80) box deltas) -- GEMMs too narrow (45 / 101 columns) for
+ * the implicit-GEMM engines -- and their autograd backward: dx (may be NULL), dw*, db* (db may be NULL); y1 / y2 are the forward
+ * outputs (needed for a sigmoid head).  x (M, K) row-major, K % 4 == 0; weights (N, K) row-major; N2 may be 0. */
+size_t frcnn_heads_workspace_bytes(int M, int K, int N1, int N2);
+int frcnn_heads_fwd(const float *x, int M, int K, const float *w1, const float *b1, int N1, int act1, const float *w2, const float *b2, int N2, int act2,
+                    float *y1, float *y2, void *workspace, size_t workspace_bytes, void *stream);
+int frcnn_heads_bwd(const float *x, int M, int K, const float *w1, int N1, int act1, const float *y1, const float *dy1,
+                    const float *w2, int N2, int act2, const float *y2, const float *dy2,
+                    float *dx, float *dw1, float *db1, float *dw2, float *db2, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Detector (models/detector.py:76-78,83-155): logits (n, C) -> classes = softmax (written to
  * classes_out), deltas (n, 4(C-1)), y_classes (n, C) one-hot, y_deltas (n,2,4(C-1)).
  * losses_out[0] = class loss, [1] = regression loss; d_probs (n,C) = dL/d(softmax output),

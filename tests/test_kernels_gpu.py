@@ -457,3 +457,37 @@ def test_act_bwd_fused_matches_separate_passes(ops, rows, c, act):
     db2 = t.full((c,), 7.0, device = "cuda")
     check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y), code, None, ptr(split), None, rows, c, None, 0, stream()), "frcnn_act_bwd_fused")
     assert t.equal(split[:dy.numel() * 4].view(t.float32).view(rows, c), hi) and float(db2[0]) == 7.0
+
+
+@pytest.mark.parametrize("m,k,n1,n2,act1", [(23 * 37, 512, 9, 36, "sigmoid"), (128, 4096, 21, 80, "none"), (5, 2048, 21, 80, "none"), (300, 4096, 21, 80, "none")])
+def test_two_heads_vs_torch(ops, m, k, n1, n2, act1):
+  """frcnn_heads_fwd / _bwd (the RPN's two 1x1 convs, the detector's two linears) against torch fp32: forward, dx, dw, db within
+  summation-order noise on random data, bit-exact on small integers (linear heads)."""
+  g = t.Generator().manual_seed(m + k)
+  code = ops.ACT_SIGMOID if act1 == "sigmoid" else ops.ACT_NONE
+  for integer in (False, True):
+    if integer:
+      x = _int_tensor(g, (m, k), -2, 2); w1 = _int_tensor(g, (n1, k), -1, 1); w2 = _int_tensor(g, (n2, k), -1, 1)
+      b1 = _int_tensor(g, (n1,), -3, 3); b2 = _int_tensor(g, (n2,), -3, 3)
+      g1 = _int_tensor(g, (m, n1), -1, 1); g2 = _int_tensor(g, (m, n2), -1, 1)
+    else:
+      x = t.randn((m, k), generator = g); w1 = t.randn((n1, k), generator = g) * k ** -0.5; w2 = t.randn((n2, k), generator = g) * k ** -0.5
+      b1 = t.randn((n1,), generator = g) * 0.1; b2 = t.randn((n2,), generator = g) * 0.1
+      g1 = t.randn((m, n1), generator = g); g2 = t.randn((m, n2), generator = g)
+    ref = [v.clone().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
+    r1 = F.linear(ref[0], ref[1], ref[2]); r2 = F.linear(ref[0], ref[3], ref[4])
+    if act1 == "sigmoid":
+      r1 = t.sigmoid(r1)
+    (r1 * g1).sum().backward(retain_graph = True); (r2 * g2).sum().backward()
+    dev = [v.cuda().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
+    y1, y2 = ops.two_heads(dev[0], dev[1], dev[2], code, dev[3], dev[4], ops.ACT_NONE)
+    t.autograd.backward([y1, y2], [g1.cuda(), g2.cuda()])
+    exact = integer and act1 != "sigmoid"
+    pairs = [(y1, r1), (y2, r2)] + [(d.grad, r.grad) for d, r in zip(dev, ref)]
+    for got, want in pairs:
+      got, want = got.detach().cpu(), want.detach()
+      if exact:
+        assert t.equal(got, want)
+      else:
+        scale = max(float(want.abs().max()), 1e-6)
+        assert float((got - want).abs().max()) <= 2e-5 * scale + 1e-6
