@@ -87,42 +87,59 @@ def init_weights(model, seed):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-  QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+  """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): an NVML polling thread (one sample every
+  ~5 ms, so a 20-step region of ~150 ms still yields tens of samples; `nvidia-smi -lms` needs ~100 ms before its first line)."""
+  REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
   def __init__(self, gpu_index):
     self.gpu_index = gpu_index
-    self.proc = None
+    self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+    self.thread, self.stop_flag, self.error = None, False, None
+
+  def _physical_index(self):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+      ids = [v.strip() for v in vis.split(",") if v.strip()]
+      if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+        return int(ids[self.gpu_index])
+    return self.gpu_index
 
   def start(self):
+    import threading
     try:
-      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
-                                   stdout = subprocess.PIPE, stderr = subprocess.DEVNULL, text = True)
-    except Exception:
-      self.proc = None
+      import pynvml
+      pynvml.nvmlInit()
+      h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception as e:                                         # noqa: BLE001
+      self.error = "nvml unavailable: %s" % e
+      return
+
+    def poll():
+      while not self.stop_flag:
+        try:
+          self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+          bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+          for name, bit in self.REASONS:
+            if bits & bit:
+              self.reasons.add(name)
+          self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+        except Exception as e:                                     # noqa: BLE001
+          self.error = str(e)
+          return
+        time.sleep(0.005)
+
+    self.thread = threading.Thread(target = poll, daemon = True)
+    self.thread.start()
 
   def stop(self):
-    if self.proc is None:
-      return dict(sm_mhz = None, sm_max_mhz = None, reasons = ["nvidia-smi unavailable"])
-    self.proc.terminate()
-    try:
-      out, _ = self.proc.communicate(timeout = 5)
-    except Exception:
-      self.proc.kill()
-      out = ""
-    sm, mx, reasons = [], [], set()
-    for line in out.strip().splitlines():
-      f = [x.strip() for x in line.split(",")]
-      if len(f) < 9:
-        continue
-      try:
-        sm.append(float(f[1])); mx.append(float(f[2]))
-      except ValueError:
-        continue
-      for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-        if val.lower().startswith("active"):
-          reasons.add(name)
-    return dict(sm_mhz = statistics.median(sm) if sm else None, sm_max_mhz = max(mx) if mx else None, reasons = sorted(reasons), samples = len(sm))
+    self.stop_flag = True
+    if self.thread is not None:
+      self.thread.join(timeout = 2)
+    if not self.sm:
+      return dict(sm_mhz = None, sm_max_mhz = self.max_mhz, reasons = [self.error or "no samples"], samples = 0)
+    return dict(sm_mhz = statistics.median(self.sm), sm_min_mhz = min(self.sm), sm_max_mhz = self.max_mhz, reasons = sorted(self.reasons), samples = len(self.sm),
+                power_w_max = max(self.power) if self.power else None, how = "NVML polled every ~5 ms during the timed region")
 
 
 # ------------------------------------------------------------------------------------------------

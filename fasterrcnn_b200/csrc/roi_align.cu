@@ -3,9 +3,11 @@
 // this op.  Feature map NHWC, proposals (y1,x1,y2,x2), output (K,C,PH,PW).
 //
 // Forward: one CTA per (RoI, 128-channel slab).  The PH*PW*S*S bilinear taps of the RoI (4 corner offsets + 4
-// weights each) are computed ONCE into shared memory by the CTA and then reused by every channel thread; the 32
-// lanes of a warp read 32 consecutive channels of each corner (coalesced 128 B); results are staged in shared
-// memory and written out as one contiguous (128 x PH*PW) run, exactly like roi_pool.cu.
+// weights each) are computed ONCE into shared memory by the CTA and then reused by every warp.  C % 4 == 0
+// (roi_align_fwd_v4_kernel): 8 warps, a warp takes every 8th bin, its 32 lanes read 4 consecutive channels each
+// (one 512-byte NHWC segment per warp-wide 128-bit load; the S*S*4 corner loads of a bin are independent, so
+// 16 vector loads per lane are in flight against the L2-resident map); otherwise one channel per thread.  Results
+// are staged in shared memory and streamed out as one contiguous (128 x PH*PW) run, exactly like roi_pool.cu.
 // Backward: deterministic and atomics-free -- a thread owns one (feature row, channel) line, rebuilds the tap table
 // per RoI in shared memory and accumulates the taps that land on its row in ascending (RoI, bin, sample) order.
 #include <math.h>
@@ -106,6 +108,97 @@ roi_align_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const fl
   for (int e = threadIdx.x; e < live * bins; e += blockDim.x) out[base + e] = s_val[e];
 }
 
+// ---- forward, 4 channels per lane; same operation order per channel as the scalar kernel ------------------------------
+constexpr int kAlignWarps = 8;
+
+// volatile: keeps the corner loads of a round back to back (see roi_pool.cu)
+__device__ __forceinline__ float4 ldg_nc_v4(const float4 *p)
+{
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void tap_fma4(float4 &v, float w, const float4 f, bool first)
+{
+  if (first) { v.x = __fmul_rn(w, f.x); v.y = __fmul_rn(w, f.y); v.z = __fmul_rn(w, f.z); v.w = __fmul_rn(w, f.w); }
+  else {
+    v.x = __fadd_rn(v.x, __fmul_rn(w, f.x)); v.y = __fadd_rn(v.y, __fmul_rn(w, f.y));
+    v.z = __fadd_rn(v.z, __fmul_rn(w, f.z)); v.w = __fadd_rn(v.w, __fmul_rn(w, f.w));
+  }
+}
+
+__global__ void __launch_bounds__(kAlignWarps * 32)
+roi_align_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, int S, float scale,
+                        int aligned, float *__restrict__ out)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const int bins = PH * PW, ss = S * S, taps = bins * ss;
+  Tap *tab = reinterpret_cast<Tap *>(smem_raw);
+  float *s_val = reinterpret_cast<float *>(tab + taps);
+  const int n = blockIdx.x, c0 = blockIdx.y * kAlignSlab;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + 4 * lane;
+  const RoiGeom r = roi_geom(proposals + 4 * (size_t)n, scale, PH, PW, aligned);
+  for (int e = threadIdx.x; e < taps; e += blockDim.x) {
+    int s = e % ss, b = e / ss;
+    int rows[2];
+    float y, x;
+    sample_xy(r, b / PW, b % PW, s / S, s % S, S, &y, &x);
+    tab[e] = make_tap(y, x, H, W, rows);
+  }
+  __syncthreads();
+  if (c < C) {
+    const float4 *fm4 = reinterpret_cast<const float4 *>(fm + c);
+    const int C4 = C >> 2;
+    const float count = (float)ss;
+    for (int b = warp; b < bins; b += kAlignWarps) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // two samples (eight corner loads, issued back to back) per round; a sample outside the map keeps its place in the
+      // sequence but reads cell 0 and is not accumulated (the table is per RoI, so the skip is warp-uniform)
+      for (int s = 0; s < ss; s += 2) {
+        Tap tp[2];
+        float4 f[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          tp[u] = tab[b * ss + min(s + u, ss - 1)];
+          if (s + u >= ss) tp[u].o00 = -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const bool ok = tp[u].o00 >= 0;
+          f[u][0] = ldg_nc_v4(fm4 + (size_t)(ok ? tp[u].o00 : 0) * C4);
+          f[u][1] = ldg_nc_v4(fm4 + (size_t)(ok ? tp[u].o01 : 0) * C4);
+          f[u][2] = ldg_nc_v4(fm4 + (size_t)(ok ? tp[u].o10 : 0) * C4);
+          f[u][3] = ldg_nc_v4(fm4 + (size_t)(ok ? tp[u].o11 : 0) * C4);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (tp[u].o00 < 0) continue;
+          float4 v;
+          tap_fma4(v, tp[u].w00, f[u][0], true);
+          tap_fma4(v, tp[u].w01, f[u][1], false);
+          tap_fma4(v, tp[u].w10, f[u][2], false);
+          tap_fma4(v, tp[u].w11, f[u][3], false);
+          acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        }
+      }
+      const int o = (4 * lane) * bins + b;
+      s_val[o] = __fdiv_rn(acc.x, count);                           // output_val /= count
+      s_val[o + bins] = __fdiv_rn(acc.y, count);
+      s_val[o + 2 * bins] = __fdiv_rn(acc.z, count);
+      s_val[o + 3 * bins] = __fdiv_rn(acc.w, count);
+    }
+  }
+  __syncthreads();
+  const int live = min(kAlignSlab, C - c0);
+  const size_t base = ((size_t)n * C + c0) * bins;
+  const int total4 = (live * bins) >> 2;
+  float4 *o4 = reinterpret_cast<float4 *>(out + base);
+  const float4 *sv4 = reinterpret_cast<const float4 *>(s_val);
+  for (int e = threadIdx.x; e < total4; e += blockDim.x) __stcs(o4 + e, sv4[e]);
+}
+
 __global__ void __launch_bounds__(256)
 roi_align_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ proposals, float scale, int aligned, int K, int H, int W, int C,
                      int PH, int PW, int S, const float *__restrict__ addend, float *__restrict__ dfm)
@@ -174,6 +267,15 @@ int frcnn_roi_align_fwd(const float *fm, int H, int W, int C, const float *propo
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_align_fwd: smem attribute");
+  }
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(fm) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "roi_align_fwd: smem attribute");
+    }
+    roi_align_fwd_v4_kernel<<<dim3(K, ceil_div(C, kAlignSlab)), kAlignWarps * 32, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
+    FRCNN_CHECK_LAUNCH("roi_align_fwd_v4_kernel");
+    return FRCNN_OK;
   }
   roi_align_fwd_kernel<<<dim3(K, ceil_div(C, kAlignSlab)), kAlignSlab, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
   FRCNN_CHECK_LAUNCH("roi_align_fwd_kernel");

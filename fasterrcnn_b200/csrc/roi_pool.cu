@@ -1,10 +1,13 @@
 // K7: RoI max pooling forward/backward (torchvision.ops.RoIPool semantics).
 //
-// Forward: one CTA per (RoI, 32-channel group), 8 warps; a warp takes every 8th bin, its 32 lanes are 32 consecutive channels
-// of one NHWC cell (128 B, fully coalesced), so a RoI's cells are scanned by 16 x 8 warps in parallel instead of one thread per
-// channel walking the whole RoI.  Each bin is scanned in the reference's row-major order with a strict '>' so that the argmax
-// is the reference's; results are staged in shared memory as [channel][49] and written out as one contiguous (32 x 49) fp32
-// run -- i.e. directly in the (K, C, 7, 7) order that fc1 (models/vgg16.py:129) consumes, with 128-bit stores.
+// Forward (roi_pool_fwd_v4_kernel, C % 4 == 0): one CTA per (RoI, 128-channel slab), 8 warps; a warp takes every 8th bin and
+// its 32 lanes read 4 consecutive channels each -- one 512-byte NHWC segment per warp-wide 128-bit load, so a bin of r x s cells
+// is r*s independent vector loads per lane (the feature map is L2 resident; what has to be hidden is L2 latency, i.e. bytes in
+// flight per thread).  Each bin is scanned in the reference's row-major order with a strict '>' per channel so that the argmax
+// is the reference's; results are staged in shared memory as [channel][49] and streamed out (st.global.cs, the output must not
+// evict the feature map from L2) as one contiguous (128 x 49) fp32 run -- i.e. directly in the (K, C, 7, 7) order that fc1
+// (models/vgg16.py:129) consumes -- with 128-bit stores; the HBM write of values + argmax is the algorithmic traffic.
+// roi_pool_fwd_kernel (one channel per lane, 32-channel groups) remains for channel counts that are not a multiple of 4.
 //
 // Backward: deterministic, atomics-free.  A CTA owns one feature-map row h and 32 channels; its 8 warps split the RoIs into 8
 // contiguous chunks, each warp accumulating into its own [W][32] line buffer in shared memory the gradient entries of its RoIs
@@ -97,6 +100,107 @@ roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const flo
   }
 }
 
+
+// volatile: keeps the four loads of a round back to back (ptxas otherwise sinks each one below the previous load's compares to
+// save registers, which serialises the L2 round trips)
+__device__ __forceinline__ float4 ldg_nc_v4(const float4 *p)
+{
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// ---- forward, 4 channels per lane ---------------------------------------------------------------------------------------
+constexpr int kRoiSlab = 128;     // channels per CTA: 32 lanes x float4
+
+__global__ void __launch_bounds__(kRoiWarps * 32)
+roi_pool_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
+                       float *__restrict__ out, int32_t *__restrict__ argmax)
+{
+  extern __shared__ float smem[];                 // [128][PH*PW] values then [128][PH*PW] argmax
+  const int bins = PH * PW;
+  float *s_val = smem;
+  int32_t *s_arg = reinterpret_cast<int32_t *>(smem + (size_t)kRoiSlab * bins);
+  const int n = blockIdx.x;
+  const int c0 = blockIdx.y * kRoiSlab;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + 4 * lane;
+  const RoiBins r = roi_bins(proposals + 4 * (size_t)n, scale, PH, PW);
+  if (c < C) {
+    const float4 *fm4 = reinterpret_cast<const float4 *>(fm + c);
+    const int C4 = C >> 2;
+    for (int b = warp; b < bins; b += kRoiWarps) {
+      const int ph = b / PW, pw = b - ph * PW;
+      int hs = (int)floorf(__fmul_rn((float)ph, r.bh)) + r.ys;
+      int he = (int)ceilf(__fmul_rn((float)(ph + 1), r.bh)) + r.ys;
+      hs = min(max(hs, 0), H); he = min(max(he, 0), H);
+      int ws = (int)floorf(__fmul_rn((float)pw, r.bw)) + r.xs;
+      int we = (int)ceilf(__fmul_rn((float)(pw + 1), r.bw)) + r.xs;
+      ws = min(max(ws, 0), W); we = min(max(we, 0), W);
+      const bool empty = (he <= hs) || (we <= ws);
+      const float init = empty ? 0.f : -FLT_MAX;
+      float b0 = init, b1 = init, b2 = init, b3 = init;
+      int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+      // the bin's cells in row-major order, four per round, software-pipelined by one round: the 128-bit loads of round r + 1 are
+      // issued before the compares of round r, so at least four L2 round trips per lane overlap whatever ptxas interleaves inside
+      // a round (a bin is typically 2-3 cells wide: too short for the w loop alone to keep loads in flight).  Slots past the end
+      // re-read the last cell -- a second look at a cell never passes the strict '>' -- so the loads carry no predicate.
+      const int nw = we - ws, total = empty ? 0 : (he - hs) * nw;
+      if (total > 0) {
+        int h = hs, w = ws, issued = 0;
+        int cell[4], ncell[4];
+        float4 v[4], nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          cell[u] = h * W + w;
+          if (++issued < total && ++w == we) { w = ws; h++; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = ldg_nc_v4(fm4 + (size_t)cell[u] * C4);
+        for (int k = 0; k < total; k += 4) {
+          const bool more = k + 4 < total;                           // warp-uniform
+          if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              ncell[u] = h * W + w;
+              if (++issued < total && ++w == we) { w = ws; h++; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) nv[u] = ldg_nc_v4(fm4 + (size_t)ncell[u] * C4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (v[u].x > b0) { b0 = v[u].x; i0 = cell[u]; }
+            if (v[u].y > b1) { b1 = v[u].y; i1 = cell[u]; }
+            if (v[u].z > b2) { b2 = v[u].z; i2 = cell[u]; }
+            if (v[u].w > b3) { b3 = v[u].w; i3 = cell[u]; }
+          }
+          if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) { v[u] = nv[u]; cell[u] = ncell[u]; }
+          }
+        }
+      }
+      const int o = (4 * lane) * bins + b;
+      s_val[o] = b0; s_val[o + bins] = b1; s_val[o + 2 * bins] = b2; s_val[o + 3 * bins] = b3;
+      s_arg[o] = i0; s_arg[o + bins] = i1; s_arg[o + 2 * bins] = i2; s_arg[o + 3 * bins] = i3;
+    }
+  }
+  __syncthreads();
+  // contiguous write-out of the slab: out[(n*C + c0) * bins ...]; live * bins and the base are multiples of 4 (C % 4 == 0)
+  const int live = min(kRoiSlab, C - c0);
+  const size_t base = ((size_t)n * C + c0) * bins;
+  const int total4 = (live * bins) >> 2;
+  float4 *o4 = reinterpret_cast<float4 *>(out + base);
+  const float4 *sv4 = reinterpret_cast<const float4 *>(s_val);
+  for (int e = threadIdx.x; e < total4; e += blockDim.x) __stcs(o4 + e, sv4[e]);
+  if (argmax) {
+    int4 *a4 = reinterpret_cast<int4 *>(argmax + base);
+    const int4 *sa4 = reinterpret_cast<const int4 *>(s_arg);
+    for (int e = threadIdx.x; e < total4; e += blockDim.x) __stcs(a4 + e, sa4[e]);
+  }
+}
+
 // grid (ceil(C/32), H); block = 8 warps x 32 channel lanes.
 __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ argmax, const float *__restrict__ proposals, float scale,
@@ -161,6 +265,17 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
 {
   FRCNN_REQUIRE(fm && proposals && out && H > 0 && W > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0, "roi_pool_fwd: bad argument");
   if (K == 0) return FRCNN_OK;
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(fm) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(argmax)) & 15) == 0) {
+    size_t smem4 = (size_t)kRoiSlab * PH * PW * (sizeof(float) + sizeof(int32_t));
+    FRCNN_REQUIRE(smem4 <= 200 * 1024, "roi_pool_fwd: pooled size too large");
+    if (smem4 > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+      if (e != cudaSuccess) return cuda_fail(e, "roi_pool_fwd: smem attribute");
+    }
+    roi_pool_fwd_v4_kernel<<<dim3(K, ceil_div(C, kRoiSlab)), kRoiWarps * 32, smem4, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
+    FRCNN_CHECK_LAUNCH("roi_pool_fwd_v4_kernel");
+    return FRCNN_OK;
+  }
   size_t smem = (size_t)kRoiChannels * PH * PW * (sizeof(float) + sizeof(int32_t));
   FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_fwd: pooled size too large");
   if (smem > 48 * 1024) {

@@ -86,9 +86,15 @@ __global__ void rpn_decode_kernel(const float *__restrict__ deltas, const float 
 // SMs and give a stable, deterministic order without a multi-pass radix sort.
 constexpr int kRankTile = 1024;
 
+// blockIdx.z = batch entry (scores / rank advance by n / 1 + n per entry).  LOW_FIRST selects the tie rule: false = higher index
+// first (argsort ascending + flip, models/rpn.py:129-130), true = lower index first (stable descending, torchvision.ops.nms).
+template <bool LOW_FIRST>
 __global__ void rank_count_kernel(const float *__restrict__ scores, const uint8_t *__restrict__ keep_mask, int n, int j_per_slice, int32_t *__restrict__ rank)
 {
   __shared__ __align__(16) float tile[kRankTile];
+  scores += (size_t)blockIdx.z * n;
+  rank += (size_t)blockIdx.z * (n + 1);
+  if (keep_mask) keep_mask += (size_t)blockIdx.z * n;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n && (keep_mask == nullptr || keep_mask[i] != 0);
   const float si = live ? scores[i] : 0.f;
@@ -109,23 +115,28 @@ __global__ void rank_count_kernel(const float *__restrict__ scores, const uint8_
       for (; q + 4 <= lim; q += 4) {
         float4 v = *reinterpret_cast<const float4 *>(&tile[q]);
         int j = base + q;
-        cnt += (v.x > si) || (v.x == si && j + 0 > i);
-        cnt += (v.y > si) || (v.y == si && j + 1 > i);
-        cnt += (v.z > si) || (v.z == si && j + 2 > i);
-        cnt += (v.w > si) || (v.w == si && j + 3 > i);
+        cnt += (v.x > si) || (v.x == si && (LOW_FIRST ? j + 0 < i : j + 0 > i));
+        cnt += (v.y > si) || (v.y == si && (LOW_FIRST ? j + 1 < i : j + 1 > i));
+        cnt += (v.z > si) || (v.z == si && (LOW_FIRST ? j + 2 < i : j + 2 > i));
+        cnt += (v.w > si) || (v.w == si && (LOW_FIRST ? j + 3 < i : j + 3 > i));
       }
       for (; q < lim; q++) {
         float v = tile[q];
-        cnt += (v > si) || (v == si && base + q > i);
+        cnt += (v > si) || (v == si && (LOW_FIRST ? base + q < i : base + q > i));
       }
     }
   }
   if (live && cnt) atomicAdd(&rank[i], cnt);
 }
 
+// blockIdx.y = batch entry: rank / count_out advance by 1 + n, order by order_stride
 __global__ void rank_scatter_kernel(const uint8_t *__restrict__ keep_mask, int n, int top_n, const int32_t *__restrict__ rank,
-                                    int32_t *__restrict__ order, int32_t *__restrict__ count_out)
+                                    int32_t *__restrict__ order, int32_t *__restrict__ count_out, int order_stride)
 {
+  rank += (size_t)blockIdx.y * (n + 1);
+  count_out += (size_t)blockIdx.y * (n + 1);
+  order += (size_t)blockIdx.y * order_stride;
+  if (keep_mask) keep_mask += (size_t)blockIdx.y * n;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = i < n && (keep_mask == nullptr || keep_mask[i] != 0);
   bool hit = false;
@@ -197,15 +208,23 @@ __device__ __forceinline__ bool iou_exceeds(const float4 &a, float area_a, const
   float w = fmaxf(0.f, __fsub_rn(t2, t0));
   float h = fmaxf(0.f, __fsub_rn(t3, t1));
   float inter = __fmul_rn(w, h);
-  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // the IEEE division costs ~8x the rest of the pair; an approximate quotient (2 ulp) decides every pair that is not within
+  // 1e-5 of the threshold, the exact one only the rest -- the decision is the reference's bit for bit either way
+  const float q = __fdividef(inter, den);
+  if (fabsf(__fsub_rn(q, thr_f)) > 1e-5f) return q > thr_f;  // NaN / inf quotients fall through to the exact path
+  float ovr = __fdiv_rn(inter, den);
   return ovr > thr_f;                                        // NaN (0/0) -> false, as in the reference op
 }
 
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ count, int capacity, float thr_f,
+nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ count, int count_stride, int capacity, float thr_f,
                 unsigned long long *__restrict__ mask, int col_blocks)
 {
-  int n = *count;
+  // blockIdx.z = batch entry (class): boxes / mask advance by one capacity-sized block, count by count_stride
+  boxes += (size_t)blockIdx.z * capacity * 4;
+  mask += (size_t)blockIdx.z * capacity * col_blocks;
+  int n = count[(size_t)blockIdx.z * count_stride];
   if (n > capacity) n = capacity;
   const int row_b = blockIdx.y, col_b = blockIdx.x;
   if (col_b < row_b) return;
@@ -254,9 +273,14 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int capacity, int col_blocks,
-                int max_keep, int32_t *__restrict__ keep_out, int32_t *__restrict__ kept_count_out)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int count_stride, int capacity, int col_blocks,
+                int max_keep, int32_t *__restrict__ keep_out, int keep_stride, int32_t *__restrict__ kept_count_out)
 {
+  // blockIdx.x = batch entry (class): one CTA walks one greedy chain
+  mask += (size_t)blockIdx.x * capacity * col_blocks;
+  count += (size_t)blockIdx.x * count_stride;
+  keep_out += (size_t)blockIdx.x * keep_stride;
+  kept_count_out += blockIdx.x;
   extern __shared__ int32_t kept_idx[];                      // max_keep entries: positions of the kept boxes
   __shared__ unsigned long long ring[4][3][64];              // per block slot: [0] diagonal tile, [1] rows at column +1, [2] at column +2
   __shared__ unsigned long long removed[4];                  // removed[c & 3]: suppression word of block c, accumulated ahead of time
@@ -344,6 +368,23 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (t == 0) *kept_count_out = kept_total;
+}
+
+// batched NMS glue: sorted[z][r] = boxes[z][order[z][r]] (r < n), and keep[z][r] = order[z][keep_pos[z][r]] (r < kept[z])
+__global__ void nms_batched_sort_boxes_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ order, int n, float *__restrict__ sorted)
+{
+  const size_t zoff = (size_t)blockIdx.y * n;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    reinterpret_cast<float4 *>(sorted)[zoff + r] = __ldg(reinterpret_cast<const float4 *>(boxes) + zoff + order[zoff + r]);
+}
+
+__global__ void nms_batched_finish_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ keep_pos, const int32_t *__restrict__ kept, int n,
+                                          int max_keep, int32_t *__restrict__ keep_out)
+{
+  const int z = blockIdx.y;
+  const int k = kept[z];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < max_keep; r += gridDim.x * blockDim.x)
+    keep_out[(size_t)z * max_keep + r] = r < k ? order[(size_t)z * n + keep_pos[(size_t)z * max_keep + r]] : -1;
 }
 
 // dst rows [*dst_count, *dst_count + m) <- src rows: appends the ground-truth boxes behind the device-counted proposals
@@ -479,9 +520,9 @@ int frcnn_topk_order(const float *scores, const uint8_t *keep_mask, int n, int t
   if (slices < 1) slices = 1;
   int j_per_slice = ceil_div(ceil_div(n, slices), kRankTile) * kRankTile;
   slices = ceil_div(n, j_per_slice);
-  rank_count_kernel<<<dim3(gx, slices), threads, 0, st>>>(scores, keep_mask, n, j_per_slice, rank);
+  rank_count_kernel<false><<<dim3(gx, slices), threads, 0, st>>>(scores, keep_mask, n, j_per_slice, rank);
   FRCNN_CHECK_LAUNCH("rank_count_kernel");
-  rank_scatter_kernel<<<gx, threads, 0, st>>>(keep_mask, n, top_n, rank, order, count_out);
+  rank_scatter_kernel<<<gx, threads, 0, st>>>(keep_mask, n, top_n, rank, order, count_out, 0);
   FRCNN_CHECK_LAUNCH("rank_scatter_kernel");
   return FRCNN_OK;
 }
@@ -512,7 +553,7 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
   if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
   cudaStream_t st = as_stream(stream);
   unsigned long long *mask = reinterpret_cast<unsigned long long *>(workspace);
-  nms_mask_kernel<<<dim3(col_blocks, col_blocks), 64, 0, st>>>(boxes, count, capacity, thr_f, mask, col_blocks);
+  nms_mask_kernel<<<dim3(col_blocks, col_blocks), 64, 0, st>>>(boxes, count, 0, capacity, thr_f, mask, col_blocks);
   FRCNN_CHECK_LAUNCH("nms_mask_kernel");
   const int keep_cap = max_keep < capacity ? max_keep : capacity;
   size_t smem = (size_t)keep_cap * sizeof(int32_t);
@@ -521,8 +562,80 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
   }
-  nms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, count, capacity, col_blocks, keep_cap, keep_out, kept_count_out);
+  nms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, count, 0, capacity, col_blocks, keep_cap, keep_out, 0, kept_count_out);
   FRCNN_CHECK_LAUNCH("nms_scan_kernel");
+  return FRCNN_OK;
+}
+
+// workspace layout of the batched NMS (each block 256-byte aligned): cnt (B, 1 + n) i32 | order (B, n) i32 | sorted (B, n, 4) f32 |
+// keep_pos (B, max_keep) i32 | mask (B, n, ceil(n / 64)) u64
+static size_t nms_batched_layout(int B, int n, int max_keep, size_t off[5])
+{
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t o = 0;
+  off[0] = o; o += up((size_t)B * (1 + n) * 4);
+  off[1] = o; o += up((size_t)B * n * 4);
+  off[2] = o; o += up((size_t)B * n * 16);
+  off[3] = o; o += up((size_t)B * max_keep * 4);
+  off[4] = o; o += up((size_t)B * n * ceil_div(n, 64) * 8);
+  return o;
+}
+
+size_t frcnn_nms_batched_workspace_bytes(int B, int n, int max_keep)
+{
+  if (B <= 0 || n <= 0 || max_keep <= 0) return 0;
+  size_t off[5];
+  return nms_batched_layout(B, n, max_keep < n ? max_keep : n, off);
+}
+
+int frcnn_nms_batched_f32(const float *boxes, const float *scores, int B, int n, double iou_threshold, int max_keep,
+                          int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(boxes && scores && keep_out && kept_count_out && B > 0 && B <= 65535 && n > 0 && max_keep > 0, "nms_batched_f32: bad argument");
+  const int keep_cap = max_keep < n ? max_keep : n;
+  size_t off[5];
+  const size_t need = nms_batched_layout(B, n, keep_cap, off);
+  if (workspace == nullptr || workspace_bytes < need) return fail(FRCNN_E_WORKSPACE, "nms_batched_f32: workspace too small");
+  FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "nms_batched_f32: boxes and workspace must be 16-byte aligned");
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  int32_t *cnt = reinterpret_cast<int32_t *>(ws + off[0]);
+  int32_t *order = reinterpret_cast<int32_t *>(ws + off[1]);
+  float *sorted = reinterpret_cast<float *>(ws + off[2]);
+  int32_t *keep_pos = reinterpret_cast<int32_t *>(ws + off[3]);
+  unsigned long long *mask = reinterpret_cast<unsigned long long *>(ws + off[4]);
+  cudaStream_t st = as_stream(stream);
+  float thr_f = (float)iou_threshold;
+  if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
+  cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)B * (1 + n) * sizeof(int32_t), st);
+  if (e != cudaSuccess) return cuda_fail(e, "nms_batched_f32: memset");
+  // 1. stable descending order per entry (rank counting, ties -> lower index first)
+  const int threads = 256;
+  const int gx = ceil_div(n, threads);
+  int slices = ceil_div(4 * kNumSMs, gx * B);
+  if (slices < 1) slices = 1;
+  int j_per_slice = ceil_div(ceil_div(n, slices), kRankTile) * kRankTile;
+  slices = ceil_div(n, j_per_slice);
+  rank_count_kernel<true><<<dim3(gx, slices, B), threads, 0, st>>>(scores, nullptr, n, j_per_slice, cnt + 1);
+  FRCNN_CHECK_LAUNCH("rank_count_kernel");
+  rank_scatter_kernel<<<dim3(gx, B), threads, 0, st>>>(nullptr, n, n, cnt + 1, order, cnt, n);
+  FRCNN_CHECK_LAUNCH("rank_scatter_kernel");
+  nms_batched_sort_boxes_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, st>>>(boxes, order, n, sorted);
+  FRCNN_CHECK_LAUNCH("nms_batched_sort_boxes_kernel");
+  // 2. suppression bit tiles of every entry in one launch, 3. one greedy-scan CTA per entry
+  const int col_blocks = ceil_div(n, 64);
+  nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), 64, 0, st>>>(sorted, cnt, 1 + n, n, thr_f, mask, col_blocks);
+  FRCNN_CHECK_LAUNCH("nms_mask_kernel");
+  size_t smem = (size_t)keep_cap * sizeof(int32_t);
+  FRCNN_REQUIRE(smem <= 200 * 1024, "nms_batched_f32: max_keep too large for the scan's kept list");
+  if (smem > 40 * 1024) {
+    e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
+  }
+  nms_scan_kernel<<<B, kScanThreads, smem, st>>>(mask, cnt, 1 + n, n, col_blocks, keep_cap, keep_pos, keep_cap, kept_count_out);
+  FRCNN_CHECK_LAUNCH("nms_scan_kernel");
+  // 4. positions in the sorted list -> original indices
+  nms_batched_finish_kernel<<<dim3(ceil_div(keep_cap, 256), B), 256, 0, st>>>(order, keep_pos, kept_count_out, n, keep_cap, keep_out);
+  FRCNN_CHECK_LAUNCH("nms_batched_finish_kernel");
   return FRCNN_OK;
 }
 

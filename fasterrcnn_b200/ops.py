@@ -712,6 +712,23 @@ def nms(boxes, scores, iou_threshold):
   return order[keep[:k].long()].long()
 
 
+def nms_batched(boxes, scores, iou_threshold, max_keep = None):
+  """B independent NMS problems in one stream-ordered sequence (per-class NMS at BASELINE config 5 sizes): boxes (B,n,4) fp32,
+  scores (B,n) fp32, unsorted.  Returns (keep (B, max_keep) int32 original indices in score order, -1 padded; counts (B) int32),
+  both on the device -- no host synchronisation."""
+  _require_cuda(boxes, scores)
+  bsz, n = int(scores.shape[0]), int(scores.shape[1])
+  b = boxes.detach().contiguous().float()
+  s = scores.detach().contiguous().float()
+  cap = n if max_keep is None else min(int(max_keep), n)
+  keep = t.empty((bsz, cap), dtype = t.int32, device = b.device)
+  counts = t.empty((bsz,), dtype = t.int32, device = b.device)
+  ws, ws_n = workspace(lib().frcnn_nms_batched_workspace_bytes(bsz, n, cap), slot = 2)
+  check(lib().frcnn_nms_batched_f32(ptr(b), ptr(s), bsz, n, float(iou_threshold), cap, ptr(keep), ptr(counts), ws, ws_n, stream()), "frcnn_nms_batched_f32")
+  _lib.count(6)
+  return keep, counts
+
+
 class ProposalBuffers:
   """Capacity-sized device buffers for the RPN proposal path (reused across steps)."""
 
@@ -773,6 +790,20 @@ def rpn_proposals(score_map, delta_map, image_shape, feature_pixels, pre_nms, po
     return out[:n], dict(order = buf.order[:n1].clone(), boxes_all = buf.boxes_all.clone(), size_ok = buf.size_ok.clone(),
                          boxes_sorted = buf.boxes_sorted[:n2].clone(), scores_sorted = buf.scores_sorted[:n2].clone(), keep = buf.keep[:n].clone())
   return out[:n]
+
+
+def rpn_decode(deltas, fh, fw, feature_pixels, img_h, img_w, min_size = 16.0):
+  """K5 alone: anchors regenerated in-kernel + delta decode + clip + min-size flag for a (fh*fw*9, 4) delta tensor.
+  Returns boxes (A,4) fp32 and size_ok (A) uint8 (rpn_proposals runs the same kernel as the first stage of the proposal path)."""
+  _require_cuda(deltas)
+  d = deltas.detach().contiguous()
+  a = fh * fw * 9
+  assert d.numel() == 4 * a
+  boxes = t.empty((a, 4), dtype = t.float32, device = d.device)
+  ok = t.empty((a,), dtype = t.uint8, device = d.device)
+  check(lib().frcnn_rpn_decode(ptr(d), None, fh, fw, int(feature_pixels), int(img_h), int(img_w), float(min_size), ptr(boxes), ptr(ok), None, None, stream()), "frcnn_rpn_decode")
+  _lib.count()
+  return boxes, ok
 
 
 def gather_rows(src, index_i32, count_i32, capacity):

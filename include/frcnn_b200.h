@@ -175,6 +175,14 @@ int frcnn_gather_filtered(const float *boxes, const float *scores, const uint8_t
 size_t frcnn_nms_workspace_bytes(int capacity);
 int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
                          int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
+/* Batched variant (BASELINE config 5: 6000 boxes x 20 classes; the per-class loop of models/faster_rcnn.py:196-220 at a size where
+ * it is worth a grid): B independent problems of n boxes each, UNSORTED -- boxes (B,n,4) fp32, scores (B,n) fp32 -- solved in
+ * one stream-ordered sequence with no host round trip: stable descending order per problem (ties -> lower index first, as
+ * torchvision.ops.nms orders), bit tiles of all problems in one launch, one greedy-scan CTA per problem.  keep_out
+ * (B, min(max_keep, n)) int32 = ORIGINAL indices of the kept boxes in score order, -1 padded; kept_count_out (B) int32. */
+size_t frcnn_nms_batched_workspace_bytes(int B, int n, int max_keep);
+int frcnn_nms_batched_f32(const float *boxes, const float *scores, int B, int n, double iou_threshold, int max_keep,
+                          int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
 /* out[r] = boxes[keep[r]] for r < *kept_count. */
 int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index, const int32_t *count, int capacity, float *dst, void *stream);
 /* dst[*dst_count + r][:] = src[r][:] for r < m (rows past dst_capacity_rows are dropped): appends the ground-truth boxes to the

@@ -204,6 +204,41 @@ def test_nms_full_size_properties(ops):
     assert np.all(np.diff(ks) <= 0)                                  # descending scores
 
 
+def test_nms_batched_matches_per_problem_oracle(ops):
+  """Config-5 shape (6000 boxes x 20 classes, thr 0.3) and a small ragged-tie case: the batched entry returns, per problem,
+  exactly the single-problem oracle's indices."""
+  rng = np.random.default_rng(7)
+  for bsz, n, thr, ties in ((20, 6000, 0.3, False), (3, 777, 0.5, True), (2, 64, 0.7, True)):
+    b = np.stack([gi.random_boxes(rng, n) for _ in range(bsz)])
+    if ties:
+      s = np.stack([rng.integers(0, 50, n).astype(np.float32) / 50 for _ in range(bsz)])     # many equal scores
+    else:
+      s = np.stack([rng.permutation(n).astype(np.float32) / n for _ in range(bsz)])
+    keep, counts = ops.nms_batched(_cuda(b), _cuda(s), thr)
+    keep, counts = keep.cpu().numpy(), counts.cpu().numpy()
+    for z in range(bsz):
+      ref = orc.nms(b[z], s[z], thr)
+      assert counts[z] == len(ref)
+      assert np.array_equal(keep[z, :counts[z]], ref)
+      assert np.all(keep[z, counts[z]:] == -1)
+  # max_keep cut: first k of the full answer
+  keep, counts = ops.nms_batched(_cuda(b), _cuda(s), thr, max_keep = 5)
+  for z in range(b.shape[0]):
+    ref = orc.nms(b[z], s[z], thr)[:5]
+    assert np.array_equal(keep[z, :counts[z]].cpu().numpy(), ref)
+
+
+def test_roi_pool_scalar_path_when_channels_not_multiple_of_4(ops):
+  """C = 6: the one-channel-per-lane kernel (the 128-bit path needs C % 4 == 0)."""
+  rng = np.random.default_rng(11)
+  fm = rng.normal(0, 1, (1, 6, 12, 17)).astype(np.float32)
+  _, rois = gi.roi_case("small")
+  out_ref, _ = orc.roi_pool_forward(fm, rois)
+  props = np.stack([rois[:, 2], rois[:, 1], rois[:, 4], rois[:, 3]], axis = 1)
+  out = ops.roi_pool(_cuda(fm), _cuda(props), (7, 7), 1.0 / 16.0)
+  assert np.array_equal(out.cpu().numpy(), out_ref)
+
+
 # ---------------------------------------------------------------- RoI pooling (K7)
 @pytest.mark.parametrize("tag", gi.ROI_CASES)
 def test_roi_pool_fwd_bit_exact_bwd_matches(ops, tag):

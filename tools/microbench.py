@@ -50,6 +50,15 @@ def main():
     ms = ev_time(lambda: ops.roi_pool(fm, props))
     alg = fm.numel() * 4 + 20 * N + 196 * C * N * 2          # output + argmax
     out.append(dict(kernel = "roi_pool_fwd", shape = "N=%d C=%d fm=%dx%d" % (N, C, H, W), ms = ms, algorithmic_MB = alg / 1e6, achieved_GBs = alg / ms / 1e6, peak_GBs = peak, frac = alg / ms / 1e6 / peak))
+    ms = ev_time(lambda: ops.roi_align(fm, props, (7, 7), 1.0 / 16.0, 2, False))
+    alg = fm.numel() * 4 + 20 * N + 196 * C * N                # output only (no argmax)
+    out.append(dict(kernel = "roi_align_fwd (sampling_ratio 2)", shape = "N=%d C=%d fm=%dx%d" % (N, C, H, W), ms = ms, algorithmic_MB = alg / 1e6, achieved_GBs = alg / ms / 1e6, peak_GBs = peak, frac = alg / ms / 1e6 / peak))
+  # training-size RoIPool forward (128 RoIs: the size inside train_step; latency, not bandwidth)
+  fm = ops.as_nhwc(t.relu(t.randn((1, 512, 37, 62), device = "cuda")))
+  props = t.from_numpy(boxes(rng, 128)).cuda()
+  ms = ev_time(lambda: ops.roi_pool(fm, props))
+  alg = fm.numel() * 4 + 20 * 128 + 196 * 512 * 128 * 2
+  out.append(dict(kernel = "roi_pool_fwd", shape = "N=128 C=512 fm=37x62", ms = ms, algorithmic_MB = alg / 1e6, achieved_GBs = alg / ms / 1e6, peak_GBs = peak, frac = alg / ms / 1e6 / peak))
   # training-size RoIPool backward (128 RoIs)
   fm = ops.as_nhwc(t.relu(t.randn((1, 512, 37, 62), device = "cuda"))).requires_grad_(True)
   props = t.from_numpy(boxes(rng, 128)).cuda()
@@ -68,6 +77,19 @@ def main():
   bs = [t.from_numpy(boxes(rng, n)).cuda() for _ in range(20)]; ss = [t.from_numpy(rng.permutation(n).astype(np.float32) / n).cuda() for _ in range(20)]
   ms = ev_time(lambda: [ops.nms(bs[i], ss[i], 0.3) for i in range(20)], iters = 5)
   out.append(dict(kernel = "nms x 20 classes", shape = "20 x N=6000 thr=0.3", ms = ms, iou_pairs_per_s = 20 * n * (n - 1) / 2 / ms * 1e3, algorithmic_MB = 20 * n * 20 / 1e6))
+  bb = t.stack(bs); sb = t.stack(ss)
+  ms = ev_time(lambda: ops.nms_batched(bb, sb, 0.3), iters = 10)
+  pairs = 20 * n * (n - 1) / 2
+  mask_bytes = 20 * n * ((n + 63) // 64) * 8 / 2               # upper-triangle bit tiles written by the mask kernel, read by the scan
+  out.append(dict(kernel = "nms_batched (rank + sort + mask + scan + finish, no host sync)", shape = "20 x N=6000 thr=0.3", ms = ms, iou_pairs_per_s = pairs / ms * 1e3,
+                  algorithmic_MB = 20 * n * 20 / 1e6, bit_tile_MB = mask_bytes / 1e6, achieved_GBs = (20 * n * 20 + mask_bytes) / ms / 1e6, peak_GBs = peak))
+  # fused anchor + decode + clip + size flag at a scale where bandwidth shows: a 592 x 992 cell map = 5.29 M anchors, 37 B / anchor
+  # (16 B deltas in, 16 B box + 1 B flag out; the score's 4 B in / 4 B out of SURVEY 8d belong to the rank / gather kernels)
+  fh, fw = 592, 992
+  deltas_big = t.randn((fh * fw * 9, 4), device = "cuda") * 0.3
+  ms = ev_time(lambda: ops.rpn_decode(deltas_big, fh, fw, 16, fh * 16, fw * 16))
+  alg = fh * fw * 9 * 33
+  out.append(dict(kernel = "rpn_decode (anchors regenerated in-kernel)", shape = "%d anchors" % (fh * fw * 9), ms = ms, algorithmic_MB = alg / 1e6, achieved_GBs = alg / ms / 1e6, peak_GBs = peak, frac = alg / ms / 1e6 / peak))
   # RPN decode at 600x1000 (20,646 anchors: latency bound) -- 40 B/anchor
   fh, fw = 37, 62
   deltas = t.randn((1, fh, fw, 36), device = "cuda") * 0.3; scores = t.rand((1, fh, fw, 9), device = "cuda")
