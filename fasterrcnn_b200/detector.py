@@ -11,8 +11,10 @@ from .backbone import LinearParams
 
 
 class DetectorNetwork(nn.Module):
-  def __init__(self, num_classes, backbone):
+  def __init__(self, num_classes, backbone, roi_op = "pool", roi_sampling_ratio = 2, roi_aligned = False):
     super().__init__()
+    assert roi_op in ("pool", "align"), "roi_op must be 'pool' (the reference's RoIPool) or 'align' (extension: torchvision roi_align semantics)"
+    self._roi_op, self._roi_sampling_ratio, self._roi_aligned = roi_op, roi_sampling_ratio, roi_aligned
     self._input_features = 7 * 7 * backbone.feature_map_channels
     self._spatial_scale = 1.0 / backbone.feature_pixels
     self._pool_to_feature_vector = backbone.pool_to_feature_vector
@@ -26,12 +28,27 @@ class DetectorNetwork(nn.Module):
   def forward(self, feature_map, proposals):
     """feature_map (1,C,H,W), proposals (N,4) (y1,x1,y2,x2) -> classes (N,num_classes), box deltas (N,4(num_classes-1))."""
     assert feature_map.shape[0] == 1, "Batch size must be 1"
-    rois = ops.roi_pool(feature_map, proposals, (7, 7), self._spatial_scale)
+    rois = self._roi(feature_map, proposals)
     y = self._pool_to_feature_vector(rois = rois)
     # class logits (21) and box deltas (80) are one narrow GEMM over the feature vectors
     classes_raw, box_deltas = ops.two_heads(y, self._classifier.weight, self._classifier.bias, ops.ACT_NONE, self._regressor.weight, self._regressor.bias, ops.ACT_NONE)
     classes = ops.softmax_rows(classes_raw)
     return classes, box_deltas
+
+
+  def _roi(self, feature_map, proposals):
+    if self._roi_op == "pool":
+      return ops.roi_pool(feature_map, proposals, (7, 7), self._spatial_scale)
+    return ops.roi_align(feature_map, proposals, (7, 7), self._spatial_scale, self._roi_sampling_ratio, self._roi_aligned)
+
+  def forward_batch(self, feature_map, proposals_list):
+    """EXTENSION (batch > 1): the RoIs of image b are pooled from feature_map[b] (detector.py:65's batch column carrying b),
+    stacked in image order and sent through the head in one pass -> classes (sum N_b, C), box deltas (sum N_b, 4(C-1))."""
+    assert feature_map.shape[0] == len(proposals_list)
+    pooled = [self._roi(feature_map[b:b + 1], p) for b, p in enumerate(proposals_list)]
+    y = self._pool_to_feature_vector(rois = t.cat(pooled, dim = 0) if len(pooled) > 1 else pooled[0])
+    classes_raw, box_deltas = ops.two_heads(y, self._classifier.weight, self._classifier.bias, ops.ACT_NONE, self._regressor.weight, self._regressor.bias, ops.ACT_NONE)
+    return ops.softmax_rows(classes_raw), box_deltas
 
 
 def class_loss(predicted_classes, y_true):

@@ -25,7 +25,10 @@ class FasterRCNNModel(nn.Module):
     detector_regression: float
     total: float
 
-  def __init__(self, num_classes, backbone, rpn_minibatch_size = 256, proposal_batch_size = 128, allow_edge_proposals = True):
+  def __init__(self, num_classes, backbone, rpn_minibatch_size = 256, proposal_batch_size = 128, allow_edge_proposals = True,
+               roi_op = "pool", roi_sampling_ratio = 2, roi_aligned = False):
+    """roi_op / roi_sampling_ratio / roi_aligned are EXTENSIONS (BASELINE config 3): "pool" is the reference's
+    RoIPool; "align" swaps in RoIAlign with torchvision.ops.roi_align semantics."""
     super().__init__()
     self._num_classes = num_classes
     self._rpn_minibatch_size = rpn_minibatch_size
@@ -35,7 +38,7 @@ class FasterRCNNModel(nn.Module):
     self.backbone = backbone
     self._stage1_feature_extractor = backbone.feature_extractor
     self._stage2_region_proposal_network = rpn.RegionProposalNetwork(feature_map_channels = backbone.feature_map_channels, allow_edge_proposals = allow_edge_proposals)
-    self._stage3_detector_network = detector.DetectorNetwork(num_classes = num_classes, backbone = backbone)
+    self._stage3_detector_network = detector.DetectorNetwork(num_classes = num_classes, backbone = backbone, roi_op = roi_op, roi_sampling_ratio = roi_sampling_ratio, roi_aligned = roi_aligned)
     self.last_step_info = {}
 
   # ---- faster_rcnn.py:80-132 ---------------------------------------------------------------------
@@ -145,6 +148,61 @@ class FasterRCNNModel(nn.Module):
     self.last_step_info = dict(num_rois = int(proposals.shape[0]))
     return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host[4]))
 
+  # ---- EXTENSION: batch > 1 (BASELINE config 3).  The reference asserts batch == 1 everywhere; its loss formulas
+  # are written for batched tensors, so the batch semantics are those formulas on the stacked maps / stacked RoIs, with proposal
+  # generation, labelling and sampling per image. ------------------------------------------------------------------------------
+  def forward_batch(self, image_data, max_proposals_pre_nms = 6000, max_proposals_post_nms = 300):
+    """image_data (B,3,H,W) -> [(proposals_b (N_b,4), classes_b (N_b,C), box_deltas_b (N_b,4(C-1)))]."""
+    image_shape = image_data.shape[1:]
+    ops.begin_step()
+    feature_map = self._stage1_feature_extractor(image_data = image_data)
+    _, _, proposals = self._stage2_region_proposal_network.forward_batch(feature_map, image_shape, max_proposals_pre_nms, max_proposals_post_nms)
+    classes, box_deltas = self._stage3_detector_network.forward_batch(feature_map, proposals)
+    out, at = [], 0
+    for p in proposals:
+      out.append((p, classes[at:at + p.shape[0]], box_deltas[at:at + p.shape[0]]))
+      at += p.shape[0]
+    return out
+
+  def predict_batch(self, image_data, score_threshold):
+    """-> [Dict[int, ndarray (n,5)]] per image (faster_rcnn.py:134-226 applied to each image's slice)."""
+    self.eval()
+    with t.no_grad():
+      return [ops.detect_postprocess(p, c, d, (image_data.shape[2], image_data.shape[3]), score_threshold, 0.3) for p, c, d in self.forward_batch(image_data)]
+
+  def train_step_batch(self, optimizer, image_data, samples):
+    """One optimizer step on B images of one size.  samples[b] holds train_step's per-image arguments: anchor_map,
+    anchor_valid_map, gt_rpn_map (1,h,w,9,6) CUDA, gt_rpn_object_indices, gt_rpn_background_indices (ndarrays), gt_boxes ([Box]).
+    RNG order: every image's RPN minibatch first (python random), then every image's proposal sample (torch CPU generator)."""
+    if not self.training:
+      self.train()
+    optimizer.zero_grad()
+    bsz = int(image_data.shape[0])
+    assert len(samples) == bsz, "one sample dict per image"
+    image_shape = image_data.shape[1:]
+    dev = image_data.device
+    ops.begin_step()
+    feature_map = self._stage1_feature_extractor(image_data = image_data)
+    score_map, delta_map, all_proposals = self._stage2_region_proposal_network.forward_batch(
+      feature_map, image_shape, 12000, 2000, anchor_map = samples[0]["anchor_map"], anchor_valid_map = samples[0]["anchor_valid_map"])
+    minibatch = t.cat([self._sample_rpn_minibatch(rpn_map = s["gt_rpn_map"], object_indices = [s["gt_rpn_object_indices"]], background_indices = [s["gt_rpn_background_indices"]], slot = b)
+                       for b, s in enumerate(samples)], dim = 0)
+    props_l, cls_l, dlt_l = [], [], []
+    for b, s in enumerate(samples):
+      props, gt_classes, gt_box_deltas = self._label_proposals(all_proposals[b], s["gt_boxes"], 0.0, 0.5)
+      props, gt_classes, gt_box_deltas = self._sample_proposals(props, gt_classes, gt_box_deltas, self._proposal_batch_size, 0.25)
+      props_l.append(props.detach()); cls_l.append(gt_classes.detach()); dlt_l.append(gt_box_deltas.detach())
+    classes, box_deltas = self._stage3_detector_network.forward_batch(feature_map, props_l)
+    rpn_l = ops.rpn_losses(score_map, delta_map, minibatch)
+    det_l = ops.detector_losses(classes, box_deltas, t.cat(cls_l), t.cat(dlt_l))
+    ones = self._ones2(dev)
+    t.autograd.backward([rpn_l, det_l], [ones, ones])
+    ops.begin_step()
+    optimizer.step()
+    host = t.cat([rpn_l.detach(), det_l.detach()]).cpu().numpy()
+    self.last_step_info = dict(num_rois = int(sum(p.shape[0] for p in props_l)), rois_per_image = [int(p.shape[0]) for p in props_l])
+    return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host.sum()))
+
   def _ones2(self, device):
     cache = self.__dict__.setdefault("_ones2_cache", {})
     key = str(device)
@@ -178,7 +236,7 @@ class FasterRCNNModel(nn.Module):
     return buf
 
   # ---- faster_rcnn.py:364-416 --------------------------------------------------------------------
-  def _sample_rpn_minibatch(self, rpn_map, object_indices, background_indices):
+  def _sample_rpn_minibatch(self, rpn_map, object_indices, background_indices, slot = 0):
     assert rpn_map.shape[0] == 1, "Batch size must be 1"
     assert len(object_indices) == 1, "Batch size must be 1"
     assert len(background_indices) == 1, "Batch size must be 1"
@@ -194,7 +252,7 @@ class FasterRCNNModel(nn.Module):
     trainable = np.concatenate([np.asarray(positive_anchors)[positive_anchor_idxs], np.asarray(negative_anchors)[negative_anchor_idxs]])
     _, fh, fw, k, _ = rpn_map.shape
     flat = (trainable[:, 0] * fw + trainable[:, 1]) * k + trainable[:, 2]
-    flat_dev = self._upload("rpn_minibatch", flat.astype(np.int64), rpn_map.device)
+    flat_dev = self._upload(("rpn_minibatch", slot), flat.astype(np.int64), rpn_map.device)    # slot: one staging pair per image of a batch
     minibatch = rpn_map.clone()
     mask = minibatch.view(-1, 6)[:, 0]
     mask.zero_()

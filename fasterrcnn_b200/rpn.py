@@ -46,6 +46,20 @@ class RegionProposalNetwork(nn.Module):
       defer_count = deferred_extra_rows is not None, extra_rows = deferred_extra_rows or 0)
     return objectness_score_map, box_deltas_map, proposals
 
+  def forward_batch(self, feature_map, image_shape, max_proposals_pre_nms, max_proposals_post_nms, anchor_map = None, anchor_valid_map = None):
+    """EXTENSION (batch > 1): one conv + head pass over all B images (rows = B*H*W pixels), then the proposal
+    path per image on its slice of the maps.  -> objectness (B,H,W,9), box deltas (B,H,W,36), [proposals_b (N_b,4)]."""
+    bsz = int(feature_map.shape[0])
+    y = ops.conv2d_act(feature_map, self._rpn_conv1.weight, self._rpn_conv1.bias, 1, 1, ops.ACT_RELU)
+    scores, deltas = ops.two_heads(y, self._rpn_class.weight, self._rpn_class.bias, ops.ACT_SIGMOID, self._rpn_boxes.weight, self._rpn_boxes.bias, ops.ACT_NONE)
+    fh, fw = int(y.shape[2]), int(y.shape[3])
+    objectness_score_map = scores.view(bsz, fh, fw, scores.shape[1])
+    box_deltas_map = deltas.view(bsz, fh, fw, deltas.shape[1])
+    anchors_dev, keep_mask = self._resolve_anchors(anchor_map, anchor_valid_map, image_shape, (fh, fw), feature_map.device)
+    proposals = [ops.rpn_proposals(objectness_score_map[b:b + 1], box_deltas_map[b:b + 1], image_shape, 16, max_proposals_pre_nms, max_proposals_post_nms,
+                                   anchors = anchors_dev, keep_mask = keep_mask).clone() for b in range(bsz)]
+    return objectness_score_map, box_deltas_map, proposals
+
   def _resolve_anchors(self, anchor_map, anchor_valid_map, image_shape, fm_hw, device):
     """The decode kernel regenerates the standard anchors itself (0 bytes of anchor traffic).  A
     caller-supplied anchor_map is honoured: if it differs from the standard map it is uploaded once

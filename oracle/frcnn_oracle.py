@@ -152,6 +152,24 @@ class _RoIPoolFn(t.autograd.Function):
     return t.from_numpy(gi), None
 
 
+class _RoIAlignFn(t.autograd.Function):
+  """EXTENSION oracle (no reference counterpart): torchvision.ops.roi_align semantics, fixed sampling_ratio; one image."""
+
+  @staticmethod
+  def forward(ctx, feature_map, rois, sampling_ratio, aligned):
+    out = roi_align_forward(feature_map.detach().numpy(), rois.detach().numpy(), (7, 7), 1.0 / 16.0, sampling_ratio, aligned)
+    ctx.save_for_backward(rois)
+    ctx.cfg = (tuple(feature_map.shape), sampling_ratio, aligned)
+    return t.from_numpy(out)
+
+  @staticmethod
+  def backward(ctx, grad_output):
+    (rois,) = ctx.saved_tensors
+    shape, s, al = ctx.cfg
+    gi = roi_align_backward(grad_output.contiguous().numpy(), rois.numpy(), shape, 1.0 / 16.0, s, al)
+    return t.from_numpy(gi), None, None, None
+
+
 # --------------------------------------------------------------------------------------------
 # Geometry (models/anchors.py, models/math_utils.py)
 # --------------------------------------------------------------------------------------------
@@ -446,6 +464,22 @@ def detector_forward(params, feature_map, proposals, pool_to_feature_vector):
   return classes, deltas
 
 
+def detector_forward_batch(params, feature_map, proposals_list, pool_to_feature_vector, roi_op = "pool", sampling_ratio = 2, aligned = False):
+  """EXTENSION (BASELINE config 3): models/detector.py:38-80 for a batch -- the RoIs of image b are pooled from
+  feature_map[b] (the batch column of detector.py:65 carries b instead of 0), stacked in image order, and go through the head
+  together.  roi_op "pool" = torchvision RoIPool (the reference's), "align" = torchvision roi_align(sampling_ratio, aligned)."""
+  pooled = []
+  for b, proposals in enumerate(proposals_list):
+    rois = t.cat([t.zeros((proposals.shape[0], 1)), proposals], dim = 1)[:, [0, 2, 1, 4, 3]].contiguous()
+    fm_b = feature_map[b:b + 1]
+    pooled.append(_RoIPoolFn.apply(fm_b, rois) if roi_op == "pool" else _RoIAlignFn.apply(fm_b, rois, sampling_ratio, aligned))
+  y = pool_to_feature_vector(t.cat(pooled, dim = 0))
+  logits = F.linear(y, params[S3 + "_classifier.weight"], params[S3 + "_classifier.bias"])
+  classes = F.softmax(logits, dim = 1)
+  deltas = F.linear(y, params[S3 + "_regressor.weight"], params[S3 + "_regressor.bias"])
+  return classes, deltas
+
+
 # --------------------------------------------------------------------------------------------
 # Losses (models/rpn.py:176-272, models/detector.py:83-155)
 # --------------------------------------------------------------------------------------------
@@ -680,6 +714,52 @@ class OracleModel:
     total.backward()
     if taps is not None:
       taps.update(feature_map = fm.detach(), score_map = score_map.detach(), delta_map = delta_map.detach(), sampled_proposals = props, sampled_classes = gt_classes, sampled_deltas = gt_deltas, classes = classes.detach(), deltas = deltas.detach())
+    if apply_update:
+      self.sgd_step(lr, momentum, weight_decay)
+    return loss
+
+  # -- EXTENSION: batch > 1 (no reference behaviour; the reference's batch-general loss formulas applied to stacked tensors) --
+  def forward_batch(self, images, roi_op = "pool", sampling_ratio = 2, aligned = False, pre_nms = 6000, post_nms = 300):
+    """images (B,3,H,W) -> [(proposals_b, classes_b, deltas_b)]: shared-size images, per-image proposals, one head pass."""
+    image_shape = tuple(images.shape[1:])
+    anchor_map, anchor_valid_map = generate_anchor_maps(image_shape, self.compute_feature_map_shape(image_shape), self.feature_pixels)
+    fm = self.features(images)
+    score_map, delta_map = rpn_heads(self.params, fm)
+    props = [rpn_proposals(score_map[b:b + 1], delta_map[b:b + 1], anchor_map, anchor_valid_map, image_shape, pre_nms, post_nms, self.allow_edge_proposals) for b in range(images.shape[0])]
+    classes, deltas = detector_forward_batch(self.params, fm, props, self.pool_to_feature_vector, roi_op, sampling_ratio, aligned)
+    out, at = [], 0
+    for p in props:
+      out.append((p, classes[at:at + p.shape[0]], deltas[at:at + p.shape[0]]))
+      at += p.shape[0]
+    return out
+
+  def train_step_batch(self, images, samples, roi_op = "pool", sampling_ratio = 2, aligned = False, lr = 1e-3, momentum = 0.9, weight_decay = 5e-4, apply_update = True):
+    """One SGD step on a batch: samples[b] = dict(anchor_map, anchor_valid_map, gt_rpn_map (1,h,w,9,6), gt_rpn_object_indices,
+    gt_rpn_background_indices, gt_corners, gt_class_idxs).  RNG order: every image's RPN minibatch (python random) in image order,
+    then every image's proposal sample (torch CPU generator) in image order.  Losses = rpn.py:176-272 / detector.py:83-155 on the
+    stacked maps / stacked RoIs (their normalisers count over the whole batch)."""
+    self.training = True
+    for v in self.params.values():
+      v.grad = None
+    image_shape = tuple(images.shape[1:])
+    fm = self.features(images)
+    score_map, delta_map = rpn_heads(self.params, fm)
+    minibatch = t.cat([sample_rpn_minibatch(s["gt_rpn_map"], s["gt_rpn_object_indices"], s["gt_rpn_background_indices"], self.rpn_minibatch_size) for s in samples], dim = 0)
+    props_l, cls_l, dlt_l = [], [], []
+    for b, s in enumerate(samples):
+      proposals = rpn_proposals(score_map[b:b + 1], delta_map[b:b + 1], s["anchor_map"], s["anchor_valid_map"], image_shape, 12000, 2000, self.allow_edge_proposals)
+      props, gt_classes, gt_deltas = label_proposals(proposals, s["gt_corners"], s["gt_class_idxs"], self.num_classes)
+      props, gt_classes, gt_deltas = sample_proposals(props, gt_classes, gt_deltas, self.proposal_batch_size, 0.25)
+      props_l.append(props.detach()); cls_l.append(gt_classes.detach()); dlt_l.append(gt_deltas.detach())
+    classes, deltas = detector_forward_batch(self.params, fm, props_l, self.pool_to_feature_vector, roi_op, sampling_ratio, aligned)
+    l1 = rpn_class_loss(score_map, minibatch)
+    l2 = rpn_regression_loss(delta_map, minibatch)
+    l3 = detector_class_loss(classes, t.cat(cls_l))
+    l4 = detector_regression_loss(deltas, t.cat(dlt_l))
+    total = l1 + l2 + l3 + l4
+    loss = Loss(l1.item(), l2.item(), l3.item(), l4.item(), total.item())
+    total.backward()
+    self.last_batch_rois = [p.shape[0] for p in props_l]
     if apply_update:
       self.sgd_step(lr, momentum, weight_decay)
     return loss

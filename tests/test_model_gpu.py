@@ -198,6 +198,91 @@ def test_config2_full_size_train_step_600x1000():
     assert rel < 2e-2, (k, rel)
 
 
+def _build_batch(kind, hw, roi_op, proposal_batch_size, weight_seed):
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import resnet
+  from oracle import resnet_oracle
+  if kind == "vgg16":
+    shapes, backbone = orc.vgg16_param_shapes(), f.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  else:
+    shapes = resnet_oracle.param_shapes(kind)
+    backbone = resnet.ResNetBackbone({"resnet50": resnet.Architecture.ResNet50, "resnet101": resnet.Architecture.ResNet101}[kind])
+  params = orc.synth_params(shapes, seed = weight_seed, heads = "spread")
+  model = f.FasterRCNNModel(num_classes = 21, backbone = backbone, proposal_batch_size = proposal_batch_size, roi_op = roi_op, roi_sampling_ratio = 2, roi_aligned = False)
+  model.load_state_dict(params)
+  oracle = orc.OracleModel(params, backbone = kind, proposal_batch_size = proposal_batch_size)
+  # two different images / ground truths of one size
+  smps = [orc.synthetic_sample(hw, seed = 21, backbone = kind),
+          orc.synthetic_sample(hw, seed = 22, backbone = kind, gt = [((30.0, 40.0, 200.0, 260.0), 3), ((120.0, 250.0, 330.0, 480.0), 12), ((10.0, 300.0, 150.0, 400.0), 9)])]
+  return model.cuda(), oracle, smps
+
+
+def _match_rows(pg, pr, tol = 5e-2):
+  dist = np.abs(pg[:, None, :] - pr[None, :, :]).max(axis = 2)
+  partner = dist.argmin(axis = 1)
+  return partner, dist[np.arange(pg.shape[0]), partner] <= tol
+
+
+@pytest.mark.parametrize("kind,roi_op", [("vgg16", "pool"), ("resnet50", "align")])
+def test_batch2_forward_matches_oracle_and_single_image_path(kind, roi_op):
+  """EXTENSION, BASELINE config 3 shape (batch 2 per GPU, RoIAlign on ResNet-50) and the RoIPool/VGG-16 twin: forward_batch
+  against the oracle's batch restatement, and (RoIPool) against this package's own single-image forward per image."""
+  model, oracle, smps = _build_batch(kind, (384, 512), roi_op, 128, weight_seed = 2)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  images = t.cat([s["image"] for s in smps], dim = 0)
+  with t.no_grad():
+    ref = oracle.forward_batch(images, roi_op = roi_op)
+  model.eval()
+  with t.no_grad():
+    got = model.forward_batch(images.cuda())
+    single = [model(image_data = images[b:b + 1].cuda()) for b in range(2)] if roi_op == "pool" else None
+  assert len(got) == 2
+  for b in range(2):
+    pg, cg, dg = [x.cpu().numpy() for x in got[b]]
+    pr, cr, dr = [x.numpy() for x in ref[b]]
+    assert abs(pg.shape[0] - pr.shape[0]) <= 3
+    partner, ok = _match_rows(pg, pr)
+    assert ok.mean() >= 0.97, (b, ok.mean())
+    np.testing.assert_allclose(cg[ok], cr[partner[ok]], rtol = 0, atol = 1e-4)
+    np.testing.assert_allclose(dg[ok], dr[partner[ok]], rtol = 0, atol = 1e-4)
+    if single is not None:                     # same kernels, same weights: the batch path must reproduce the per-image path
+      ps, cs, ds = [x.cpu().numpy() for x in single[b]]
+      partner, ok = _match_rows(pg, ps, tol = 1e-3)
+      assert ok.mean() >= 0.99
+      np.testing.assert_allclose(cg[ok], cs[partner[ok]], rtol = 0, atol = 2e-5)
+
+
+@pytest.mark.parametrize("kind,roi_op,rois", [("resnet50", "align", 300), ("vgg16", "pool", 128)])
+def test_batch2_train_step_matches_oracle(kind, roi_op, rois):
+  """EXTENSION, BASELINE config 3: ResNet-50, batch 2, 300 RoIs per image through RoIAlign -- losses, every parameter gradient and
+  the post-step weights against the oracle's batch restatement (same RNG order); VGG-16 / RoIPool as the second case."""
+  model, oracle, smps = _build_batch(kind, (384, 512), roi_op, rois, weight_seed = 4)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  images = t.cat([s["image"] for s in smps], dim = 0)
+  params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
+  optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)
+  random.seed(3); np.random.seed(3); t.manual_seed(3)
+  ref = oracle.train_step_batch(images, smps, roi_op = roi_op)
+  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
+  samples = [dict(anchor_map = s["anchor_map"], anchor_valid_map = s["anchor_valid_map"], gt_rpn_map = s["gt_rpn_map"].cuda(),
+                  gt_rpn_object_indices = s["gt_rpn_object_indices"], gt_rpn_background_indices = s["gt_rpn_background_indices"],
+                  gt_boxes = [Box(b, c) for b, c in zip(s["gt_corners"], s["gt_class_idxs"])]) for s in smps]
+  random.seed(3); np.random.seed(3); t.manual_seed(3)
+  got = model.train_step_batch(optimizer, images.cuda(), samples)
+  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
+  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
+  np.testing.assert_allclose(a, b, rtol = 5e-4, atol = 1e-5)
+  assert model.last_step_info["rois_per_image"] == oracle.last_batch_rois
+  grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+  assert set(grads) == set(ref_grads)
+  for k in ref_grads:
+    ga, gb = grads[k].double(), ref_grads[k].double()
+    rel = float((ga - gb).norm() / (gb.norm() + 1e-12))
+    assert rel < 2e-2, (k, rel)
+  for k, p in model.named_parameters():
+    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5)
+
+
 def test_checkpoint_round_trip_and_caffe_partial_load(tmp_path):
   """state.save / state.load (reference state.py:221-288): own-format round trip is bit-exact; a Caffe VGG-16 file initialises
   the 13 convs AND fc1/fc2 (the reference loses the fc layers to a key mismatch) and leaves the heads untouched."""

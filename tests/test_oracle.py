@@ -142,3 +142,26 @@ def test_e2e_forward_predict_train_match_reference(golden_dir, tag):
     ref_norm = float(g["%s_w2_norm/%s" % (tag, k)])
     assert abs(v.detach().double().norm().item() - ref_norm) <= 1e-6 * max(ref_norm, 1.0), k
     np.testing.assert_allclose(v.detach().reshape(-1)[:64].numpy(), g["%s_w2_head/%s" % (tag, k)], rtol = 1e-5, atol = 1e-7)
+
+
+def test_oracle_batch_extension_reduces_to_single_image_step():
+  """EXTENSION (batch > 1, no reference behaviour): the batch restatement with B = 1 is bit-identical to the pinned single-image
+  restatement (losses, post-step weights, forward outputs); RoIAlign batch forward runs for B = 2."""
+  import random
+  t.set_num_threads(min(8, os.cpu_count() or 8))
+  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 4, heads = "spread")
+  smp = orc.synthetic_sample((320, 400), seed = 21)
+  o1, o2 = orc.OracleModel(params), orc.OracleModel(params)
+  random.seed(3); t.manual_seed(3)
+  a = o1.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                    smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"])
+  random.seed(3); t.manual_seed(3)
+  b = o2.train_step_batch(smp["image"], [smp])
+  assert (a.rpn_class, a.rpn_regression, a.detector_class, a.detector_regression) == (b.rpn_class, b.rpn_regression, b.detector_class, b.detector_regression)
+  for k in o1.params:
+    assert t.equal(o1.params[k], o2.params[k]), k
+  with t.no_grad():
+    f1, f2 = o1.forward(smp["image"]), o2.forward_batch(smp["image"])[0]
+    assert all(t.equal(x, y) for x, y in zip(f1, f2))
+    fa = o2.forward_batch(t.cat([smp["image"], smp["image"] * 0.5]), roi_op = "align")
+  assert len(fa) == 2 and fa[0][1].shape[1] == 21 and fa[1][2].shape[1] == 80

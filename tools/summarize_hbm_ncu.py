@@ -7,7 +7,7 @@ import os
 import sys
 
 COLS = [("gpu__time_duration.sum", "us"), ("launch__grid_size", "CTAs"), ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "dram rd MB"),
-        ("dram__bytes_write.sum", "dram wr MB"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+        ("dram__bytes_write.sum", "dram wr MB"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"), ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %")]
 
@@ -33,7 +33,14 @@ def main():
     key = next((k for k in alg if k in name), None)
     if key is None:
       key = name.split("(")[0].split("::")[-1][:40]
-    last[key] = r                                                # keep the last (warm) launch of each kernel
+    grid = int(float(r[col["launch__grid_size"]].replace(",", "")))
+    biggest = max((g for (k, g) in last if k == key), default = 0)
+    if grid < biggest:
+      continue                                                   # a smaller launch of the same kernel (e.g. the 128-RoI forward before the backward)
+    if grid > biggest:
+      last.pop((key, biggest), None)
+    last[(key, grid)] = r                                        # keep the last (warm) launch of each kernel at its largest grid
+  last = {k: v for (k, _), v in last.items()}
   out = ["| kernel | " + " | ".join(c[1] for c in COLS) + " | algorithmic MB | achieved GB/s | of measured peak (%.0f GB/s) | dram traffic / algorithmic |" % peak,
          "|" + "---|" * (len(COLS) + 5)]
   for key, r in last.items():
