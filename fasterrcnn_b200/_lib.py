@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfrcnn_sm100.so")
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
-ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3XTF32 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3XTF32, ENGINE_TC_3XF16 = 0, 1, 2, 3
 
 _vp, _i, _f, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
 _GEOM = [_i] * 9
@@ -38,6 +38,11 @@ _SIGNATURES = {
   "frcnn_conv2d_fwd_presplit": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),
   "frcnn_conv2d_dgrad_presplit": (_i, [_vp] * 6 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_conv2d_wgrad_presplit": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
+  "frcnn_f16_split_bytes": (_sz, [_sz]),
+  "frcnn_f16_split": (_i, [_vp, _sz, _vp, _vp]),
+  "frcnn_conv2d_fwd_f16": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),
+  "frcnn_conv2d_dgrad_f16": (_i, [_vp] * 6 + _GEOM + [_vp, _sz, _vp]),
+  "frcnn_conv2d_wgrad_f16": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_sigmoid_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_bias_grad_workspace_bytes": (_sz, [_sz, _i]),

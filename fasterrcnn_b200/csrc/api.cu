@@ -19,25 +19,27 @@ int simt_conv2d_wgrad(const float *dy, const float *x, float *dw,
                       int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                       void *workspace, size_t workspace_bytes, cudaStream_t st);
 
-// conv_tc.cu (tcgen05 engine)
-bool tc_fwd_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
-size_t tc_fwd_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+// conv_tc.cu (tcgen05 engines; mode 0 = fwd, 1 = dgrad, 2 = wgrad; f16 selects the fp16 engine)
+bool tc_supported(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, bool f16);
+size_t tc_workspace(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, bool f16);
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split);
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16);
 size_t tf32_split_bytes(size_t count);
+size_t f16_split_bytes(size_t count);
 void tc_set_trace(void *buf);
 int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
-bool tc_dgrad_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
-size_t tc_dgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int f16_split(const float *x, size_t count, void *out, cudaStream_t st);
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split);
-bool tc_wgrad_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
-size_t tc_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split, bool f16);
 int tc_conv2d_wgrad(const float *dy, const float *x, float *dw,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *x_split);
+                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *x_split, bool f16);
+
+// FRCNN_ENGINE_AUTO = the 3xTF32 tcgen05 engine wherever the shape allows, else the CUDA-core engine; the fp16 engine is chosen explicitly
+static bool engine_f16(int engine) { return engine == FRCNN_ENGINE_TC_3XF16; }
+static bool engine_forced_tc(int engine) { return engine == FRCNN_ENGINE_TC_3XTF32 || engine == FRCNN_ENGINE_TC_3XF16; }
 
 }  // namespace frcnn
 
@@ -54,9 +56,9 @@ const char *frcnn_last_error_string(void) { return g_last_error; }
 size_t frcnn_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
 {
   size_t a = simt_fwd_workspace(GEOM_ARGS);
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_fwd_supported(GEOM_ARGS)) {
-    size_t b = tc_fwd_workspace(GEOM_ARGS);
-    return engine == FRCNN_ENGINE_TC_3XTF32 ? b : (a > b ? a : b);
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(0, GEOM_ARGS, engine_f16(engine))) {
+    size_t b = tc_workspace(0, GEOM_ARGS, engine_f16(engine));
+    return engine_forced_tc(engine) ? b : (a > b ? a : b);
   }
   return a;
 }
@@ -67,18 +69,19 @@ int frcnn_conv2d_fwd(const float *x, const float *w, const float *scale, const f
 {
   FRCNN_REQUIRE(x && w && y, "conv2d_fwd: null pointer");
   FRCNN_REQUIRE(act >= FRCNN_ACT_NONE && act <= FRCNN_ACT_SIGMOID, "conv2d_fwd: unknown activation");
-  if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_fwd_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd: shape not supported by the tcgen05 engine");
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_fwd_supported(GEOM_ARGS))
-    return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
+  const bool f16 = engine_f16(engine);
+  if (engine_forced_tc(engine) && !tc_supported(0, GEOM_ARGS, f16)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd: shape not supported by the tcgen05 engine");
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(0, GEOM_ARGS, f16))
+    return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, f16);
   return simt_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream));
 }
 
 size_t frcnn_conv2d_dgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
 {
   size_t a = simt_dgrad_workspace(GEOM_ARGS);
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_dgrad_supported(GEOM_ARGS)) {
-    size_t b = tc_dgrad_workspace(GEOM_ARGS);
-    return engine == FRCNN_ENGINE_TC_3XTF32 ? b : (a > b ? a : b);
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(1, GEOM_ARGS, engine_f16(engine))) {
+    size_t b = tc_workspace(1, GEOM_ARGS, engine_f16(engine));
+    return engine_forced_tc(engine) ? b : (a > b ? a : b);
   }
   return a;
 }
@@ -88,18 +91,19 @@ int frcnn_conv2d_dgrad(const float *dy, const float *w, const float *addend, flo
                        int engine, void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad: null pointer");
-  if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_dgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tcgen05 engine");
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_dgrad_supported(GEOM_ARGS))
-    return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
+  const bool f16 = engine_f16(engine);
+  if (engine_forced_tc(engine) && !tc_supported(1, GEOM_ARGS, f16)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad: shape not supported by the tcgen05 engine");
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(1, GEOM_ARGS, f16))
+    return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, f16);
   return simt_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
 }
 
 size_t frcnn_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
 {
   size_t a = simt_wgrad_workspace(GEOM_ARGS);
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_wgrad_supported(GEOM_ARGS)) {
-    size_t b = tc_wgrad_workspace(GEOM_ARGS);
-    return engine == FRCNN_ENGINE_TC_3XTF32 ? b : (a > b ? a : b);
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(2, GEOM_ARGS, engine_f16(engine))) {
+    size_t b = tc_workspace(2, GEOM_ARGS, engine_f16(engine));
+    return engine_forced_tc(engine) ? b : (a > b ? a : b);
   }
   return a;
 }
@@ -109,19 +113,18 @@ int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
                        int engine, void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(dy && x && dw, "conv2d_wgrad: null pointer");
-  if (engine == FRCNN_ENGINE_TC_3XTF32 && !tc_wgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tcgen05 engine");
-  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_wgrad_supported(GEOM_ARGS))
-    return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr);
+  const bool f16 = engine_f16(engine);
+  if (engine_forced_tc(engine) && !tc_supported(2, GEOM_ARGS, f16)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad: shape not supported by the tcgen05 engine");
+  if (engine != FRCNN_ENGINE_SIMT_FP32 && tc_supported(2, GEOM_ARGS, f16))
+    return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, f16);
   return simt_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream));
 }
 
 /* ---- tf32 hi/lo operand splits shared between the passes of one step -------------------------------- */
 int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
 {
-  if (engine == FRCNN_ENGINE_SIMT_FP32) return 0;
-  if (pass == 0) return tc_fwd_supported(GEOM_ARGS) ? 1 : 0;
-  if (pass == 1) return tc_dgrad_supported(GEOM_ARGS) ? 1 : 0;
-  return tc_wgrad_supported(GEOM_ARGS) ? 1 : 0;
+  if (engine == FRCNN_ENGINE_SIMT_FP32 || pass < 0 || pass > 2) return 0;
+  return tc_supported(pass, GEOM_ARGS, engine_f16(engine)) ? 1 : 0;
 }
 
 size_t frcnn_tf32_split_bytes(size_t count) { return tf32_split_bytes(count); }
@@ -139,8 +142,8 @@ int frcnn_conv2d_fwd_presplit(const float *x, const float *w, const void *x_spli
                               void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(x && w && y, "conv2d_fwd_presplit: null pointer");
-  if (!tc_fwd_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd_presplit: shape not supported by the tcgen05 engine");
-  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split);
+  if (!tc_supported(0, GEOM_ARGS, false)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split, false);
 }
 
 int frcnn_conv2d_dgrad_presplit(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
@@ -148,8 +151,8 @@ int frcnn_conv2d_dgrad_presplit(const float *dy, const float *w, const void *dy_
                                 void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad_presplit: null pointer");
-  if (!tc_dgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad_presplit: shape not supported by the tcgen05 engine");
-  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split);
+  if (!tc_supported(1, GEOM_ARGS, false)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split, false);
 }
 
 int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
@@ -157,8 +160,45 @@ int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_
                                 void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(dy && x && dw, "conv2d_wgrad_presplit: null pointer");
-  if (!tc_wgrad_supported(GEOM_ARGS)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad_presplit: shape not supported by the tcgen05 engine");
-  return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, x_split);
+  if (!tc_supported(2, GEOM_ARGS, false)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad_presplit: shape not supported by the tcgen05 engine");
+  return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, x_split, false);
+}
+
+/* ---- fp16 engine (FRCNN_ENGINE_TC_3XF16): operand splits and the GEMM entry points that take them ---------------- */
+size_t frcnn_f16_split_bytes(size_t count) { return f16_split_bytes(count); }
+
+int frcnn_f16_split(const float *x, size_t count, void *out, void *stream)
+{
+  FRCNN_REQUIRE(x && out && count > 0, "f16_split: bad argument");
+  FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0, "f16_split: x must be 16-byte, out 128-byte aligned");
+  return f16_split(x, count, out, as_stream(stream));
+}
+
+int frcnn_conv2d_fwd_f16(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
+                         const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+                         void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(x && w && y, "conv2d_fwd_f16: null pointer");
+  if (!tc_supported(0, GEOM_ARGS, true)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd_f16: shape not supported by the fp16 tcgen05 engine");
+  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split, true);
+}
+
+int frcnn_conv2d_dgrad_f16(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad_f16: null pointer");
+  if (!tc_supported(1, GEOM_ARGS, true)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad_f16: shape not supported by the fp16 tcgen05 engine");
+  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split, true);
+}
+
+int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && x && dw, "conv2d_wgrad_f16: null pointer");
+  if (!tc_supported(2, GEOM_ARGS, true)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_wgrad_f16: shape not supported by the fp16 tcgen05 engine");
+  return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, x_split, true);
 }
 
 }  // extern "C"

@@ -23,8 +23,16 @@
 //   FWD    pixels x Cout x (tap,ci) : A = x patch   (K-major, 4-D map)   B = w[co][(tap,ci)] (K-major, 2-D map)
 //   DGRAD  pixels x Cin  x (tap,co) : A = dy patch  (K-major, flipped tap) B = w[co][tap][ci] (N-major, 3-D map)
 //   WGRAD  Cout   x Cin  x pixels   : A = dy patch  (M-major)            B = shifted x patch (N-major), one tap per CTA
+//
+// Second engine, FRCNN_ENGINE_TC_3XF16 (template parameter F16): the same kernel on kind::f16 -- twice the tensor-pipe rate and half
+// the operand bytes per multiply-accumulate.  Operands are the per-tensor power-of-two scaled split  x * 2^e = hi + lo / 2048  with
+// hi = fp16(x * 2^e), lo = fp16((x * 2^e - hi) * 2048) (e chosen from the tensor's absolute maximum so that |hi| < 2^14: both halves
+// keep 11 significant bits in the fp16 normal range); the three products and the [main | corr] accumulator columns are those of the
+// tf32 scheme, the drain folds corr / 2048 and the 2^-(e_a + e_b) rescale into its two FMAs (powers of two: exact).  A k-block is
+// 64 elements (one 128-byte swizzle row of fp16), MN-major operands use the plain SWIZZLE_128B layout with 64-channel atoms.
 #include <stdlib.h>
 #include <atomic>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -69,6 +77,61 @@ __global__ void split_hi_lo_kernel(const float *__restrict__ x, float *__restric
   }
 }
 
+// ---- fp16 engine: x * 2^e = hi + lo / 2048.  Buffer = [header 1024 B | hi (count fp16, padded to 1024 B) | lo (same)];
+// header word 0 = bit pattern of max |x| (atomicMax on the unsigned image: order-preserving for non-negative floats),
+// word 1 = e.  Three stream-ordered steps: clear the header, amax, split (every thread derives e from word 0). ----
+constexpr int kF16Header = 1024;
+constexpr int kF16LoShift = 11;             // lo is stored multiplied by 2^11
+
+__global__ void amax_kernel(const float *__restrict__ x, size_t count, unsigned *__restrict__ header)
+{
+  const size_t n4 = count / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(header, __float_as_uint(m));
+}
+
+// e such that max|x| * 2^e lies in [2^13, 2^14); clamped so that 2^-(e_a + e_b) stays a normal float
+__device__ __forceinline__ int f16_exponent(unsigned amax_bits)
+{
+  if (amax_bits == 0u) return 0;
+  int e = 140 - (int)((amax_bits >> 23) & 0xffu);
+  return e > 60 ? 60 : (e < -60 ? -60 : e);
+}
+
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
+
+__device__ __forceinline__ void split16(float x, float s, __half &hi, __half &lo)
+{
+  const float xs = __fmul_rn(x, s);                                   // exact (power of two) unless it underflows
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(__fmul_rn(__fsub_rn(xs, __half2float(hi)), 2048.0f));
+}
+
+__global__ void split_f16_kernel(const float *__restrict__ x, int *__restrict__ header, __half *__restrict__ hi, __half *__restrict__ lo, size_t count)
+{
+  const int e = f16_exponent(reinterpret_cast<const unsigned *>(header)[0]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) header[1] = e;
+  const float s = pow2i(e);
+  const size_t n4 = count / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    __half h[4], l[4];
+    split16(v.x, s, h[0], l[0]); split16(v.y, s, h[1], l[1]); split16(v.z, s, h[2], l[2]); split16(v.w, s, h[3], l[3]);
+    reinterpret_cast<uint2 *>(hi)[i] = *reinterpret_cast<const uint2 *>(h);
+    reinterpret_cast<uint2 *>(lo)[i] = *reinterpret_cast<const uint2 *>(l);
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) split16(x[i], s, hi[i], lo[i]);
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
@@ -91,6 +154,7 @@ struct TcGeom {
   float *sk_slots;                // gridDim.x x (128 x BN) fp32
   unsigned long long *sk_flags;   // gridDim.x
   unsigned long long sk_tag;      // unique per launch (stale workspace contents can never match)
+  const int *a_exp, *b_exp;       // fp16 engine: device words holding the operands' scale exponents (NULL for tf32)
 };
 
 // one work item of the persistent loop: an output tile (or one split-K slice of it)
@@ -181,6 +245,7 @@ constexpr int kBK = 32;                       // fp32 elements per 128-byte swiz
 constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
 constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
 constexpr int kChunkKB = 8;                   // k-blocks (32 accumulations per column) inside the tensor core before a register drain
+constexpr int kChunkKB16 = 4;                 // fp16 engine: a k-block holds 64 accumulations per column -> same chain length
 
 __device__ __forceinline__ float tc_act(float v, int act)
 {
@@ -189,7 +254,7 @@ __device__ __forceinline__ float tc_act(float v, int act)
   return v;
 }
 
-template <int MODE, int BN, int STAGES>
+template <int MODE, int BN, int STAGES, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -199,6 +264,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   constexpr bool kAMajorMN = (MODE == TC_WGRAD);
   constexpr bool kBMajorMN = (MODE != TC_FWD);
+  constexpr int kElems = F16 ? 64 : 32;        // operand elements per 128-byte row = K extent of a k-block = channels of an MN-major atom
+  constexpr int kChunk = F16 ? kChunkKB16 : kChunkKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * kStageBytes);
@@ -233,7 +300,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       // ===== TMA producers: warp 0 feeds the A operand, warp 6 the B operand (up to 8 box loads each per k-block: issuing them
       // from one thread was the limit of the filter-gradient mainloop).  Both run ahead across work items. =====
       const bool feed_a = (warp == 0);
-      const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kBK;          // channel blocks per tap (FWD/DGRAD)
+      const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kElems;       // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
       int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
       TcCursor cur = tc_cursor(g);
@@ -254,14 +321,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
             const int kh = t.tap_w / g.KW, kw = t.tap_w - kh * g.KW;
             if (feed_a) {                                                      // A: dy, 128 output channels = 4 atoms in one box
-              tma_load_5d(a_hi, &map_a_hi, &full[s], 0, px, py, im, t.m0 / 32);
-              tma_load_5d(a_lo, &map_a_lo, &full[s], 0, px, py, im, t.m0 / 32);
+              tma_load_5d(a_hi, &map_a_hi, &full[s], 0, px, py, im, t.m0 / kElems);
+              tma_load_5d(a_lo, &map_a_lo, &full[s], 0, px, py, im, t.m0 / kElems);
             } else {                                                           // B: x shifted by the tap, BN / 32 atoms in one box
-              tma_load_5d(b_hi, &map_b_hi, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / 32);
-              tma_load_5d(b_lo, &map_b_lo, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / 32);
+              tma_load_5d(b_hi, &map_b_hi, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
+              tma_load_5d(b_lo, &map_b_lo, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
             }
           } else {
-            const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kBK;
+            const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kElems;
             const int kh = tap / g.KW, kw = tap - kh * g.KW;
             const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
             const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
@@ -272,8 +339,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, t.n0);
               tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, t.n0);
             } else {                                                           // B: w[co0..+32][tap][n0 .. n0+BN) as BN / 32 atoms in one box
-              tma_load_4d(b_hi, &map_b_hi, &full[s], 0, tap, c0, t.n0 / 32);
-              tma_load_4d(b_lo, &map_b_lo, &full[s], 0, tap, c0, t.n0 / 32);
+              tma_load_4d(b_hi, &map_b_hi, &full[s], 0, tap, c0, t.n0 / kElems);
+              tma_load_4d(b_lo, &map_b_lo, &full[s], 0, tap, c0, t.n0 / kElems);
             }
           }
           if (it == 0 && feed_a) TC_TRACE(2);
@@ -283,8 +350,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc_main = make_idesc_tf32(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);   // A_hi x [B_hi | B_lo]
-      constexpr uint32_t idesc_corr = make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);       // A_lo x B_hi
+      constexpr uint32_t idesc_main = F16 ? make_idesc_f16(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
+                                          : make_idesc_tf32(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);   // A_hi x [B_hi | B_lo]
+      constexpr uint32_t idesc_corr = F16 ? make_idesc_f16(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
+                                          : make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);       // A_lo x B_hi
       const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
       const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
       uint32_t accumulate = 0;
@@ -295,7 +364,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       bool first_item = true;
       while (tc_next<MODE, BN>(g, cur, t)) {
         for (int i = 0; i < t.nkb; i++, it++) {
-          if (i % kChunkKB == 0) {                                   // new accumulation chain in the other TMEM buffer
+          if (i % kChunk == 0) {                                     // new accumulation chain in the other TMEM buffer
             const int b = chunk & 1;
             mbar_wait(&acc_empty[b], ((chunk >> 1) & 1) ^ 1);        // drained by the epilogue warps (first use passes)
             tc_fence_after();
@@ -310,17 +379,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t a_lo = a_hi + kABytes;
           const uint32_t b_hi = a_hi + 2 * kABytes;                  // b_lo follows at + kBBytes
 #pragma unroll
-          for (int k = 0; k < kBK / 8; k++) {
-            constexpr uint32_t a_lt = kAMajorMN ? kLayoutSW128Base32B : kLayoutSW128, b_lt = kBMajorMN ? kLayoutSW128Base32B : kLayoutSW128;
+          for (int k = 0; k < 4; k++) {                              // four MMAs per k-block: K = 8 (tf32) / 16 (fp16) = 32 bytes of a K-major row each
+            constexpr uint32_t mn_lt = F16 ? kLayoutSW128 : kLayoutSW128Base32B;
+            constexpr uint32_t a_lt = kAMajorMN ? mn_lt : kLayoutSW128, b_lt = kBMajorMN ? mn_lt : kLayoutSW128;
             const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);   // covers b_hi then b_lo (contiguous)
-            umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate);   // [main | corr] (+)= A_hi * [B_hi | B_lo]
-            umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);       // corr += A_lo * B_hi
+            if (F16) {
+              umma_f16(tmem_acc, da_hi, db, idesc_main, accumulate);
+              umma_f16(tmem_acc + BN, da_lo, db, idesc_corr, 1);
+            } else {
+              umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate); // [main | corr] (+)= A_hi * [B_hi | B_lo]
+              umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);     // corr += A_lo * B_hi
+            }
             accumulate = 1;
           }
           umma_commit(&empty[s]);                                    // frees the operand slot when these MMAs retire
-          if (i % kChunkKB == kChunkKB - 1 || i == t.nkb - 1) {
+          if (i % kChunk == kChunk - 1 || i == t.nkb - 1) {
             umma_commit(&acc_full[chunk & 1]);                       // chain complete -> epilogue warps may drain it
             chunk++;
           }
@@ -336,6 +411,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool raw = g.splits > 1;
+    // fp16 engine: main columns hold sum(hi_a hi_b) of operands scaled by 2^e_a, 2^e_b, corr columns additionally by 2^11; both
+    // factors are powers of two, so the FMAs below are exact rescales followed by the same round-to-nearest add as the tf32 path
+    float s_main = 1.0f, s_corr = 1.0f;
+    if (F16) {
+      const int e = __ldg(g.a_exp) + __ldg(g.b_exp);
+      s_main = pow2i(-e);
+      s_corr = pow2i(-e - kF16LoShift);
+    }
     int cg = 0;                                                      // accumulation chains drained so far, across all items
     TcCursor cur = tc_cursor(g);
     TcItem t;
@@ -344,7 +427,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; j++) acc[j] = 0.f;
-      const int nchunks = (t.nkb + kChunkKB - 1) / kChunkKB;
+      const int nchunks = (t.nkb + kChunk - 1) / kChunk;
       for (int c = 0; c < nchunks; c++, cg++) {
         const int b = cg & 1;
         mbar_wait(&acc_full[b], (cg >> 1) & 1);
@@ -354,10 +437,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + BN + cc * 32, v);    // corr: A_hi*B_lo + A_lo*B_hi
 #pragma unroll
-          for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];          // fp32 round-to-nearest, outside the tensor core
+          for (int j = 0; j < 32; j++) acc[cc * 32 + j] = F16 ? fmaf(v[j], s_corr, acc[cc * 32 + j]) : acc[cc * 32 + j] + v[j];   // fp32 round-to-nearest, outside the tensor core
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 2 * BN + cc * 32, v);         // main: A_hi*B_hi
 #pragma unroll
-          for (int j = 0; j < 32; j++) acc[cc * 32 + j] += v[j];
+          for (int j = 0; j < 32; j++) acc[cc * 32 + j] = F16 ? fmaf(v[j], s_main, acc[cc * 32 + j]) : acc[cc * 32 + j] + v[j];
         }
         tc_fence_before();
         __syncwarp();
@@ -485,54 +568,59 @@ static EncodeTiledFn encode_fn()
   return fn;
 }
 
-// mn_major: the tile feeds an MN-major (transposed) tf32 operand -> 32-byte-atom swizzle
-static bool encode(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box, bool mn_major)
+// mn_major: the tile feeds an MN-major (transposed) operand; 32-bit elements then need the 32-byte-atom swizzle, fp16 the plain one.
+// Dimensions are in elements, strides in bytes; elem = 4 (tf32 engine) or 2 (fp16 engine).
+static bool encode(CUtensorMap *m, const void *base, int elem, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box, bool mn_major)
 {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn f = encode_fn();
   if (!f) return false;
-  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const bool f16 = elem == 2;
+  return f(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           (mn_major && !f16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// activation (N,H,W,C) fp32 as a 4-D tensor (C, W, H, N); box {32, box_w, box_h, box_n}
-static bool make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h, int box_n, bool mn_major = false)
+// activation (N,H,W,C) as a 4-D tensor (C, W, H, N); box {one 128-byte row of channels, box_w, box_h, box_n}
+static bool make_act_map(CUtensorMap *m, const void *base, int elem, int N, int H, int W, int C, int box_w, int box_h, int box_n, bool mn_major = false)
 {
+  const cuuint64_t e = (cuuint64_t)elem;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
-  return encode(m, base, 4, dims, strides, box, mn_major);
+  cuuint64_t strides[3] = {(cuuint64_t)C * e, (cuuint64_t)W * C * e, (cuuint64_t)H * W * C * e};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  return encode(m, base, elem, 4, dims, strides, box, mn_major);
 }
 
-// matrix (rows, K) fp32 row-major as a 2-D tensor (K, rows); box {32, box_rows}
-static bool make_mat_map(CUtensorMap *m, const float *base, int rows, int K, int box_rows)
+// matrix (rows, K) row-major as a 2-D tensor (K, rows); box {one 128-byte row, box_rows}
+static bool make_mat_map(CUtensorMap *m, const void *base, int elem, int rows, int K, int box_rows)
 {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  return encode(m, base, 2, dims, strides, box, false);
+  cuuint64_t strides[1] = {(cuuint64_t)K * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
+  return encode(m, base, elem, 2, dims, strides, box, false);
 }
 
-// MN-major operand tiles are stacks of 32-channel atoms ([atom][32 k-rows][32 channels], 4 KB each).  Splitting the channel axis
-// into (32, C/32) and putting the atom index LAST in the tensor map lets ONE box load deliver the whole stack in exactly that
-// order (the producer thread's issue rate of small boxes was the limit of the filter-gradient mainloop):
-// activation (N,H,W,C) as the 5-D tensor (32, W, H, N, C/32); box {32, box_w, box_h, box_n, atoms}
-static bool make_act_map_atoms(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h, int box_n, int atoms)
+// MN-major operand tiles are stacks of atoms of A = 128 / elem channels ([atom][k-rows][A channels]: 32 x 32 fp32 = 4 KB, 64 x 64 fp16 =
+// 8 KB).  Splitting the channel axis into (A, C/A) and putting the atom index LAST in the tensor map lets ONE box load deliver the whole
+// stack in exactly that order (the producer thread's issue rate of small boxes was the limit of the filter-gradient mainloop):
+// activation (N,H,W,C) as the 5-D tensor (A, W, H, N, C/A); box {A, box_w, box_h, box_n, atoms}
+static bool make_act_map_atoms(CUtensorMap *m, const void *base, int elem, int N, int H, int W, int C, int box_w, int box_h, int box_n, int atoms)
 {
-  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 32)};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, 128};
-  cuuint32_t box[5] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n, (cuuint32_t)atoms};
-  return encode(m, base, 5, dims, strides, box, true);
+  const cuuint64_t e = (cuuint64_t)elem, A = 128 / elem;
+  cuuint64_t dims[5] = {A, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)C / A};
+  cuuint64_t strides[4] = {(cuuint64_t)C * e, (cuuint64_t)W * C * e, (cuuint64_t)H * W * C * e, 128};
+  cuuint32_t box[5] = {(cuuint32_t)A, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n, (cuuint32_t)atoms};
+  return encode(m, base, elem, 5, dims, strides, box, true);
 }
 
-// filter (Cout, taps, Cin) as the 4-D tensor (32, taps, Cout, Cin/32); box {32 ci, 1 tap, 32 co, atoms}
-static bool make_filter_map_atoms(CUtensorMap *m, const float *base, int Cout, int taps, int Cin, int atoms)
+// filter (Cout, taps, Cin) as the 4-D tensor (A, taps, Cout, Cin/A); box {A ci, 1 tap, A co (the k-block), atoms}
+static bool make_filter_map_atoms(CUtensorMap *m, const void *base, int elem, int Cout, int taps, int Cin, int atoms)
 {
-  cuuint64_t dims[4] = {32, (cuuint64_t)taps, (cuuint64_t)Cout, (cuuint64_t)(Cin / 32)};
-  cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)taps * Cin * 4, 128};
-  cuuint32_t box[4] = {32, 1, 32, (cuuint32_t)atoms};
-  return encode(m, base, 4, dims, strides, box, true);
+  const cuuint64_t e = (cuuint64_t)elem, A = 128 / elem;
+  cuuint64_t dims[4] = {A, (cuuint64_t)taps, (cuuint64_t)Cout, (cuuint64_t)Cin / A};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * e, (cuuint64_t)taps * Cin * e, 128};
+  cuuint32_t box[4] = {(cuuint32_t)A, 1, (cuuint32_t)A, (cuuint32_t)atoms};
+  return encode(m, base, elem, 4, dims, strides, box, true);
 }
 
 struct TcPlan {
@@ -564,8 +652,11 @@ static void best_patch(int total, int N, int H, int W, int *pw, int *ph, int *pn
     }
 }
 
-static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, TcPlan *p)
+static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, TcPlan *p, bool f16 = false)
 {
+  const int kel = f16 ? 64 : 32;                                          // elements per k-block row / channels per MN-major atom
+  const int chunk = f16 ? kChunkKB16 : kChunkKB;
+  const size_t esz = f16 ? 2 : 4;
   if (stride != 1 || KH != KW || 2 * pad != KH - 1) return false;        // stride-1 "same" convs, 1x1, linear
   if (KH == 1 && H == 1 && W == 1) { p->N = 1; p->H = 1; p->W = N; }      // linear: rows become the W axis
   else { p->N = N; p->H = H; p->W = W; }
@@ -573,8 +664,8 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   if (pixels < 64) return false;                                         // tiny problems stay on the CUDA-core engine
   const int ntot = (mode == TC_FWD) ? Cout : Cin;                         // GEMM N extent
   if (ntot % 64 != 0) return false;
-  if (mode == TC_FWD && Cin % 32 != 0) return false;
-  if (mode == TC_DGRAD && Cout % 32 != 0) return false;
+  if (mode == TC_FWD && Cin % kel != 0) return false;
+  if (mode == TC_DGRAD && Cout % kel != 0) return false;
   if (mode == TC_WGRAD && (Cout % 128 != 0 || Cin % 64 != 0)) return false;
   p->BN = (ntot % 128 == 0) ? 128 : 64;
   p->stages = p->BN == 128 ? 3 : 4;
@@ -583,7 +674,7 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   const int taps = KH * KW;
   int ctas;
   if (mode == TC_WGRAD) {
-    best_patch(32, p->N, p->H, p->W, &p->pw, &p->ph, &p->pn);
+    best_patch(kel, p->N, p->H, p->W, &p->pw, &p->ph, &p->pn);
     p->patches_w = ceil_div(p->W, p->pw);
     p->patches_h = ceil_div(p->H, p->ph);
     p->pgroups = ceil_div(p->N, p->pn);
@@ -596,7 +687,7 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->tiles_w = ceil_div(p->W, p->tile_w);
     p->tiles_h = ceil_div(p->H, p->tile_h);
     p->groups = ceil_div(p->N, p->tile_n);
-    p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / 32);
+    p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / kel);
     p->m_tiles = p->groups * p->tiles_w * p->tiles_h;
     p->n_tiles = ntot / p->BN;
     ctas = p->m_tiles * p->n_tiles;
@@ -615,7 +706,7 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->streamk = (use_streamk && ctas >= kNumSMs / 2 && ctas < 8 * kNumSMs) ? 1 : 0;
   p->units = (long long)ctas * p->total_kb;
   if (p->streamk) {
-    long long gsz = p->units / kChunkKB;                             // at least one accumulation chain per CTA
+    long long gsz = p->units / chunk;                                // at least one accumulation chain per CTA
     if (gsz > kNumSMs) gsz = kNumSMs;
     if (gsz < 1) gsz = 1;
     p->grid = (int)gsz;
@@ -623,7 +714,7 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     const double t_kb = (p->BN == 128) ? 0.56 : 0.42;               // us per k-block (measured, smem-bandwidth bound mainloop)
     const double t_item = 2.5;                                       // us of per-item pipeline refill / final drain not overlapped
     double best_t = -1.0;
-    const int max_splits = p->total_kb / kChunkKB > 32 ? 32 : p->total_kb / kChunkKB;
+    const int max_splits = p->total_kb / chunk > 32 ? 32 : p->total_kb / chunk;
     for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); sp++) {
       const int kbs = ceil_div(p->total_kb, sp);
       if (ceil_div(p->total_kb, kbs) != sp) continue;                // slice lengths that do not produce exactly sp splits
@@ -642,11 +733,13 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
   else if (mode == TC_DGRAD) { p->a_count = act_out; p->b_count = filt; out_elems = act_in; }
   else { p->a_count = act_out; p->b_count = act_in; out_elems = filt; }
-  p->a_hi_off = 0;
-  p->a_lo_off = align_up(p->a_count * 4, 1024);
-  p->b_hi_off = 2 * p->a_lo_off;
-  p->b_lo_off = p->b_hi_off + align_up(p->b_count * 4, 1024);
-  p->partial_off = p->b_lo_off + align_up(p->b_count * 4, 1024);
+  // internal operand splits (used when the caller passes none): tf32 = [hi | lo]; fp16 = [header | hi | lo] per operand
+  const size_t hdr = f16 ? kF16Header : 0;
+  p->a_hi_off = hdr;
+  p->a_lo_off = p->a_hi_off + align_up(p->a_count * esz, 1024);
+  p->b_hi_off = p->a_lo_off + align_up(p->a_count * esz, 1024) + hdr;
+  p->b_lo_off = p->b_hi_off + align_up(p->b_count * esz, 1024);
+  p->partial_off = p->b_lo_off + align_up(p->b_count * esz, 1024);
   if (p->streamk) {
     p->flags_off = p->partial_off + align_up((size_t)p->grid * 128 * p->BN * 4, 1024);
     p->total_bytes = p->flags_off + align_up((size_t)p->grid * 8, 1024);
@@ -657,13 +750,13 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   return true;
 }
 
-template <int MODE, int BN, int STAGES>
+template <int MODE, int BN, int STAGES, bool F16>
 static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float *out, float *partial, const Epilogue &epi, cudaStream_t st)
 {
   constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kBK * 4) + 1024 + 256;
-  static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
-  tc_conv_kernel<MODE, BN, STAGES><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  tc_conv_kernel<MODE, BN, STAGES, F16><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;
 }
@@ -683,70 +776,99 @@ int tf32_split(const float *x, size_t count, void *out, cudaStream_t st)
   return FRCNN_OK;
 }
 
-// a_split / b_split: optional buffers produced by tf32_split for the two operands (NULL = split here)
+size_t f16_split_bytes(size_t count) { return kF16Header + 2 * align_up(count * 2, 1024); }
+
+int f16_split(const float *x, size_t count, void *out, cudaStream_t st)
+{
+  uint8_t *o = reinterpret_cast<uint8_t *>(out);
+  cudaError_t e = cudaMemsetAsync(o, 0, 8, st);
+  if (e != cudaSuccess) return cuda_fail(e, "f16_split: memset");
+  amax_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, count, reinterpret_cast<unsigned *>(o));
+  FRCNN_CHECK_LAUNCH("amax_kernel");
+  __half *hi = reinterpret_cast<__half *>(o + kF16Header);
+  __half *lo = reinterpret_cast<__half *>(o + kF16Header + align_up(count * 2, 1024));
+  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<int *>(o), hi, lo, count);
+  FRCNN_CHECK_LAUNCH("split_f16_kernel");
+  return FRCNN_OK;
+}
+
+// a_split / b_split: optional buffers produced by tf32_split / f16_split for the two operands (NULL = split here)
 static int run_tc(int mode, const float *a, const float *b, float *out, const Epilogue &epi,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *a_split = nullptr, const void *b_split = nullptr)
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *a_split = nullptr, const void *b_split = nullptr, bool f16 = false)
 {
   TcPlan p;
-  if (!make_tc_plan(mode, N, H, W, Cin, Cout, KH, KW, stride, pad, &p)) return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: unsupported shape");
+  if (!make_tc_plan(mode, N, H, W, Cin, Cout, KH, KW, stride, pad, &p, f16)) return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: unsupported shape");
   if (workspace == nullptr || workspace_bytes < p.total_bytes) return fail(FRCNN_E_WORKSPACE, "tcgen05 engine: workspace too small");
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return fail(FRCNN_E_BADARG, "tcgen05 engine: operands and workspace must be 16-byte aligned");
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(epi.scale) & 15) || (reinterpret_cast<uintptr_t>(epi.bias) & 15) ||
       (reinterpret_cast<uintptr_t>(epi.residual) & 15))
     return fail(FRCNN_E_BADARG, "tcgen05 engine: output, scale, bias and residual must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(a_split) & 127) || (reinterpret_cast<uintptr_t>(b_split) & 127))
+    return fail(FRCNN_E_BADARG, "tcgen05 engine: operand split buffers must be 128-byte aligned");
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-  float *a_hi = reinterpret_cast<float *>(ws + p.a_hi_off);
-  float *a_lo = reinterpret_cast<float *>(ws + p.a_lo_off);
-  float *b_hi = reinterpret_cast<float *>(ws + p.b_hi_off);
-  float *b_lo = reinterpret_cast<float *>(ws + p.b_lo_off);
+  const size_t esz = f16 ? 2 : 4, hdr = f16 ? kF16Header : 0;
+  const void *a_hi = ws + p.a_hi_off, *a_lo = ws + p.a_lo_off, *b_hi = ws + p.b_hi_off, *b_lo = ws + p.b_lo_off;
+  const int *a_exp = nullptr, *b_exp = nullptr;
   float *partial = reinterpret_cast<float *>(ws + p.partial_off);
   if (a_split) {
-    a_hi = const_cast<float *>(reinterpret_cast<const float *>(a_split));
-    a_lo = const_cast<float *>(reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(a_split) + align_up(p.a_count * 4, 1024)));
+    a_hi = reinterpret_cast<const uint8_t *>(a_split) + hdr;
+    a_lo = reinterpret_cast<const uint8_t *>(a_split) + hdr + align_up(p.a_count * esz, 1024);
+  } else if (f16) {
+    int rc = f16_split(a, p.a_count, ws + p.a_hi_off - hdr, st);
+    if (rc != FRCNN_OK) return rc;
   } else {
-    split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, a_hi, a_lo, p.a_count);
+    split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, (float *)a_hi, (float *)a_lo, p.a_count);
     FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(a)");
   }
   if (b_split) {
-    b_hi = const_cast<float *>(reinterpret_cast<const float *>(b_split));
-    b_lo = const_cast<float *>(reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(b_split) + align_up(p.b_count * 4, 1024)));
+    b_hi = reinterpret_cast<const uint8_t *>(b_split) + hdr;
+    b_lo = reinterpret_cast<const uint8_t *>(b_split) + hdr + align_up(p.b_count * esz, 1024);
+  } else if (f16) {
+    int rc = f16_split(b, p.b_count, ws + p.b_hi_off - hdr, st);
+    if (rc != FRCNN_OK) return rc;
   } else {
-    split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, b_hi, b_lo, p.b_count);
+    split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, (float *)b_hi, (float *)b_lo, p.b_count);
     FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(b)");
   }
-  a = a_hi;
-  b = b_hi;
+  if (f16) {                                                          // scale exponents: header word 1 of each operand's split
+    a_exp = reinterpret_cast<const int *>(reinterpret_cast<const uint8_t *>(a_hi) - hdr) + 1;
+    b_exp = reinterpret_cast<const int *>(reinterpret_cast<const uint8_t *>(b_hi) - hdr) + 1;
+  }
 
-  const int taps = KH * KW;
+  const int taps = KH * KW, el = (int)esz, atom = 128 / el;
   CUtensorMap maps[4];
   bool ok;
   dim3 grid;
   if (mode == TC_FWD) {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) &&
-         make_mat_map(&maps[2], b, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, Cout, taps * Cin, p.BN);
+    ok = make_act_map(&maps[0], a_hi, el, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, el, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) &&
+         make_mat_map(&maps[2], b_hi, el, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, el, Cout, taps * Cin, p.BN);
   } else if (mode == TC_DGRAD) {
-    ok = make_act_map(&maps[0], a, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
-         make_filter_map_atoms(&maps[2], b, Cout, taps, Cin, p.BN / 32) && make_filter_map_atoms(&maps[3], b_lo, Cout, taps, Cin, p.BN / 32);
+    ok = make_act_map(&maps[0], a_hi, el, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, el, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
+         make_filter_map_atoms(&maps[2], b_hi, el, Cout, taps, Cin, p.BN / atom) && make_filter_map_atoms(&maps[3], b_lo, el, Cout, taps, Cin, p.BN / atom);
   } else {
-    ok = make_act_map_atoms(&maps[0], a, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 4) && make_act_map_atoms(&maps[1], a_lo, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 4) &&
-         make_act_map_atoms(&maps[2], b, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / 32) && make_act_map_atoms(&maps[3], b_lo, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / 32);
+    ok = make_act_map_atoms(&maps[0], a_hi, el, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 128 / atom) && make_act_map_atoms(&maps[1], a_lo, el, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 128 / atom) &&
+         make_act_map_atoms(&maps[2], b_hi, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / atom) && make_act_map_atoms(&maps[3], b_lo, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / atom);
   }
   if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 
-  static const int dbg_lbo = getenv("FRCNN_TC_MN_LBO") ? atoi(getenv("FRCNN_TC_MN_LBO")) : kAtomBytes;
-  static const int dbg_sbo = getenv("FRCNN_TC_MN_SBO") ? atoi(getenv("FRCNN_TC_MN_SBO")) : 512;
-  static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 1024;
+  // MN-major descriptor strides: tf32 = 32-channel atoms of 32 k-rows (4 KB), 4-row K atoms (512 B), 8 k-rows per MMA (1 KB);
+  // fp16 = 64-channel atoms of 64 k-rows (8 KB), 8-row K atoms (1 KB), 16 k-rows per MMA (2 KB)
+  static const int dbg_lbo = getenv("FRCNN_TC_MN_LBO") ? atoi(getenv("FRCNN_TC_MN_LBO")) : 0;
+  static const int dbg_sbo = getenv("FRCNN_TC_MN_SBO") ? atoi(getenv("FRCNN_TC_MN_SBO")) : 0;
+  static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 0;
+  const int mn_lbo = dbg_lbo ? dbg_lbo : (f16 ? 8192 : kAtomBytes), mn_sbo = dbg_sbo ? dbg_sbo : (f16 ? 1024 : 512), mn_kstep = dbg_kstep ? dbg_kstep : (f16 ? 2048 : 1024);
   static std::atomic<unsigned long long> launch_serial{0};
   grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, dbg_lbo, dbg_sbo, dbg_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
+           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
-           0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull)};
+           0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp};
   int rc;
-#define TC_LAUNCH(M)                                                                          \
-  (p.BN == 128 ? launch_tc<M, 128, 3>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4>(maps, g, grid, out, partial, epi, st))
+#define TC_LAUNCH(M)                                                                                                                      \
+  (f16 ? (p.BN == 128 ? launch_tc<M, 128, 3, true>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, true>(maps, g, grid, out, partial, epi, st)) \
+       : (p.BN == 128 ? launch_tc<M, 128, 3, false>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, false>(maps, g, grid, out, partial, epi, st)))
   if (mode == TC_FWD) rc = TC_LAUNCH(TC_FWD);
   else if (mode == TC_DGRAD) rc = TC_LAUNCH(TC_DGRAD);
   else rc = TC_LAUNCH(TC_WGRAD);
@@ -765,32 +887,35 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
 #define GEOM_PARAMS int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad
 #define GEOM_ARGS N, H, W, Cin, Cout, KH, KW, stride, pad
 
-bool tc_fwd_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_FWD, GEOM_ARGS, &p); }
-bool tc_dgrad_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_DGRAD, GEOM_ARGS, &p); }
-bool tc_wgrad_supported(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_WGRAD, GEOM_ARGS, &p); }
-size_t tc_fwd_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_FWD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
-size_t tc_dgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_DGRAD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
-size_t tc_wgrad_workspace(GEOM_PARAMS) { TcPlan p; return make_tc_plan(TC_WGRAD, GEOM_ARGS, &p) ? p.total_bytes : 0; }
+// mode: TC_FWD / TC_DGRAD / TC_WGRAD; f16: the fp16 engine (FRCNN_ENGINE_TC_3XF16) instead of tf32
+bool tc_supported(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16); }
+size_t tc_workspace(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16) ? p.total_bytes : 0; }
+bool tc_fwd_supported(GEOM_PARAMS) { return tc_supported(TC_FWD, GEOM_ARGS, false); }
+bool tc_dgrad_supported(GEOM_PARAMS) { return tc_supported(TC_DGRAD, GEOM_ARGS, false); }
+bool tc_wgrad_supported(GEOM_PARAMS) { return tc_supported(TC_WGRAD, GEOM_ARGS, false); }
+size_t tc_fwd_workspace(GEOM_PARAMS) { return tc_workspace(TC_FWD, GEOM_ARGS, false); }
+size_t tc_dgrad_workspace(GEOM_PARAMS) { return tc_workspace(TC_DGRAD, GEOM_ARGS, false); }
+size_t tc_wgrad_workspace(GEOM_PARAMS) { return tc_workspace(TC_WGRAD, GEOM_ARGS, false); }
 
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
-                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split)
+                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16)
 {
   Epilogue epi{scale, bias, residual, act};
-  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st, x_split, w_split);
+  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st, x_split, w_split, f16);
 }
 
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,
-                    const void *dy_split, const void *w_split)
+                    const void *dy_split, const void *w_split, bool f16)
 {
   Epilogue epi{nullptr, nullptr, addend, FRCNN_ACT_NONE};
-  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, w_split);
+  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, w_split, f16);
 }
 
 int tc_conv2d_wgrad(const float *dy, const float *x, float *dw, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,
-                    const void *dy_split, const void *x_split)
+                    const void *dy_split, const void *x_split, bool f16)
 {
   Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
-  return run_tc(TC_WGRAD, dy, x, dw, none, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, x_split);
+  return run_tc(TC_WGRAD, dy, x, dw, none, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, x_split, f16);
 }
 
 }  // namespace frcnn

@@ -103,6 +103,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, kind::f16 (fp16 operands, fp32 accumulation): twice the tf32 rate per element, K = 16 per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -141,6 +151,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v)
 // 32-bit MN-major operands (tf32 "transposed") must use layout type 1 = SWIZZLE_128B_BASE32B: 32-byte
 // chunks swizzled within the 128-byte row over a 4-row period (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 // the K atom is then 4 rows (512 B): SBO = 512, LBO = distance between 32-column atoms.
+// 16-bit MN-major operands (fp16) use the plain SWIZZLE_128B layout: 128-B rows of 64 elements along M/N, K atom = 8 rows
+// (SBO = 1024 B), LBO = distance between 64-column atoms, advancing K by 16 rows = +2048 B.
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
 {
@@ -159,6 +171,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major)
 {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with fp16 operands (a_format = b_format = 0) and fp32 accumulation
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major)
+{
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

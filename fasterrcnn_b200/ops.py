@@ -20,13 +20,24 @@ from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, check, lib, ptr, stream, work
 import os as _os
 import weakref
 
-_ENGINES = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32}
+_ENGINES = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32, "f16": _lib.ENGINE_TC_3XF16}
 _engine = {"value": _ENGINES[_os.environ.get("FRCNN_ENGINE", "auto")]}
 
 
 def set_engine(name):
-  """'auto' | 'simt' (exact fp32 CUDA-core) | 'tc' (tcgen05 3xTF32)."""
+  """'auto' | 'simt' (exact fp32 CUDA-core) | 'tc' (tcgen05 3xTF32) | 'f16' (tcgen05 3xFP16 on scaled hi/lo splits; shapes it does not
+  take fall back to the CUDA-core engine)."""
   _engine["value"] = _ENGINES[name]
+  _split_cache.clear()                                             # cached operand splits are engine specific
+  _weight_splits.clear()
+
+
+def _f16():
+  return _engine["value"] == _lib.ENGINE_TC_3XF16
+
+
+def split_bytes(count):
+  return lib().frcnn_f16_split_bytes(count) if _f16() else lib().frcnn_tf32_split_bytes(count)
 
 
 def get_engine():
@@ -169,7 +180,7 @@ def weight_split_buffer(param):
   if e is None or e["ref"]() is not param:
     for k in [k for k, v in _weight_splits.items() if v["ref"]() is None or v["ref"]() is param]:
       del _weight_splits[k]                                        # dead parameters and this parameter's old address
-    e = dict(ref = weakref.ref(param), buf = t.empty((lib().frcnn_tf32_split_bytes(param.numel()),), dtype = t.uint8, device = param.device), version = -1)
+    e = dict(ref = weakref.ref(param), buf = t.empty((split_bytes(param.numel()),), dtype = t.uint8, device = param.device), version = -1)
     _weight_splits[key] = e
   return e
 
@@ -185,9 +196,13 @@ def tf32_split(x, cache = True):
   hit = _split_cache.get(key)
   if hit is not None:
     return hit[0]
-  buf = t.empty((lib().frcnn_tf32_split_bytes(x.numel()),), dtype = t.uint8, device = x.device)
-  check(lib().frcnn_tf32_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_tf32_split")
-  _lib.count()
+  buf = t.empty((split_bytes(x.numel()),), dtype = t.uint8, device = x.device)
+  if _f16():
+    check(lib().frcnn_f16_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_f16_split")
+    _lib.count(2)
+  else:
+    check(lib().frcnn_tf32_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_tf32_split")
+    _lib.count()
   if cache:
     _split_cache[key] = (buf, x)                 # holding x keeps its address from being recycled while cached
   return buf
@@ -202,25 +217,26 @@ def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, s
   eng = _engine["value"]
   L = lib()
   presplit = (a_split is not None or b_split is not None)
+  f16 = _f16()
   if pass_ == 0:
     ws, ws_n = workspace(L.frcnn_conv2d_fwd_workspace_bytes(*geom, eng))
     t0 = kernel_timer.begin()
     if presplit:
-      check(L.frcnn_conv2d_fwd_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ws, ws_n, stream()), "frcnn_conv2d_fwd_presplit")
+      check((L.frcnn_conv2d_fwd_f16 if f16 else L.frcnn_conv2d_fwd_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ws, ws_n, stream()), "frcnn_conv2d_fwd_presplit")
     else:
       check(L.frcnn_conv2d_fwd(ptr(a), ptr(b), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
   elif pass_ == 1:
     ws, ws_n = workspace(L.frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
     t0 = kernel_timer.begin()
     if presplit:
-      check(L.frcnn_conv2d_dgrad_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_dgrad_presplit")
+      check((L.frcnn_conv2d_dgrad_f16 if f16 else L.frcnn_conv2d_dgrad_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_dgrad_presplit")
     else:
       check(L.frcnn_conv2d_dgrad(ptr(a), ptr(b), ptr(addend), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
   else:
     ws, ws_n = workspace(L.frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
     t0 = kernel_timer.begin()
     if presplit:
-      check(L.frcnn_conv2d_wgrad_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_wgrad_presplit")
+      check((L.frcnn_conv2d_wgrad_f16 if f16 else L.frcnn_conv2d_wgrad_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_wgrad_presplit")
     else:
       check(L.frcnn_conv2d_wgrad(ptr(a), ptr(b), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_wgrad")
   kernel_timer.end(t0, kind, gflop)
@@ -303,6 +319,8 @@ def _act_bwd(dy, y, act, c, want_split, want_bias, need_fp32):
   One frcnn_act_bwd_fused launch when the channel count allows it, else the separate kernels."""
   rows = dy.numel() // c
   L = lib()
+  if _f16():
+    want_split = False                     # the fused kernel writes the tf32 [hi | lo] layout; the fp16 engine splits dz in its own pass
   if act in (ACT_NONE, ACT_RELU) and rows > 0 and (want_split or want_bias) and L.frcnn_act_bwd_fused_supported(rows, c):
     write_dz = act == ACT_RELU and (need_fp32 or not want_split)
     dz = t.empty_like(y) if write_dz else None
@@ -886,7 +904,7 @@ def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale =
   _require_cuda(param, grad, momentum_buf)
   assert param.is_contiguous() or param.is_contiguous(memory_format = t.channels_last)
   assert grad.stride() == param.stride() and momentum_buf.stride() == param.stride()
-  e = weight_split_buffer(param) if carry_split else None
+  e = weight_split_buffer(param) if (carry_split and not _f16()) else None      # the fused SGD kernel writes the tf32 split layout
   check(lib().frcnn_sgd_step_split(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step),
                                    ptr(e["buf"]) if e is not None else None, stream()), "frcnn_sgd_step_split")
   if e is not None:

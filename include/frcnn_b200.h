@@ -44,6 +44,7 @@ extern "C" {
 #define FRCNN_ENGINE_AUTO 0
 #define FRCNN_ENGINE_SIMT_FP32 1   /* CUDA-core fp32 FMA implicit GEMM (exact fp32 products) */
 #define FRCNN_ENGINE_TC_3XTF32 2   /* tcgen05 kind::tf32, error-compensated 3-product split, fp32 TMEM accumulators */
+#define FRCNN_ENGINE_TC_3XF16 3    /* tcgen05 kind::f16 on per-tensor power-of-two scaled fp16 hi/lo splits (same three products, 2x the rate) */
 
 int frcnn_version(void);
 const char *frcnn_last_error_string(void);
@@ -103,6 +104,23 @@ int frcnn_conv2d_dgrad_presplit(const float *dy, const float *w, const void *dy_
 int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
                                 int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* fp16 engine (FRCNN_ENGINE_TC_3XF16): the same three-product scheme on kind::f16.  frcnn_f16_split writes, into a caller-owned
+ * buffer of frcnn_f16_split_bytes(count) bytes, [header | hi | lo] with x * 2^e = hi + lo / 2048 (e from the tensor's absolute maximum,
+ * found on the device in the same call; stored in the header and read by the GEMM kernel, no host round trip).  The *_f16 entry points
+ * mirror the *_presplit ones (either split pointer may be NULL = split internally into the workspace); results are fp32 and agree with
+ * the tf32 engine to fp32 rounding (tests/test_kernels_gpu.py).  Shapes: channel counts multiples of 64. */
+size_t frcnn_f16_split_bytes(size_t count);
+int frcnn_f16_split(const float *x, size_t count, void *out, void *stream);
+int frcnn_conv2d_fwd_f16(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
+                         const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
+                         void *workspace, size_t workspace_bytes, void *stream);
+int frcnn_conv2d_dgrad_f16(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           void *workspace, size_t workspace_bytes, void *stream);
+int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- elementwise / pooling pieces of the backward pass -------------------------------------
  * dz = dy * (y > 0)   (ReLU backward, models/vgg16.py:76-96 under autograd); in place allowed. */

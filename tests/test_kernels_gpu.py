@@ -458,6 +458,104 @@ def test_tcgen05_linear_backward_matches_fp64(ops):
   assert float((wc.grad.double().cpu() - dw64).abs().max()) <= 1e-4 * float(dw64.abs().max())
 
 
+# ---------------------------------------------------------------- fp16 tcgen05 engine (FRCNN_ENGINE_TC_3XF16)
+def test_f16_split_reconstructs_fp32(ops):
+  """x * 2^e = hi + lo / 2048 with e from the tensor's amax: max |hi| in [2^13, 2^14); reconstruction error <= 2^-22 of |x| for
+  elements within 2^-27 of the maximum (both halves in fp16's normal range), and <= 2^-36 * 2^-e absolutely below that."""
+  from fasterrcnn_b200._lib import lib, ptr, check, stream
+  L = lib()
+  g = t.Generator().manual_seed(41)
+  for n, scale in ((1000003, 1.0), (4096 * 64, 3.7e-6), (12345, 8.1e4)):
+    x = (t.randn((n,), generator = g) * scale).cuda()
+    x[::7] *= 1e-6                                                   # wide dynamic range
+    buf = t.empty((L.frcnn_f16_split_bytes(n),), dtype = t.uint8, device = "cuda")
+    check(L.frcnn_f16_split(ptr(x), n, ptr(buf), stream()), "frcnn_f16_split")
+    hdr = buf[:8].view(t.int32).cpu()
+    assert int(hdr[0]) == int(x.abs().max().view(t.int32))
+    e = int(hdr[1])
+    half_bytes = (2 * n + 1023) // 1024 * 1024
+    hi = buf[1024:1024 + 2 * n].view(t.float16).double()
+    lo = buf[1024 + half_bytes:1024 + half_bytes + 2 * n].view(t.float16).double()
+    assert 2.0 ** 13 <= float(hi.abs().max()) <= 2.0 ** 14
+    rec = (hi + lo / 2048.0) * 2.0 ** (-e)
+    err = (rec - x.double()).abs()
+    bound = t.maximum(x.double().abs() * 2.0 ** -21, t.full_like(err, 2.0 ** -35 * 2.0 ** (-e)))
+    assert bool((err <= bound).all()), float((err / bound).max())
+
+
+F16_CASES = [
+  ("vgg_b5_512_37x62", 1, 37, 62, 512, 512, 3, 1),
+  ("vgg_b3_128to256_150x250", 1, 150, 250, 128, 256, 3, 1),
+  ("vgg_b2_64to128_60x100", 1, 60, 100, 64, 128, 3, 1),
+  ("pointwise_512to128_37x62", 1, 37, 62, 512, 128, 1, 0),
+  ("batch2_256_19x23", 2, 19, 23, 256, 256, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES, ids = [c[0] for c in F16_CASES])
+def test_f16_engine_fwd_dgrad_wgrad_match_fp32_engine(ops, case):
+  """The fp16 tensor-core engine (scaled hi/lo fp16 splits, three kind::f16 products) against the exact-fp32 CUDA-core engine:
+  same bars as the tf32 engine (2e-5 / 5e-5 of the output scale); operands deliberately far from unit scale."""
+  _, n, h, w, cin, cout, k, pad = case
+  g = t.Generator().manual_seed(43)
+  x = ops.as_nhwc((t.randn((n, cin, h, w), generator = g) * 37.0).cuda())
+  dy = ops.as_nhwc((t.randn((n, cout, h, w), generator = g) * 2.5e-4).cuda())
+  wt = (t.randn((cout, cin, k, k), generator = g) * (2.0 / (cin * k * k)) ** 0.5).cuda().contiguous(memory_format = t.channels_last)
+  b = (t.randn((cout,), generator = g) * 0.1).cuda()
+  ops.set_engine("simt")
+  y_ref = ops.conv2d_fwd_raw(x, wt, b, 1, pad, ops.ACT_RELU)
+  dx_ref = ops.conv2d_dgrad_raw(dy, wt, (n, cin, h, w), 1, pad)
+  dw_ref = ops.conv2d_wgrad_raw(dy, x, (cout, cin, k, k), 1, pad)
+  ops.set_engine("f16")
+  try:
+    assert ops._uses_tc(0, (n, h, w, cin, cout, k, k, 1, pad)) and ops._uses_tc(1, (n, h, w, cin, cout, k, k, 1, pad)) and ops._uses_tc(2, (n, h, w, cin, cout, k, k, 1, pad))
+    y = ops.conv2d_fwd_raw(x, wt, b, 1, pad, ops.ACT_RELU)
+    dx = ops.conv2d_dgrad_raw(dy, wt, (n, cin, h, w), 1, pad)
+    dw = ops.conv2d_wgrad_raw(dy, x, (cout, cin, k, k), 1, pad)
+  finally:
+    ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
+  assert float((y - y_ref).abs().max()) <= 2e-5 * float(y_ref.abs().max())
+  assert float((dx - dx_ref).abs().max()) <= 2e-5 * float(dx_ref.abs().max())
+  assert float((dw - dw_ref).abs().max()) <= 5e-5 * float(dw_ref.abs().max())
+
+
+def test_f16_engine_exact_on_integer_data_and_long_k(ops):
+  """Small integers: every fp16 product and fp32 partial sum is exact -> bit-exact vs torch through conv + ReLU and both
+  gradients; K = 25088 linear layer (fc1) forward / backward against fp64 at the tf32 engine's bar."""
+  ops.set_engine("f16")
+  try:
+    g = t.Generator().manual_seed(47)
+    x = _int_tensor(g, (1, 64, 40, 56), -2, 2)
+    wt = _int_tensor(g, (128, 64, 3, 3), -1, 1)
+    b = _int_tensor(g, (128,), -3, 3)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, padding = 1))
+    gy = _int_tensor(g, tuple(yr.shape), -1, 1)
+    yr.backward(gy)
+    xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.conv2d_act(xc, wc, bc, 1, 1, ops.ACT_RELU)
+    assert np.array_equal(y.detach().cpu().numpy(), yr.detach().numpy())
+    y.backward(gy.cuda())
+    assert np.array_equal(xc.grad.cpu().numpy(), xr.grad.numpy())
+    assert np.array_equal(wc.grad.cpu().numpy(), wr.grad.numpy())
+    assert np.array_equal(bc.grad.cpu().numpy(), br.grad.numpy())
+
+    x = t.randn((128, 25088), generator = g)
+    wt = t.randn((4096, 25088), generator = g) * (1.0 / 25088) ** 0.5
+    gy = t.randn((128, 4096), generator = g)
+    y64 = x.double() @ wt.double().t()
+    dx64 = gy.double() @ wt.double()
+    dw64 = gy.double().t() @ x.double()
+    xc, wc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True)
+    y = ops.linear_act(xc, wc, None, ops.ACT_NONE)
+    y.backward(gy.cuda())
+  finally:
+    ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
+  assert float((y.detach().double().cpu() - y64).abs().max()) <= 1e-5 * float(y64.abs().max())
+  assert float((xc.grad.double().cpu() - dx64).abs().max()) <= 1e-4 * float(dx64.abs().max())
+  assert float((wc.grad.double().cpu() - dw64).abs().max()) <= 1e-4 * float(dw64.abs().max())
+
+
 @pytest.mark.parametrize("rows,c,act", [(37 * 45, 256, "relu"), (2294, 512, "relu"), (128, 4096, "relu"), (1000, 64, "none"), (77, 2048, "none")])
 def test_act_bwd_fused_matches_separate_passes(ops, rows, c, act):
   """frcnn_act_bwd_fused = relu-backward + tf32 operand split + bias row-sum in one pass: dz bit-exact, hi + lo == dz exactly with
