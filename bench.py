@@ -36,6 +36,19 @@ METRIC = "images/sec fwd+bwd @ 1000x600, batch=1/GPU"
 GT = [((100.0, 150.0, 400.0, 600.0), 7), ((50.0, 650.0, 500.0, 850.0), 15)]
 
 
+# engine -> (config.engine, roofline.note, dtype)
+ENGINE_NOTES = {
+  "f16": ("tcgen05 3xFP16 implicit GEMM for conv/linear fwd, dgrad and wgrad: operands split per tensor into power-of-two scaled fp16 hi + lo/2048 halves, three kind::f16 "
+          "products per MAC accumulated in fp32 (TMEM, drained to registers every 256 k) -> fp32-grade results; exact-fp32 CUDA-core kernels for the RGB stem and the 9/21/36/80-wide heads",
+          "algorithmic FLOPs (2*M*N*K) per launch / CUDA-event time; the tcgen05 kernels execute 3 fp16 products per algorithmic MAC, so the algorithmic rate is capped at 1/3 of the "
+          "dense fp16/bf16 figure used as denominator", "f16x3->f32"),
+  "tf32": ("tcgen05 3xTF32 (fp32-grade) implicit GEMM for conv/linear fwd, dgrad and wgrad; exact-fp32 CUDA-core kernels for the RGB stem and the 9/21/36/80-wide heads",
+           "algorithmic FLOPs (2*M*N*K) per launch / CUDA-event time; tcgen05 kernels execute 3 TF32 products per algorithmic MAC (3xTF32, fp32-grade), TF32 dense peak is 1/2 of the bf16 "
+           "figure used as denominator", "tf32x3->f32"),
+  "simt": ("exact-fp32 CUDA-core implicit GEMM everywhere", "algorithmic FLOPs / CUDA-event time on the CUDA cores; the tensor peak is not the bound", "f32"),
+}
+
+
 class Box:
   def __init__(self, corners, class_index):
     self.corners, self.class_index, self.class_name = np.asarray(corners, dtype = np.float32), class_index, str(class_index)
@@ -292,6 +305,7 @@ def run_ours(args, rank, local_rank, world):
       dist.destroy_process_group()
     return
   peaks = measured_peaks()
+  engine_name = {_lib.ENGINE_TC_3XF16: "f16", _lib.ENGINE_AUTO: "tf32", _lib.ENGINE_TC_3XTF32: "tf32", _lib.ENGINE_SIMT_FP32: "simt"}[ops.get_engine()]
   value = world * args.steps / (ms_dev / 1e3)
   e2e_value = world * args.steps / (ms_e2e / 1e3)
   h2d = step.h2d_bytes
@@ -305,7 +319,7 @@ def run_ours(args, rank, local_rank, world):
     traffic, traffic_source = ncu_traffic(top[0]) or (None, None)
     roofline = dict(bound = "tensor", kernel = top[0], achieved = achieved, peak = peaks["tflops"], unit = "TFLOP/s", frac = achieved / peaks["tflops"], traffic = traffic, traffic_unit = "bytes per launch (dram read + write, ncu --set full)", traffic_source = traffic_source,
                     peak_source = peaks["source"], launches = st["launches"], ms_per_step = st["ms"] / args.steps,
-                    note = "algorithmic FLOPs (2*M*N*K) per launch / CUDA-event time; tcgen05 kernels execute 3 TF32 products per algorithmic MAC (3xTF32, fp32-grade), TF32 dense peak is 1/2 of the bf16 figure used as denominator",
+                    note = ENGINE_NOTES[engine_name][1],
                     families = {k: dict(tflops = v["gflop"] / v["ms"], ms_per_step = v["ms"] / args.steps, launches = v["launches"]) for k, v in gemm_stats.items()})
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
@@ -313,10 +327,10 @@ def run_ours(args, rank, local_rank, world):
     cpu = dict(value = len(times) / sum(times), unit = "images/s", cores = cores, kind = "port",
                sample = "4 timed + 1 warm-up train_steps of the CPU oracle port on the same 600x1000 workload, %d threads" % cores)
   line = dict(metric = METRIC, value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
-              higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = "f32", data = "synthetic",
+              higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = ENGINE_NOTES[engine_name][2], data = "synthetic",
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
                             parallelism = "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)" % world,
-                            engine = "auto: tcgen05 3xTF32 (fp32-grade) implicit GEMM for conv/linear fwd, dgrad and wgrad; exact-fp32 CUDA-core kernels for the RGB stem and the 9/21/36/80-wide heads",
+                            engine = ENGINE_NOTES[engine_name][0],
                             l2 = "per-step working set (~1.7 GB of weights, activations, gradients) exceeds the 126 MB L2; no explicit flush"),
               e2e = dict(value = e2e_value, unit = "images/s", h2d_bytes_per_step = h2d, d2h_bytes_per_step = d2h, ms_per_step = ms_e2e / args.steps),
               gpu_launches = launches, clocks = clocks, roofline = roofline, cpu_baseline = cpu,

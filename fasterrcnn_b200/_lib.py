@@ -50,6 +50,8 @@ _SIGNATURES = {
   "frcnn_act_bwd_fused_supported": (_i, [_sz, _i]),
   "frcnn_act_bwd_fused_workspace_bytes": (_sz, [_sz, _i]),
   "frcnn_act_bwd_fused": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _sz, _vp]),
+  "frcnn_act_bwd_fused_f16": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _sz, _vp]),
+  "frcnn_sgd_step_split_f16": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp, _vp]),
   "frcnn_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -39,7 +39,9 @@ int tc_conv2d_wgrad(const float *dy, const float *x, float *dw,
 
 // FRCNN_ENGINE_AUTO = the 3xTF32 tcgen05 engine wherever the shape allows, else the CUDA-core engine; the fp16 engine is chosen explicitly
 static bool engine_f16(int engine) { return engine == FRCNN_ENGINE_TC_3XF16; }
-static bool engine_forced_tc(int engine) { return engine == FRCNN_ENGINE_TC_3XTF32 || engine == FRCNN_ENGINE_TC_3XF16; }
+// TC_3XTF32 is strict (unsupported shapes are an error: the kernel tests rely on it); TC_3XF16 behaves like AUTO with the fp16 tensor
+// engine: shapes it does not take (the RGB stem, narrow heads, strided convs) run on the CUDA-core engine
+static bool engine_forced_tc(int engine) { return engine == FRCNN_ENGINE_TC_3XTF32; }
 
 }  // namespace frcnn
 

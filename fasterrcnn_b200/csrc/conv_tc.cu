@@ -32,9 +32,9 @@
 // 64 elements (one 128-byte swizzle row of fp16), MN-major operands use the plain SWIZZLE_128B layout with 64-channel atoms.
 #include <stdlib.h>
 #include <atomic>
-#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "f16_split.cuh"
 
 namespace frcnn {
 
@@ -77,14 +77,12 @@ __global__ void split_hi_lo_kernel(const float *__restrict__ x, float *__restric
   }
 }
 
-// ---- fp16 engine: x * 2^e = hi + lo / 2048.  Buffer = [header 1024 B | hi (count fp16, padded to 1024 B) | lo (same)];
-// header word 0 = bit pattern of max |x| (atomicMax on the unsigned image: order-preserving for non-negative floats),
-// word 1 = e.  Three stream-ordered steps: clear the header, amax, split (every thread derives e from word 0). ----
-constexpr int kF16Header = 1024;
-constexpr int kF16LoShift = 11;             // lo is stored multiplied by 2^11
-
-__global__ void amax_kernel(const float *__restrict__ x, size_t count, unsigned *__restrict__ header)
+// ---- fp16 engine operand split (format: f16_split.cuh): amax pass (per-block partial maxima, no initialisation needed), then the
+// split pass, whose every block reduces the partials to the tensor's exponent ----
+__global__ void __launch_bounds__(512)
+f16_amax_partials_kernel(const float *__restrict__ x, size_t count, unsigned *__restrict__ header)
 {
+  __shared__ float red[16];
   const size_t n4 = count / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   float m = 0.f;
@@ -95,39 +93,43 @@ __global__ void amax_kernel(const float *__restrict__ x, size_t count, unsigned 
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) m = fmaxf(m, fabsf(x[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(header, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 16; i++) m = fmaxf(m, red[i]);
+    header[kF16PartialsAt + blockIdx.x] = __float_as_uint(m);
+  }
 }
 
-// e such that max|x| * 2^e lies in [2^13, 2^14); clamped so that 2^-(e_a + e_b) stays a normal float
-__device__ __forceinline__ int f16_exponent(unsigned amax_bits)
+int f16_amax_grid(size_t count)
 {
-  if (amax_bits == 0u) return 0;
-  int e = 140 - (int)((amax_bits >> 23) & 0xffu);
-  return e > 60 ? 60 : (e < -60 ? -60 : e);
+  size_t want = ceil_div<size_t>(count / 4 + 1, 512 * 4);             // >= 4 float4 per thread before adding blocks
+  if (want > (size_t)kF16MaxPartials) want = kF16MaxPartials;
+  return want < 1 ? 1 : (int)want;
 }
 
-__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
-
-__device__ __forceinline__ void split16(float x, float s, __half &hi, __half &lo)
+int f16_launch_amax(const float *x, size_t count, void *header, cudaStream_t st)
 {
-  const float xs = __fmul_rn(x, s);                                   // exact (power of two) unless it underflows
-  hi = __float2half_rn(xs);
-  lo = __float2half_rn(__fmul_rn(__fsub_rn(xs, __half2float(hi)), 2048.0f));
+  const int G = f16_amax_grid(count);
+  f16_amax_partials_kernel<<<G, 512, 0, st>>>(x, count, reinterpret_cast<unsigned *>(header));
+  return G;
 }
 
-__global__ void split_f16_kernel(const float *__restrict__ x, int *__restrict__ header, __half *__restrict__ hi, __half *__restrict__ lo, size_t count)
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float *__restrict__ x, unsigned *__restrict__ header, int G, __half *__restrict__ hi, __half *__restrict__ lo, size_t count)
 {
-  const int e = f16_exponent(reinterpret_cast<const unsigned *>(header)[0]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) header[1] = e;
+  __shared__ unsigned scratch[32];
+  const unsigned amax = f16_reduce_partials(header, G, scratch);
+  const int e = f16_exponent(amax);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { header[0] = amax; header[1] = (unsigned)e; }
   const float s = pow2i(e);
   const size_t n4 = count / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
-    __half h[4], l[4];
-    split16(v.x, s, h[0], l[0]); split16(v.y, s, h[1], l[1]); split16(v.z, s, h[2], l[2]); split16(v.w, s, h[3], l[3]);
-    reinterpret_cast<uint2 *>(hi)[i] = *reinterpret_cast<const uint2 *>(h);
-    reinterpret_cast<uint2 *>(lo)[i] = *reinterpret_cast<const uint2 *>(l);
+    uint2 h, l;
+    split16x4(__ldg(reinterpret_cast<const float4 *>(x) + i), s, h, l);
+    reinterpret_cast<uint2 *>(hi)[i] = h;
+    reinterpret_cast<uint2 *>(lo)[i] = l;
   }
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) split16(x[i], s, hi[i], lo[i]);
 }
@@ -776,18 +778,16 @@ int tf32_split(const float *x, size_t count, void *out, cudaStream_t st)
   return FRCNN_OK;
 }
 
-size_t f16_split_bytes(size_t count) { return kF16Header + 2 * align_up(count * 2, 1024); }
+size_t f16_split_bytes(size_t count) { return kF16Header + 2 * f16_half_bytes(count); }
 
 int f16_split(const float *x, size_t count, void *out, cudaStream_t st)
 {
   uint8_t *o = reinterpret_cast<uint8_t *>(out);
-  cudaError_t e = cudaMemsetAsync(o, 0, 8, st);
-  if (e != cudaSuccess) return cuda_fail(e, "f16_split: memset");
-  amax_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, count, reinterpret_cast<unsigned *>(o));
-  FRCNN_CHECK_LAUNCH("amax_kernel");
+  const int G = f16_launch_amax(x, count, o, st);
+  FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
   __half *hi = reinterpret_cast<__half *>(o + kF16Header);
-  __half *lo = reinterpret_cast<__half *>(o + kF16Header + align_up(count * 2, 1024));
-  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<int *>(o), hi, lo, count);
+  __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
+  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<unsigned *>(o), G, hi, lo, count);
   FRCNN_CHECK_LAUNCH("split_f16_kernel");
   return FRCNN_OK;
 }

@@ -2,6 +2,7 @@
 // multiples of the SM count, 128-bit accesses where the channel count allows, read-only loads
 // through the non-coherent path.
 #include "common.cuh"
+#include "f16_split.cuh"
 
 namespace frcnn {
 
@@ -88,9 +89,12 @@ __device__ __forceinline__ float sgd_one(float p, float g, float &buf, float lr,
 }
 
 // hi / lo (optional): the updated weights' tf32 operand split for the next step's tcgen05 GEMMs, written in the same pass
+// hi16 / lo16 / e16 (optional): the fp16 engine's split of the updated weights instead, with the exponent the buffer already holds
 __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, size_t count,
-                           float lr, float mom, float wd, float gs, int first, float *__restrict__ hi, float *__restrict__ lo)
+                           float lr, float mom, float wd, float gs, int first, float *__restrict__ hi, float *__restrict__ lo,
+                           __half *__restrict__ hi16, __half *__restrict__ lo16, const int *__restrict__ e16)
 {
+  const float s16 = hi16 ? pow2i(__ldg(e16)) : 1.0f;
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -110,6 +114,12 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
       reinterpret_cast<float4 *>(hi)[i] = h;
       reinterpret_cast<float4 *>(lo)[i] = l;
     }
+    if (hi16) {
+      uint2 h, l;
+      split16x4(pv, s16, h, l);
+      reinterpret_cast<uint2 *>(hi16)[i] = h;
+      reinterpret_cast<uint2 *>(lo16)[i] = l;
+    }
   }
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
     float b = first ? 0.f : buf[i];
@@ -117,6 +127,7 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
     p[i] = v;
     buf[i] = b;
     if (hi) { const float h = fused_tf32_rna(v); hi[i] = h; lo[i] = v - h; }
+    if (hi16) split16(v, s16, hi16[i], lo16[i]);
   }
 }
 
@@ -181,9 +192,18 @@ __global__ void bias_grad_stage2(const float *__restrict__ partial, float *__res
 template <int MODE>     // 0: dz = dy   1: dz = y > 0 ? dy : 0
 __global__ void __launch_bounds__(256)
 act_bwd_fused_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, float *__restrict__ hi, float *__restrict__ lo,
-                     float *__restrict__ partial, size_t rows, int C, int slab_c, int rows_per_block)
+                     float *__restrict__ partial, size_t rows, int C, int slab_c, int rows_per_block,
+                     unsigned *__restrict__ hdr16, int G16, __half *__restrict__ hi16, __half *__restrict__ lo16)
 {
   __shared__ float4 red[256];
+  // fp16 engine: exponent from the partial maxima of |dy| (the amax pass ran just before; |dz| <= |dy| under the ReLU mask)
+  float s16 = 1.0f;
+  if (hi16) {
+    const unsigned amax = f16_reduce_partials(hdr16, G16, reinterpret_cast<unsigned *>(red));
+    const int e = f16_exponent(amax);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { hdr16[0] = amax; hdr16[1] = (unsigned)e; }
+    s16 = pow2i(e);
+  }
   const int groups = slab_c / 4;                       // float4 groups per row inside this CTA's channel slab (divides 256)
   const int lanes = 256 / groups;
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
@@ -207,6 +227,12 @@ act_bwd_fused_kernel(const float *__restrict__ dy, const float *__restrict__ y, 
       l.x = g.x - h.x; l.y = g.y - h.y; l.z = g.z - h.z; l.w = g.w - h.w;
       reinterpret_cast<float4 *>(hi)[e] = h;
       reinterpret_cast<float4 *>(lo)[e] = l;
+    }
+    if (hi16) {
+      uint2 h, l;
+      split16x4(g, s16, h, l);
+      reinterpret_cast<uint2 *>(hi16)[e] = h;
+      reinterpret_cast<uint2 *>(lo16)[e] = l;
     }
     s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
   }
@@ -414,7 +440,23 @@ int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, s
     hi = reinterpret_cast<float *>(param_split);
     lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(param_split) + (count * 4 + 1023) / 1024 * 1024);   // frcnn_tf32_split layout
   }
-  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo);
+  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo,
+                                                                                  nullptr, nullptr, nullptr);
+  FRCNN_CHECK_LAUNCH("sgd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                             float grad_scale, int first_step, void *param_split, void *stream)
+{
+  FRCNN_REQUIRE(param && grad && momentum_buf && param_split && count > 0, "sgd_step_split_f16: bad argument");
+  FRCNN_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf) | reinterpret_cast<uintptr_t>(param_split)) & 15) == 0,
+                "sgd_step_split_f16: pointers must be 16-byte aligned");
+  uint8_t *o = reinterpret_cast<uint8_t *>(param_split);
+  __half *hi = reinterpret_cast<__half *>(o + kF16Header);
+  __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
+  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, nullptr,
+                                                                                  hi, lo, reinterpret_cast<const int *>(o) + 1);
   FRCNN_CHECK_LAUNCH("sgd_kernel");
   return FRCNN_OK;
 }
@@ -466,8 +508,8 @@ size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C)
   return (size_t)bx * C * sizeof(float);
 }
 
-int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
-                        void *workspace, size_t workspace_bytes, void *stream)
+static int act_bwd_fused_impl(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                              void *workspace, size_t workspace_bytes, void *stream, bool f16)
 {
   FRCNN_REQUIRE(dy && rows > 0 && C > 0, "act_bwd_fused: bad argument");
   FRCNN_REQUIRE(act == FRCNN_ACT_NONE || (act == FRCNN_ACT_RELU && y), "act_bwd_fused: activation must be NONE or RELU (with y)");
@@ -479,22 +521,45 @@ int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, voi
     if (workspace == nullptr || workspace_bytes < (size_t)bx * C * sizeof(float)) return fail(FRCNN_E_WORKSPACE, "act_bwd_fused: workspace too small");
     partial = reinterpret_cast<float *>(workspace);
   }
+  cudaStream_t st = as_stream(stream);
+  const size_t count = rows * (size_t)C;
   float *hi = nullptr, *lo = nullptr;
-  if (dz_split) {
-    const size_t count = rows * (size_t)C;
+  __half *hi16 = nullptr, *lo16 = nullptr;
+  unsigned *hdr16 = nullptr;
+  int G16 = 0;
+  if (dz_split && !f16) {
     hi = reinterpret_cast<float *>(dz_split);
     lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(dz_split) + (count * 4 + 1023) / 1024 * 1024);     // frcnn_tf32_split layout
+  } else if (dz_split) {
+    uint8_t *o = reinterpret_cast<uint8_t *>(dz_split);                                                             // frcnn_f16_split layout
+    FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0, "act_bwd_fused_f16: dz_split must be 16-byte aligned");
+    hdr16 = reinterpret_cast<unsigned *>(o);
+    hi16 = reinterpret_cast<__half *>(o + kF16Header);
+    lo16 = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
+    G16 = f16_launch_amax(dy, count, o, st);                     // max |dy| bounds max |dz|: the exponent is known before dz is formed
+    FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
   }
   dim3 grid(bx, C / sc);
-  cudaStream_t st = as_stream(stream);
-  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per);
-  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per);
+  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, G16, hi16, lo16);
+  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, G16, hi16, lo16);
   FRCNN_CHECK_LAUNCH("act_bwd_fused_kernel");
   if (dbias) {
     bias_grad_stage2<<<ceil_div(C, 32), 256, 0, st>>>(partial, dbias, bx, C);
     FRCNN_CHECK_LAUNCH("bias_grad_stage2");
   }
   return FRCNN_OK;
+}
+
+int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
+  return act_bwd_fused_impl(dy, y, act, dz, dz_split, dbias, rows, C, workspace, workspace_bytes, stream, false);
+}
+
+int frcnn_act_bwd_fused_f16(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                            void *workspace, size_t workspace_bytes, void *stream)
+{
+  return act_bwd_fused_impl(dy, y, act, dz, dz_split, dbias, rows, C, workspace, workspace_bytes, stream, true);
 }
 
 int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)

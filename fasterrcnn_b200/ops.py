@@ -20,13 +20,15 @@ from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, check, lib, ptr, stream, work
 import os as _os
 import weakref
 
-_ENGINES = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT_FP32, "tc": _lib.ENGINE_TC_3XTF32, "f16": _lib.ENGINE_TC_3XF16}
+# "auto" (default) = the fp16 tensor-core engine wherever its shapes allow, CUDA cores elsewhere; "tf32" = the same policy with the 3xTF32
+# tensor-core engine; "tc" = 3xTF32 strictly (unsupported shapes raise); "simt" = exact-fp32 CUDA cores only
+_ENGINES = {"auto": _lib.ENGINE_TC_3XF16, "f16": _lib.ENGINE_TC_3XF16, "tf32": _lib.ENGINE_AUTO, "tc": _lib.ENGINE_TC_3XTF32, "simt": _lib.ENGINE_SIMT_FP32}
 _engine = {"value": _ENGINES[_os.environ.get("FRCNN_ENGINE", "auto")]}
 
 
 def set_engine(name):
-  """'auto' | 'simt' (exact fp32 CUDA-core) | 'tc' (tcgen05 3xTF32) | 'f16' (tcgen05 3xFP16 on scaled hi/lo splits; shapes it does not
-  take fall back to the CUDA-core engine)."""
+  """'auto' = 'f16' (tcgen05 3xFP16 on scaled hi/lo splits; shapes it does not take run on the CUDA-core engine) | 'tf32' (tcgen05
+  3xTF32 with the same fallback) | 'tc' (3xTF32, strict) | 'simt' (exact fp32 CUDA-core)."""
   _engine["value"] = _ENGINES[name]
   _split_cache.clear()                                             # cached operand splits are engine specific
   _weight_splits.clear()
@@ -90,7 +92,9 @@ _launch_log = open(_os.environ["FRCNN_LAUNCH_LOG"], "w") if _os.environ.get("FRC
 
 def _engine_name(supported_tc):
   e = _engine["value"]
-  return "tcgen05_3xtf32" if (e != _lib.ENGINE_SIMT_FP32 and supported_tc) else "simt_fp32"
+  if e == _lib.ENGINE_SIMT_FP32 or not supported_tc:
+    return "simt_fp32"
+  return "tcgen05_3xf16" if e == _lib.ENGINE_TC_3XF16 else "tcgen05_3xtf32"
 
 
 def _require_cuda(*tensors):
@@ -319,20 +323,19 @@ def _act_bwd(dy, y, act, c, want_split, want_bias, need_fp32):
   One frcnn_act_bwd_fused launch when the channel count allows it, else the separate kernels."""
   rows = dy.numel() // c
   L = lib()
-  if _f16():
-    want_split = False                     # the fused kernel writes the tf32 [hi | lo] layout; the fp16 engine splits dz in its own pass
+  f16 = _f16()
   if act in (ACT_NONE, ACT_RELU) and rows > 0 and (want_split or want_bias) and L.frcnn_act_bwd_fused_supported(rows, c):
     write_dz = act == ACT_RELU and (need_fp32 or not want_split)
     dz = t.empty_like(y) if write_dz else None
-    split = t.empty((L.frcnn_tf32_split_bytes(dy.numel()),), dtype = t.uint8, device = dy.device) if want_split else None
+    split = t.empty((split_bytes(dy.numel()),), dtype = t.uint8, device = dy.device) if want_split else None
     db = t.empty((c,), dtype = t.float32, device = dy.device) if want_bias else None
     ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1) if want_bias else (None, 0)
-    check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
-    _lib.count(2 if want_bias else 1)
+    check((L.frcnn_act_bwd_fused_f16 if f16 else L.frcnn_act_bwd_fused)(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
+    _lib.count((2 if want_bias else 1) + (1 if f16 and want_split else 0))
     if dz is None and act == ACT_NONE:
       dz = dy
     elif dz is None:                                             # placeholder over the hi half, in y's physical (channels-last) layout
-      flat = split[:dy.numel() * 4].view(t.float32)
+      flat = (split[4096:4096 + dy.numel() * 4] if f16 else split[:dy.numel() * 4]).view(t.float32)     # (fp16 layout: hi + lo halves = 4 B / element)
       dz = flat.view(y.shape[0], y.shape[2], y.shape[3], y.shape[1]).permute(0, 3, 1, 2) if y.dim() == 4 else flat.view(y.shape)
     return dz, split, db
   if act == ACT_RELU:
@@ -904,9 +907,20 @@ def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale =
   _require_cuda(param, grad, momentum_buf)
   assert param.is_contiguous() or param.is_contiguous(memory_format = t.channels_last)
   assert grad.stride() == param.stride() and momentum_buf.stride() == param.stride()
-  e = weight_split_buffer(param) if (carry_split and not _f16()) else None      # the fused SGD kernel writes the tf32 split layout
-  check(lib().frcnn_sgd_step_split(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step),
-                                   ptr(e["buf"]) if e is not None else None, stream()), "frcnn_sgd_step_split")
+  e = weight_split_buffer(param) if carry_split else None
+  if e is not None and _f16():
+    # fp16 engine: the carried split keeps the exponent its buffer holds; a full split (fresh amax) seeds it and refreshes it every 64 steps
+    age = e.get("age", 64)
+    if age >= 64 or e["version"] != param._version:
+      check(lib().frcnn_f16_split(ptr(param), param.numel(), ptr(e["buf"]), stream()), "frcnn_f16_split")
+      _lib.count(2)
+      age = 0
+    e["age"] = age + 1
+    check(lib().frcnn_sgd_step_split_f16(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step),
+                                         ptr(e["buf"]), stream()), "frcnn_sgd_step_split_f16")
+  else:
+    check(lib().frcnn_sgd_step_split(ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr), float(momentum), float(weight_decay), float(grad_scale), int(first_step),
+                                     ptr(e["buf"]) if e is not None else None, stream()), "frcnn_sgd_step_split")
   if e is not None:
     e["version"] = param._version                                  # the raw-pointer update does not bump torch's version counter
   _lib.count()

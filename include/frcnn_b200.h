@@ -137,6 +137,10 @@ int frcnn_act_bwd_fused_supported(size_t rows, int C);
 size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C);
 int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
                         void *workspace, size_t workspace_bytes, void *stream);
+/* fp16-engine twin: dz_split receives the frcnn_f16_split layout; its exponent comes from max |dy| (an amax pass over dy runs first, on
+ * the same stream: max |dz| <= max |dy| under the ReLU mask), so dz is never materialised in fp32 unless dz != NULL. */
+int frcnn_act_bwd_fused_f16(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
+                            void *workspace, size_t workspace_bytes, void *stream);
 /* 2x2 stride-2 max pool, floor mode (nn.MaxPool2d(2,2) models/vgg16.py:78,82,87,92), NHWC. */
 int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
 /* dz[n,h,w,c] = dy[n,h/2,w/2,c] if (h,w) is the first maximum of its window and x > 0, else 0
@@ -273,6 +277,12 @@ int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t 
  * may be NULL) so the next step's tcgen05 GEMMs do not need a separate split pass over the weights. */
 int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
                          float grad_scale, int first_step, void *param_split, void *stream);
+
+/* fp16-engine twin: param_split is a frcnn_f16_split buffer that ALREADY holds a split of these weights; the updated weights are
+ * re-split with the exponent stored there (weights move by lr * update per step; the caller refreshes the exponent with a full
+ * frcnn_f16_split every few dozen steps; values saturate at the fp16 maximum instead of overflowing). */
+int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                             float grad_scale, int first_step, void *param_split, void *stream);
 
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one

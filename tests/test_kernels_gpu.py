@@ -45,7 +45,7 @@ def _int_tensor(g, shape, lo, hi):
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids = [c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "tf32", "auto"])
 def test_conv_fwd_dgrad_wgrad_vs_torch_fp32(ops, case, engine):
   """Linear part (no activation): fp32 tolerance = accumulation-order noise only (1e-4 of the output scale)."""
   _, n, h, w, cin, cout, k, stride, pad = case
@@ -71,7 +71,7 @@ def test_conv_fwd_dgrad_wgrad_vs_torch_fp32(ops, case, engine):
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids = [c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "tf32", "auto"])
 def test_conv_relu_exact_on_integer_data(ops, case, engine):
   """Small-integer operands: every product and partial sum is exact in fp32 (and in the 3xTF32
   split), so the result is independent of the accumulation order -> BIT-EXACT vs torch, including
@@ -474,8 +474,8 @@ def test_f16_split_reconstructs_fp32(ops):
     assert int(hdr[0]) == int(x.abs().max().view(t.int32))
     e = int(hdr[1])
     half_bytes = (2 * n + 1023) // 1024 * 1024
-    hi = buf[1024:1024 + 2 * n].view(t.float16).double()
-    lo = buf[1024 + half_bytes:1024 + half_bytes + 2 * n].view(t.float16).double()
+    hi = buf[4096:4096 + 2 * n].view(t.float16).double()
+    lo = buf[4096 + half_bytes:4096 + half_bytes + 2 * n].view(t.float16).double()
     assert 2.0 ** 13 <= float(hi.abs().max()) <= 2.0 ** 14
     rec = (hi + lo / 2048.0) * 2.0 ** (-e)
     err = (rec - x.double()).abs()
@@ -554,6 +554,46 @@ def test_f16_engine_exact_on_integer_data_and_long_k(ops):
   assert float((y.detach().double().cpu() - y64).abs().max()) <= 1e-5 * float(y64.abs().max())
   assert float((xc.grad.double().cpu() - dx64).abs().max()) <= 1e-4 * float(dx64.abs().max())
   assert float((wc.grad.double().cpu() - dw64).abs().max()) <= 1e-4 * float(dw64.abs().max())
+
+
+@pytest.mark.parametrize("rows,c,act", [(37 * 45, 256, "relu"), (128, 4096, "relu"), (1000, 64, "none")])
+def test_f16_fused_split_producers_match_the_plain_split(ops, rows, c, act):
+  """frcnn_act_bwd_fused_f16 (exponent from max |dy|) and frcnn_sgd_step_split_f16 (exponent kept from the seeding split) write
+  operand splits that reconstruct dz / the updated weights to the format's accuracy."""
+  from fasterrcnn_b200._lib import lib, ptr, check, stream, workspace
+  L = lib()
+  g = t.Generator().manual_seed(rows * 3 + c)
+  n = rows * c
+  half_bytes = (2 * n + 1023) // 1024 * 1024
+
+  def unpack(buf):
+    e = int(buf[4:8].view(t.int32).cpu())
+    hi = buf[4096:4096 + 2 * n].view(t.float16).double()
+    lo = buf[4096 + half_bytes:4096 + half_bytes + 2 * n].view(t.float16).double()
+    return (hi + lo / 2048.0) * 2.0 ** (-e), e, float(hi.abs().max())
+
+  dy = (t.randn((rows, c), generator = g) * 3e-3).cuda()
+  y = t.randn((rows, c), generator = g).cuda()
+  code = ops.ACT_RELU if act == "relu" else ops.ACT_NONE
+  split = t.empty((L.frcnn_f16_split_bytes(n),), dtype = t.uint8, device = "cuda")
+  db = t.empty((c,), dtype = t.float32, device = "cuda")
+  ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1)
+  check(L.frcnn_act_bwd_fused_f16(ptr(dy), ptr(y), code, None, ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused_f16")
+  want = (t.where(y > 0, dy, t.zeros_like(dy)) if act == "relu" else dy).double().reshape(-1)
+  rec, e, hmax = unpack(split)
+  assert hmax < 2.0 ** 14 and float(dy.abs().max()) * 2.0 ** e >= 2.0 ** 13
+  assert float((rec - want).abs().max()) <= 2.0 ** -21 * float(dy.abs().max())
+  assert float((db.double() - want.reshape(rows, c).sum(0)).abs().max()) <= 1e-5 * float(want.abs().reshape(rows, c).sum(0).max())
+
+  p = (t.randn((n,), generator = g) * 0.02).cuda(); gr = t.randn((n,), generator = g).cuda(); buf = t.zeros_like(p)
+  ps = t.empty((L.frcnn_f16_split_bytes(n),), dtype = t.uint8, device = "cuda")
+  check(L.frcnn_f16_split(ptr(p), n, ptr(ps), stream()), "frcnn_f16_split")
+  p_ref = p.clone(); buf_ref = buf.clone()
+  check(L.frcnn_sgd_step(ptr(p_ref), ptr(gr), ptr(buf_ref), n, 1e-3, 0.9, 5e-4, 1.0, 1, stream()), "frcnn_sgd_step")
+  check(L.frcnn_sgd_step_split_f16(ptr(p), ptr(gr), ptr(buf), n, 1e-3, 0.9, 5e-4, 1.0, 1, ptr(ps), stream()), "frcnn_sgd_step_split_f16")
+  assert t.equal(p, p_ref) and t.equal(buf, buf_ref)
+  rec, e, hmax = unpack(ps)
+  assert float((rec - p.double()).abs().max()) <= 2.0 ** -21 * float(p.abs().max())
 
 
 @pytest.mark.parametrize("rows,c,act", [(37 * 45, 256, "relu"), (2294, 512, "relu"), (128, 4096, "relu"), (1000, 64, "none"), (77, 2048, "none")])
