@@ -40,8 +40,10 @@ _SIGNATURES = {
   "frcnn_conv2d_wgrad_presplit": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_f16_split_bytes": (_sz, [_sz]),
   "frcnn_f16_split": (_i, [_vp, _sz, _vp, _vp]),
-  "frcnn_conv2d_fwd_f16": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),
-  "frcnn_conv2d_dgrad_f16": (_i, [_vp] * 6 + _GEOM + [_vp, _sz, _vp]),
+  "frcnn_conv2d_amax_slots": (_i, [_i] + _GEOM),
+  "frcnn_f16_split_from_amax": (_i, [_vp, _sz, _vp, _i, _vp, _vp]),
+  "frcnn_conv2d_fwd_f16": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _vp, _sz, _vp]),
+  "frcnn_conv2d_dgrad_f16": (_i, [_vp] * 6 + _GEOM + [_vp, _vp, _sz, _vp]),
   "frcnn_conv2d_wgrad_f16": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_sigmoid_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
@@ -50,7 +52,7 @@ _SIGNATURES = {
   "frcnn_act_bwd_fused_supported": (_i, [_sz, _i]),
   "frcnn_act_bwd_fused_workspace_bytes": (_sz, [_sz, _i]),
   "frcnn_act_bwd_fused": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _sz, _vp]),
-  "frcnn_act_bwd_fused_f16": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _sz, _vp]),
+  "frcnn_act_bwd_fused_f16": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _i, _vp, _sz, _vp]),
   "frcnn_sgd_step_split_f16": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp, _vp]),
   "frcnn_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

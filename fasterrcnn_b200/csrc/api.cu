@@ -24,15 +24,16 @@ bool tc_supported(int mode, int N, int H, int W, int Cin, int Cout, int KH, int 
 size_t tc_workspace(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, bool f16);
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16);
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16, void *amax_out = nullptr);
+int tc_amax_slots(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, bool f16);
 size_t tf32_split_bytes(size_t count);
 size_t f16_split_bytes(size_t count);
 void tc_set_trace(void *buf);
 int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
-int f16_split(const float *x, size_t count, void *out, cudaStream_t st);
+int f16_split(const float *x, size_t count, void *out, cudaStream_t st, const void *partials, int G);
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split, bool f16);
+                    void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split, bool f16, void *amax_out = nullptr);
 int tc_conv2d_wgrad(const float *dy, const float *x, float *dw,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                     void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *x_split, bool f16);
@@ -173,25 +174,37 @@ int frcnn_f16_split(const float *x, size_t count, void *out, void *stream)
 {
   FRCNN_REQUIRE(x && out && count > 0, "f16_split: bad argument");
   FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0, "f16_split: x must be 16-byte, out 128-byte aligned");
-  return f16_split(x, count, out, as_stream(stream));
+  return f16_split(x, count, out, as_stream(stream), nullptr, 0);
+}
+
+int frcnn_f16_split_from_amax(const float *x, size_t count, const void *amax, int slots, void *out, void *stream)
+{
+  FRCNN_REQUIRE(x && out && amax && count > 0 && slots > 0 && slots <= 1000, "f16_split_from_amax: bad argument");
+  FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0, "f16_split_from_amax: x must be 16-byte, out 128-byte aligned");
+  return f16_split(x, count, out, as_stream(stream), amax, slots);
+}
+
+int frcnn_conv2d_amax_slots(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad)
+{
+  return (pass == 0 || pass == 1) ? tc_amax_slots(pass, GEOM_ARGS, true) : 0;
 }
 
 int frcnn_conv2d_fwd_f16(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
                          const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
-                         void *workspace, size_t workspace_bytes, void *stream)
+                         void *y_amax, void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(x && w && y, "conv2d_fwd_f16: null pointer");
   if (!tc_supported(0, GEOM_ARGS, true)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_fwd_f16: shape not supported by the fp16 tcgen05 engine");
-  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split, true);
+  return tc_conv2d_fwd(x, w, scale, bias, residual, y, GEOM_ARGS, act, workspace, workspace_bytes, as_stream(stream), x_split, w_split, true, y_amax);
 }
 
 int frcnn_conv2d_dgrad_f16(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
                            int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                           void *workspace, size_t workspace_bytes, void *stream)
+                           void *dx_amax, void *workspace, size_t workspace_bytes, void *stream)
 {
   FRCNN_REQUIRE(dy && w && dx, "conv2d_dgrad_f16: null pointer");
   if (!tc_supported(1, GEOM_ARGS, true)) return fail(FRCNN_E_UNSUPPORTED, "conv2d_dgrad_f16: shape not supported by the fp16 tcgen05 engine");
-  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split, true);
+  return tc_conv2d_dgrad(dy, w, addend, dx, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, w_split, true, dx_amax);
 }
 
 int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,

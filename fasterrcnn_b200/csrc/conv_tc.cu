@@ -116,10 +116,11 @@ int f16_launch_amax(const float *x, size_t count, void *header, cudaStream_t st)
 }
 
 __global__ void __launch_bounds__(256)
-split_f16_kernel(const float *__restrict__ x, unsigned *__restrict__ header, int G, __half *__restrict__ hi, __half *__restrict__ lo, size_t count)
+split_f16_kernel(const float *__restrict__ x, unsigned *__restrict__ header, const unsigned *__restrict__ partials, int G, __half *__restrict__ hi, __half *__restrict__ lo,
+                 size_t count)
 {
   __shared__ unsigned scratch[32];
-  const unsigned amax = f16_reduce_partials(header, G, scratch);
+  const unsigned amax = f16_reduce_partials(partials, G, scratch);
   const int e = f16_exponent(amax);
   if (blockIdx.x == 0 && threadIdx.x == 0) { header[0] = amax; header[1] = (unsigned)e; }
   const float s = pow2i(e);
@@ -157,6 +158,7 @@ struct TcGeom {
   unsigned long long *sk_flags;   // gridDim.x
   unsigned long long sk_tag;      // unique per launch (stale workspace contents can never match)
   const int *a_exp, *b_exp;       // fp16 engine: device words holding the operands' scale exponents (NULL for tf32)
+  unsigned *amax_out;             // optional: CTA b stores the bit pattern of max |final output| over its tiles at amax_out[kF16PartialsAt + b]
 };
 
 // one work item of the persistent loop: an output tile (or one split-K slice of it)
@@ -422,6 +424,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       s_corr = pow2i(-e - kF16LoShift);
     }
     int cg = 0;                                                      // accumulation chains drained so far, across all items
+    float out_max = 0.f;                                             // max |final output| written by this thread (amax_out)
     TcCursor cur = tc_cursor(g);
     TcItem t;
     bool first_item = true;
@@ -531,12 +534,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < BN; j++) acc[j] = 1.0f / (1.0f + expf(-acc[j]));
           }
+          if (g.amax_out) {
+#pragma unroll
+            for (int j = 0; j < BN; j++) out_max = fmaxf(out_max, fabsf(acc[j]));
+          }
         }
 #pragma unroll
         for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
       if (first_item && threadIdx.x == 64) TC_TRACE(7);
       first_item = false;
+    }
+    if (g.amax_out) {
+      // the operand split of this output needs its absolute maximum: one partial per CTA, so the consumer needs no amax pass
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) out_max = fmaxf(out_max, __shfl_xor_sync(0xffffffffu, out_max, o));
+      float *wmax = reinterpret_cast<float *>(tmem_slot + 1);        // 4 words behind the TMEM slot (inside the 256-byte tail)
+      if (lane == 0) wmax[q] = out_max;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) g.amax_out[kF16PartialsAt + blockIdx.x] = __float_as_uint(fmaxf(fmaxf(wmax[0], wmax[1]), fmaxf(wmax[2], wmax[3])));
     }
     if (threadIdx.x == 64) TC_TRACE(8);
   }
@@ -780,14 +796,19 @@ int tf32_split(const float *x, size_t count, void *out, cudaStream_t st)
 
 size_t f16_split_bytes(size_t count) { return kF16Header + 2 * f16_half_bytes(count); }
 
-int f16_split(const float *x, size_t count, void *out, cudaStream_t st)
+// partials != NULL: G partial maxima (bit patterns, laid out like a header: first one at word kF16PartialsAt) already produced by the
+// kernel that wrote x (the GEMM epilogue) -- or valid for a superset of x (an un-pooled map) -- so the amax pass is skipped
+int f16_split(const float *x, size_t count, void *out, cudaStream_t st, const void *partials, int G)
 {
   uint8_t *o = reinterpret_cast<uint8_t *>(out);
-  const int G = f16_launch_amax(x, count, o, st);
-  FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
+  if (partials == nullptr) {
+    G = f16_launch_amax(x, count, o, st);
+    FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
+    partials = o;
+  }
   __half *hi = reinterpret_cast<__half *>(o + kF16Header);
   __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
-  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<unsigned *>(o), G, hi, lo, count);
+  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<unsigned *>(o), reinterpret_cast<const unsigned *>(partials), G, hi, lo, count);
   FRCNN_CHECK_LAUNCH("split_f16_kernel");
   return FRCNN_OK;
 }
@@ -795,7 +816,8 @@ int f16_split(const float *x, size_t count, void *out, cudaStream_t st)
 // a_split / b_split: optional buffers produced by tf32_split / f16_split for the two operands (NULL = split here)
 static int run_tc(int mode, const float *a, const float *b, float *out, const Epilogue &epi,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *a_split = nullptr, const void *b_split = nullptr, bool f16 = false)
+                  void *workspace, size_t workspace_bytes, cudaStream_t st, const void *a_split = nullptr, const void *b_split = nullptr, bool f16 = false,
+                  void *amax_out = nullptr)
 {
   TcPlan p;
   if (!make_tc_plan(mode, N, H, W, Cin, Cout, KH, KW, stride, pad, &p, f16)) return fail(FRCNN_E_UNSUPPORTED, "tcgen05 engine: unsupported shape");
@@ -816,7 +838,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
     a_hi = reinterpret_cast<const uint8_t *>(a_split) + hdr;
     a_lo = reinterpret_cast<const uint8_t *>(a_split) + hdr + align_up(p.a_count * esz, 1024);
   } else if (f16) {
-    int rc = f16_split(a, p.a_count, ws + p.a_hi_off - hdr, st);
+    int rc = f16_split(a, p.a_count, ws + p.a_hi_off - hdr, st, nullptr, 0);
     if (rc != FRCNN_OK) return rc;
   } else {
     split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, (float *)a_hi, (float *)a_lo, p.a_count);
@@ -826,7 +848,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
     b_hi = reinterpret_cast<const uint8_t *>(b_split) + hdr;
     b_lo = reinterpret_cast<const uint8_t *>(b_split) + hdr + align_up(p.b_count * esz, 1024);
   } else if (f16) {
-    int rc = f16_split(b, p.b_count, ws + p.b_hi_off - hdr, st);
+    int rc = f16_split(b, p.b_count, ws + p.b_hi_off - hdr, st, nullptr, 0);
     if (rc != FRCNN_OK) return rc;
   } else {
     split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, (float *)b_hi, (float *)b_lo, p.b_count);
@@ -864,7 +886,8 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
            p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
-           0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp};
+           0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp,
+           (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr};
   int rc;
 #define TC_LAUNCH(M)                                                                                                                      \
   (f16 ? (p.BN == 128 ? launch_tc<M, 128, 3, true>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, true>(maps, g, grid, out, partial, epi, st)) \
@@ -890,6 +913,8 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
 // mode: TC_FWD / TC_DGRAD / TC_WGRAD; f16: the fp16 engine (FRCNN_ENGINE_TC_3XF16) instead of tf32
 bool tc_supported(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16); }
 size_t tc_workspace(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16) ? p.total_bytes : 0; }
+// number of per-CTA output maxima a fwd / dgrad launch of this shape writes when given an amax buffer (0: none -- split-K shapes, wgrad)
+int tc_amax_slots(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return (mode != TC_WGRAD && make_tc_plan(mode, GEOM_ARGS, &p, f16) && p.splits == 1) ? p.grid : 0; }
 bool tc_fwd_supported(GEOM_PARAMS) { return tc_supported(TC_FWD, GEOM_ARGS, false); }
 bool tc_dgrad_supported(GEOM_PARAMS) { return tc_supported(TC_DGRAD, GEOM_ARGS, false); }
 bool tc_wgrad_supported(GEOM_PARAMS) { return tc_supported(TC_WGRAD, GEOM_ARGS, false); }
@@ -898,17 +923,17 @@ size_t tc_dgrad_workspace(GEOM_PARAMS) { return tc_workspace(TC_DGRAD, GEOM_ARGS
 size_t tc_wgrad_workspace(GEOM_PARAMS) { return tc_workspace(TC_WGRAD, GEOM_ARGS, false); }
 
 int tc_conv2d_fwd(const float *x, const float *w, const float *scale, const float *bias, const float *residual, float *y,
-                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16)
+                  GEOM_PARAMS, int act, void *workspace, size_t workspace_bytes, cudaStream_t st, const void *x_split, const void *w_split, bool f16, void *amax_out)
 {
   Epilogue epi{scale, bias, residual, act};
-  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st, x_split, w_split, f16);
+  return run_tc(TC_FWD, x, w, y, epi, GEOM_ARGS, workspace, workspace_bytes, st, x_split, w_split, f16, amax_out);
 }
 
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,
-                    const void *dy_split, const void *w_split, bool f16)
+                    const void *dy_split, const void *w_split, bool f16, void *amax_out)
 {
   Epilogue epi{nullptr, nullptr, addend, FRCNN_ACT_NONE};
-  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, w_split, f16);
+  return run_tc(TC_DGRAD, dy, w, dx, epi, GEOM_ARGS, workspace, workspace_bytes, st, dy_split, w_split, f16, amax_out);
 }
 
 int tc_conv2d_wgrad(const float *dy, const float *x, float *dw, GEOM_PARAMS, void *workspace, size_t workspace_bytes, cudaStream_t st,

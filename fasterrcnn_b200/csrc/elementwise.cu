@@ -193,13 +193,13 @@ template <int MODE>     // 0: dz = dy   1: dz = y > 0 ? dy : 0
 __global__ void __launch_bounds__(256)
 act_bwd_fused_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, float *__restrict__ hi, float *__restrict__ lo,
                      float *__restrict__ partial, size_t rows, int C, int slab_c, int rows_per_block,
-                     unsigned *__restrict__ hdr16, int G16, __half *__restrict__ hi16, __half *__restrict__ lo16)
+                     unsigned *__restrict__ hdr16, const unsigned *__restrict__ partials16, int G16, __half *__restrict__ hi16, __half *__restrict__ lo16)
 {
   __shared__ float4 red[256];
   // fp16 engine: exponent from the partial maxima of |dy| (the amax pass ran just before; |dz| <= |dy| under the ReLU mask)
   float s16 = 1.0f;
   if (hi16) {
-    const unsigned amax = f16_reduce_partials(hdr16, G16, reinterpret_cast<unsigned *>(red));
+    const unsigned amax = f16_reduce_partials(partials16, G16, reinterpret_cast<unsigned *>(red));
     const int e = f16_exponent(amax);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { hdr16[0] = amax; hdr16[1] = (unsigned)e; }
     s16 = pow2i(e);
@@ -509,7 +509,7 @@ size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C)
 }
 
 static int act_bwd_fused_impl(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
-                              void *workspace, size_t workspace_bytes, void *stream, bool f16)
+                              void *workspace, size_t workspace_bytes, void *stream, bool f16, const void *dy_amax = nullptr, int dy_amax_slots = 0)
 {
   FRCNN_REQUIRE(dy && rows > 0 && C > 0, "act_bwd_fused: bad argument");
   FRCNN_REQUIRE(act == FRCNN_ACT_NONE || (act == FRCNN_ACT_RELU && y), "act_bwd_fused: activation must be NONE or RELU (with y)");
@@ -526,6 +526,7 @@ static int act_bwd_fused_impl(const float *dy, const float *y, int act, float *d
   float *hi = nullptr, *lo = nullptr;
   __half *hi16 = nullptr, *lo16 = nullptr;
   unsigned *hdr16 = nullptr;
+  const unsigned *partials16 = nullptr;
   int G16 = 0;
   if (dz_split && !f16) {
     hi = reinterpret_cast<float *>(dz_split);
@@ -536,12 +537,18 @@ static int act_bwd_fused_impl(const float *dy, const float *y, int act, float *d
     hdr16 = reinterpret_cast<unsigned *>(o);
     hi16 = reinterpret_cast<__half *>(o + kF16Header);
     lo16 = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
-    G16 = f16_launch_amax(dy, count, o, st);                     // max |dy| bounds max |dz|: the exponent is known before dz is formed
-    FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
+    if (dy_amax) {                                               // partial maxima of dy left behind by the kernel that produced it
+      partials16 = reinterpret_cast<const unsigned *>(dy_amax);
+      G16 = dy_amax_slots;
+    } else {
+      G16 = f16_launch_amax(dy, count, o, st);                   // max |dy| bounds max |dz|: the exponent is known before dz is formed
+      FRCNN_CHECK_LAUNCH("f16_amax_partials_kernel");
+      partials16 = hdr16;
+    }
   }
   dim3 grid(bx, C / sc);
-  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, G16, hi16, lo16);
-  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, G16, hi16, lo16);
+  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
+  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
   FRCNN_CHECK_LAUNCH("act_bwd_fused_kernel");
   if (dbias) {
     bias_grad_stage2<<<ceil_div(C, 32), 256, 0, st>>>(partial, dbias, bx, C);
@@ -557,9 +564,10 @@ int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, voi
 }
 
 int frcnn_act_bwd_fused_f16(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
-                            void *workspace, size_t workspace_bytes, void *stream)
+                            const void *dy_amax, int dy_amax_slots, void *workspace, size_t workspace_bytes, void *stream)
 {
-  return act_bwd_fused_impl(dy, y, act, dz, dz_split, dbias, rows, C, workspace, workspace_bytes, stream, true);
+  FRCNN_REQUIRE(dy_amax == nullptr || (dy_amax_slots > 0 && dy_amax_slots <= 1000), "act_bwd_fused_f16: bad amax slot count");
+  return act_bwd_fused_impl(dy, y, act, dz, dz_split, dbias, rows, C, workspace, workspace_bytes, stream, true, dy_amax, dy_amax_slots);
 }
 
 int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)

@@ -50,7 +50,7 @@ __device__ __forceinline__ void split16x4(const float4 &v, float s, uint2 &hi, u
 
 // every thread of the block gets the maximum of the G partial maxima (bit patterns of non-negative floats: integer order);
 // scratch = 32 words of shared memory
-__device__ __forceinline__ unsigned f16_reduce_partials(const unsigned *__restrict__ header, int G, unsigned *scratch)
+__device__ __forceinline__ unsigned f16_reduce_partials(const unsigned *__restrict__ header, int G, unsigned *scratch)   // header: words [16, 16 + G) are read
 {
   unsigned m = 0u;
   for (int i = threadIdx.x; i < G; i += blockDim.x) m = max(m, __ldg(header + kF16PartialsAt + i));

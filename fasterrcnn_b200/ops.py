@@ -159,6 +159,45 @@ _uses_tc_cache = {}
 def begin_step():
   """Drops the cached operand splits (called at the start of every forward / train_step)."""
   _split_cache.clear()
+  _amax_hints.clear()
+
+
+# fp16 engine: a GEMM launch can leave the per-CTA maxima of |output| behind (frcnn_conv2d_amax_slots); the later operand split of
+# that output -- or of a tensor it bounds (its max-pooled map, its ReLU-masked gradient) -- then needs no pass for the maximum.
+_amax_hints = {}               # (data_ptr, numel, version) -> (int32 buffer of 16 + slots words, slots, tensor kept alive)
+_amax_slots_cache = {}
+
+
+def _amax_slots(pass_, geom):
+  r = _amax_slots_cache.get((pass_, geom))
+  if r is None:
+    r = int(lib().frcnn_conv2d_amax_slots(pass_, *geom))
+    _amax_slots_cache[(pass_, geom)] = r
+  return r
+
+
+def _amax_buffer(pass_, geom, device):
+  """int32 buffer for the output maxima of an fp16-engine fwd / dgrad launch of this shape, or None."""
+  if not _f16() or not _uses_tc(pass_, geom):
+    return None
+  slots = _amax_slots(pass_, geom)
+  return t.empty((16 + slots,), dtype = t.int32, device = device) if slots > 0 else None
+
+
+def _set_amax_hint(x, buf):
+  if buf is not None:
+    _amax_hints[(x.data_ptr(), x.numel(), x._version)] = (buf, buf.numel() - 16, x)
+
+
+def _amax_hint(x):
+  return _amax_hints.get((x.data_ptr(), x.numel(), x._version))
+
+
+def _copy_amax_hint(src, dst):
+  """dst's values are bounded by src's (pooling, masking): src's maxima serve dst."""
+  h = _amax_hint(src)
+  if h is not None:
+    _amax_hints[(dst.data_ptr(), dst.numel(), dst._version)] = (h[0], h[1], dst)
 
 
 def _uses_tc(pass_, geom):
@@ -202,8 +241,13 @@ def tf32_split(x, cache = True):
     return hit[0]
   buf = t.empty((split_bytes(x.numel()),), dtype = t.uint8, device = x.device)
   if _f16():
-    check(lib().frcnn_f16_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_f16_split")
-    _lib.count(2)
+    h = _amax_hint(x)
+    if h is not None:
+      check(lib().frcnn_f16_split_from_amax(ptr(x), x.numel(), ptr(h[0]), h[1], ptr(buf), stream()), "frcnn_f16_split_from_amax")
+      _lib.count()
+    else:
+      check(lib().frcnn_f16_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_f16_split")
+      _lib.count(2)
   else:
     check(lib().frcnn_tf32_split(ptr(x), x.numel(), ptr(buf), stream()), "frcnn_tf32_split")
     _lib.count()
@@ -216,24 +260,30 @@ def drop_split(x):
   _split_cache.pop((x.data_ptr(), x.numel(), x._version), None)
 
 
-def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, scale = None, bias = None, residual = None, act = ACT_NONE, addend = None):
+def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, scale = None, bias = None, residual = None, act = ACT_NONE, addend = None, amax_out = None):
   """One implicit-GEMM launch.  pass 0: a=x, b=w, out=y | pass 1: a=dy, b=w, out=dx | pass 2: a=dy, b=x, out=dw."""
   eng = _engine["value"]
   L = lib()
-  presplit = (a_split is not None or b_split is not None)
-  f16 = _f16()
+  f16 = _f16() and _uses_tc(pass_, geom)
+  presplit = (a_split is not None or b_split is not None) or f16
   if pass_ == 0:
     ws, ws_n = workspace(L.frcnn_conv2d_fwd_workspace_bytes(*geom, eng))
     t0 = kernel_timer.begin()
     if presplit:
-      check((L.frcnn_conv2d_fwd_f16 if f16 else L.frcnn_conv2d_fwd_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ws, ws_n, stream()), "frcnn_conv2d_fwd_presplit")
+      if f16:
+        check(L.frcnn_conv2d_fwd_f16(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ptr(amax_out), ws, ws_n, stream()), "frcnn_conv2d_fwd_f16")
+      else:
+        check(L.frcnn_conv2d_fwd_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, ws, ws_n, stream()), "frcnn_conv2d_fwd_presplit")
     else:
       check(L.frcnn_conv2d_fwd(ptr(a), ptr(b), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
   elif pass_ == 1:
     ws, ws_n = workspace(L.frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
     t0 = kernel_timer.begin()
     if presplit:
-      check((L.frcnn_conv2d_dgrad_f16 if f16 else L.frcnn_conv2d_dgrad_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_dgrad_presplit")
+      if f16:
+        check(L.frcnn_conv2d_dgrad_f16(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ptr(amax_out), ws, ws_n, stream()), "frcnn_conv2d_dgrad_f16")
+      else:
+        check(L.frcnn_conv2d_dgrad_presplit(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(addend), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_dgrad_presplit")
     else:
       check(L.frcnn_conv2d_dgrad(ptr(a), ptr(b), ptr(addend), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
   else:
@@ -266,7 +316,9 @@ def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None, 
       xs = tf32_split(x)
     if reuse_w:
       ws_ = tf32_split(w)
-  _gemm(0, x, w, y, geom, "conv_fwd", 2e-9 * n * ho * wo * cout * kh * kw * cin, xs, ws_, scale = scale, bias = bias, residual = residual, act = act)
+  amax = _amax_buffer(0, geom, x.device)
+  _gemm(0, x, w, y, geom, "conv_fwd", 2e-9 * n * ho * wo * cout * kh * kw * cin, xs, ws_, scale = scale, bias = bias, residual = residual, act = act, amax_out = amax)
+  _set_amax_hint(y, amax)
   return y
 
 
@@ -282,7 +334,9 @@ def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = Fals
       ds = dy_split
     elif reuse_dy:
       ds = tf32_split(dy)
-  _gemm(1, dy, w, dx, geom, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, ws_, addend = addend)
+  amax = _amax_buffer(1, geom, dy.device)
+  _gemm(1, dy, w, dx, geom, "conv_dgrad", 2e-9 * dy.shape[0] * dy.shape[2] * dy.shape[3] * cout * kh * kw * cin, ds, ws_, addend = addend, amax_out = amax)
+  _set_amax_hint(dx, amax)
   return dx
 
 
@@ -330,8 +384,13 @@ def _act_bwd(dy, y, act, c, want_split, want_bias, need_fp32):
     split = t.empty((split_bytes(dy.numel()),), dtype = t.uint8, device = dy.device) if want_split else None
     db = t.empty((c,), dtype = t.float32, device = dy.device) if want_bias else None
     ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1) if want_bias else (None, 0)
-    check((L.frcnn_act_bwd_fused_f16 if f16 else L.frcnn_act_bwd_fused)(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
-    _lib.count((2 if want_bias else 1) + (1 if f16 and want_split else 0))
+    if f16:
+      h = _amax_hint(dy) if want_split else None
+      check(L.frcnn_act_bwd_fused_f16(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c,
+                                      ptr(h[0]) if h is not None else None, h[1] if h is not None else 0, ws, ws_n, stream()), "frcnn_act_bwd_fused_f16")
+    else:
+      check(L.frcnn_act_bwd_fused(ptr(dy), ptr(y) if act == ACT_RELU else None, act, ptr(dz), ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused")
+    _lib.count((2 if want_bias else 1) + (1 if f16 and want_split and h is None else 0))
     if dz is None and act == ACT_NONE:
       dz = dy
     elif dz is None:                                             # placeholder over the hi half, in y's physical (channels-last) layout
@@ -385,6 +444,7 @@ class _ConvAct(t.autograd.Function):
       yp = _empty_nhwc(n, c, h // 2, wd // 2, y.device)
       check(lib().frcnn_maxpool2x2_fwd(ptr(y), ptr(yp), n, h, wd, c, stream()), "frcnn_maxpool2x2_fwd")
       _lib.count()
+      _copy_amax_hint(y, yp)
       ctx.save_for_backward(xp, wp, y)
       return yp
     ctx.save_for_backward(xp, wp, y)
@@ -405,6 +465,7 @@ class _ConvAct(t.autograd.Function):
       dz = t.empty_like(y)
       check(lib().frcnn_maxpool2x2_relu_bwd(ptr(dy), ptr(y), ptr(dz), n, h, wd, c, stream()), "frcnn_maxpool2x2_relu_bwd")
       _lib.count()
+      _copy_amax_hint(dy, dz)
       dy, act = dz, ACT_NONE                                                # ReLU mask already applied by the pooling backward
     dz, dz_split, db = _act_bwd(dy, y, act, c, tc_dx or tc_dw, want_bias, need_fp32)
     dx = dw = None
@@ -439,7 +500,9 @@ class _LinearAct(t.autograd.Function):
         ws_ = tf32_split(w2)
         if ctx.needs_input_grad[1]:
           xs = tf32_split(x2)
-      _gemm(0, x2, w2, y, geom, "linear_fwd", 2e-9 * m * k * nout, xs, ws_, bias = b.detach() if b is not None else None, act = act)
+      amax = _amax_buffer(0, geom, x2.device)
+      _gemm(0, x2, w2, y, geom, "linear_fwd", 2e-9 * m * k * nout, xs, ws_, bias = b.detach() if b is not None else None, act = act, amax_out = amax)
+      _set_amax_hint(y, amax)
     ctx.save_for_backward(x2, w2, y)
     return y
 
@@ -463,7 +526,9 @@ class _LinearAct(t.autograd.Function):
       if tc_dx:
         ws_ = tf32_split(w2)
         ds = dz_split if dz_split is not None else (tf32_split(dz) if want_dw else None)
-      _gemm(1, dz, w2, dx, geom, "linear_dgrad", 2e-9 * m * k * nout, ds, ws_)
+      amax = _amax_buffer(1, geom, x2.device)
+      _gemm(1, dz, w2, dx, geom, "linear_dgrad", 2e-9 * m * k * nout, ds, ws_, amax_out = amax)
+      _set_amax_hint(dx, amax)
     if want_dw:
       dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
       ds = xs = None

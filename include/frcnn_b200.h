@@ -112,12 +112,18 @@ int frcnn_conv2d_wgrad_presplit(const float *dy, const float *x, const void *dy_
  * the tf32 engine to fp32 rounding (tests/test_kernels_gpu.py).  Shapes: channel counts multiples of 64. */
 size_t frcnn_f16_split_bytes(size_t count);
 int frcnn_f16_split(const float *x, size_t count, void *out, void *stream);
+/* The absolute maximum can come from the kernel that PRODUCED the tensor: the fwd / dgrad entry points below take an optional device
+ * buffer y_amax / dx_amax of (16 + slots) 32-bit words, slots = frcnn_conv2d_amax_slots(pass, geometry) (0 = this shape cannot provide
+ * it), into which every CTA stores the maximum |output| of its tiles (words [16, 16 + slots)); frcnn_f16_split_from_amax then splits
+ * without a pass over the tensor for its maximum.  The maxima may belong to a superset of x (an un-pooled map, an unmasked gradient). */
+int frcnn_conv2d_amax_slots(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int frcnn_f16_split_from_amax(const float *x, size_t count, const void *amax, int slots, void *out, void *stream);
 int frcnn_conv2d_fwd_f16(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
                          const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
-                         void *workspace, size_t workspace_bytes, void *stream);
+                         void *y_amax, void *workspace, size_t workspace_bytes, void *stream);
 int frcnn_conv2d_dgrad_f16(const float *dy, const float *w, const void *dy_split, const void *w_split, const float *addend, float *dx,
                            int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                           void *workspace, size_t workspace_bytes, void *stream);
+                           void *dx_amax, void *workspace, size_t workspace_bytes, void *stream);
 int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split, const void *x_split, float *dw,
                            int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                            void *workspace, size_t workspace_bytes, void *stream);
@@ -137,10 +143,11 @@ int frcnn_act_bwd_fused_supported(size_t rows, int C);
 size_t frcnn_act_bwd_fused_workspace_bytes(size_t rows, int C);
 int frcnn_act_bwd_fused(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
                         void *workspace, size_t workspace_bytes, void *stream);
-/* fp16-engine twin: dz_split receives the frcnn_f16_split layout; its exponent comes from max |dy| (an amax pass over dy runs first, on
- * the same stream: max |dz| <= max |dy| under the ReLU mask), so dz is never materialised in fp32 unless dz != NULL. */
+/* fp16-engine twin: dz_split receives the frcnn_f16_split layout; its exponent comes from max |dy| (max |dz| <= max |dy| under the ReLU
+ * mask): either the producer's maxima (dy_amax, dy_amax_slots: see frcnn_conv2d_amax_slots) or, when dy_amax == NULL, an amax pass over
+ * dy on the same stream.  dz is never materialised in fp32 unless dz != NULL. */
 int frcnn_act_bwd_fused_f16(const float *dy, const float *y, int act, float *dz, void *dz_split, float *dbias, size_t rows, int C,
-                            void *workspace, size_t workspace_bytes, void *stream);
+                            const void *dy_amax, int dy_amax_slots, void *workspace, size_t workspace_bytes, void *stream);
 /* 2x2 stride-2 max pool, floor mode (nn.MaxPool2d(2,2) models/vgg16.py:78,82,87,92), NHWC. */
 int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
 /* dz[n,h,w,c] = dy[n,h/2,w/2,c] if (h,w) is the first maximum of its window and x > 0, else 0

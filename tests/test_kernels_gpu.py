@@ -496,7 +496,7 @@ F16_CASES = [
 def test_f16_engine_fwd_dgrad_wgrad_match_fp32_engine(ops, case):
   """The fp16 tensor-core engine (scaled hi/lo fp16 splits, three kind::f16 products) against the exact-fp32 CUDA-core engine:
   same bars as the tf32 engine (2e-5 / 5e-5 of the output scale); operands deliberately far from unit scale."""
-  _, n, h, w, cin, cout, k, pad = case
+  name, n, h, w, cin, cout, k, pad = case
   g = t.Generator().manual_seed(43)
   x = ops.as_nhwc((t.randn((n, cin, h, w), generator = g) * 37.0).cuda())
   dy = ops.as_nhwc((t.randn((n, cout, h, w), generator = g) * 2.5e-4).cuda())
@@ -512,6 +512,20 @@ def test_f16_engine_fwd_dgrad_wgrad_match_fp32_engine(ops, case):
     y = ops.conv2d_fwd_raw(x, wt, b, 1, pad, ops.ACT_RELU)
     dx = ops.conv2d_dgrad_raw(dy, wt, (n, cin, h, w), 1, pad)
     dw = ops.conv2d_wgrad_raw(dy, x, (cout, cin, k, k), 1, pad)
+    # the epilogue leaves the per-CTA maxima of |output| behind: their maximum IS the tensor's, and the split built from them
+    # equals the split built by the amax pass
+    hints = 0
+    for out in (y, dx):
+      hnt = ops._amax_hint(out)
+      if hnt is not None:
+        hints += 1
+        assert int(hnt[0][16:16 + hnt[1]].max()) == int(out.abs().max().view(t.int32))
+        a = ops.tf32_split(out, cache = False)
+        ops._amax_hints.clear()
+        bfull = ops.tf32_split(out, cache = False)
+        nb, half = 2 * out.numel(), (2 * out.numel() + 1023) // 1024 * 1024          # (padding bytes behind each half are not written)
+        assert t.equal(a[4:8], bfull[4:8]) and t.equal(a[4096:4096 + nb], bfull[4096:4096 + nb]) and t.equal(a[4096 + half:4096 + half + nb], bfull[4096 + half:4096 + half + nb])
+    assert hints >= 1 or name.startswith("batch2")
   finally:
     ops.set_engine(os.environ.get("FRCNN_ENGINE", "auto"))
   assert float((y - y_ref).abs().max()) <= 2e-5 * float(y_ref.abs().max())
@@ -578,7 +592,7 @@ def test_f16_fused_split_producers_match_the_plain_split(ops, rows, c, act):
   split = t.empty((L.frcnn_f16_split_bytes(n),), dtype = t.uint8, device = "cuda")
   db = t.empty((c,), dtype = t.float32, device = "cuda")
   ws, ws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1)
-  check(L.frcnn_act_bwd_fused_f16(ptr(dy), ptr(y), code, None, ptr(split), ptr(db), rows, c, ws, ws_n, stream()), "frcnn_act_bwd_fused_f16")
+  check(L.frcnn_act_bwd_fused_f16(ptr(dy), ptr(y), code, None, ptr(split), ptr(db), rows, c, None, 0, ws, ws_n, stream()), "frcnn_act_bwd_fused_f16")
   want = (t.where(y > 0, dy, t.zeros_like(dy)) if act == "relu" else dy).double().reshape(-1)
   rec, e, hmax = unpack(split)
   assert hmax < 2.0 ** 14 and float(dy.abs().max()) * 2.0 ** e >= 2.0 ** 13
