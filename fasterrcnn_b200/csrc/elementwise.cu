@@ -461,6 +461,24 @@ int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_bu
   return FRCNN_OK;
 }
 
+int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
+                         const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
+                         int split_format, float grad_scale, void *stream)
+{
+  FRCNN_REQUIRE(n >= 0 && (n == 0 || (params && grads && momentum_bufs && counts && lrs && momenta && weight_decays && first_steps)), "sgd_step_multi: bad argument");
+  FRCNN_REQUIRE(split_format >= 0 && split_format <= 2, "sgd_step_multi: split_format must be 0 (none), 1 (tf32) or 2 (fp16)");
+  for (int i = 0; i < n; i++) {
+    void *split = (param_splits && split_format != 0) ? param_splits[i] : nullptr;
+    int rc;
+    if (split && split_format == 2)
+      rc = frcnn_sgd_step_split_f16(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, stream);
+    else
+      rc = frcnn_sgd_step_split(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, stream);
+    if (rc != FRCNN_OK) return rc;
+  }
+  return FRCNN_OK;
+}
+
 int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
                    float grad_scale, int first_step, void *stream)
 {

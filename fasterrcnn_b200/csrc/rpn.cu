@@ -259,8 +259,9 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cou
 //   * kept boxes of blocks c-2 and c-1: their rows at columns +2 / +1, OR-ed in right after those blocks are resolved;
 //   * the diagonal tile and those two row slices of every block depend on nothing and stream in three blocks ahead
 //     (cp.async, 4-slot ring).
-// Per iteration the chain is: lane 0 walks the surviving boxes of the block (ffs + one shared-memory load per KEPT box),
-// barrier, <=64 shared-memory atomics, barrier.  Stops at max_keep.
+// Per iteration the chain is: warp 0 visits, in order, the surviving boxes of the block that suppress something inside it (ffs + one
+// register shuffle per such box; boxes with an empty diagonal row need no visit), writes the kept positions in parallel, barrier,
+// <=64 shared-memory atomics, barrier.  Stops at max_keep.
 constexpr int kScanThreads = 1024;
 constexpr int kScanGather = kScanThreads - 32;               // threads of warps 1..31 do the gathers
 constexpr int kScanDefer = 3;                                // gather loads kept in flight per thread (covers max_keep <= 2976)
@@ -314,24 +315,40 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
   for (int b = 0; b < nblocks; b++) {
     const int kept_before = kept_total;
     if (kept_before >= max_keep) break;                      // uniform (read after a barrier)
-    if (t == 0) {
+    if (t < 32) {
+      // warp 0 resolves the block.  Only boxes that suppress something inside the block (non-zero diagonal row) have to be visited
+      // in order; all the others are kept iff they are still alive at the end.  Lane l holds rows l and l + 32 of the diagonal tile.
       const int lim = n - b * 64 < 64 ? n - b * 64 : 64;
       const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
-      unsigned long long alive = ~removed[b & 3] & valid;
-      unsigned long long kept = 0ull;
-      int total = kept_before;
       const unsigned long long *diag = ring[b & 3][0];
-      while (alive && total < max_keep) {                    // ascending position = descending score: the greedy order
-        const int q = __ffsll((long long)alive) - 1;
-        kept |= 1ull << q;
-        kept_idx[total] = b * 64 + q;
-        keep_out[total] = b * 64 + q;
-        total++;
-        alive &= ~(diag[q] | (1ull << q));
+      const unsigned long long r0 = diag[t], r1 = diag[t + 32];
+      const unsigned long long nz = (unsigned long long)__ballot_sync(0xffffffffu, r0 != 0ull) | ((unsigned long long)__ballot_sync(0xffffffffu, r1 != 0ull) << 32);
+      unsigned long long alive = ~removed[b & 3] & valid;
+      unsigned long long pending = alive & nz;
+      while (pending) {                                        // ascending position = descending score: the greedy order
+        const int q = __ffsll((long long)pending) - 1;
+        const unsigned long long lo_row = __shfl_sync(0xffffffffu, r0, q & 31), hi_row = __shfl_sync(0xffffffffu, r1, q & 31);
+        alive &= ~(q < 32 ? lo_row : hi_row);                  // a row only holds later positions (upper triangle)
+        pending &= alive & ~(1ull << q);
       }
-      kept_bits_s = kept;
-      kept_total = total;
-      removed[b & 3] = 0ull;                                 // slot is reused by block b + 4 (first written at iteration b + 2)
+      unsigned long long kept = alive;
+      const int room = max_keep - kept_before;
+      while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll((long long)kept)));      // only in the block that reaches max_keep
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const int bit = t + 32 * half;
+        if ((kept >> bit) & 1ull) {
+          const int pos = kept_before + __popcll(kept & ((1ull << bit) - 1ull));
+          kept_idx[pos] = b * 64 + bit;
+          keep_out[pos] = b * 64 + bit;
+        }
+      }
+      __syncwarp();
+      if (t == 0) {
+        kept_bits_s = kept;
+        kept_total = kept_before + __popcll(kept);
+        removed[b & 3] = 0ull;                                 // slot is reused by block b + 4 (first written at iteration b + 2)
+      }
     } else if (t >= 32) {
       if (pend_col >= 0) {                                   // fold the gather issued one iteration ago (column b + 1)
         unsigned long long acc = pend[0] | pend[1] | pend[2] | pend_sync;

@@ -260,14 +260,22 @@ def drop_split(x):
   _split_cache.pop((x.data_ptr(), x.numel(), x._version), None)
 
 
+_gemm_workspace_cache = {}
+
+
 def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, scale = None, bias = None, residual = None, act = ACT_NONE, addend = None, amax_out = None):
   """One implicit-GEMM launch.  pass 0: a=x, b=w, out=y | pass 1: a=dy, b=w, out=dx | pass 2: a=dy, b=x, out=dw."""
   eng = _engine["value"]
   L = lib()
   f16 = _f16() and _uses_tc(pass_, geom)
   presplit = (a_split is not None or b_split is not None) or f16
+  wkey = (pass_, geom, eng)
+  need = _gemm_workspace_cache.get(wkey)
+  if need is None:
+    need = (L.frcnn_conv2d_fwd_workspace_bytes, L.frcnn_conv2d_dgrad_workspace_bytes, L.frcnn_conv2d_wgrad_workspace_bytes)[pass_](*geom, eng)
+    _gemm_workspace_cache[wkey] = need
   if pass_ == 0:
-    ws, ws_n = workspace(L.frcnn_conv2d_fwd_workspace_bytes(*geom, eng))
+    ws, ws_n = workspace(need)
     t0 = kernel_timer.begin()
     if presplit:
       if f16:
@@ -277,7 +285,7 @@ def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, s
     else:
       check(L.frcnn_conv2d_fwd(ptr(a), ptr(b), ptr(scale), ptr(bias), ptr(residual), ptr(out), *geom, act, eng, ws, ws_n, stream()), "frcnn_conv2d_fwd")
   elif pass_ == 1:
-    ws, ws_n = workspace(L.frcnn_conv2d_dgrad_workspace_bytes(*geom, eng))
+    ws, ws_n = workspace(need)
     t0 = kernel_timer.begin()
     if presplit:
       if f16:
@@ -287,7 +295,7 @@ def _gemm(pass_, a, b, out, geom, kind, gflop, a_split = None, b_split = None, s
     else:
       check(L.frcnn_conv2d_dgrad(ptr(a), ptr(b), ptr(addend), ptr(out), *geom, eng, ws, ws_n, stream()), "frcnn_conv2d_dgrad")
   else:
-    ws, ws_n = workspace(L.frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
+    ws, ws_n = workspace(need)
     t0 = kernel_timer.begin()
     if presplit:
       check((L.frcnn_conv2d_wgrad_f16 if f16 else L.frcnn_conv2d_wgrad_presplit)(ptr(a), ptr(b), ptr(a_split), ptr(b_split), ptr(out), *geom, ws, ws_n, stream()), "frcnn_conv2d_wgrad_presplit")
@@ -476,7 +484,17 @@ class _ConvAct(t.autograd.Function):
     return dx, dw, db, None, None, None, None
 
 
+class _NoGradCtx:
+  """Stand-in for the autograd context when nothing upstream needs a gradient (frozen VGG-16 blocks 1-2, inference)."""
+  needs_input_grad = (False,) * 8
+
+  def save_for_backward(self, *tensors):
+    pass
+
+
 def conv2d_act(x, weight, bias, stride = 1, pad = 1, act = ACT_RELU, pool = False):
+  if not t.is_grad_enabled() or not (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+    return _ConvAct.forward(_NoGradCtx(), x, weight, bias, stride, pad, act, pool)      # no autograd node, no saved activations
   return _ConvAct.apply(x, weight, bias, stride, pad, act, pool)
 
 
@@ -989,3 +1007,39 @@ def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale =
   if e is not None:
     e["version"] = param._version                                  # the raw-pointer update does not bump torch's version counter
   _lib.count()
+
+
+def sgd_step_multi(entries, grad_scale = 1.0):
+  """optimizer.step() for a list of (param, grad, momentum_buf, lr, momentum, weight_decay, first_step, carry_split) in one C call
+  (frcnn_sgd_step_multi): the per-tensor kernels are launched back to back from C instead of one ctypes round trip each."""
+  import ctypes
+  n = len(entries)
+  if n == 0:
+    return
+  f16 = _f16()
+  L = lib()
+  st = stream()
+  vp, sz, fl, it = ctypes.c_void_p * n, ctypes.c_size_t * n, ctypes.c_float * n, ctypes.c_int * n
+  params, grads, bufs, splits = [], [], [], []
+  carried = []
+  for param, grad, buf, lr, momentum, wd, first, carry in entries:
+    _require_cuda(param, grad, buf)
+    assert grad.stride() == param.stride() and buf.stride() == param.stride()
+    e = weight_split_buffer(param) if carry else None
+    if e is not None and f16:
+      age = e.get("age", 64)
+      if age >= 64 or e["version"] != param._version:           # (re)seed the carried split's exponent from a fresh amax
+        check(L.frcnn_f16_split(ptr(param), param.numel(), ptr(e["buf"]), st), "frcnn_f16_split")
+        _lib.count(2)
+        age = 0
+      e["age"] = age + 1
+    params.append(param.data_ptr()); grads.append(grad.data_ptr()); bufs.append(buf.data_ptr())
+    splits.append(e["buf"].data_ptr() if e is not None else None)
+    carried.append((e, param))
+  check(L.frcnn_sgd_step_multi(n, vp(*params), vp(*grads), vp(*bufs), sz(*[x[0].numel() for x in entries]), fl(*[float(x[3]) for x in entries]),
+                               fl(*[float(x[4]) for x in entries]), fl(*[float(x[5]) for x in entries]), it(*[int(x[6]) for x in entries]), vp(*splits),
+                               2 if f16 else 1, float(grad_scale), st), "frcnn_sgd_step_multi")
+  for e, param in carried:
+    if e is not None:
+      e["version"] = param._version                                # the raw-pointer update does not bump torch's version counter
+  _lib.count(n)

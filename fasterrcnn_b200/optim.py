@@ -26,6 +26,7 @@ class FusedSGD(t.optim.Optimizer):
   @t.no_grad()
   def step(self, closure = None):
     assert closure is None
+    entries = []
     for group in self.param_groups:
       for p in group["params"]:
         if p.grad is None:
@@ -38,7 +39,8 @@ class FusedSGD(t.optim.Optimizer):
         if g.stride() != p.stride():
           g = g.contiguous(memory_format = t.channels_last) if p.dim() == 4 and not p.is_contiguous() else g.contiguous()
         # matrices / filters feed the tcgen05 GEMMs next step: their operand split is produced by the same kernel
-        ops.sgd_step(p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], self.grad_scale, first, carry_split = p.dim() >= 2 and p.numel() >= 4096)
+        entries.append((p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], first, p.dim() >= 2 and p.numel() >= 4096))
+    ops.sgd_step_multi(entries, self.grad_scale)                 # every parameter group in one C call
 
 
 class DataParallel:

@@ -291,6 +291,13 @@ int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, s
 int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
                              float grad_scale, int first_step, void *param_split, void *stream);
 
+/* The whole optimizer step (optimizer.step() of models/faster_rcnn.py:359 over every parameter group) in ONE call: n tensors, host arrays
+ * of device pointers / sizes / per-group hyper-parameters; param_splits[i] (may be NULL) receives the updated weights' operand split in
+ * the format named by split_format (0 none, 1 tf32, 2 fp16 -- see the single-tensor entry points).  Same kernels, launched back to back. */
+int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
+                         const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
+                         int split_format, float grad_scale, void *stream);
+
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one
  * launch: decode in fp64 with stds (0.1,0.1,0.2,0.2), clip to [0,img_h-1]x[0,img_w-1], keep
