@@ -5,7 +5,7 @@ python's ``random`` in the same sequence, and the same per-file caches.  What di
 
   * anchor maps and the RPN ground-truth map come from the package's device kernels (``anchors.generate_anchor_maps`` /
     ``generate_rpn_map``: frcnn_rpn_decode's anchor generator, frcnn_rpn_targets) -- the reference computes them in NumPy per sample;
-    ``anchor_fns`` swaps in other implementations (the CPU tests pass the oracle's);
+    ``anchor_fns`` swaps in other implementations with the same signatures (used by the CPU-only tests);
   * ``prefetch = n`` decodes / resizes / standardises up to n upcoming images on a background thread while the current step runs
     (file decode is the only part of a step that never touches the GPU); the order of samples and of RNG draws is unchanged.
 """
