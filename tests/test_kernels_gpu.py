@@ -160,6 +160,30 @@ def test_anchor_generation_bit_exact(ops, tag):
   assert np.array_equal(v_dev.cpu().numpy(), av)
 
 
+@pytest.mark.parametrize("tag", list(gi.GEOMETRY_CASES))
+def test_rpn_ground_truth_map_on_device(golden_dir, tag):
+  """frcnn_rpn_targets (anchors.generate_rpn_map, reference models/anchors.py:137-262) against the restatement pinned on the reference's
+  digests: trainable / object flags, (ty, tx) and both index lists bit-exact; (th, tw) = log(gt / anchor) within 1 ulp (correctly rounded
+  here, NumPy's SIMD float32 log on the CPU)."""
+  from fasterrcnn_b200 import anchors
+
+  class B:
+    def __init__(self, c):
+      self.corners = np.asarray(c, dtype = np.float32)
+  h, w = gi.GEOMETRY_CASES[tag]
+  fm = (512, h // 16, w // 16)
+  am, av = orc.generate_anchor_maps((3, h, w), fm, 16)
+  gt = np.array([b for b, _ in gi.gt_boxes_for(h, w)], dtype = np.float32)
+  ref_map, ref_obj, ref_bg = orc.generate_rpn_map(am, av, gt)
+  geo = np.load(os.path.join(golden_dir, "geometry.npz"))
+  assert np.array_equal(ref_obj.astype(np.int16), geo[tag + "_obj"]) and len(ref_bg) == int(geo[tag + "_nbg"])       # restatement == reference
+  am_dev, av_dev = anchors.generate_anchor_maps((3, h, w), fm, 16)
+  got_map, got_obj, got_bg = anchors.generate_rpn_map(am_dev, av_dev, [B(c) for c in gt])
+  assert np.array_equal(got_map[..., 0:4], ref_map[..., 0:4])
+  np.testing.assert_allclose(got_map[..., 4:6], ref_map[..., 4:6], rtol = 1.2e-7, atol = 1e-9)
+  assert np.array_equal(got_obj, ref_obj) and np.array_equal(got_bg, ref_bg)
+
+
 @pytest.mark.parametrize("tag", gi.RPN_CASES)
 def test_rpn_proposal_stage_matches_reference_golden(ops, golden_dir, tag):
   g = np.load(os.path.join(golden_dir, "rpn_stage.npz"))
