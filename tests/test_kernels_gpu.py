@@ -163,7 +163,7 @@ def test_anchor_generation_bit_exact(ops, tag):
 @pytest.mark.parametrize("tag", list(gi.GEOMETRY_CASES))
 def test_rpn_ground_truth_map_on_device(golden_dir, tag):
   """frcnn_rpn_targets (anchors.generate_rpn_map, reference models/anchors.py:137-262) against the restatement pinned on the reference's
-  digests: trainable / object flags, (ty, tx) and both index lists bit-exact; (th, tw) = log(gt / anchor) within 1 ulp (correctly rounded
+  digests: trainable / object flags, (ty, tx) and both index lists bit-exact; (th, tw) = log(gt / anchor) within 2 ulp (correctly rounded
   here, NumPy's SIMD float32 log on the CPU)."""
   from fasterrcnn_b200 import anchors
 
@@ -180,7 +180,7 @@ def test_rpn_ground_truth_map_on_device(golden_dir, tag):
   am_dev, av_dev = anchors.generate_anchor_maps((3, h, w), fm, 16)
   got_map, got_obj, got_bg = anchors.generate_rpn_map(am_dev, av_dev, [B(c) for c in gt])
   assert np.array_equal(got_map[..., 0:4], ref_map[..., 0:4])
-  np.testing.assert_allclose(got_map[..., 4:6], ref_map[..., 4:6], rtol = 1.2e-7, atol = 1e-9)
+  np.testing.assert_allclose(got_map[..., 4:6], ref_map[..., 4:6], rtol = 2.4e-7, atol = 1e-8)
   assert np.array_equal(got_obj, ref_obj) and np.array_equal(got_bg, ref_bg)
 
 

@@ -356,7 +356,7 @@ def test_voc_dataset_with_device_anchor_kernels_matches_reference_golden(tmp_pat
   for smp in samples[:4]:
     ref_map, ref_obj, ref_bg = orc.generate_rpn_map(smp.anchor_map, smp.anchor_valid_map, np.array([b.corners for b in smp.gt_boxes], dtype = np.float32))
     assert np.array_equal(smp.gt_rpn_map[..., 0:4], ref_map[..., 0:4])
-    np.testing.assert_allclose(smp.gt_rpn_map[..., 4:6], ref_map[..., 4:6], rtol = 1.2e-7, atol = 1e-9)
+    np.testing.assert_allclose(smp.gt_rpn_map[..., 4:6], ref_map[..., 4:6], rtol = 2.4e-7, atol = 1e-8)   # 2 ulp: NumPy's float32 log near 1
     assert np.array_equal(smp.gt_rpn_object_indices, ref_obj) and np.array_equal(smp.gt_rpn_background_indices, ref_bg)
   model = f.FasterRCNNModel(num_classes = 21, backbone = backbone).cuda()
   from fasterrcnn_b200 import optim
