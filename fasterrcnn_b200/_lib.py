@@ -122,12 +122,27 @@ def check(status, what):
 
 
 _raw_stream = getattr(t._C, "_cuda_getCurrentRawStream", None)
+_device = {"index": None}
+
+
+def device_index():
+  """Index of this process's CUDA device.  One process drives one GPU, so the index is looked up once: asking torch on
+  every launch (lazy-init checks + a driver query) was ~0.3 ms of host time per train step.  reset_device() re-reads it."""
+  idx = _device["index"]
+  if idx is None:
+    idx = _device["index"] = t.cuda.current_device()
+  return idx
+
+
+def reset_device():
+  _device["index"] = None
+  _workspaces.clear()
 
 
 def stream():
-  """cudaStream_t of torch's current stream on the current device (the C ABI launches on it)."""
+  """cudaStream_t of torch's current stream on this process's device (the C ABI launches on it)."""
   if _raw_stream is not None:
-    return _raw_stream(t.cuda.current_device())          # one C call instead of building a torch.cuda.Stream object per launch
+    return _raw_stream(device_index())                   # one C call instead of building a torch.cuda.Stream object per launch
   return t.cuda.current_stream().cuda_stream
 
 
@@ -140,20 +155,19 @@ def ptr(x):
   return x.data_ptr()
 
 
-# ---- stream-ordered scratch space (grown on demand, one per device) ----------------------------
+# ---- stream-ordered scratch space (grown on demand, one per slot) ----------------------------
 _workspaces = {}
 
 
 def workspace(nbytes, slot = 0):
-  """Returns (ptr, nbytes) of a cached scratch buffer on the current device."""
+  """Returns (ptr, nbytes) of a cached scratch buffer on this process's device."""
   if nbytes == 0:
     return None, 0
-  key = (t.cuda.current_device(), slot)
-  buf = _workspaces.get(key)
-  if buf is None or buf.numel() < nbytes:
-    buf = t.empty(int(nbytes * 1.25) + 256, dtype = t.uint8, device = "cuda")
-    _workspaces[key] = buf
-  return buf.data_ptr(), buf.numel()
+  entry = _workspaces.get(slot)
+  if entry is None or entry[1] < nbytes:
+    buf = t.empty(int(nbytes * 1.25) + 256, dtype = t.uint8, device = t.device("cuda", device_index()))
+    entry = _workspaces[slot] = (buf.data_ptr(), buf.numel(), buf)
+  return entry[0], entry[1]
 
 
 # kernels launched through this module since the last reset (bench.py's gpu_launches evidence)

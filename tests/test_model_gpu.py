@@ -286,6 +286,56 @@ def test_batch2_train_step_matches_oracle(kind, roi_op, rois):
     np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5)
 
 
+def test_resnet101_forward_and_train_step_match_oracle():
+  """BASELINE config 4's backbone (ResNet-101, batch 1 per GPU; the 8-GPU part of that config is bench.py --gpus 8): forward and one
+  train step against the CPU restatement -- 23 bottlenecks in layer3, frozen BN folded into the filters, stride-2 / 7x7 convs on the
+  CUDA-core engine, everything else on the tensor cores."""
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import resnet
+  from oracle import resnet_oracle
+  params = orc.synth_params(resnet_oracle.param_shapes("resnet101"), seed = 6, heads = "spread")
+  for k in params:
+    if k.endswith("bn3.weight"):
+      params[k] = params[k] * 0.3                      # 33 residual blocks with Kaiming-scale branches overflow the synthetic init otherwise
+  model = f.FasterRCNNModel(num_classes = 21, backbone = resnet.ResNetBackbone(resnet.Architecture.ResNet101), allow_edge_proposals = True)
+  model.load_state_dict(params)
+  model = model.cuda()
+  oracle = orc.OracleModel(params, backbone = "resnet101")
+  smp = orc.synthetic_sample((320, 416), seed = 6, backbone = "resnet101")
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  with t.no_grad():
+    p_ref, c_ref, d_ref = oracle.forward(smp["image"])
+  model.eval()
+  with t.no_grad():
+    props, classes, deltas = model(image_data = smp["image"].cuda())
+  assert abs(props.shape[0] - p_ref.shape[0]) <= 3
+  partner, ok = _match_rows(props.cpu().numpy(), p_ref.numpy())
+  assert ok.mean() >= 0.97, ok.mean()
+  row = np.abs(classes.cpu().numpy()[ok] - c_ref.numpy()[partner[ok]]).max(axis = 1)
+  assert (row <= 1e-4).mean() >= 0.99, (row > 1e-4).sum()
+  params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
+  optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)
+  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
+  random.seed(2); np.random.seed(2); t.manual_seed(2)
+  ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = False)
+  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
+  random.seed(2); np.random.seed(2); t.manual_seed(2)
+  got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
+                         gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
+                         gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
+  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
+  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
+  np.testing.assert_allclose(a, b, rtol = 1e-3, atol = 1e-5)
+  worst = 0.0
+  for k, p in model.named_parameters():
+    if p.grad is None:
+      continue
+    ga, gb = p.grad.detach().cpu().double(), ref_grads[k].double()
+    worst = max(worst, float((ga - gb).norm() / (gb.norm() + 1e-12)))
+  assert worst < 2e-2, worst
+
+
 def test_checkpoint_round_trip_and_caffe_partial_load(tmp_path):
   """state.save / state.load (reference state.py:221-288): own-format round trip is bit-exact; a Caffe VGG-16 file initialises
   the 13 convs AND fc1/fc2 (the reference loses the fc layers to a key mismatch) and leaves the heads untouched."""
