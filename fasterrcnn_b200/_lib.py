@@ -45,6 +45,7 @@ _SIGNATURES = {
   "frcnn_conv2d_fwd_f16": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _vp, _sz, _vp]),
   "frcnn_conv2d_dgrad_f16": (_i, [_vp] * 6 + _GEOM + [_vp, _vp, _sz, _vp]),
   "frcnn_conv2d_wgrad_f16": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
+  "frcnn_conv2d_bwd_f16": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _GEOM + [_vp, _sz, _vp, _sz, _vp]),
   "frcnn_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_sigmoid_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_bias_grad_workspace_bytes": (_sz, [_sz, _i]),

@@ -216,4 +216,34 @@ int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split
   return tc_conv2d_wgrad(dy, x, dw, GEOM_ARGS, workspace, workspace_bytes, as_stream(stream), dy_split, x_split, true);
 }
 
+/* The whole backward of `y = [maxpool2x2] act(conv(x, w) + b)` on the fp16 engine in one call: (pooling + ReLU backward) -> fused
+ * activation-backward / operand split / bias row-sum -> data gradient -> filter gradient.  Same kernels as the single entry points, launched
+ * back to back from C: what it saves is four host round trips per layer. */
+int frcnn_conv2d_bwd_f16(const float *dy, const float *y, int act, int pooled, const float *x, const void *x_split, const float *w, const void *w_split,
+                         const void *dy_amax, int dy_amax_slots, float *dz_full, void *dz_split, float *dbias, float *dx, void *dx_amax, float *dw,
+                         int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                         void *bias_workspace, size_t bias_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(dy && x && w && dz_split && (dx || dw), "conv2d_bwd_f16: null pointer");
+  FRCNN_REQUIRE(stride == 1, "conv2d_bwd_f16: stride-1 layers only");
+  const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+  const size_t rows = (size_t)N * Ho * Wo;
+  const float *g = dy;
+  if (pooled) {                                          // dy is the gradient of the pooled map: route it to the window maxima under the ReLU mask
+    FRCNN_REQUIRE(y && dz_full && act == FRCNN_ACT_RELU, "conv2d_bwd_f16: pooled layers need y, a full-resolution scratch map and a ReLU");
+    int rc = frcnn_maxpool2x2_relu_bwd(dy, y, dz_full, N, Ho, Wo, Cout, stream);
+    if (rc != FRCNN_OK) return rc;
+    g = dz_full;
+    act = FRCNN_ACT_NONE;
+  }
+  int rc = frcnn_act_bwd_fused_f16(g, y, act, nullptr, dz_split, dbias, rows, Cout, dy_amax, dy_amax_slots, bias_workspace, bias_workspace_bytes, stream);
+  if (rc != FRCNN_OK) return rc;
+  if (dx) {
+    rc = frcnn_conv2d_dgrad_f16(g, w, dz_split, w_split, nullptr, dx, GEOM_ARGS, dx_amax, workspace, workspace_bytes, stream);
+    if (rc != FRCNN_OK) return rc;
+  }
+  if (dw) rc = frcnn_conv2d_wgrad_f16(g, x, dz_split, x_split, dw, GEOM_ARGS, workspace, workspace_bytes, stream);
+  return rc;
+}
+
 }  // extern "C"

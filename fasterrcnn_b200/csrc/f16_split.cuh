@@ -35,7 +35,7 @@ __device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) 
 __device__ __forceinline__ void split16(float x, float s, __half &hi, __half &lo)
 {
   float xs = __fmul_rn(x, s);                                         // exact (power of two) unless it underflows
-  xs = fminf(fmaxf(xs, -65504.0f), 65504.0f);
+  xs = xs > 65504.0f ? 65504.0f : (xs < -65504.0f ? -65504.0f : xs);   // comparisons, not fmin / fmax: a NaN stays a NaN and reaches the output
   hi = __float2half_rn(xs);
   lo = __float2half_rn(__fmul_rn(__fsub_rn(xs, __half2float(hi)), 2048.0f));
 }

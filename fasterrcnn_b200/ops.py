@@ -434,6 +434,54 @@ def _phys_filter(w):
 # autograd functions
 # ------------------------------------------------------------------------------------------------
 
+def _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, act, rows, c):
+  """One-call layer backward (frcnn_conv2d_bwd_f16): fp16 engine, both gradients on the tensor cores (or dx not wanted), an activation the
+  fused kernel handles; the per-launch timer of the roofline leg keeps the separate calls."""
+  if not _f16() or kernel_timer.enabled or _launch_log is not None or not want_dw or not tc_dw or (want_dx and not tc_dx):
+    return False
+  if act not in (ACT_NONE, ACT_RELU) or rows == 0 or geom[7] != 1:
+    return False
+  return bool(lib().frcnn_act_bwd_fused_supported(rows, c))
+
+
+def _conv_bwd_fused(dy, y, act, pool, xp, wp, geom, w_shape, want_dx, want_bias):
+  """-> (dx, dw, db) of one conv / linear layer through frcnn_conv2d_bwd_f16.  dy / y / xp are NHWC-physical maps or (rows, C) matrices."""
+  L = lib()
+  dev = y.device
+  c = geom[4]
+  rows = y.numel() // c
+  dz_full = t.empty_like(y) if pool else None
+  split = t.empty((split_bytes(y.numel()),), dtype = t.uint8, device = dev)
+  db = t.empty((c,), dtype = t.float32, device = dev) if want_bias else None
+  if y.dim() == 4:
+    dx = _empty_nhwc(*xp.shape, dev) if want_dx else None
+    cout, cin, kh, kw = w_shape
+    dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = dev) if (kh == 1 and kw == 1) else t.empty((cout, cin, kh, kw), dtype = t.float32, device = dev, memory_format = t.channels_last)
+  else:
+    dx = t.empty(tuple(xp.shape), dtype = t.float32, device = dev) if want_dx else None
+    dw = t.empty(tuple(w_shape), dtype = t.float32, device = dev)
+  h = _amax_hint(dy)
+  dx_amax = _amax_buffer(1, geom, dev) if want_dx else None
+  w_split = tf32_split(wp)
+  kx = (xp.data_ptr(), xp.numel(), xp._version)
+  x_split = _split_cache[kx][0] if kx in _split_cache else None
+  eng = _engine["value"]
+  wkey = ("bwd", geom, eng)
+  need = _gemm_workspace_cache.get(wkey)
+  if need is None:
+    need = max(L.frcnn_conv2d_dgrad_workspace_bytes(*geom, eng), L.frcnn_conv2d_wgrad_workspace_bytes(*geom, eng))
+    _gemm_workspace_cache[wkey] = need
+  ws, ws_n = workspace(need)
+  bws, bws_n = workspace(L.frcnn_act_bwd_fused_workspace_bytes(rows, c), slot = 1) if want_bias else (None, 0)
+  check(L.frcnn_conv2d_bwd_f16(ptr(dy), ptr(y), act, int(bool(pool)), ptr(xp), ptr(x_split), ptr(wp), ptr(w_split), ptr(h[0]) if h is not None else None, h[1] if h is not None else 0,
+                               ptr(dz_full), ptr(split), ptr(db), ptr(dx), ptr(dx_amax), ptr(dw), *geom, bws, bws_n, ws, ws_n, stream()), "frcnn_conv2d_bwd_f16")
+  _lib.count(3 + (1 if pool else 0) + (1 if h is None else 0) + (1 if want_bias else 0) + (0 if want_dx else -1))
+  if dx is not None:
+    _set_amax_hint(dx, dx_amax)
+  drop_split(xp)
+  return dx, dw, db
+
+
 class _ConvAct(t.autograd.Function):
   """y = [maxpool2x2] act(conv2d(x, w) + b).  Backward: fused (pool+)activation backward, then
   dgrad / wgrad / bias-grad kernels."""
@@ -470,6 +518,8 @@ class _ConvAct(t.autograd.Function):
     need_fp32 = (want_dx and not tc_dx) or (want_dw and not tc_dw)          # a CUDA-core GEMM reads dz itself
     want_bias = ctx.has_bias and ctx.needs_input_grad[2]
     act = ctx.act
+    if _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, act, y.numel() // c, c):
+      return _conv_bwd_fused(dy, y, act, ctx.pool, xp, wp, geom, ctx.w_shape, want_dx, want_bias) + (None, None, None, None)
     if ctx.pool:
       dz = t.empty_like(y)
       check(lib().frcnn_maxpool2x2_relu_bwd(ptr(dy), ptr(y), ptr(dz), n, h, wd, c, stream()), "frcnn_maxpool2x2_relu_bwd")
@@ -536,6 +586,8 @@ class _LinearAct(t.autograd.Function):
     geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
     want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     tc_dx, tc_dw = want_dx and _uses_tc(1, geom), want_dw and _uses_tc(2, geom)
+    if _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, ctx.act, m, nout):
+      return _conv_bwd_fused(dy, y, ctx.act, False, x2, w2, geom, tuple(w2.shape), want_dx, ctx.has_bias and ctx.needs_input_grad[2]) + (None,)
     need_fp32 = (want_dx and not tc_dx) or (want_dw and not tc_dw)
     dz, dz_split, db = _act_bwd(dy, y, ctx.act, nout, tc_dx or tc_dw, ctx.has_bias and ctx.needs_input_grad[2], need_fp32)
     dx = dw = None

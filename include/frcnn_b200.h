@@ -128,6 +128,16 @@ int frcnn_conv2d_wgrad_f16(const float *dy, const float *x, const void *dy_split
                            int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* Backward of one `y = [maxpool2x2] act(conv / linear(x, w) + b)` layer on the fp16 engine in ONE call (autograd's convolution_backward +
+ * relu / max_pool2d backward reached from models/faster_rcnn.py:356): optional pooling backward into dz_full (pooled != 0: dy is the pooled
+ * map's gradient, y the un-pooled activation), fused activation-backward -> dz_split (+ dbias, may be NULL), data gradient dx (may be NULL;
+ * dx_amax as in frcnn_conv2d_dgrad_f16), filter gradient dw (may be NULL).  x_split / w_split / dy_amax may be NULL (split / scanned here).
+ * bias_workspace >= frcnn_act_bwd_fused_workspace_bytes, workspace >= max of the dgrad / wgrad workspace queries (engine 3). */
+int frcnn_conv2d_bwd_f16(const float *dy, const float *y, int act, int pooled, const float *x, const void *x_split, const float *w, const void *w_split,
+                         const void *dy_amax, int dy_amax_slots, float *dz_full, void *dz_split, float *dbias, float *dx, void *dx_amax, float *dw,
+                         int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                         void *bias_workspace, size_t bias_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- elementwise / pooling pieces of the backward pass -------------------------------------
  * dz = dy * (y > 0)   (ReLU backward, models/vgg16.py:76-96 under autograd); in place allowed. */
 int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
