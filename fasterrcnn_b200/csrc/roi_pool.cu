@@ -4,9 +4,12 @@
 // its 32 lanes read 4 consecutive channels each -- one 512-byte NHWC segment per warp-wide 128-bit load, so a bin of r x s cells
 // is r*s independent vector loads per lane (the feature map is L2 resident; what has to be hidden is L2 latency, i.e. bytes in
 // flight per thread).  Each bin is scanned in the reference's row-major order with a strict '>' per channel so that the argmax
-// is the reference's; results are staged in shared memory as [channel][49] and streamed out (st.global.cs, the output must not
+// is the reference's; the values are staged in shared memory as [channel][49] and streamed out (st.global.cs, the output must not
 // evict the feature map from L2) as one contiguous (128 x 49) fp32 run -- i.e. directly in the (K, C, 7, 7) order that fc1
-// (models/vgg16.py:129) consumes -- with 128-bit stores; the HBM write of values + argmax is the algorithmic traffic.
+// (models/vgg16.py:129) consumes -- with 128-bit stores.  The argmax is private to this file (forward writes it, backward reads
+// it), so it is kept bin-major, (K, 49, C): the forward stores it straight from registers (a warp's four channels per lane are
+// one coalesced 512-byte run per bin, no staging), the backward reads it with lane = channel, coalesced.  The HBM write of
+// values + argmax is the algorithmic traffic.
 // roi_pool_fwd_kernel (one channel per lane, 32-channel groups) remains for channel counts that are not a multiple of 4.
 //
 // Backward: deterministic, atomics-free.  A CTA owns one feature-map row h and 32 channels; its 8 warps split the RoIs into 8
@@ -46,10 +49,9 @@ __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
                     float *__restrict__ out, int32_t *__restrict__ argmax)
 {
-  extern __shared__ float smem[];                 // [32][PH*PW] values then [32][PH*PW] argmax
+  extern __shared__ float smem[];                 // [32][PH*PW] values
   const int bins = PH * PW;
   float *s_val = smem;
-  int32_t *s_arg = reinterpret_cast<int32_t *>(smem + (size_t)kRoiChannels * bins);
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * kRoiChannels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,7 +77,7 @@ roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const flo
         }
       }
       s_val[lane * bins + b] = best;
-      s_arg[lane * bins + b] = besti;
+      if (argmax) argmax[((size_t)n * bins + b) * C + c] = besti;      // bin-major argmax: coalesced over the warp's channels
     }
   }
   __syncthreads();
@@ -85,18 +87,10 @@ roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const flo
   const int total = live * bins;
   if (((base | (size_t)total) & 3) == 0) {
     float4 *o4 = reinterpret_cast<float4 *>(out + base);
-    int4 *a4 = reinterpret_cast<int4 *>(argmax + base);
     const float4 *sv4 = reinterpret_cast<const float4 *>(s_val);
-    const int4 *sa4 = reinterpret_cast<const int4 *>(s_arg);
-    for (int e = threadIdx.x; e < total / 4; e += blockDim.x) {
-      o4[e] = sv4[e];
-      if (argmax) a4[e] = sa4[e];
-    }
+    for (int e = threadIdx.x; e < total / 4; e += blockDim.x) o4[e] = sv4[e];
   } else {
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      out[base + e] = s_val[e];
-      if (argmax) argmax[base + e] = s_arg[e];
-    }
+    for (int e = threadIdx.x; e < total; e += blockDim.x) out[base + e] = s_val[e];
   }
 }
 
@@ -117,10 +111,9 @@ __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
                        float *__restrict__ out, int32_t *__restrict__ argmax)
 {
-  extern __shared__ float smem[];                 // [128][PH*PW] values then [128][PH*PW] argmax
+  extern __shared__ float smem[];                 // [128][PH*PW] values
   const int bins = PH * PW;
   float *s_val = smem;
-  int32_t *s_arg = reinterpret_cast<int32_t *>(smem + (size_t)kRoiSlab * bins);
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * kRoiSlab;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -183,7 +176,7 @@ roi_pool_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const 
       }
       const int o = (4 * lane) * bins + b;
       s_val[o] = b0; s_val[o + bins] = b1; s_val[o + 2 * bins] = b2; s_val[o + 3 * bins] = b3;
-      s_arg[o] = i0; s_arg[o + bins] = i1; s_arg[o + 2 * bins] = i2; s_arg[o + 3 * bins] = i3;
+      if (argmax) __stcs(reinterpret_cast<int4 *>(argmax + ((size_t)n * bins + b) * C + c), make_int4(i0, i1, i2, i3));   // bin-major, 512 B per warp
     }
   }
   __syncthreads();
@@ -194,11 +187,6 @@ roi_pool_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const 
   float4 *o4 = reinterpret_cast<float4 *>(out + base);
   const float4 *sv4 = reinterpret_cast<const float4 *>(s_val);
   for (int e = threadIdx.x; e < total4; e += blockDim.x) __stcs(o4 + e, sv4[e]);
-  if (argmax) {
-    int4 *a4 = reinterpret_cast<int4 *>(argmax + base);
-    const int4 *sa4 = reinterpret_cast<const int4 *>(s_arg);
-    for (int e = threadIdx.x; e < total4; e += blockDim.x) __stcs(a4 + e, sa4[e]);
-  }
 }
 
 // grid (ceil(C/32), H); block = 8 warps x 32 channel lanes.
@@ -229,14 +217,28 @@ roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ 
     const int per = (K + kRoiWarps - 1) / kRoiWarps;
     const int n_end = min(K, (warp + 1) * per);
     for (int n = warp * per; n < n_end; n++) {
-      const int32_t *a = argmax + ((size_t)n * C + c) * bins;
+      const int32_t *a = argmax + (size_t)n * bins * C + c;              // bin-major: a[bin * C], lanes = consecutive channels
       const float *g = dout + ((size_t)n * C + c) * bins;
       for (int ph = 0; ph < PH; ph++) {
         const int packed = rows[n * PH + ph];
-        if (h < (packed >> 16) || h >= (packed & 0xffff)) continue;
-        for (int pw = 0; pw < PW; pw++) {
-          int idx = __ldg(a + ph * PW + pw);
-          if (idx >= lo && idx < hi) mine[(idx - lo) * 32 + lane] += __ldg(g + ph * PW + pw);
+        if (h < (packed >> 16) || h >= (packed & 0xffff)) continue;       // warp-uniform: the table is per (RoI, bin row)
+        if (PW == 7) {
+          // the bin row's 7 argmax words and 7 gradients are loaded before the first test (14 loads in flight per lane): with one
+          // load per iteration the walk was a chain of L2 round trips (~120 us for 128 RoIs)
+          int idx[7];
+          float gv[7];
+#pragma unroll
+          for (int pw = 0; pw < 7; pw++) idx[pw] = __ldg(a + (size_t)(ph * 7 + pw) * C);
+#pragma unroll
+          for (int pw = 0; pw < 7; pw++) gv[pw] = __ldg(g + ph * 7 + pw);
+#pragma unroll
+          for (int pw = 0; pw < 7; pw++)
+            if (idx[pw] >= lo && idx[pw] < hi) mine[(idx[pw] - lo) * 32 + lane] += gv[pw];
+        } else {
+          for (int pw = 0; pw < PW; pw++) {
+            int idx = __ldg(a + (size_t)(ph * PW + pw) * C);
+            if (idx >= lo && idx < hi) mine[(idx - lo) * 32 + lane] += __ldg(g + ph * PW + pw);
+          }
         }
       }
     }
@@ -266,7 +268,7 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
   FRCNN_REQUIRE(fm && proposals && out && H > 0 && W > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0, "roi_pool_fwd: bad argument");
   if (K == 0) return FRCNN_OK;
   if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(fm) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(argmax)) & 15) == 0) {
-    size_t smem4 = (size_t)kRoiSlab * PH * PW * (sizeof(float) + sizeof(int32_t));
+    size_t smem4 = (size_t)kRoiSlab * PH * PW * sizeof(float);
     FRCNN_REQUIRE(smem4 <= 200 * 1024, "roi_pool_fwd: pooled size too large");
     if (smem4 > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
@@ -276,7 +278,7 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
     FRCNN_CHECK_LAUNCH("roi_pool_fwd_v4_kernel");
     return FRCNN_OK;
   }
-  size_t smem = (size_t)kRoiChannels * PH * PW * (sizeof(float) + sizeof(int32_t));
+  size_t smem = (size_t)kRoiChannels * PH * PW * sizeof(float);
   FRCNN_REQUIRE(smem <= 200 * 1024, "roi_pool_fwd: pooled size too large");
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

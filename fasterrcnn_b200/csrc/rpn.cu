@@ -518,7 +518,7 @@ int frcnn_rpn_decode(const float *deltas, const float *anchors_in, int fh, int f
   FRCNN_REQUIRE(deltas && boxes && size_ok && fh > 0 && fw > 0 && feature_pixels > 0 && img_h > 0 && img_w > 0, "rpn_decode: bad argument");
   const int A = fh * fw * 9;
   static const AnchorSizes sizes = make_anchor_sizes();
-  rpn_decode_kernel<<<elementwise_grid(A, 128, 4), 128, 0, as_stream(stream)>>>(deltas, anchors_in, fh, fw, (double)feature_pixels, (float)img_h, (float)img_w, min_size, sizes, boxes, size_ok, anchors_out, valid_out);
+  rpn_decode_kernel<<<elementwise_grid(A, 128, 8), 128, 0, as_stream(stream)>>>(deltas, anchors_in, fh, fw, (double)feature_pixels, (float)img_h, (float)img_w, min_size, sizes, boxes, size_ok, anchors_out, valid_out);
   FRCNN_CHECK_LAUNCH("rpn_decode_kernel");
   return FRCNN_OK;
 }

@@ -683,7 +683,7 @@ class _RoIPool(t.autograd.Function):
     k = props.shape[0]
     ph, pw = output_size
     out = t.empty((k, c, ph, pw), dtype = t.float32, device = fm.device)
-    arg = t.empty((k, c, ph, pw), dtype = t.int32, device = fm.device)
+    arg = t.empty((k, ph * pw, c), dtype = t.int32, device = fm.device)      # bin-major: private to the forward / backward kernel pair
     if k > 0:
       check(lib().frcnn_roi_pool_fwd(ptr(fm), h, w, c, ptr(props), k, ph, pw, float(spatial_scale), ptr(out), ptr(arg), stream()), "frcnn_roi_pool_fwd")
       _lib.count()

@@ -232,7 +232,8 @@ int frcnn_append_rows_f32(float *dst, const int32_t *dst_count, int dst_capacity
 /* ---- K7: RoI max pooling (torchvision.ops.RoIPool((7,7), 1/16); models/detector.py:27,65-72)
  * fm NHWC (1,H,W,C); proposals (K,4) fp32 (y1,x1,y2,x2) as the reference holds them (the
  * (b,x1,y1,x2,y2) swap of detector.py:68-69 is folded in).  out (K,C,PH,PW) fp32 -- the layout
- * fc1 consumes (models/vgg16.py:129) -- argmax (K,C,PH,PW) int32 = h*W+w or -1. */
+ * fc1 consumes (models/vgg16.py:129) -- argmax int32 = h*W+w or -1, laid out bin-major (K,PH*PW,C): it is private to this pair of
+ * entry points (forward writes it, backward reads it), and this order is the coalesced one for both. */
 int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *proposals, int K, int PH, int PW, float spatial_scale,
                        float *out, int32_t *argmax, void *stream);
 /* dfm (H,W,C) NHWC = scatter-add of dout through argmax; deterministic (no atomics): one

@@ -280,6 +280,8 @@ def test_roi_pool_fwd_bit_exact_bwd_matches(ops, tag):
   fmc = _cuda(fm).requires_grad_(True)
   out = ops.roi_pool(fmc, _cuda(props), (7, 7), 1.0 / 16.0)
   assert np.array_equal(out.detach().cpu().numpy(), out_ref)
+  arg = out.grad_fn.saved_tensors[0].cpu().numpy()                                  # (K, 49, C) bin-major
+  assert np.array_equal(arg.transpose(0, 2, 1).reshape(arg_ref.shape), arg_ref)     # same argmax cell (or -1) as the library op, every bin
   go = gi.roi_grad(tag, out_ref.shape)
   out.backward(_cuda(go))
   gin_ref = orc.roi_pool_backward(go, arg_ref, rois, fm.shape)
