@@ -257,6 +257,10 @@ def run_ours(args, rank, local_rank, world):
   if world > 1:
     dist.init_process_group("nccl", device_id = dev)
 
+  # programmatic dependent launch (frcnn_set_pdl): on for the bench unless FRCNN_PDL=0 -- results are bit-identical either way
+  # (profiles/r01_pdl_ab.json: same losses over 35 steps, same detections; 5.68 -> 5.43 ms/step)
+  pdl = os.environ.get("FRCNN_PDL", "1") not in ("", "0")
+  _lib.set_pdl(pdl)
   step = make_train_step(dev, rank)
 
   def barrier():
@@ -331,6 +335,7 @@ def run_ours(args, rank, local_rank, world):
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
                             parallelism = "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)" % world,
                             engine = ENGINE_NOTES[engine_name][0],
+                            pdl = "on (programmatic dependent launch between the library's kernels; FRCNN_PDL=0 turns it off)" if pdl else "off",
                             l2 = "per-step working set (~1.7 GB of weights, activations, gradients) exceeds the 126 MB L2; no explicit flush"),
               e2e = dict(value = e2e_value, unit = "images/s", h2d_bytes_per_step = h2d, d2h_bytes_per_step = d2h, ms_per_step = ms_e2e / args.steps),
               gpu_launches = launches, clocks = clocks, roofline = roofline, cpu_baseline = cpu,

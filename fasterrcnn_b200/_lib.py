@@ -23,6 +23,7 @@ _GEOM = [_i] * 9
 _SIGNATURES = {
   "frcnn_version": (_i, []),
   "frcnn_last_error_string": (ctypes.c_char_p, []),
+  "frcnn_set_pdl": (_i, [_i]),
   "frcnn_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_conv2d_fwd_workspace_bytes": (_sz, _GEOM + [_i]),
@@ -110,6 +111,12 @@ def lib():
       fn.argtypes = argtypes
     _lib = handle
   return _lib
+
+
+def set_pdl(enabled):
+  """Programmatic dependent launch for every kernel of the library (include/frcnn_b200.h: frcnn_set_pdl); returns the previous setting.
+  Default = the FRCNN_PDL environment variable (off when unset)."""
+  return bool(lib().frcnn_set_pdl(1 if enabled else 0))
 
 
 def exported_symbols():

@@ -5,6 +5,17 @@ namespace frcnn {
 
 thread_local char g_last_error[512] = "";
 
+int g_pdl = -1;
+
+bool pdl_enabled()
+{
+  if (g_pdl < 0) {
+    const char *e = getenv("FRCNN_PDL");
+    g_pdl = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return g_pdl != 0;
+}
+
 // conv_simt.cu
 size_t simt_fwd_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 size_t simt_dgrad_workspace(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
@@ -55,6 +66,13 @@ extern "C" {
 int frcnn_version(void) { return 100; }
 
 const char *frcnn_last_error_string(void) { return g_last_error; }
+
+int frcnn_set_pdl(int enabled)
+{
+  const int before = pdl_enabled() ? 1 : 0;
+  g_pdl = enabled ? 1 : 0;
+  return before;
+}
 
 size_t frcnn_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine)
 {

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/frcnn_b200.h"
 
 namespace frcnn {
@@ -37,6 +39,39 @@ inline int cuda_fail(cudaError_t e, const char *where)
   } while (0)
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch (opt-in: FRCNN_PDL=1 or frcnn_set_pdl(1)) ------------------------------------------------
+// Every kernel of this library starts with pdl_enter(): `launch_dependents` lets the NEXT kernel of the stream become resident as
+// soon as all CTAs of this one have started (its barrier init / TMEM allocation / index arithmetic then overlap this kernel's tail
+// and the launch-to-launch gap disappears), `wait` blocks until the PREVIOUS kernel has completed and its writes are visible.
+// Because every kernel waits before its first global access and before it can finish, completion stays transitive along the
+// stream (kernel n+1 cannot finish before kernel n), so buffers are never read early or overwritten while still in use.
+// Launched without the attribute (the default) both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+extern int g_pdl;        // api.cu: -1 = read FRCNN_PDL on first use
+bool pdl_enabled();
+
+// the one way kernels are launched: <<<>>> semantics, plus the programmatic-serialization attribute when PDL is on
+template <typename... Params, typename... Args>
+inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through FRCNN_CHECK_LAUNCH (cudaGetLastError)
+}
 
 template <typename T>
 inline T ceil_div(T a, T b) { return (a + b - 1) / b; }

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256, 2)
 igemm_kernel(const float *__restrict__ src, const float *__restrict__ wgt, float *__restrict__ dst,
              Epilogue epi, ConvGeom g, int M, int Nn, int K, int C, int chunks_per_split, int splits)
 {
+  pdl_enter();
   constexpr int TM = BM / 16, TN = BN / 16;
   constexpr int A_LD = BM / 64;                  // float4 loads per thread for the A tile
   constexpr int B_LD = BN / 64;
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(256, 2)
 wgrad_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dst,
              ConvGeom g, int M, int Nn, int Kpix, int chunks_per_split, int splits)
 {
+  pdl_enter();
   constexpr int TM = BM / 16, TN = BN / 16;
   constexpr int A_TPR = BM / 4, A_RPP = 256 / A_TPR, A_LD = BK / A_RPP;
   constexpr int B_TPR = BN / 4, B_RPP = 256 / B_TPR, B_LD = BK / B_RPP;
@@ -432,6 +434,7 @@ wgrad_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *_
 // fixed summation order inside a slice, slices combined by the deterministic split-K reduce.
 __global__ void wgrad_scalar_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dst, ConvGeom g, int pix_per_slice)
 {
+  pdl_enter();
   const size_t total = (size_t)g.Cout * g.KH * g.KW * g.Cin;
   const int npix = g.N * g.Ho * g.Wo;
   const int p0 = blockIdx.y * pix_per_slice;
@@ -466,6 +469,7 @@ static int scalar_wgrad_slices(const ConvGeom &g)
 // split-K second stage: out = epilogue(sum_z partial[z]) in fixed z order (deterministic)
 __global__ void splitk_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, int M, int Nn, int splits, Epilogue epi)
 {
+  pdl_enter();
   size_t total = (size_t)M * Nn;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -478,7 +482,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, float *_
 int launch_splitk_reduce(const float *partial, float *out, int M, int Nn, int splits, const Epilogue &epi, cudaStream_t st)
 {
   size_t total = (size_t)M * Nn;
-  splitk_reduce_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(partial, out, M, Nn, splits, epi);
+  launch(splitk_reduce_kernel, elementwise_grid(total, 256), 256, 0, st, partial, out, M, Nn, splits, epi);
   FRCNN_CHECK_LAUNCH("splitk_reduce_kernel");
   return FRCNN_OK;
 }
@@ -544,14 +548,14 @@ static int launch_igemm(const float *src, const float *wgt, float *dst, const Ep
   bool vec = (C % 4 == 0) && (K % 4 == 0);
   if (MODE == MODE_DGRAD) vec = vec && (g.Cin % 4 == 0);   // N-major weight rows are read as float4 along Cin
   Epilogue kernel_epi = epi;
-#define LAUNCH(BNV, VECV) igemm_kernel<MODE, 128, BNV, VECV><<<grid, 256, 0, st>>>(src, wgt, target, kernel_epi, g, M, Nn, K, C, p.chunks_per_split, p.splits)
+#define LAUNCH(BNV, VECV) launch(igemm_kernel<MODE, 128, BNV, VECV>, grid, 256, 0, st, src, wgt, target, kernel_epi, g, M, Nn, K, C, p.chunks_per_split, p.splits)
   if (p.BN == 128) { if (vec) LAUNCH(128, true); else LAUNCH(128, false); }
   else { if (vec) LAUNCH(64, true); else LAUNCH(64, false); }
 #undef LAUNCH
   FRCNN_CHECK_LAUNCH("igemm_kernel");
   if (p.splits > 1) {
     size_t total = (size_t)M * Nn;
-    splitk_reduce_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(target, dst, M, Nn, p.splits, epi);
+    launch(splitk_reduce_kernel, elementwise_grid(total, 256), 256, 0, st, target, dst, M, Nn, p.splits, epi);
     FRCNN_CHECK_LAUNCH("splitk_reduce_kernel");
   }
   return FRCNN_OK;
@@ -604,6 +608,7 @@ constexpr int kStemTW = 16, kStemTH = 8;
 __global__ void __launch_bounds__(256, 2)
 stem3x3_kernel(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ y, Epilogue epi, int N, int H, int W, int Cout)
 {
+  pdl_enter();
   __shared__ float xs[kStemTH + 2][(kStemTW + 2) * 3];
   __shared__ __align__(16) float ws[27][64];
   const int tiles_w = (W + kStemTW - 1) / kStemTW, tiles_h = (H + kStemTH - 1) / kStemTH;
@@ -675,7 +680,7 @@ int simt_conv2d_fwd(const float *x, const float *w, const float *scale, const fl
   Epilogue epi{scale, bias, residual, act};
   if (Cin == 3 && KH == 3 && KW == 3 && stride == 1 && pad == 1 && Cout % 64 == 0 && residual == nullptr) {
     const int tiles = N * ceil_div(H, kStemTH) * ceil_div(W, kStemTW);
-    stem3x3_kernel<<<dim3(tiles, Cout / 64), 256, 0, st>>>(x, w, y, epi, N, H, W, Cout);
+    launch(stem3x3_kernel, dim3(tiles, Cout / 64), 256, 0, st, x, w, y, epi, N, H, W, Cout);
     FRCNN_CHECK_LAUNCH("stem3x3_kernel");
     return FRCNN_OK;
   }
@@ -709,7 +714,7 @@ int simt_conv2d_wgrad(const float *dy, const float *x, float *dw,
       if (workspace == nullptr || workspace_bytes < (size_t)slices * total * sizeof(float)) return fail(FRCNN_E_WORKSPACE, "conv2d_wgrad: workspace too small for the K slices");
       target = reinterpret_cast<float *>(workspace);
     }
-    wgrad_scalar_kernel<<<dim3(elementwise_grid(total, 128, 2), slices), 128, 0, st>>>(dy, x, target, g, per);
+    launch(wgrad_scalar_kernel, dim3(elementwise_grid(total, 128, 2), slices), 128, 0, st, dy, x, target, g, per);
     FRCNN_CHECK_LAUNCH("wgrad_scalar_kernel");
     if (slices > 1) {
       Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
@@ -726,13 +731,13 @@ int simt_conv2d_wgrad(const float *dy, const float *x, float *dw,
     target = reinterpret_cast<float *>(workspace);
   }
   dim3 grid(p.grid_m, p.grid_n, p.splits);
-  if (p.BN == 128) wgrad_kernel<128, 128><<<grid, 256, 0, st>>>(dy, x, target, g, M, Nn, Kpix, p.chunks_per_split, p.splits);
-  else wgrad_kernel<128, 64><<<grid, 256, 0, st>>>(dy, x, target, g, M, Nn, Kpix, p.chunks_per_split, p.splits);
+  if (p.BN == 128) launch(wgrad_kernel<128, 128>, grid, 256, 0, st, dy, x, target, g, M, Nn, Kpix, p.chunks_per_split, p.splits);
+  else launch(wgrad_kernel<128, 64>, grid, 256, 0, st, dy, x, target, g, M, Nn, Kpix, p.chunks_per_split, p.splits);
   FRCNN_CHECK_LAUNCH("wgrad_kernel");
   if (p.splits > 1) {
     Epilogue none{nullptr, nullptr, nullptr, FRCNN_ACT_NONE};
     size_t total = (size_t)M * Nn;
-    splitk_reduce_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(target, dw, M, Nn, p.splits, none);
+    launch(splitk_reduce_kernel, elementwise_grid(total, 256), 256, 0, st, target, dw, M, Nn, p.splits, none);
     FRCNN_CHECK_LAUNCH("splitk_reduce_kernel");
   }
   return FRCNN_OK;

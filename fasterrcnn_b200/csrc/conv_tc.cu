@@ -60,6 +60,7 @@ __device__ __forceinline__ float tf32_rna(float x)
 
 __global__ void split_hi_lo_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, size_t count)
 {
+  pdl_enter();
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -82,6 +83,7 @@ __global__ void split_hi_lo_kernel(const float *__restrict__ x, float *__restric
 __global__ void __launch_bounds__(512)
 f16_amax_partials_kernel(const float *__restrict__ x, size_t count, unsigned *__restrict__ header)
 {
+  pdl_enter();
   __shared__ float red[16];
   const size_t n4 = count / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -111,7 +113,7 @@ int f16_amax_grid(size_t count)
 int f16_launch_amax(const float *x, size_t count, void *header, cudaStream_t st)
 {
   const int G = f16_amax_grid(count);
-  f16_amax_partials_kernel<<<G, 512, 0, st>>>(x, count, reinterpret_cast<unsigned *>(header));
+  launch(f16_amax_partials_kernel, G, 512, 0, st, x, count, reinterpret_cast<unsigned *>(header));
   return G;
 }
 
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256)
 split_f16_kernel(const float *__restrict__ x, unsigned *__restrict__ header, const unsigned *__restrict__ partials, int G, __half *__restrict__ hi, __half *__restrict__ lo,
                  size_t count)
 {
+  pdl_enter();
   __shared__ unsigned scratch[32];
   const unsigned amax = f16_reduce_partials(partials, G, scratch);
   const int e = f16_exponent(amax);
@@ -281,7 +284,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KHW = g.KH * g.KW;
 
-  if (threadIdx.x == 0) TC_TRACE(0);
+  pdl_trigger();                                                     // the next kernel's CTAs may become resident behind this one
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }      // full: one arrive.expect_tx per producer
     for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
@@ -297,8 +300,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                                        // set-up above touched no global memory: it overlaps the previous kernel's tail
 
-  if (threadIdx.x == 0) TC_TRACE(1);
+  if (threadIdx.x == 0) { TC_TRACE(0); TC_TRACE(1); }
   if (warp == 0 || warp == 6) {
     if (lane == 0) {
       // ===== TMA producers: warp 0 feeds the A operand, warp 6 the B operand (up to 8 box loads each per k-block: issuing them
@@ -774,7 +778,7 @@ static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float 
   constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kBK * 4) + 1024 + 256;
   static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
-  tc_conv_kernel<MODE, BN, STAGES, F16><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  launch(tc_conv_kernel<MODE, BN, STAGES, F16>, grid, kTcThreads, smem, st, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;
 }
@@ -789,7 +793,7 @@ int tf32_split(const float *x, size_t count, void *out, cudaStream_t st)
 {
   float *hi = reinterpret_cast<float *>(out);
   float *lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(out) + align_up(count * 4, 1024));
-  split_hi_lo_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, hi, lo, count);
+  launch(split_hi_lo_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, st, x, hi, lo, count);
   FRCNN_CHECK_LAUNCH("split_hi_lo_kernel");
   return FRCNN_OK;
 }
@@ -808,7 +812,7 @@ int f16_split(const float *x, size_t count, void *out, cudaStream_t st, const vo
   }
   __half *hi = reinterpret_cast<__half *>(o + kF16Header);
   __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
-  split_f16_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, st>>>(x, reinterpret_cast<unsigned *>(o), reinterpret_cast<const unsigned *>(partials), G, hi, lo, count);
+  launch(split_f16_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, st, x, reinterpret_cast<unsigned *>(o), reinterpret_cast<const unsigned *>(partials), G, hi, lo, count);
   FRCNN_CHECK_LAUNCH("split_f16_kernel");
   return FRCNN_OK;
 }
@@ -841,7 +845,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
     int rc = f16_split(a, p.a_count, ws + p.a_hi_off - hdr, st, nullptr, 0);
     if (rc != FRCNN_OK) return rc;
   } else {
-    split_hi_lo_kernel<<<elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st>>>(a, (float *)a_hi, (float *)a_lo, p.a_count);
+    launch(split_hi_lo_kernel, elementwise_grid(p.a_count / 4 + 1, 256), 256, 0, st, a, (float *)a_hi, (float *)a_lo, p.a_count);
     FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(a)");
   }
   if (b_split) {
@@ -851,7 +855,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
     int rc = f16_split(b, p.b_count, ws + p.b_hi_off - hdr, st, nullptr, 0);
     if (rc != FRCNN_OK) return rc;
   } else {
-    split_hi_lo_kernel<<<elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st>>>(b, (float *)b_hi, (float *)b_lo, p.b_count);
+    launch(split_hi_lo_kernel, elementwise_grid(p.b_count / 4 + 1, 256), 256, 0, st, b, (float *)b_hi, (float *)b_lo, p.b_count);
     FRCNN_CHECK_LAUNCH("split_hi_lo_kernel(b)");
   }
   if (f16) {                                                          // scale exponents: header word 1 of each operand's split

@@ -11,6 +11,7 @@ __global__ void label_proposals_kernel(const float *__restrict__ proposals, int 
                                        int m, int num_classes, float min_object_iou, float *__restrict__ best_iou_out, int32_t *__restrict__ class_out,
                                        float *__restrict__ onehot, float *__restrict__ packed)
 {
+  pdl_enter();
   const int D = 4 * (num_classes - 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = __ldg(reinterpret_cast<const float4 *>(proposals) + i);
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(1024)
 rpn_losses_kernel(const float *__restrict__ scores, const float *__restrict__ deltas, const float *__restrict__ y_true, int A,
                   float *__restrict__ losses_out, float *__restrict__ d_scores, float *__restrict__ d_deltas)
 {
+  pdl_enter();
   __shared__ double scratch[32];
   double cls_sum = 0.0, reg_sum = 0.0, cnt = 0.0;
   for (int a = threadIdx.x; a < A; a += blockDim.x) {
@@ -136,6 +138,7 @@ rpn_losses_kernel(const float *__restrict__ scores, const float *__restrict__ de
 // ---- softmax over rows (F.softmax(dim=1), models/detector.py:77): one warp per row ------------------
 __global__ void softmax_rows_kernel(const float *__restrict__ logits, float *__restrict__ probs, int n, int C)
 {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -154,6 +157,7 @@ __global__ void softmax_rows_kernel(const float *__restrict__ logits, float *__r
 // softmax backward: dlogit_c = p_c (g_c - sum_k g_k p_k); one warp per row
 __global__ void softmax_rows_bwd_kernel(const float *__restrict__ probs, const float *__restrict__ d_probs, float *__restrict__ d_logits, int n, int C)
 {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -169,6 +173,7 @@ __global__ void softmax_rows_bwd_kernel(const float *__restrict__ probs, const f
 // sigmoid backward: dz = dy * (1 - y) * y
 __global__ void sigmoid_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, size_t count)
 {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     float s = y[i];
     dz[i] = dy[i] * (1.f - s) * s;
@@ -181,6 +186,7 @@ detector_losses_kernel(const float *__restrict__ probs, const float *__restrict_
                        const float *__restrict__ y_deltas, int n, int C, float *__restrict__ losses_out,
                        float *__restrict__ d_probs, float *__restrict__ d_deltas)
 {
+  pdl_enter();
   __shared__ double scratch[32];
   const int D = 4 * (C - 1);
   const float N = (float)((double)n + 1e-7);
@@ -225,6 +231,7 @@ __global__ void __launch_bounds__(kMaxDet)
 detect_postprocess_kernel(const float *__restrict__ proposals, const float *__restrict__ classes, const float *__restrict__ deltas, int n, int C,
                           double max_y, double max_x, float score_threshold, double iou_threshold, double *__restrict__ out, int32_t *__restrict__ out_counts)
 {
+  pdl_enter();
   __shared__ double bx[kMaxDet][4];
   __shared__ double area[kMaxDet];
   __shared__ float sc[kMaxDet];
@@ -306,7 +313,7 @@ int frcnn_label_proposals(const float *proposals, int n, const float *gt_boxes, 
                           float min_object_iou, float *best_iou, int32_t *class_idx, float *onehot, float *packed_targets, void *stream)
 {
   FRCNN_REQUIRE(proposals && gt_boxes && gt_classes && best_iou && class_idx && onehot && packed_targets && n > 0 && m > 0 && num_classes > 1, "label_proposals: bad argument");
-  label_proposals_kernel<<<elementwise_grid(n, 128, 2), 128, 0, as_stream(stream)>>>(proposals, n, gt_boxes, gt_classes, m, num_classes, min_object_iou, best_iou, class_idx, onehot, packed_targets);
+  launch(label_proposals_kernel, elementwise_grid(n, 128, 2), 128, 0, as_stream(stream), proposals, n, gt_boxes, gt_classes, m, num_classes, min_object_iou, best_iou, class_idx, onehot, packed_targets);
   FRCNN_CHECK_LAUNCH("label_proposals_kernel");
   return FRCNN_OK;
 }
@@ -315,7 +322,7 @@ int frcnn_rpn_losses(const float *scores, const float *deltas, const float *y_tr
 {
   FRCNN_REQUIRE(scores && deltas && y_true && losses_out && A > 0, "rpn_losses: bad argument");
   FRCNN_REQUIRE((d_scores == nullptr) == (d_deltas == nullptr), "rpn_losses: gradients must both be given or both be NULL");
-  rpn_losses_kernel<<<1, 1024, 0, as_stream(stream)>>>(scores, deltas, y_true, A, losses_out, d_scores, d_deltas);
+  launch(rpn_losses_kernel, 1, 1024, 0, as_stream(stream), scores, deltas, y_true, A, losses_out, d_scores, d_deltas);
   FRCNN_CHECK_LAUNCH("rpn_losses_kernel");
   return FRCNN_OK;
 }
@@ -324,7 +331,7 @@ int frcnn_softmax_rows(const float *logits, float *probs, int n, int C, void *st
 {
   FRCNN_REQUIRE(logits && probs && n >= 0 && C > 0, "softmax_rows: bad argument");
   if (n == 0) return FRCNN_OK;
-  softmax_rows_kernel<<<ceil_div(n, 4), 128, 0, as_stream(stream)>>>(logits, probs, n, C);
+  launch(softmax_rows_kernel, ceil_div(n, 4), 128, 0, as_stream(stream), logits, probs, n, C);
   FRCNN_CHECK_LAUNCH("softmax_rows_kernel");
   return FRCNN_OK;
 }
@@ -333,7 +340,7 @@ int frcnn_softmax_rows_bwd(const float *probs, const float *d_probs, float *d_lo
 {
   FRCNN_REQUIRE(probs && d_probs && d_logits && n >= 0 && C > 0, "softmax_rows_bwd: bad argument");
   if (n == 0) return FRCNN_OK;
-  softmax_rows_bwd_kernel<<<ceil_div(n, 4), 128, 0, as_stream(stream)>>>(probs, d_probs, d_logits, n, C);
+  launch(softmax_rows_bwd_kernel, ceil_div(n, 4), 128, 0, as_stream(stream), probs, d_probs, d_logits, n, C);
   FRCNN_CHECK_LAUNCH("softmax_rows_bwd_kernel");
   return FRCNN_OK;
 }
@@ -342,7 +349,7 @@ int frcnn_sigmoid_bwd(const float *dy, const float *y, float *dz, size_t count, 
 {
   FRCNN_REQUIRE(dy && y && dz, "sigmoid_bwd: null pointer");
   if (count == 0) return FRCNN_OK;
-  sigmoid_bwd_kernel<<<elementwise_grid(count, 256), 256, 0, as_stream(stream)>>>(dy, y, dz, count);
+  launch(sigmoid_bwd_kernel, elementwise_grid(count, 256), 256, 0, as_stream(stream), dy, y, dz, count);
   FRCNN_CHECK_LAUNCH("sigmoid_bwd_kernel");
   return FRCNN_OK;
 }
@@ -351,7 +358,7 @@ int frcnn_detector_losses(const float *probs, const float *deltas, const float *
                           float *losses_out, float *d_probs, float *d_deltas, void *stream)
 {
   FRCNN_REQUIRE(probs && deltas && y_classes && y_deltas && losses_out && n > 0 && C > 1, "detector_losses: bad argument");
-  detector_losses_kernel<<<1, 1024, 0, as_stream(stream)>>>(probs, deltas, y_classes, y_deltas, n, C, losses_out, d_probs, d_deltas);
+  launch(detector_losses_kernel, 1, 1024, 0, as_stream(stream), probs, deltas, y_classes, y_deltas, n, C, losses_out, d_probs, d_deltas);
   FRCNN_CHECK_LAUNCH("detector_losses_kernel");
   return FRCNN_OK;
 }
@@ -361,7 +368,7 @@ int frcnn_detect_postprocess(const float *proposals, const float *classes, const
 {
   FRCNN_REQUIRE(proposals && classes && deltas && out && out_counts && n > 0 && C > 1 && img_h > 0 && img_w > 0, "detect_postprocess: bad argument");
   FRCNN_REQUIRE(n <= kMaxDet, "detect_postprocess: more than 512 proposals");
-  detect_postprocess_kernel<<<C - 1, kMaxDet, 0, as_stream(stream)>>>(proposals, classes, deltas, n, C, (double)(img_h - 1), (double)(img_w - 1), score_threshold, iou_threshold, out, out_counts);
+  launch(detect_postprocess_kernel, C - 1, kMaxDet, 0, as_stream(stream), proposals, classes, deltas, n, C, (double)(img_h - 1), (double)(img_w - 1), score_threshold, iou_threshold, out, out_counts);
   FRCNN_CHECK_LAUNCH("detect_postprocess_kernel");
   return FRCNN_OK;
 }

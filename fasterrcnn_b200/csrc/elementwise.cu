@@ -9,6 +9,7 @@ namespace frcnn {
 // ---- layout: (N, C, HW) <-> (N, HW, C) through a 32x33 shared tile -------------------------
 __global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols, int tiles_r, int tiles_c, int batch)
 {
+  pdl_enter();
   // src: (batch, rows, cols) -> dst: (batch, cols, rows)
   __shared__ float tile[32][33];
   const int total = batch * tiles_r * tiles_c;
@@ -37,7 +38,7 @@ static int launch_transpose(const float *src, float *dst, int batch, int rows, i
   long long total = (long long)batch * tiles_r * tiles_c;
   int grid = (int)(total < (long long)kNumSMs * 16 ? total : (long long)kNumSMs * 16);
   if (grid < 1) grid = 1;
-  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, rows, cols, tiles_r, tiles_c, batch);
+  launch(transpose_kernel, grid, dim3(32, 8), 0, st, src, dst, rows, cols, tiles_r, tiles_c, batch);
   FRCNN_CHECK_LAUNCH("transpose_kernel");
   return FRCNN_OK;
 }
@@ -45,6 +46,7 @@ static int launch_transpose(const float *src, float *dst, int batch, int rows, i
 // ---- relu backward / add / sgd ---------------------------------------------------------------
 __global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, size_t count)
 {
+  pdl_enter();
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -60,6 +62,7 @@ __global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__res
 
 __global__ void add_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, size_t count)
 {
+  pdl_enter();
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -94,6 +97,7 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
                            float lr, float mom, float wd, float gs, int first, float *__restrict__ hi, float *__restrict__ lo,
                            __half *__restrict__ hi16, __half *__restrict__ lo16, const int *__restrict__ e16)
 {
+  pdl_enter();
   const float s16 = hi16 ? pow2i(__ldg(e16)) : 1.0f;
   size_t n4 = count / 4;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -135,6 +139,7 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, f
 // filter rows, and un-folds it from the filter gradient)
 __global__ void scale_rows_kernel(const float *__restrict__ x, const float *__restrict__ scale, float *__restrict__ out, size_t rows, size_t row_len)
 {
+  pdl_enter();
   size_t total = rows * row_len;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
     out[e] = x[e] * __ldg(scale + e / row_len);
@@ -145,6 +150,7 @@ constexpr int kBiasRowsPerBlock = 64;
 
 __global__ void bias_grad_stage1(const float *__restrict__ dz, float *__restrict__ partial, size_t rows, int C)
 {
+  pdl_enter();
   // block b sums rows [b*64, b*64+64) for every channel; 4 independent row streams per thread keep
   // enough loads in flight, combined in a fixed order (deterministic)
   size_t r0 = (size_t)blockIdx.x * kBiasRowsPerBlock;
@@ -165,6 +171,7 @@ __global__ void bias_grad_stage1(const float *__restrict__ dz, float *__restrict
 
 __global__ void bias_grad_stage2(const float *__restrict__ partial, float *__restrict__ dbias, int blocks, int C)
 {
+  pdl_enter();
   // one warp per channel group of 32: lanes = channels (coalesced), 8 row-slices per CTA combined through shared memory
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -195,6 +202,7 @@ act_bwd_fused_kernel(const float *__restrict__ dy, const float *__restrict__ y, 
                      float *__restrict__ partial, size_t rows, int C, int slab_c, int rows_per_block,
                      unsigned *__restrict__ hdr16, const unsigned *__restrict__ partials16, int G16, __half *__restrict__ hi16, __half *__restrict__ lo16)
 {
+  pdl_enter();
   __shared__ float4 red[256];
   // fp16 engine: exponent from the partial maxima of |dy| (the amax pass ran just before; |dz| <= |dy| under the ReLU mask)
   float s16 = 1.0f;
@@ -272,6 +280,7 @@ static bool act_bwd_fused_plan(size_t rows, int C, int *slab_c, int *blocks_x, i
 template <int VEC>
 __global__ void maxpool2x2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
 {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2, Cv = C / VEC;
   size_t total = (size_t)N * Ho * Wo * Cv;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -310,6 +319,7 @@ __device__ __forceinline__ float pool_relu_grad(float v00, float v01, float v10,
 
 __global__ void maxpool2x2_relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dz, int N, int H, int W, int C)
 {
+  pdl_enter();
   // one thread per (n, window-or-edge cell, channel); windows cover rows/cols < 2*Ho / 2*Wo, the
   // odd trailing row/column (floor mode) receives zero gradient.
   const int Ho = H / 2, Wo = W / 2;
@@ -345,6 +355,7 @@ __global__ void maxpool2x2_relu_bwd_kernel(const float *__restrict__ dy, const f
 
 __global__ void maxpool3x3s2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int Ho, int Wo)
 {
+  pdl_enter();
   size_t total = (size_t)N * Ho * Wo * C;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -368,6 +379,7 @@ __global__ void maxpool3x3s2_fwd_kernel(const float *__restrict__ x, float *__re
 
 __global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
 {
+  pdl_enter();
   // y.mean(-1).mean(-1) (models/resnet.py:117): mean over W for every row, then mean of the row means
   size_t total = (size_t)N * C;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -385,6 +397,7 @@ __global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__re
 
 __global__ void spatial_mean_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, int N, int HW, int C)
 {
+  pdl_enter();
   size_t total = (size_t)N * HW * C;
   const float inv = 1.0f / (float)HW;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -416,7 +429,7 @@ int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, voi
 {
   FRCNN_REQUIRE(dy && y && dz, "relu_bwd: null pointer");
   if (count == 0) return FRCNN_OK;
-  relu_bwd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(dy, y, dz, count);
+  launch(relu_bwd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), dy, y, dz, count);
   FRCNN_CHECK_LAUNCH("relu_bwd_kernel");
   return FRCNN_OK;
 }
@@ -425,7 +438,7 @@ int frcnn_add(const float *a, const float *b, float *out, size_t count, void *st
 {
   FRCNN_REQUIRE(a && b && out, "add: null pointer");
   if (count == 0) return FRCNN_OK;
-  add_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(a, b, out, count);
+  launch(add_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), a, b, out, count);
   FRCNN_CHECK_LAUNCH("add_kernel");
   return FRCNN_OK;
 }
@@ -440,7 +453,7 @@ int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, s
     hi = reinterpret_cast<float *>(param_split);
     lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(param_split) + (count * 4 + 1023) / 1024 * 1024);   // frcnn_tf32_split layout
   }
-  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo,
+  launch(sgd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo,
                                                                                   nullptr, nullptr, nullptr);
   FRCNN_CHECK_LAUNCH("sgd_kernel");
   return FRCNN_OK;
@@ -455,7 +468,7 @@ int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_bu
   uint8_t *o = reinterpret_cast<uint8_t *>(param_split);
   __half *hi = reinterpret_cast<__half *>(o + kF16Header);
   __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
-  sgd_kernel<<<elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, nullptr,
+  launch(sgd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, nullptr,
                                                                                   hi, lo, reinterpret_cast<const int *>(o) + 1);
   FRCNN_CHECK_LAUNCH("sgd_kernel");
   return FRCNN_OK;
@@ -489,7 +502,7 @@ int frcnn_scale_rows(const float *x, const float *scale, float *out, size_t rows
 {
   FRCNN_REQUIRE(x && scale && out, "scale_rows: null pointer");
   if (rows * row_len == 0) return FRCNN_OK;
-  scale_rows_kernel<<<elementwise_grid(rows * row_len, 256), 256, 0, as_stream(stream)>>>(x, scale, out, rows, row_len);
+  launch(scale_rows_kernel, elementwise_grid(rows * row_len, 256), 256, 0, as_stream(stream), x, scale, out, rows, row_len);
   FRCNN_CHECK_LAUNCH("scale_rows_kernel");
   return FRCNN_OK;
 }
@@ -506,9 +519,9 @@ int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *wor
   if (workspace == nullptr || workspace_bytes < frcnn_bias_grad_workspace_bytes(rows, C)) return fail(FRCNN_E_WORKSPACE, "bias_grad: workspace too small");
   int blocks = (int)ceil_div<size_t>(rows, kBiasRowsPerBlock);
   float *partial = reinterpret_cast<float *>(workspace);
-  bias_grad_stage1<<<blocks, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream)>>>(dz, partial, rows, C);
+  launch(bias_grad_stage1, blocks, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, as_stream(stream), dz, partial, rows, C);
   FRCNN_CHECK_LAUNCH("bias_grad_stage1");
-  bias_grad_stage2<<<ceil_div(C, 32), 256, 0, as_stream(stream)>>>(partial, dbias, blocks, C);
+  launch(bias_grad_stage2, ceil_div(C, 32), 256, 0, as_stream(stream), partial, dbias, blocks, C);
   FRCNN_CHECK_LAUNCH("bias_grad_stage2");
   return FRCNN_OK;
 }
@@ -565,11 +578,11 @@ static int act_bwd_fused_impl(const float *dy, const float *y, int act, float *d
     }
   }
   dim3 grid(bx, C / sc);
-  if (act == FRCNN_ACT_RELU) act_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
-  else act_bwd_fused_kernel<0><<<grid, 256, 0, st>>>(dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
+  if (act == FRCNN_ACT_RELU) launch(act_bwd_fused_kernel<1>, grid, 256, 0, st, dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
+  else launch(act_bwd_fused_kernel<0>, grid, 256, 0, st, dy, y, dz, hi, lo, partial, rows, C, sc, per, hdr16, partials16, G16, hi16, lo16);
   FRCNN_CHECK_LAUNCH("act_bwd_fused_kernel");
   if (dbias) {
-    bias_grad_stage2<<<ceil_div(C, 32), 256, 0, st>>>(partial, dbias, bx, C);
+    launch(bias_grad_stage2, ceil_div(C, 32), 256, 0, st, partial, dbias, bx, C);
     FRCNN_CHECK_LAUNCH("bias_grad_stage2");
   }
   return FRCNN_OK;
@@ -592,8 +605,8 @@ int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, v
 {
   FRCNN_REQUIRE(x && y && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2x2_fwd: bad argument");
   size_t total = (size_t)N * (H / 2) * (W / 2) * C;
-  if (C % 4 == 0) maxpool2x2_fwd_kernel<4><<<elementwise_grid(total / 4, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
-  else maxpool2x2_fwd_kernel<1><<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
+  if (C % 4 == 0) launch(maxpool2x2_fwd_kernel<4>, elementwise_grid(total / 4, 256), 256, 0, as_stream(stream), x, y, N, H, W, C);
+  else launch(maxpool2x2_fwd_kernel<1>, elementwise_grid(total, 256), 256, 0, as_stream(stream), x, y, N, H, W, C);
   FRCNN_CHECK_LAUNCH("maxpool2x2_fwd_kernel");
   return FRCNN_OK;
 }
@@ -602,7 +615,7 @@ int frcnn_maxpool2x2_relu_bwd(const float *dy, const float *x, float *dz, int N,
 {
   FRCNN_REQUIRE(dy && x && dz && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2x2_relu_bwd: bad argument");
   size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * C;
-  maxpool2x2_relu_bwd_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, x, dz, N, H, W, C);
+  launch(maxpool2x2_relu_bwd_kernel, elementwise_grid(total, 256), 256, 0, as_stream(stream), dy, x, dz, N, H, W, C);
   FRCNN_CHECK_LAUNCH("maxpool2x2_relu_bwd_kernel");
   return FRCNN_OK;
 }
@@ -612,7 +625,7 @@ int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C,
   FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "maxpool3x3s2_fwd: bad argument");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   size_t total = (size_t)N * Ho * Wo * C;
-  maxpool3x3s2_fwd_kernel<<<elementwise_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, Ho, Wo);
+  launch(maxpool3x3s2_fwd_kernel, elementwise_grid(total, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
   FRCNN_CHECK_LAUNCH("maxpool3x3s2_fwd_kernel");
   return FRCNN_OK;
 }
@@ -620,7 +633,7 @@ int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C,
 int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream)
 {
   FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "spatial_mean_fwd: bad argument");
-  spatial_mean_fwd_kernel<<<elementwise_grid((size_t)N * C, 256), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
+  launch(spatial_mean_fwd_kernel, elementwise_grid((size_t)N * C, 256), 256, 0, as_stream(stream), x, y, N, H, W, C);
   FRCNN_CHECK_LAUNCH("spatial_mean_fwd_kernel");
   return FRCNN_OK;
 }
@@ -628,7 +641,7 @@ int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int H, int W, int C,
 int frcnn_spatial_mean_bwd(const float *dy, float *dx, int N, int HW, int C, void *stream)
 {
   FRCNN_REQUIRE(dy && dx && N > 0 && HW > 0 && C > 0, "spatial_mean_bwd: bad argument");
-  spatial_mean_bwd_kernel<<<elementwise_grid((size_t)N * HW * C, 256), 256, 0, as_stream(stream)>>>(dy, dx, N, HW, C);
+  launch(spatial_mean_bwd_kernel, elementwise_grid((size_t)N * HW * C, 256), 256, 0, as_stream(stream), dy, dx, N, HW, C);
   FRCNN_CHECK_LAUNCH("spatial_mean_bwd_kernel");
   return FRCNN_OK;
 }

@@ -32,6 +32,7 @@ __device__ __forceinline__ float head_act(float v, int act)
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const float *__restrict__ x, int M, int K, Heads h, float *__restrict__ y1, float *__restrict__ y2, float *__restrict__ partial, int k_per_slice)
 {
+  pdl_enter();
   __shared__ __align__(16) float ws[kHeadCols][kHeadChunk + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = blockIdx.x * kHeadRows + warp;
@@ -89,6 +90,7 @@ heads_fwd_kernel(const float *__restrict__ x, int M, int K, Heads h, float *__re
 
 __global__ void heads_fwd_reduce_kernel(const float *__restrict__ partial, int M, Heads h, int kslices, float *__restrict__ y1, float *__restrict__ y2)
 {
+  pdl_enter();
   const int N = h.N1 + h.N2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M * N) return;
@@ -103,6 +105,7 @@ __global__ void heads_fwd_reduce_kernel(const float *__restrict__ partial, int M
 __global__ void heads_dz_kernel(const float *__restrict__ dy1, const float *__restrict__ y1, const float *__restrict__ dy2, const float *__restrict__ y2,
                                 int M, Heads h, float *__restrict__ dz)
 {
+  pdl_enter();
   const int N = h.N1 + h.N2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M * N) return;
@@ -119,6 +122,7 @@ __global__ void heads_dz_kernel(const float *__restrict__ dy1, const float *__re
 // dx[m][k..k+4) = sum_n dz[m][n] * w[n][k..k+4)   (n ascending);  grid over M * K / 4 threads
 __global__ void heads_dgrad_kernel(const float *__restrict__ dz, int M, int K, Heads h, const float *__restrict__ addend, float *__restrict__ dx)
 {
+  pdl_enter();
   const int N = h.N1 + h.N2;
   const int k4 = K / 4;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(256)
 heads_wgrad_kernel(const float *__restrict__ dz, const float *__restrict__ x, int M, int K, int N, int rows_per_slice,
                    float *__restrict__ partial, float *__restrict__ partial_b)
 {
+  pdl_enter();
   const int n = blockIdx.x;
   const int q = blockIdx.y * 256 + threadIdx.x;
   const int k4 = K / 4;
@@ -165,6 +170,7 @@ heads_wgrad_kernel(const float *__restrict__ dz, const float *__restrict__ x, in
 __global__ void heads_wgrad_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ partial_b, int K, Heads h, int slices,
                                           float *__restrict__ dw1, float *__restrict__ db1, float *__restrict__ dw2, float *__restrict__ db2)
 {
+  pdl_enter();
   const int N = h.N1 + h.N2;
   const int k4 = K / 4;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,10 +241,10 @@ int frcnn_heads_fwd(const float *x, int M, int K, const float *w1, const float *
     if (workspace == nullptr || workspace_bytes < (size_t)ks * M * N * sizeof(float)) return fail(FRCNN_E_WORKSPACE, "heads_fwd: workspace too small");
     partial = reinterpret_cast<float *>(workspace);
   }
-  heads_fwd_kernel<<<dim3(ceil_div(M, kHeadRows), ceil_div(N, kHeadCols), ks), 256, 0, st>>>(x, M, K, h, y1, y2, partial, kper);
+  launch(heads_fwd_kernel, dim3(ceil_div(M, kHeadRows), ceil_div(N, kHeadCols), ks), 256, 0, st, x, M, K, h, y1, y2, partial, kper);
   FRCNN_CHECK_LAUNCH("heads_fwd_kernel");
   if (ks > 1) {
-    heads_fwd_reduce_kernel<<<ceil_div(M * N, 256), 256, 0, st>>>(partial, M, h, ks, y1, y2);
+    launch(heads_fwd_reduce_kernel, ceil_div(M * N, 256), 256, 0, st, partial, M, h, ks, y1, y2);
     FRCNN_CHECK_LAUNCH("heads_fwd_reduce_kernel");
   }
   return FRCNN_OK;
@@ -259,15 +265,15 @@ int frcnn_heads_bwd(const float *x, int M, int K, const float *w1, int N1, int a
   float *dz = reinterpret_cast<float *>(workspace);
   float *partial = dz + (((size_t)M * N + 63) / 64) * 64;
   float *partial_b = partial + (size_t)ms * N * K;
-  heads_dz_kernel<<<ceil_div(M * N, 256), 256, 0, st>>>(dy1, y1, dy2, y2, M, h, dz);
+  launch(heads_dz_kernel, ceil_div(M * N, 256), 256, 0, st, dy1, y1, dy2, y2, M, h, dz);
   FRCNN_CHECK_LAUNCH("heads_dz_kernel");
   if (dx) {
-    heads_dgrad_kernel<<<(unsigned)ceil_div<size_t>((size_t)M * (K / 4), 256), 256, 0, st>>>(dz, M, K, h, nullptr, dx);
+    launch(heads_dgrad_kernel, (unsigned)ceil_div<size_t>((size_t)M * (K / 4), 256), 256, 0, st, dz, M, K, h, nullptr, dx);
     FRCNN_CHECK_LAUNCH("heads_dgrad_kernel");
   }
-  heads_wgrad_kernel<<<dim3(N, ceil_div(K / 4, 256), ms), 256, 0, st>>>(dz, x, M, K, N, rows, partial, partial_b);
+  launch(heads_wgrad_kernel, dim3(N, ceil_div(K / 4, 256), ms), 256, 0, st, dz, x, M, K, N, rows, partial, partial_b);
   FRCNN_CHECK_LAUNCH("heads_wgrad_kernel");
-  heads_wgrad_reduce_kernel<<<(unsigned)ceil_div<size_t>((size_t)N * (K / 4), 256), 256, 0, st>>>(partial, partial_b, K, h, ms, dw1, db1, dw2, db2);
+  launch(heads_wgrad_reduce_kernel, (unsigned)ceil_div<size_t>((size_t)N * (K / 4), 256), 256, 0, st, partial, partial_b, K, h, ms, dw1, db1, dw2, db2);
   FRCNN_CHECK_LAUNCH("heads_wgrad_reduce_kernel");
   return FRCNN_OK;
 }

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kAlignSlab)
 roi_align_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, int S, float scale,
                      int aligned, float *__restrict__ out)
 {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const int bins = PH * PW, taps = bins * S * S;
   Tap *tab = reinterpret_cast<Tap *>(smem_raw);
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kAlignWarps * 32)
 roi_align_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, int S, float scale,
                         int aligned, float *__restrict__ out)
 {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const int bins = PH * PW, ss = S * S, taps = bins * ss;
   Tap *tab = reinterpret_cast<Tap *>(smem_raw);
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(256)
 roi_align_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ proposals, float scale, int aligned, int K, int H, int W, int C,
                      int PH, int PW, int S, const float *__restrict__ addend, float *__restrict__ dfm)
 {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const int bins = PH * PW, taps = bins * S * S;
   float *line = reinterpret_cast<float *>(smem_raw);                      // [W][256]
@@ -273,11 +276,11 @@ int frcnn_roi_align_fwd(const float *fm, int H, int W, int C, const float *propo
       cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "roi_align_fwd: smem attribute");
     }
-    roi_align_fwd_v4_kernel<<<dim3(K, ceil_div(C, kAlignSlab)), kAlignWarps * 32, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
+    launch(roi_align_fwd_v4_kernel, dim3(K, ceil_div(C, kAlignSlab)), kAlignWarps * 32, smem, as_stream(stream), fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
     FRCNN_CHECK_LAUNCH("roi_align_fwd_v4_kernel");
     return FRCNN_OK;
   }
-  roi_align_fwd_kernel<<<dim3(K, ceil_div(C, kAlignSlab)), kAlignSlab, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
+  launch(roi_align_fwd_kernel, dim3(K, ceil_div(C, kAlignSlab)), kAlignSlab, smem, as_stream(stream), fm, H, W, C, proposals, PH, PW, sampling_ratio, spatial_scale, aligned, out);
   FRCNN_CHECK_LAUNCH("roi_align_fwd_kernel");
   return FRCNN_OK;
 }
@@ -294,7 +297,7 @@ int frcnn_roi_align_bwd(const float *dout, const float *proposals, int K, int H,
     cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_align_bwd: smem attribute");
   }
-  roi_align_bwd_kernel<<<dim3(ceil_div(C, 32), ceil_div(H, 8)), 256, smem, as_stream(stream)>>>(dout, proposals, spatial_scale, aligned, K, H, W, C, PH, PW, sampling_ratio, addend, dfm);
+  launch(roi_align_bwd_kernel, dim3(ceil_div(C, 32), ceil_div(H, 8)), 256, smem, as_stream(stream), dout, proposals, spatial_scale, aligned, K, H, W, C, PH, PW, sampling_ratio, addend, dfm);
   FRCNN_CHECK_LAUNCH("roi_align_bwd_kernel");
   return FRCNN_OK;
 }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_fwd_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
                     float *__restrict__ out, int32_t *__restrict__ argmax)
 {
+  pdl_enter();
   extern __shared__ float smem[];                 // [32][PH*PW] values
   const int bins = PH * PW;
   float *s_val = smem;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_fwd_v4_kernel(const float *__restrict__ fm, int H, int W, int C, const float *__restrict__ proposals, int PH, int PW, float scale,
                        float *__restrict__ out, int32_t *__restrict__ argmax)
 {
+  pdl_enter();
   extern __shared__ float smem[];                 // [128][PH*PW] values
   const int bins = PH * PW;
   float *s_val = smem;
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_pool_bwd_kernel(const float *__restrict__ dout, const int32_t *__restrict__ argmax, const float *__restrict__ proposals, float scale,
                     int K, int H, int W, int C, int PH, int PW, const float *__restrict__ addend, float *__restrict__ dfm)
 {
+  pdl_enter();
   extern __shared__ float line[];                 // [8 chunks][W][32] floats, then the (K x PH) row-range table
   int32_t *rows = reinterpret_cast<int32_t *>(line + (size_t)kRoiWarps * W * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -274,7 +277,7 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
       cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
       if (e != cudaSuccess) return cuda_fail(e, "roi_pool_fwd: smem attribute");
     }
-    roi_pool_fwd_v4_kernel<<<dim3(K, ceil_div(C, kRoiSlab)), kRoiWarps * 32, smem4, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
+    launch(roi_pool_fwd_v4_kernel, dim3(K, ceil_div(C, kRoiSlab)), kRoiWarps * 32, smem4, as_stream(stream), fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
     FRCNN_CHECK_LAUNCH("roi_pool_fwd_v4_kernel");
     return FRCNN_OK;
   }
@@ -284,7 +287,7 @@ int frcnn_roi_pool_fwd(const float *fm, int H, int W, int C, const float *propos
     cudaError_t e = cudaFuncSetAttribute(roi_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_pool_fwd: smem attribute");
   }
-  roi_pool_fwd_kernel<<<dim3(K, ceil_div(C, kRoiChannels)), kRoiWarps * 32, smem, as_stream(stream)>>>(fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
+  launch(roi_pool_fwd_kernel, dim3(K, ceil_div(C, kRoiChannels)), kRoiWarps * 32, smem, as_stream(stream), fm, H, W, C, proposals, PH, PW, spatial_scale, out, argmax);
   FRCNN_CHECK_LAUNCH("roi_pool_fwd_kernel");
   return FRCNN_OK;
 }
@@ -300,7 +303,7 @@ int frcnn_roi_pool_bwd(const float *dout, const int32_t *argmax, const float *pr
     cudaError_t e = cudaFuncSetAttribute(roi_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "roi_pool_bwd: smem attribute");
   }
-  roi_pool_bwd_kernel<<<dim3(ceil_div(C, 32), H), kRoiWarps * 32, smem, as_stream(stream)>>>(dout, argmax, proposals, spatial_scale, K, H, W, C, PH, PW, addend, dfm);
+  launch(roi_pool_bwd_kernel, dim3(ceil_div(C, 32), H), kRoiWarps * 32, smem, as_stream(stream), dout, argmax, proposals, spatial_scale, K, H, W, C, PH, PW, addend, dfm);
   FRCNN_CHECK_LAUNCH("roi_pool_bwd_kernel");
   return FRCNN_OK;
 }

@@ -37,6 +37,7 @@ __global__ void rpn_decode_kernel(const float *__restrict__ deltas, const float 
                                   float min_size, AnchorSizes sizes, float *__restrict__ boxes, uint8_t *__restrict__ size_ok,
                                   float *__restrict__ anchors_out, float *__restrict__ valid_out)
 {
+  pdl_enter();
   const int A = fh * fw * 9;
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
     int k = a % 9;
@@ -91,6 +92,7 @@ constexpr int kRankTile = 1024;
 template <bool LOW_FIRST>
 __global__ void rank_count_kernel(const float *__restrict__ scores, const uint8_t *__restrict__ keep_mask, int n, int j_per_slice, int32_t *__restrict__ rank)
 {
+  pdl_enter();
   __shared__ __align__(16) float tile[kRankTile];
   scores += (size_t)blockIdx.z * n;
   rank += (size_t)blockIdx.z * (n + 1);
@@ -133,6 +135,7 @@ __global__ void rank_count_kernel(const float *__restrict__ scores, const uint8_
 __global__ void rank_scatter_kernel(const uint8_t *__restrict__ keep_mask, int n, int top_n, const int32_t *__restrict__ rank,
                                     int32_t *__restrict__ order, int32_t *__restrict__ count_out, int order_stride)
 {
+  pdl_enter();
   rank += (size_t)blockIdx.y * (n + 1);
   count_out += (size_t)blockIdx.y * (n + 1);
   order += (size_t)blockIdx.y * order_stride;
@@ -154,6 +157,7 @@ gather_filtered_kernel(const float *__restrict__ boxes, const float *__restrict_
                        const int32_t *__restrict__ order, const int32_t *__restrict__ count, int capacity,
                        float *__restrict__ boxes_out, float *__restrict__ scores_out, int32_t *__restrict__ count_out)
 {
+  pdl_enter();
   __shared__ int warp_sums[32];
   __shared__ int carry;
   int n = *count;
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ count, int count_stride, int capacity, float thr_f,
                 unsigned long long *__restrict__ mask, int col_blocks)
 {
+  pdl_enter();
   // blockIdx.z = batch entry (class): boxes / mask advance by one capacity-sized block, count by count_stride
   boxes += (size_t)blockIdx.z * capacity * 4;
   mask += (size_t)blockIdx.z * capacity * col_blocks;
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ count, int count_stride, int capacity, int col_blocks,
                 int max_keep, int32_t *__restrict__ keep_out, int keep_stride, int32_t *__restrict__ kept_count_out)
 {
+  pdl_enter();
   // blockIdx.x = batch entry (class): one CTA walks one greedy chain
   mask += (size_t)blockIdx.x * capacity * col_blocks;
   count += (size_t)blockIdx.x * count_stride;
@@ -390,6 +396,7 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
 // batched NMS glue: sorted[z][r] = boxes[z][order[z][r]] (r < n), and keep[z][r] = order[z][keep_pos[z][r]] (r < kept[z])
 __global__ void nms_batched_sort_boxes_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ order, int n, float *__restrict__ sorted)
 {
+  pdl_enter();
   const size_t zoff = (size_t)blockIdx.y * n;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
     reinterpret_cast<float4 *>(sorted)[zoff + r] = __ldg(reinterpret_cast<const float4 *>(boxes) + zoff + order[zoff + r]);
@@ -398,6 +405,7 @@ __global__ void nms_batched_sort_boxes_kernel(const float *__restrict__ boxes, c
 __global__ void nms_batched_finish_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ keep_pos, const int32_t *__restrict__ kept, int n,
                                           int max_keep, int32_t *__restrict__ keep_out)
 {
+  pdl_enter();
   const int z = blockIdx.y;
   const int k = kept[z];
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < max_keep; r += gridDim.x * blockDim.x)
@@ -409,6 +417,7 @@ __global__ void nms_batched_finish_kernel(const int32_t *__restrict__ order, con
 __global__ void append_rows_kernel(float *__restrict__ dst, const int32_t *__restrict__ dst_count, int dst_capacity_rows, int row_floats,
                                    const float *__restrict__ src, int m)
 {
+  pdl_enter();
   int n = *dst_count;
   if (n < 0) n = 0;
   const int total = m * row_floats;
@@ -421,6 +430,7 @@ __global__ void append_rows_kernel(float *__restrict__ dst, const int32_t *__res
 __global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats, const int32_t *__restrict__ index, const int32_t *__restrict__ count,
                                    int capacity, float *__restrict__ dst)
 {
+  pdl_enter();
   int n = *count;
   if (n > capacity) n = capacity;
   size_t total = (size_t)n * row_floats;
@@ -458,6 +468,7 @@ __device__ __forceinline__ void anchor_corners(const float4 &a, float &y1, float
 __global__ void rpn_targets_pass1(const float *__restrict__ anchors, const float *__restrict__ valid, int A, const float *__restrict__ gt, int M,
                                   long long *__restrict__ gt_max_bits)
 {
+  pdl_enter();
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
     float4 an = __ldg(reinterpret_cast<const float4 *>(anchors) + a);
     float y1, x1, y2, x2;
@@ -473,6 +484,7 @@ __global__ void rpn_targets_pass1(const float *__restrict__ anchors, const float
 __global__ void rpn_targets_pass2(const float *__restrict__ anchors, const float *__restrict__ valid, int A, const float *__restrict__ gt, int M,
                                   const long long *__restrict__ gt_max_bits, double object_thr, double background_thr, float *__restrict__ rpn_map)
 {
+  pdl_enter();
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
     float4 an = __ldg(reinterpret_cast<const float4 *>(anchors) + a);
     float y1, x1, y2, x2;
@@ -518,7 +530,7 @@ int frcnn_rpn_decode(const float *deltas, const float *anchors_in, int fh, int f
   FRCNN_REQUIRE(deltas && boxes && size_ok && fh > 0 && fw > 0 && feature_pixels > 0 && img_h > 0 && img_w > 0, "rpn_decode: bad argument");
   const int A = fh * fw * 9;
   static const AnchorSizes sizes = make_anchor_sizes();
-  rpn_decode_kernel<<<elementwise_grid(A, 128, 8), 128, 0, as_stream(stream)>>>(deltas, anchors_in, fh, fw, (double)feature_pixels, (float)img_h, (float)img_w, min_size, sizes, boxes, size_ok, anchors_out, valid_out);
+  launch(rpn_decode_kernel, elementwise_grid(A, 128, 8), 128, 0, as_stream(stream), deltas, anchors_in, fh, fw, (double)feature_pixels, (float)img_h, (float)img_w, min_size, sizes, boxes, size_ok, anchors_out, valid_out);
   FRCNN_CHECK_LAUNCH("rpn_decode_kernel");
   return FRCNN_OK;
 }
@@ -537,9 +549,9 @@ int frcnn_topk_order(const float *scores, const uint8_t *keep_mask, int n, int t
   if (slices < 1) slices = 1;
   int j_per_slice = ceil_div(ceil_div(n, slices), kRankTile) * kRankTile;
   slices = ceil_div(n, j_per_slice);
-  rank_count_kernel<false><<<dim3(gx, slices), threads, 0, st>>>(scores, keep_mask, n, j_per_slice, rank);
+  launch(rank_count_kernel<false>, dim3(gx, slices), threads, 0, st, scores, keep_mask, n, j_per_slice, rank);
   FRCNN_CHECK_LAUNCH("rank_count_kernel");
-  rank_scatter_kernel<<<gx, threads, 0, st>>>(keep_mask, n, top_n, rank, order, count_out, 0);
+  launch(rank_scatter_kernel, gx, threads, 0, st, keep_mask, n, top_n, rank, order, count_out, 0);
   FRCNN_CHECK_LAUNCH("rank_scatter_kernel");
   return FRCNN_OK;
 }
@@ -548,7 +560,7 @@ int frcnn_gather_filtered(const float *boxes, const float *scores, const uint8_t
                           const int32_t *count, int capacity, float *boxes_out, float *scores_out, int32_t *count_out, void *stream)
 {
   FRCNN_REQUIRE(boxes && scores && size_ok && order && count && boxes_out && scores_out && count_out && capacity > 0, "gather_filtered: bad argument");
-  gather_filtered_kernel<<<1, 1024, 0, as_stream(stream)>>>(boxes, scores, size_ok, order, count, capacity, boxes_out, scores_out, count_out);
+  launch(gather_filtered_kernel, 1, 1024, 0, as_stream(stream), boxes, scores, size_ok, order, count, capacity, boxes_out, scores_out, count_out);
   FRCNN_CHECK_LAUNCH("gather_filtered_kernel");
   return FRCNN_OK;
 }
@@ -570,7 +582,7 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
   if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
   cudaStream_t st = as_stream(stream);
   unsigned long long *mask = reinterpret_cast<unsigned long long *>(workspace);
-  nms_mask_kernel<<<dim3(col_blocks, col_blocks), 64, 0, st>>>(boxes, count, 0, capacity, thr_f, mask, col_blocks);
+  launch(nms_mask_kernel, dim3(col_blocks, col_blocks), 64, 0, st, boxes, count, 0, capacity, thr_f, mask, col_blocks);
   FRCNN_CHECK_LAUNCH("nms_mask_kernel");
   const int keep_cap = max_keep < capacity ? max_keep : capacity;
   size_t smem = (size_t)keep_cap * sizeof(int32_t);
@@ -579,7 +591,7 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
   }
-  nms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, count, 0, capacity, col_blocks, keep_cap, keep_out, 0, kept_count_out);
+  launch(nms_scan_kernel, 1, kScanThreads, smem, st, mask, count, 0, capacity, col_blocks, keep_cap, keep_out, 0, kept_count_out);
   FRCNN_CHECK_LAUNCH("nms_scan_kernel");
   return FRCNN_OK;
 }
@@ -632,15 +644,15 @@ int frcnn_nms_batched_f32(const float *boxes, const float *scores, int B, int n,
   if (slices < 1) slices = 1;
   int j_per_slice = ceil_div(ceil_div(n, slices), kRankTile) * kRankTile;
   slices = ceil_div(n, j_per_slice);
-  rank_count_kernel<true><<<dim3(gx, slices, B), threads, 0, st>>>(scores, nullptr, n, j_per_slice, cnt + 1);
+  launch(rank_count_kernel<true>, dim3(gx, slices, B), threads, 0, st, scores, nullptr, n, j_per_slice, cnt + 1);
   FRCNN_CHECK_LAUNCH("rank_count_kernel");
-  rank_scatter_kernel<<<dim3(gx, B), threads, 0, st>>>(nullptr, n, n, cnt + 1, order, cnt, n);
+  launch(rank_scatter_kernel, dim3(gx, B), threads, 0, st, nullptr, n, n, cnt + 1, order, cnt, n);
   FRCNN_CHECK_LAUNCH("rank_scatter_kernel");
-  nms_batched_sort_boxes_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, st>>>(boxes, order, n, sorted);
+  launch(nms_batched_sort_boxes_kernel, dim3(ceil_div(n, 256), B), 256, 0, st, boxes, order, n, sorted);
   FRCNN_CHECK_LAUNCH("nms_batched_sort_boxes_kernel");
   // 2. suppression bit tiles of every entry in one launch, 3. one greedy-scan CTA per entry
   const int col_blocks = ceil_div(n, 64);
-  nms_mask_kernel<<<dim3(col_blocks, col_blocks, B), 64, 0, st>>>(sorted, cnt, 1 + n, n, thr_f, mask, col_blocks);
+  launch(nms_mask_kernel, dim3(col_blocks, col_blocks, B), 64, 0, st, sorted, cnt, 1 + n, n, thr_f, mask, col_blocks);
   FRCNN_CHECK_LAUNCH("nms_mask_kernel");
   size_t smem = (size_t)keep_cap * sizeof(int32_t);
   FRCNN_REQUIRE(smem <= 200 * 1024, "nms_batched_f32: max_keep too large for the scan's kept list");
@@ -648,10 +660,10 @@ int frcnn_nms_batched_f32(const float *boxes, const float *scores, int B, int n,
     e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
   }
-  nms_scan_kernel<<<B, kScanThreads, smem, st>>>(mask, cnt, 1 + n, n, col_blocks, keep_cap, keep_pos, keep_cap, kept_count_out);
+  launch(nms_scan_kernel, B, kScanThreads, smem, st, mask, cnt, 1 + n, n, col_blocks, keep_cap, keep_pos, keep_cap, kept_count_out);
   FRCNN_CHECK_LAUNCH("nms_scan_kernel");
   // 4. positions in the sorted list -> original indices
-  nms_batched_finish_kernel<<<dim3(ceil_div(keep_cap, 256), B), 256, 0, st>>>(order, keep_pos, kept_count_out, n, keep_cap, keep_out);
+  launch(nms_batched_finish_kernel, dim3(ceil_div(keep_cap, 256), B), 256, 0, st, order, keep_pos, kept_count_out, n, keep_cap, keep_out);
   FRCNN_CHECK_LAUNCH("nms_batched_finish_kernel");
   return FRCNN_OK;
 }
@@ -659,7 +671,7 @@ int frcnn_nms_batched_f32(const float *boxes, const float *scores, int B, int n,
 int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index, const int32_t *count, int capacity, float *dst, void *stream)
 {
   FRCNN_REQUIRE(src && index && count && dst && row_floats > 0 && capacity > 0, "gather_rows_f32: bad argument");
-  gather_rows_kernel<<<elementwise_grid((size_t)capacity * row_floats, 256), 256, 0, as_stream(stream)>>>(src, row_floats, index, count, capacity, dst);
+  launch(gather_rows_kernel, elementwise_grid((size_t)capacity * row_floats, 256), 256, 0, as_stream(stream), src, row_floats, index, count, capacity, dst);
   FRCNN_CHECK_LAUNCH("gather_rows_kernel");
   return FRCNN_OK;
 }
@@ -667,7 +679,7 @@ int frcnn_gather_rows_f32(const float *src, int row_floats, const int32_t *index
 int frcnn_append_rows_f32(float *dst, const int32_t *dst_count, int dst_capacity_rows, int row_floats, const float *src, int m, void *stream)
 {
   FRCNN_REQUIRE(dst && dst_count && src && dst_capacity_rows > 0 && row_floats > 0 && m > 0, "append_rows_f32: bad argument");
-  append_rows_kernel<<<ceil_div(m * row_floats, 128), 128, 0, as_stream(stream)>>>(dst, dst_count, dst_capacity_rows, row_floats, src, m);
+  launch(append_rows_kernel, ceil_div(m * row_floats, 128), 128, 0, as_stream(stream), dst, dst_count, dst_capacity_rows, row_floats, src, m);
   FRCNN_CHECK_LAUNCH("append_rows_kernel");
   return FRCNN_OK;
 }
@@ -683,9 +695,9 @@ int frcnn_rpn_targets(const float *anchors, const float *valid, int A, const flo
   // memset to 0x80 gives a large-magnitude negative int64, below the image of -1.0 and of every IoU >= 0
   cudaError_t e = cudaMemsetAsync(gt_max, 0x80, (size_t)M * sizeof(long long), st);
   if (e != cudaSuccess) return cuda_fail(e, "rpn_targets: memset");
-  rpn_targets_pass1<<<elementwise_grid(A, 128, 2), 128, 0, st>>>(anchors, valid, A, gt_boxes, M, gt_max);
+  launch(rpn_targets_pass1, elementwise_grid(A, 128, 2), 128, 0, st, anchors, valid, A, gt_boxes, M, gt_max);
   FRCNN_CHECK_LAUNCH("rpn_targets_pass1");
-  rpn_targets_pass2<<<elementwise_grid(A, 128, 2), 128, 0, st>>>(anchors, valid, A, gt_boxes, M, gt_max, object_iou_threshold, background_iou_threshold, rpn_map);
+  launch(rpn_targets_pass2, elementwise_grid(A, 128, 2), 128, 0, st, anchors, valid, A, gt_boxes, M, gt_max, object_iou_threshold, background_iou_threshold, rpn_map);
   FRCNN_CHECK_LAUNCH("rpn_targets_pass2");
   return FRCNN_OK;
 }
