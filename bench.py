@@ -257,9 +257,11 @@ def run_ours(args, rank, local_rank, world):
   if world > 1:
     dist.init_process_group("nccl", device_id = dev)
 
-  # programmatic dependent launch (frcnn_set_pdl): on for the bench unless FRCNN_PDL=0 -- results are bit-identical either way
-  # (profiles/r01_pdl_ab.json: same losses over 35 steps, same detections; 5.68 -> 5.43 ms/step)
-  pdl = os.environ.get("FRCNN_PDL", "1") not in ("", "0")
+  # programmatic dependent launch (frcnn_set_pdl): results are bit-identical either way (profiles/r01_pdl_ab.json: same losses over
+  # 35 steps, same detections; 5.68 -> 5.43 ms/step on one GPU).  Default: on for the single-GPU line, where it was measured; off at
+  # N > 1 until its interplay with the overlapped NCCL all-reduce (early-resident CTAs compete with NCCL's for SM slots) has been
+  # measured too.  FRCNN_PDL=0 / 1 overrides.
+  pdl = os.environ.get("FRCNN_PDL", "1" if world == 1 else "0") not in ("", "0")
   _lib.set_pdl(pdl)
   step = make_train_step(dev, rank)
 
