@@ -57,3 +57,21 @@ def test_state_dict_keys_match_reference_layout():
     assert tuple(sd[k].shape) == tuple(shape)
   frozen = [k for k, p in model.named_parameters() if not p.requires_grad]
   assert sorted(frozen) == sorted(k for k in shapes if k not in orc.trainable_keys_vgg16(shapes))
+
+
+def test_sass_carries_the_blackwell_instructions():
+  """The built library really is sm_100a tcgen05 / TMA / PDL code (B200_PROFILING.md: the SASS mnemonics that prove it): every kernel
+  entry has griddepcontrol (PREEXIT + ACQBULK), the GEMM kernel has UTCHMMA (tcgen05.mma), UTMALDG (TMA tile loads), LDTM (tcgen05.ld)."""
+  import shutil
+  import subprocess
+  from fasterrcnn_b200 import _lib
+  cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+  if not os.path.exists(cuobjdump):
+    pytest.skip("cuobjdump not available")
+  sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output = True, text = True, timeout = 300).stdout
+  assert "sm_100a" in sass
+  kernels = len(re.findall(r"^\s*Function : ", sass, flags = re.M))
+  assert kernels >= 50
+  count = lambda op: len(re.findall(r"\b%s\b" % op, sass))
+  assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0
+  assert count("PREEXIT") == kernels and count("ACQBULK") == kernels            # one griddepcontrol pair per kernel
