@@ -241,6 +241,7 @@ def make_train_step(dev, rank = 0):
 
   step.h2d_bytes = image_host.numel() * 4 + gt_map_host.numel() * 4
   step.model = model
+  step.optimizer = optimizer
   return step
 
 
@@ -337,6 +338,7 @@ def run_ours(args, rank, local_rank, world):
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
                             parallelism = "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)" % world,
                             engine = ENGINE_NOTES[engine_name][0],
+                            sm_reserve = step.optimizer.sm_reserve,     # SMs the GEMMs leave to NCCL while reductions are in flight (FRCNN_DP_SM_RESERVE)
                             pdl = "on (programmatic dependent launch between the library's kernels; FRCNN_PDL=0 turns it off)" if pdl else "off",
                             l2 = "per-step working set (~1.7 GB of weights, activations, gradients) exceeds the 126 MB L2; no explicit flush"),
               e2e = dict(value = e2e_value, unit = "images/s", h2d_bytes_per_step = h2d, d2h_bytes_per_step = d2h, ms_per_step = ms_e2e / args.steps),

@@ -24,6 +24,7 @@ _SIGNATURES = {
   "frcnn_version": (_i, []),
   "frcnn_last_error_string": (ctypes.c_char_p, []),
   "frcnn_set_pdl": (_i, [_i]),
+  "frcnn_set_sm_reserve": (_i, [_i]),
   "frcnn_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_conv2d_fwd_workspace_bytes": (_sz, _GEOM + [_i]),
@@ -117,6 +118,11 @@ def set_pdl(enabled):
   """Programmatic dependent launch for every kernel of the library (include/frcnn_b200.h: frcnn_set_pdl); returns the previous setting.
   Default = the FRCNN_PDL environment variable (off when unset)."""
   return bool(lib().frcnn_set_pdl(1 if enabled else 0))
+
+
+def set_sm_reserve(sms):
+  """SMs the persistent GEMM launches leave to a concurrent collective (include/frcnn_b200.h: frcnn_set_sm_reserve); returns the previous value."""
+  return int(lib().frcnn_set_sm_reserve(int(sms)))
 
 
 def exported_symbols():

@@ -6,6 +6,7 @@ namespace frcnn {
 thread_local char g_last_error[512] = "";
 
 int g_pdl = -1;
+int g_sm_reserve = 0;
 
 bool pdl_enabled()
 {
@@ -66,6 +67,13 @@ extern "C" {
 int frcnn_version(void) { return 100; }
 
 const char *frcnn_last_error_string(void) { return g_last_error; }
+
+int frcnn_set_sm_reserve(int sms)
+{
+  const int before = g_sm_reserve;
+  g_sm_reserve = sms < 0 ? 0 : (sms > kNumSMs - 16 ? kNumSMs - 16 : sms);
+  return before;
+}
 
 int frcnn_set_pdl(int enabled)
 {

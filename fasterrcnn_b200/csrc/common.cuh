@@ -54,6 +54,15 @@ __device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 extern int g_pdl;        // api.cu: -1 = read FRCNN_PDL on first use
 bool pdl_enabled();
 
+// SMs the persistent (one CTA per SM) GEMM launches may occupy: kNumSMs minus the ones the caller set aside for a concurrent
+// collective's CTAs (frcnn_set_sm_reserve; api.cu).  A persistent grid that finds some SMs taken runs a second, nearly empty wave.
+extern int g_sm_reserve;
+inline int sm_budget()
+{
+  int n = kNumSMs - g_sm_reserve;
+  return n < 16 ? 16 : (n > kNumSMs ? kNumSMs : n);
+}
+
 // the one way kernels are launched: <<<>>> semantics, plus the programmatic-serialization attribute when PDL is on
 template <typename... Params, typename... Args>
 inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)

@@ -162,6 +162,7 @@ struct TcGeom {
   unsigned long long sk_tag;      // unique per launch (stale workspace contents can never match)
   const int *a_exp, *b_exp;       // fp16 engine: device words holding the operands' scale exponents (NULL for tf32)
   unsigned *amax_out;             // optional: CTA b stores the bit pattern of max |final output| over its tiles at amax_out[kF16PartialsAt + b]
+  int amax_slots;                 // slots the consumer reads (the grid of an unreserved launch); CTA 0 zero-fills [gridDim.x, amax_slots)
 };
 
 // one work item of the persistent loop: an output tile (or one split-K slice of it)
@@ -557,6 +558,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (lane == 0) wmax[q] = out_max;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) g.amax_out[kF16PartialsAt + blockIdx.x] = __float_as_uint(fmaxf(fmaxf(wmax[0], wmax[1]), fmaxf(wmax[2], wmax[3])));
+      // a launch on fewer CTAs than the consumer expects partials from (frcnn_set_sm_reserve): the missing ones are zero
+      if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 192)
+        for (int sl = (int)gridDim.x + (threadIdx.x - 64); sl < g.amax_slots; sl += 128) g.amax_out[kF16PartialsAt + sl] = 0u;
     }
     if (threadIdx.x == 64) TC_TRACE(8);
   }
@@ -653,6 +657,7 @@ struct TcPlan {
   int total_kb, splits, kb_per_split;
   int m_tiles, n_tiles, items;       // persistent-loop work items (see TcGeom)
   int streamk, grid;                 // stream-K decomposition (default) and its CTA count
+  int grid_max;                      // the CTA count with no SMs reserved: sizes the workspace layout and the amax slots, whatever `grid` is
   long long units;
   size_t flags_off;
   size_t a_hi_off, a_lo_off, b_hi_off, b_lo_off, partial_off, total_bytes;
@@ -727,11 +732,14 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   // and with many waves of tiles the quantisation loss is below 1/8 of a tile per SM anyway.
   p->streamk = (use_streamk && ctas >= kNumSMs / 2 && ctas < 8 * kNumSMs) ? 1 : 0;
   p->units = (long long)ctas * p->total_kb;
+  // SMs this launch may occupy: all of them, minus the ones set aside for a concurrent collective (frcnn_set_sm_reserve).  Only the
+  // CTA count follows it; the decomposition (stream-K or split-K, number of splits) and the workspace layout never change.
+  const int sms = sm_budget();
   if (p->streamk) {
     long long gsz = p->units / chunk;                                // at least one accumulation chain per CTA
-    if (gsz > kNumSMs) gsz = kNumSMs;
     if (gsz < 1) gsz = 1;
-    p->grid = (int)gsz;
+    p->grid_max = (int)(gsz > kNumSMs ? kNumSMs : gsz);
+    p->grid = (int)(gsz > sms ? sms : gsz);
   } else {
     const double t_kb = (p->BN == 128) ? 0.56 : 0.42;               // us per k-block (measured, smem-bandwidth bound mainloop)
     const double t_item = 2.5;                                       // us of per-item pipeline refill / final drain not overlapped
@@ -749,7 +757,10 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->kb_per_split = ceil_div(p->total_kb, splits);
   p->splits = ceil_div(p->total_kb, p->kb_per_split);
   p->items = ctas * p->splits;
-  if (!p->streamk) p->grid = p->items > kNumSMs ? kNumSMs : p->items;
+  if (!p->streamk) {
+    p->grid_max = p->items > kNumSMs ? kNumSMs : p->items;
+    p->grid = p->items > sms ? sms : p->items;
+  }
   const size_t act_in = (size_t)pixels * Cin, act_out = (size_t)pixels * Cout, filt = (size_t)Cout * taps * Cin;
   size_t out_elems;
   if (mode == TC_FWD) { p->a_count = act_in; p->b_count = filt; out_elems = act_out; }
@@ -763,8 +774,8 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->b_lo_off = p->b_hi_off + align_up(p->b_count * esz, 1024);
   p->partial_off = p->b_lo_off + align_up(p->b_count * esz, 1024);
   if (p->streamk) {
-    p->flags_off = p->partial_off + align_up((size_t)p->grid * 128 * p->BN * 4, 1024);
-    p->total_bytes = p->flags_off + align_up((size_t)p->grid * 8, 1024);
+    p->flags_off = p->partial_off + align_up((size_t)p->grid_max * 128 * p->BN * 4, 1024);
+    p->total_bytes = p->flags_off + align_up((size_t)p->grid_max * 8, 1024);
   } else {
     p->flags_off = 0;
     p->total_bytes = p->partial_off + (p->splits > 1 ? (size_t)p->splits * out_elems * 4 : 0);
@@ -891,7 +902,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
            p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
            0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp,
-           (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr};
+           (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr, p.grid_max};
   int rc;
 #define TC_LAUNCH(M)                                                                                                                      \
   (f16 ? (p.BN == 128 ? launch_tc<M, 128, 3, true>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, true>(maps, g, grid, out, partial, epi, st)) \
@@ -918,7 +929,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
 bool tc_supported(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16); }
 size_t tc_workspace(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return make_tc_plan(mode, GEOM_ARGS, &p, f16) ? p.total_bytes : 0; }
 // number of per-CTA output maxima a fwd / dgrad launch of this shape writes when given an amax buffer (0: none -- split-K shapes, wgrad)
-int tc_amax_slots(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return (mode != TC_WGRAD && make_tc_plan(mode, GEOM_ARGS, &p, f16) && p.splits == 1) ? p.grid : 0; }
+int tc_amax_slots(int mode, GEOM_PARAMS, bool f16) { TcPlan p; return (mode != TC_WGRAD && make_tc_plan(mode, GEOM_ARGS, &p, f16) && p.splits == 1) ? p.grid_max : 0; }
 bool tc_fwd_supported(GEOM_PARAMS) { return tc_supported(TC_FWD, GEOM_ARGS, false); }
 bool tc_dgrad_supported(GEOM_PARAMS) { return tc_supported(TC_DGRAD, GEOM_ARGS, false); }
 bool tc_wgrad_supported(GEOM_PARAMS) { return tc_supported(TC_WGRAD, GEOM_ARGS, false); }

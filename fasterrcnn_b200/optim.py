@@ -11,7 +11,12 @@ DataParallel   one process per GPU: wraps any optimizer; gradient
                backward still running on the compute stream; ``step()`` waits for the handles and
                applies the update with grad_scale = 1/world_size.
 Only tensors owned by the wrapped optimizer are reduced (the reference never steps biases).
+               While reductions are in flight (first gradient hook .. step()) the persistent tcgen05 GEMMs can be told to leave
+               ``sm_reserve`` SMs to NCCL's resident CTAs (frcnn_set_sm_reserve; FRCNN_DP_SM_RESERVE, default 0 = off): a one-CTA-per-SM
+               grid that finds SMs taken runs a second, nearly empty wave, which is what the 2-GPU run loses.
 """
+import os
+
 import torch as t
 import torch.distributed as dist
 
@@ -47,10 +52,14 @@ class DataParallel:
   """Optimizer wrapper: overlapped gradient all-reduce + (optionally fused) update.  Quacks like the
   optimizer ``FasterRCNNModel.train_step`` expects (zero_grad / step / param_groups)."""
 
-  def __init__(self, optimizer, process_group = None):
+  def __init__(self, optimizer, process_group = None, sm_reserve = None):
     self.optimizer = optimizer
     self.group = process_group
     self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+    if sm_reserve is None:
+      sm_reserve = int(os.environ.get("FRCNN_DP_SM_RESERVE", "0"))
+    self.sm_reserve = int(sm_reserve) if self.world_size > 1 else 0
+    self._reserved = False
     self._handles = []
     self._hooks = []
     self.bytes_reduced_last_step = 0
@@ -67,6 +76,10 @@ class DataParallel:
     return self.optimizer.param_groups
 
   def _on_grad_ready(self, p):
+    if self.sm_reserve > 0 and not self._reserved:
+      from . import _lib
+      _lib.set_sm_reserve(self.sm_reserve)                      # GEMMs launched from here on leave room for NCCL's CTAs
+      self._reserved = True
     # the gradient was produced on the current (compute) stream; NCCL orders itself after it
     self._handles.append((p, dist.all_reduce(p.grad, op = dist.ReduceOp.SUM, group = self.group, async_op = True)))
 
@@ -80,6 +93,10 @@ class DataParallel:
       h.wait()                                                  # compute stream waits for the reduction
       nbytes += p.grad.numel() * p.grad.element_size()
     self.bytes_reduced_last_step = nbytes
+    if self._reserved:
+      from . import _lib
+      _lib.set_sm_reserve(0)                                    # the reductions are behind the compute stream now: all SMs again
+      self._reserved = False
     if self.world_size > 1 and not isinstance(self.optimizer, FusedSGD):
       for p, _ in self._handles:
         p.grad.div_(self.world_size)

@@ -53,6 +53,12 @@ const char *frcnn_last_error_string(void);
  * global access, which removes the launch-to-launch gap of the ~145 dependent launches of a train step.  Results do not change.
  * Returns the previous setting.  (No reference counterpart: launch plumbing.) */
 int frcnn_set_pdl(int enabled);
+/* SMs set aside for a concurrent collective (default 0): the persistent tcgen05 GEMM launches -- one CTA per SM, equal stream-K shares --
+ * use 148 - sms CTAs while it is set, so that they stay one wave next to NCCL's resident CTAs instead of queueing a second, nearly empty
+ * one behind them.  Only the CTA count changes: decomposition, workspace sizes and results are the same (the summation order inside a
+ * stream-K tile follows the CTA ranges, so the fp32 rounding of a straddling tile may differ in the last bit).  Returns the previous
+ * value.  Used by optim.DataParallel around the window in which gradient all-reduces overlap the backward. */
+int frcnn_set_sm_reserve(int sms);
 
 /* ---- layout ------------------------------------------------------------------------------
  * API tensors are NCHW (models/faster_rcnn.py:86-89); kernels run NHWC. */
