@@ -330,9 +330,9 @@ def run_ours(args, rank, local_rank, world):
                     families = {k: dict(tflops = v["gflop"] / v["ms"], ms_per_step = v["ms"] / args.steps, launches = v["launches"]) for k, v in gemm_stats.items()})
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
-    times, cores = cpu_port_times(4, 1)
+    times, cores = cpu_port_times(10, 2)                           # ~10-20 s of CPU work on the box's cores
     cpu = dict(value = len(times) / sum(times), unit = "images/s", cores = cores, kind = "port",
-               sample = "4 timed + 1 warm-up train_steps of the CPU oracle port on the same 600x1000 workload, %d threads" % cores)
+               sample = "10 timed + 2 warm-up train_steps of the CPU oracle port on the same 600x1000 workload, %d threads" % cores)
   line = dict(metric = METRIC, value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
               higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = ENGINE_NOTES[engine_name][2], data = "synthetic",
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
