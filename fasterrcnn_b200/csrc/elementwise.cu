@@ -443,8 +443,22 @@ int frcnn_add(const float *a, const float *b, float *out, size_t count, void *st
   return FRCNN_OK;
 }
 
-int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
-                         float grad_scale, int first_step, void *param_split, void *stream)
+// ctas_per_sm: cap of the grid-stride launch (default 8 x 148 CTAs, each looping over its share).  A large value (>= count / 1024 / 148)
+// makes the launch non-persistent -- one short-lived CTA per 1024 elements -- which is what a side-stream launch next to the persistent
+// GEMM kernels wants: 256 threads x 32 registers fit beside a GEMM CTA, and a short CTA never keeps an SM from the next GEMM launch.
+static int sgd_launch(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                      float grad_scale, int first_step, float *hi, float *lo, __half *hi16, __half *lo16, const int *e16, int ctas_per_sm, void *stream)
+{
+  const size_t want = ceil_div<size_t>(count / 4 + 1, 256);
+  size_t cap = (size_t)kNumSMs * (size_t)(ctas_per_sm > 0 ? ctas_per_sm : 8);
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  launch(sgd_kernel, grid, 256, 0, as_stream(stream), param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo, hi16, lo16, e16);
+  FRCNN_CHECK_LAUNCH("sgd_kernel");
+  return FRCNN_OK;
+}
+
+static int sgd_step_split_tf32(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                               float grad_scale, int first_step, void *param_split, int ctas_per_sm, void *stream)
 {
   FRCNN_REQUIRE(param && grad && momentum_buf, "sgd_step: null pointer");
   if (count == 0) return FRCNN_OK;
@@ -453,14 +467,11 @@ int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, s
     hi = reinterpret_cast<float *>(param_split);
     lo = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(param_split) + (count * 4 + 1023) / 1024 * 1024);   // frcnn_tf32_split layout
   }
-  launch(sgd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo,
-                                                                                  nullptr, nullptr, nullptr);
-  FRCNN_CHECK_LAUNCH("sgd_kernel");
-  return FRCNN_OK;
+  return sgd_launch(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, hi, lo, nullptr, nullptr, nullptr, ctas_per_sm, stream);
 }
 
-int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
-                             float grad_scale, int first_step, void *param_split, void *stream)
+static int sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                              float grad_scale, int first_step, void *param_split, int ctas_per_sm, void *stream)
 {
   FRCNN_REQUIRE(param && grad && momentum_buf && param_split && count > 0, "sgd_step_split_f16: bad argument");
   FRCNN_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf) | reinterpret_cast<uintptr_t>(param_split)) & 15) == 0,
@@ -468,15 +479,24 @@ int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_bu
   uint8_t *o = reinterpret_cast<uint8_t *>(param_split);
   __half *hi = reinterpret_cast<__half *>(o + kF16Header);
   __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
-  launch(sgd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, nullptr,
-                                                                                  hi, lo, reinterpret_cast<const int *>(o) + 1);
-  FRCNN_CHECK_LAUNCH("sgd_kernel");
-  return FRCNN_OK;
+  return sgd_launch(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, nullptr, nullptr, hi, lo, reinterpret_cast<const int *>(o) + 1, ctas_per_sm, stream);
 }
 
-int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
-                         const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
-                         int split_format, float grad_scale, void *stream)
+int frcnn_sgd_step_split(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                         float grad_scale, int first_step, void *param_split, void *stream)
+{
+  return sgd_step_split_tf32(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, param_split, 0, stream);
+}
+
+int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,
+                             float grad_scale, int first_step, void *param_split, void *stream)
+{
+  return sgd_step_split_f16(param, grad, momentum_buf, count, lr, momentum, weight_decay, grad_scale, first_step, param_split, 0, stream);
+}
+
+int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
+                            const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
+                            int split_format, float grad_scale, int ctas_per_sm, void *stream)
 {
   FRCNN_REQUIRE(n >= 0 && (n == 0 || (params && grads && momentum_bufs && counts && lrs && momenta && weight_decays && first_steps)), "sgd_step_multi: bad argument");
   FRCNN_REQUIRE(split_format >= 0 && split_format <= 2, "sgd_step_multi: split_format must be 0 (none), 1 (tf32) or 2 (fp16)");
@@ -484,12 +504,19 @@ int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads,
     void *split = (param_splits && split_format != 0) ? param_splits[i] : nullptr;
     int rc;
     if (split && split_format == 2)
-      rc = frcnn_sgd_step_split_f16(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, stream);
+      rc = sgd_step_split_f16(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, ctas_per_sm, stream);
     else
-      rc = frcnn_sgd_step_split(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, stream);
+      rc = sgd_step_split_tf32(params[i], grads[i], momentum_bufs[i], counts[i], lrs[i], momenta[i], weight_decays[i], grad_scale, first_steps[i], split, ctas_per_sm, stream);
     if (rc != FRCNN_OK) return rc;
   }
   return FRCNN_OK;
+}
+
+int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
+                         const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
+                         int split_format, float grad_scale, void *stream)
+{
+  return frcnn_sgd_step_multi_ex(n, params, grads, momentum_bufs, counts, lrs, momenta, weight_decays, first_steps, param_splits, split_format, grad_scale, 0, stream);
 }
 
 int frcnn_sgd_step(float *param, const float *grad, float *momentum_buf, size_t count, float lr, float momentum, float weight_decay,

@@ -1062,9 +1062,10 @@ def sgd_step(param, grad, momentum_buf, lr, momentum, weight_decay, grad_scale =
   _lib.count()
 
 
-def sgd_step_multi(entries, grad_scale = 1.0):
+def sgd_step_multi(entries, grad_scale = 1.0, ctas_per_sm = 0):
   """optimizer.step() for a list of (param, grad, momentum_buf, lr, momentum, weight_decay, first_step, carry_split) in one C call
-  (frcnn_sgd_step_multi): the per-tensor kernels are launched back to back from C instead of one ctypes round trip each."""
+  (frcnn_sgd_step_multi_ex): the per-tensor kernels are launched back to back from C instead of one ctypes round trip each.
+  ctas_per_sm: launch shape (0 = default grid-stride launch; large = short-lived CTAs for a side-stream update, see the header)."""
   import ctypes
   n = len(entries)
   if n == 0:
@@ -1089,9 +1090,9 @@ def sgd_step_multi(entries, grad_scale = 1.0):
     params.append(param.data_ptr()); grads.append(grad.data_ptr()); bufs.append(buf.data_ptr())
     splits.append(e["buf"].data_ptr() if e is not None else None)
     carried.append((e, param))
-  check(L.frcnn_sgd_step_multi(n, vp(*params), vp(*grads), vp(*bufs), sz(*[x[0].numel() for x in entries]), fl(*[float(x[3]) for x in entries]),
-                               fl(*[float(x[4]) for x in entries]), fl(*[float(x[5]) for x in entries]), it(*[int(x[6]) for x in entries]), vp(*splits),
-                               2 if f16 else 1, float(grad_scale), st), "frcnn_sgd_step_multi")
+  check(L.frcnn_sgd_step_multi_ex(n, vp(*params), vp(*grads), vp(*bufs), sz(*[x[0].numel() for x in entries]), fl(*[float(x[3]) for x in entries]),
+                                  fl(*[float(x[4]) for x in entries]), fl(*[float(x[5]) for x in entries]), it(*[int(x[6]) for x in entries]), vp(*splits),
+                                  2 if f16 else 1, float(grad_scale), int(ctas_per_sm), st), "frcnn_sgd_step_multi_ex")
   for e, param in carried:
     if e is not None:
       e["version"] = param._version                                # the raw-pointer update does not bump torch's version counter

@@ -24,9 +24,52 @@ from . import ops
 
 
 class FusedSGD(t.optim.Optimizer):
-  def __init__(self, params, lr = 1e-3, momentum = 0.9, weight_decay = 0.0):
+  """eager (EXPERIMENT, off by default; FRCNN_EAGER_SGD=1): tensors of at least ``eager_min_numel`` elements (VGG-16: fc1, fc2 = 87 % of the
+  optimizer's bytes) are updated from a post-accumulate-grad hook on a side stream, as soon as their gradient exists, while the
+  tensor-pipe-bound convolution backward still runs on the compute stream -- the update is HBM-bound and its 256-thread / 32-register CTAs
+  fit beside a GEMM CTA.  ``step()`` then covers the remaining tensors and joins the side stream.  Same arithmetic, same result; only the
+  schedule differs.  Single-GPU only (with DataParallel the gradient is not final in the hook).  Unmeasured in round 1."""
+
+  def __init__(self, params, lr = 1e-3, momentum = 0.9, weight_decay = 0.0, eager = None, eager_min_numel = 1 << 23, eager_ctas_per_sm = None):
     super().__init__(params, dict(lr = lr, momentum = momentum, weight_decay = weight_decay))
     self.grad_scale = 1.0
+    if eager is None:
+      eager = os.environ.get("FRCNN_EAGER_SGD", "0") not in ("", "0")
+    self.eager = bool(eager)
+    self.eager_ctas_per_sm = int(os.environ.get("FRCNN_EAGER_SGD_CTAS", "1")) if eager_ctas_per_sm is None else int(eager_ctas_per_sm)
+    self._side, self._eager_done, self._eager_hooks, self._group_of = None, set(), [], {}
+    if self.eager:
+      for group in self.param_groups:
+        for p in group["params"]:
+          self._group_of[id(p)] = group
+          if p.requires_grad and p.numel() >= eager_min_numel:
+            self._eager_hooks.append(p.register_post_accumulate_grad_hook(self._eager_update))
+
+  def _entry(self, p, group):
+    state = self.state[p]
+    first = "momentum_buffer" not in state
+    if first:
+      state["momentum_buffer"] = t.empty_like(p)          # preserves the channels_last strides of filters
+    g = p.grad
+    if g.stride() != p.stride():
+      g = g.contiguous(memory_format = t.channels_last) if p.dim() == 4 and not p.is_contiguous() else g.contiguous()
+    # matrices / filters feed the tcgen05 GEMMs next step: their operand split is produced by the same kernel
+    return (p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], first, p.dim() >= 2 and p.numel() >= 4096)
+
+  @t.no_grad()
+  def _eager_update(self, p):
+    if self.grad_scale != 1.0 or not p.is_cuda or p.grad is None:
+      return                                                 # data-parallel run: the gradient still has to be reduced
+    main = t.cuda.current_stream()
+    if self._side is None:
+      self._side = t.cuda.Stream()
+    ready = t.cuda.Event()
+    ready.record(main)                                       # behind this layer's dgrad (last reader of the weights) and wgrad
+    entry = self._entry(p, self._group_of[id(p)])            # allocations happen on the compute stream's pool
+    with t.cuda.stream(self._side):
+      self._side.wait_event(ready)
+      ops.sgd_step_multi([entry], self.grad_scale, self.eager_ctas_per_sm)
+    self._eager_done.add(id(p))
 
   @t.no_grad()
   def step(self, closure = None):
@@ -34,18 +77,13 @@ class FusedSGD(t.optim.Optimizer):
     entries = []
     for group in self.param_groups:
       for p in group["params"]:
-        if p.grad is None:
+        if p.grad is None or id(p) in self._eager_done:
           continue
-        state = self.state[p]
-        first = "momentum_buffer" not in state
-        if first:
-          state["momentum_buffer"] = t.empty_like(p)          # preserves the channels_last strides of filters
-        g = p.grad
-        if g.stride() != p.stride():
-          g = g.contiguous(memory_format = t.channels_last) if p.dim() == 4 and not p.is_contiguous() else g.contiguous()
-        # matrices / filters feed the tcgen05 GEMMs next step: their operand split is produced by the same kernel
-        entries.append((p, g, state["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"], first, p.dim() >= 2 and p.numel() >= 4096))
+        entries.append(self._entry(p, group))
     ops.sgd_step_multi(entries, self.grad_scale)                 # every parameter group in one C call
+    if self._eager_done:
+      t.cuda.current_stream().wait_stream(self._side)            # the next forward reads the eagerly updated weights
+      self._eager_done.clear()
 
 
 class DataParallel:

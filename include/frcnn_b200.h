@@ -319,6 +319,13 @@ int frcnn_sgd_step_split_f16(float *param, const float *grad, float *momentum_bu
 int frcnn_sgd_step_multi(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
                          const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
                          int split_format, float grad_scale, void *stream);
+/* Same, with the launch shape exposed: ctas_per_sm caps the grid-stride launch (<= 0: the default 8 CTAs per SM, each looping over its
+ * share).  A large value gives one short-lived 256-thread CTA per 1024 elements: the shape for updating a tensor on a side stream WHILE
+ * the backward's persistent GEMM kernels run (256 threads x 32 registers fit beside a GEMM CTA; a short CTA never holds an SM back from
+ * the next GEMM launch).  Used by optim.FusedSGD(eager = True). */
+int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *grads, float *const *momentum_bufs, const size_t *counts,
+                            const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
+                            int split_format, float grad_scale, int ctas_per_sm, void *stream);
 
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one
