@@ -5,16 +5,19 @@ namespace frcnn {
 
 thread_local char g_last_error[512] = "";
 
-int g_pdl = -1;
-int g_sm_reserve = 0;
+// the two process-wide switches of the library (launch plumbing; see the header)
+std::atomic<int> g_pdl{-1};
+std::atomic<int> g_sm_reserve{0};
 
 bool pdl_enabled()
 {
-  if (g_pdl < 0) {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char *e = getenv("FRCNN_PDL");
-    g_pdl = (e && e[0] && e[0] != '0') ? 1 : 0;
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
   }
-  return g_pdl != 0;
+  return v != 0;
 }
 
 // conv_simt.cu
@@ -70,15 +73,13 @@ const char *frcnn_last_error_string(void) { return g_last_error; }
 
 int frcnn_set_sm_reserve(int sms)
 {
-  const int before = g_sm_reserve;
-  g_sm_reserve = sms < 0 ? 0 : (sms > kNumSMs - 16 ? kNumSMs - 16 : sms);
-  return before;
+  return g_sm_reserve.exchange(sms < 0 ? 0 : (sms > kNumSMs - 16 ? kNumSMs - 16 : sms), std::memory_order_relaxed);
 }
 
 int frcnn_set_pdl(int enabled)
 {
   const int before = pdl_enabled() ? 1 : 0;
-  g_pdl = enabled ? 1 : 0;
+  g_pdl.store(enabled ? 1 : 0, std::memory_order_relaxed);
   return before;
 }
 

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <utility>
+#include <atomic>
 #include "../../include/frcnn_b200.h"
 
 namespace frcnn {
@@ -51,15 +52,15 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
-extern int g_pdl;        // api.cu: -1 = read FRCNN_PDL on first use
+extern std::atomic<int> g_pdl;        // api.cu: -1 = read FRCNN_PDL on first use
 bool pdl_enabled();
 
 // SMs the persistent (one CTA per SM) GEMM launches may occupy: kNumSMs minus the ones the caller set aside for a concurrent
 // collective's CTAs (frcnn_set_sm_reserve; api.cu).  A persistent grid that finds some SMs taken runs a second, nearly empty wave.
-extern int g_sm_reserve;
+extern std::atomic<int> g_sm_reserve;
 inline int sm_budget()
 {
-  int n = kNumSMs - g_sm_reserve;
+  int n = kNumSMs - g_sm_reserve.load(std::memory_order_relaxed);
   return n < 16 ? 16 : (n > kNumSMs ? kNumSMs : n);
 }
 
