@@ -327,6 +327,9 @@ def run_ours(args, rank, local_rank, world):
     roofline = dict(bound = "tensor", kernel = top[0], achieved = achieved, peak = peaks["tflops"], unit = "TFLOP/s", frac = achieved / peaks["tflops"], traffic = traffic, traffic_unit = "bytes per launch (dram read + write, ncu --set full)", traffic_source = traffic_source,
                     peak_source = peaks["source"], launches = st["launches"], ms_per_step = st["ms"] / args.steps,
                     note = ENGINE_NOTES[engine_name][1],
+                    # what the tensor pipe actually executes: 3 MMA products per algorithmic MAC on the tcgen05 engines (1 on the CUDA-core engine)
+                    mma_products_per_mac = 1 if engine_name == "simt" else 3,
+                    tensor_pipe_frac = (1 if engine_name == "simt" else 3) * achieved / peaks["tflops"],
                     families = {k: dict(tflops = v["gflop"] / v["ms"], ms_per_step = v["ms"] / args.steps, launches = v["launches"]) for k, v in gemm_stats.items()})
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
