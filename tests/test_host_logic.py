@@ -176,3 +176,29 @@ def test_voc_dataset_matches_reference_golden(tmp_path, golden_dir, prefetch):
                                                         allow_difficult = True, anchor_fns = _oracle_anchor_fns())._gt_boxes_by_filepath[first[1].filepath])
   with pytest.raises(FileNotFoundError):
     voc.Dataset(split = "trainval", image_preprocessing_params = params, compute_feature_map_shape_fn = shape_fn, dir = str(tmp_path / "missing"))
+
+
+# ---- bench.py contract (CPU-checkable part) ----------------------------------------------------
+def test_bench_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference` (the CPU port of the reference step on the host cores) prints ONE JSON line with the keys the driver
+  reads; `bench.py` itself refuses to run without a CUDA device (no CPU path for the product arm)."""
+  import json
+  import subprocess
+  import sys
+  import torch as t
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output = True, text = True, timeout = 600, cwd = root)
+  assert out.returncode == 0, out.stderr[-2000:]
+  lines = [l for l in out.stdout.splitlines() if l.strip()]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+  assert d["metric"].startswith("images/sec fwd+bwd @ 1000x600")
+  assert d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+  assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+  assert d["e2e"] == dict(value = d["value"], unit = "images/s", h2d_bytes_per_step = 0, d2h_bytes_per_step = 0)
+  assert "workload" in d["config"] and "model" not in d["config"]
+  if not t.cuda.is_available():
+    ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output = True, text = True, timeout = 600, cwd = root)
+    assert ours.returncode != 0 and "no CPU path" in (ours.stderr + ours.stdout)
