@@ -75,3 +75,28 @@ def test_sass_carries_the_blackwell_instructions():
   count = lambda op: len(re.findall(r"\b%s\b" % op, sass))
   assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0
   assert count("PREEXIT") == kernels and count("ACQBULK") == kernels            # one griddepcontrol pair per kernel
+
+
+def test_sm_reserve_changes_neither_workspace_sizes_nor_amax_slots():
+  """frcnn_set_sm_reserve only shrinks the CTA count of the persistent GEMM launches: the sizes callers cache per geometry (workspace
+  bytes, number of per-CTA output maxima) must not depend on it.  Pure host calls -- no device needed."""
+  from fasterrcnn_b200 import _lib
+  L = _lib.lib()
+  geoms = [(1, 600, 1000, 64, 64, 3, 3, 1, 1), (1, 150, 250, 256, 256, 3, 3, 1, 1), (1, 37, 62, 512, 512, 3, 3, 1, 1), (1, 38, 63, 1024, 256, 1, 1, 1, 0),
+           (128, 1, 1, 25088, 4096, 1, 1, 1, 0), (128, 1, 1, 4096, 4096, 1, 1, 1, 0), (2, 75, 125, 512, 512, 3, 3, 1, 1)]
+  def sizes():
+    out = []
+    for g in geoms:
+      for eng in (_lib.ENGINE_TC_3XF16, _lib.ENGINE_AUTO):
+        out.append((L.frcnn_conv2d_fwd_workspace_bytes(*g, eng), L.frcnn_conv2d_dgrad_workspace_bytes(*g, eng), L.frcnn_conv2d_wgrad_workspace_bytes(*g, eng)))
+      out.append((L.frcnn_conv2d_amax_slots(0, *g), L.frcnn_conv2d_amax_slots(1, *g)))
+    return out
+  base = sizes()
+  assert any(s[0] > 0 for s in base)
+  try:
+    for reserve in (8, 20, 64, 1000):
+      _lib.set_sm_reserve(reserve)
+      assert sizes() == base, reserve
+  finally:
+    assert _lib.set_sm_reserve(0) == 132          # 1000 was clamped to 148 - 16
+  assert max(s[0] for s in base[2::3]) <= 148     # amax slots = CTAs of an unreserved launch
