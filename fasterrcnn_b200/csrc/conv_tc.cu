@@ -286,6 +286,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int KHW = g.KH * g.KW;
 
   pdl_trigger();                                                     // the next kernel's CTAs may become resident behind this one
+  const unsigned long long t_entry = (g.trace && threadIdx.x == 0) ? tc_globaltimer() : 0ull;   // stored after the wait: no global access before it
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }      // full: one arrive.expect_tx per producer
     for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
@@ -303,7 +304,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                                        // set-up above touched no global memory: it overlaps the previous kernel's tail
 
-  if (threadIdx.x == 0) { TC_TRACE(0); TC_TRACE(1); }
+  if (threadIdx.x == 0 && g.trace) { g.trace[(size_t)blockIdx.x * 16] = t_entry; TC_TRACE(1); }
   if (warp == 0 || warp == 6) {
     if (lane == 0) {
       // ===== TMA producers: warp 0 feeds the A operand, warp 6 the B operand (up to 8 box loads each per k-block: issuing them
