@@ -3,8 +3,8 @@ TEST INFRASTRUCTURE ONLY -- loader for the UNMODIFIED reference (trzy/FasterRCNN
 
 Imports ``pytorch.FasterRCNN`` from ``/root/reference`` on CPU so that
 ``oracle/make_golden.py`` can execute the reference itself and dump golden vectors,
-and so that ``tests/test_oracle_vs_reference.py`` can pin the restatement in
-``oracle/frcnn_oracle.py`` against it.  ``/root/reference`` only exists in the build
+and so that ``oracle/check_vs_live_reference.py`` (run by tests/test_oracle.py in a subprocess) can pin
+the restatement in ``oracle/frcnn_oracle.py`` against it on fresh cases.  ``/root/reference`` only exists in the build
 container: nothing that runs on the GPU box may import this module.
 
 The patches below are ENVIRONMENT patches, not algorithm changes:

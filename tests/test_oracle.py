@@ -165,3 +165,20 @@ def test_oracle_batch_extension_reduces_to_single_image_step():
     assert all(t.equal(x, y) for x, y in zip(f1, f2))
     fa = o2.forward_batch(t.cat([smp["image"], smp["image"] * 0.5]), roi_op = "align")
   assert len(fa) == 2 and fa[0][1].shape[1] == 21 and fa[1][2].shape[1] == 80
+
+
+def test_oracle_matches_live_reference_on_fresh_case():
+  """Beyond the committed goldens: the UNMODIFIED reference is executed live (build container only -- /root/reference does not exist on
+  the GPU box) on a seed / size / ground-truth layout outside the golden set and compared with the restatement: anchors and RPN maps bit
+  for bit, forward / predict / two train steps (losses, every gradient, every post-step weight) within 1e-5.  Subprocess: the shim
+  patches Tensor.cuda process-wide.  FRCNN_LIVE_CASES=3 runs all cases of oracle/check_vs_live_reference.py (incl. the score-tie case)."""
+  import subprocess
+  import sys
+  from oracle import ref_shim
+  if not ref_shim.available():
+    pytest.skip("reference tree not present (GPU box)")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  n = os.environ.get("FRCNN_LIVE_CASES", "1")
+  out = subprocess.run([sys.executable, os.path.join(root, "oracle", "check_vs_live_reference.py"), "--cases", n], capture_output = True, text = True, timeout = 1200, cwd = root)
+  assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+  assert "PASS: restatement == live reference" in out.stdout
