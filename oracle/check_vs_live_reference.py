@@ -29,16 +29,33 @@ CASES = [
 ]
 
 
-def run_case(ref, hw, wseed, sseed, heads, gt):
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = wseed, heads = heads)
-  smp = orc.synthetic_sample(hw, seed = sseed, gt = gt)
+# ResNet cases (--resnet): the same comparison through the reference's torchvision-bottleneck backbones (frozen BN; layer4 as the head)
+RESNET_CASES = [
+  ("resnet101", (320, 400), 21, 8, "spread", [((30.0, 40.0, 250.0, 300.0), 5), ((120.0, 200.0, 310.0, 390.0), 17)]),
+  ("resnet50", (304, 368), 22, 9, "spread", [((20.0, 30.0, 280.0, 200.0), 2)]),
+]
+
+
+def run_case(ref, hw, wseed, sseed, heads, gt, backbone = "vgg16"):
+  import math
+  if backbone == "vgg16":
+    params = orc.synth_params(orc.vgg16_param_shapes(), seed = wseed, heads = heads)
+    ref_backbone = ref.vgg16.VGG16Backbone(dropout_probability = 0.0)
+    fm_shape = (512, hw[0] // 16, hw[1] // 16)
+  else:
+    from oracle import resnet_oracle
+    ref_shim.patch_resnet_offline()
+    params = orc.synth_params(resnet_oracle.param_shapes(backbone), seed = wseed, heads = heads)
+    ref_backbone = ref.resnet.ResNetBackbone(architecture = {"resnet50": ref.resnet.Architecture.ResNet50, "resnet101": ref.resnet.Architecture.ResNet101}[backbone])
+    fm_shape = (1024, math.ceil(hw[0] / 16), math.ceil(hw[1] / 16))
+  smp = orc.synthetic_sample(hw, seed = sseed, gt = gt, backbone = backbone)
   image = smp["image"]
-  model = ref.faster_rcnn.FasterRCNNModel(num_classes = 21, backbone = ref.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
+  model = ref.faster_rcnn.FasterRCNNModel(num_classes = 21, backbone = ref_backbone, allow_edge_proposals = True)
   model.load_state_dict(params)
-  oracle = orc.OracleModel(params)
+  oracle = orc.OracleModel(params, backbone = backbone)
 
   # the restated anchor / RPN-map generators against the reference's, bit for bit
-  am, av = ref.anchors.generate_anchor_maps(image_shape = (3,) + hw, feature_map_shape = (512, hw[0] // 16, hw[1] // 16), feature_pixels = 16)
+  am, av = ref.anchors.generate_anchor_maps(image_shape = (3,) + hw, feature_map_shape = fm_shape, feature_pixels = 16)
   boxes = [ref.Box(class_index = c, class_name = str(c), corners = b) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
   rm, obj, bg = ref.anchors.generate_rpn_map(anchor_map = am, anchor_valid_map = av, gt_boxes = boxes)
   assert np.array_equal(am, smp["anchor_map"]) and np.array_equal(av, smp["anchor_valid_map"])
@@ -93,15 +110,17 @@ def run_case(ref, hw, wseed, sseed, heads, gt):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--cases", type = int, default = len(CASES))
+  ap.add_argument("--resnet", action = "store_true", help = "the ResNet-101 / ResNet-50 cases instead of the VGG-16 ones")
   args = ap.parse_args()
   if not ref_shim.available():
     print("SKIP: reference tree not present")
     return 0
   t.set_num_threads(min(8, os.cpu_count() or 8))
   ref = ref_shim.load()
-  for case in CASES[:args.cases]:
-    print("OK", run_case(ref, *case), flush = True)
-  print("PASS: restatement == live reference on %d fresh cases" % min(args.cases, len(CASES)))
+  cases = [c[1:] + (c[0],) for c in RESNET_CASES] if args.resnet else CASES
+  for case in cases[:args.cases]:
+    print("OK", case[-1] if args.resnet else "vgg16", run_case(ref, *case), flush = True)
+  print("PASS: restatement == live reference on %d fresh cases" % min(args.cases, len(cases)))
   return 0
 
 
