@@ -202,3 +202,26 @@ def test_bench_reference_arm_prints_the_contract_line():
   if not t.cuda.is_available():
     ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output = True, text = True, timeout = 600, cwd = root)
     assert ours.returncode != 0 and "no CPU path" in (ours.stderr + ours.stdout)
+
+
+# ---- host half of proposal sampling (faster_rcnn.py:526-561) --------------------------------------
+def test_proposal_sampling_draws_match_the_restated_reference():
+  """FasterRCNNModel._sample_proposal_indices (the one piece of train_step's data path that stays on the host, so that seeded runs
+  draw the same samples as the reference) against the pinned restatement: same rows, same order, same RNG consumption -- on label
+  vectors with many / few / no positives, fewer rows than the batch, and sampling switched off."""
+  import fasterrcnn_b200 as f
+  model = f.FasterRCNNModel(21, f.vgg16.VGG16Backbone(0.0))
+  rng = np.random.RandomState(3)
+  cases = [(2002, 0.03), (2002, 0.5), (300, 0.0), (300, 1.0), (40, 0.3), (128, 0.25), (5, 0.4)]
+  for n, pos_rate in cases:
+    cls = np.where(rng.rand(n) < pos_rate, rng.randint(1, 21, n), 0).astype(np.int32)
+    onehot = t.zeros((n, 21)); onehot[t.arange(n), t.from_numpy(cls).long()] = 1.0
+    rows = t.arange(n, dtype = t.float32).reshape(n, 1).repeat(1, 4)                     # "proposals" that carry their own row index
+    deltas = t.zeros((n, 2, 80))
+    t.manual_seed(n); ref_rows, _, _ = orc.sample_proposals(rows, onehot, deltas, 128, 0.25)
+    after_ref = t.rand(1).item()                                                        # where the generator stands afterwards
+    t.manual_seed(n); idx = model._sample_proposal_indices(cls, 128, 0.25)
+    after = t.rand(1).item()
+    assert np.array_equal(idx, ref_rows[:, 0].numpy().astype(np.int64)), (n, pos_rate)
+    assert after == after_ref
+  assert model._sample_proposal_indices(np.zeros((7,), np.int32), 0, 0.25) is None       # max_proposals <= 0: keep every row
