@@ -209,7 +209,7 @@ def run_reference(args, rank):
   print(json.dumps(line), flush = True)
 
 
-def make_train_step(dev, rank = 0):
+def make_train_step(dev, rank = 0, world = 1):
   """Builds the benchmark workload on `dev`: model + fused optimizer + one synthetic sample.  Returns step(from_host) -> Loss."""
   import fasterrcnn_b200 as f
   from fasterrcnn_b200 import anchors as fanchors, optim
@@ -217,7 +217,11 @@ def make_train_step(dev, rank = 0):
   model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
   init_weights(model, seed = 0)                                   # identical replicas
   model = model.cuda()
-  optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
+  if world > 1 and os.environ.get("FRCNN_DP_FUSED", "0") not in ("", "0"):
+    # EXPERIMENT (unmeasured in round 1): reduce-scatter + SGD + all-gather as one kernel over NVLink / NVSwitch (csrc/dp_sgd.cu)
+    optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9)
+  else:
+    optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
 
   # per-rank synthetic sample (each rank its own image)
   g = t.Generator(device = "cpu").manual_seed(1000 + rank)
@@ -264,7 +268,7 @@ def run_ours(args, rank, local_rank, world):
   # measured too.  FRCNN_PDL=0 / 1 overrides.
   pdl = os.environ.get("FRCNN_PDL", "1" if world == 1 else "0") not in ("", "0")
   _lib.set_pdl(pdl)
-  step = make_train_step(dev, rank)
+  step = make_train_step(dev, rank, world)
 
   def barrier():
     if world > 1:
@@ -339,7 +343,8 @@ def run_ours(args, rank, local_rank, world):
   line = dict(metric = METRIC, value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
               higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = ENGINE_NOTES[engine_name][2], data = "synthetic",
               config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
-                            parallelism = "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)" % world,
+                            parallelism = ("dp%d (one process per GPU, fused reduce-scatter + SGD + all-gather kernel over NVLink multimem)" if isinstance(step.optimizer, optim.NvlsShardedSGD)
+                                           else "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)") % world,
                             engine = ENGINE_NOTES[engine_name][0],
                             sm_reserve = step.optimizer.sm_reserve,     # SMs the GEMMs leave to NCCL while reductions are in flight (FRCNN_DP_SM_RESERVE)
                             pdl = "on (programmatic dependent launch between the library's kernels; FRCNN_PDL=0 turns it off)" if pdl else "off",

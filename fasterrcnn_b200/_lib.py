@@ -90,6 +90,7 @@ _SIGNATURES = {
   "frcnn_sgd_step_split": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _vp, _vp]),
   "frcnn_sgd_step_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp]),
   "frcnn_sgd_step_multi_ex": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
+  "frcnn_dp_sgd_fused": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _sz, _f, _f, _f, _f, _i, _i, _vp]),
   "frcnn_detect_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _d, _vp, _vp, _vp]),
 }
 

@@ -147,6 +147,113 @@ class DataParallel:
     self._hooks = []
 
 
+class NvlsShardedSGD:
+  """EXPERIMENT (opt-in, written after round 1's GPU budget had ended -- unmeasured; bench.py: FRCNN_DP_FUSED=1 at N > 1).
+
+  The data-parallel optimizer step as ONE hand-written kernel per rank over NVLink / NVSwitch instead of "NCCL all-reduce, then
+  optimizer.step()": reduce-scatter of the weight gradients (multimem.ld_reduce: summed inside the switch), torch.optim.SGD on this
+  rank's 1 / world shard (the momentum buffer exists only for the shard), all-gather of the updated weights (multimem.st) -- see
+  csrc/dp_sgd.cu.  The optimizer's tensors are moved into two flat symmetric-memory arenas (torch.distributed._symmetric_memory gives
+  the peer / multicast mappings and the stream-ordered cross-rank barrier): ``W`` -- the parameters become views of it -- and ``G``, into
+  which each gradient is copied from a post-accumulate hook the moment autograd has produced it.
+  Quacks like the optimizer FasterRCNNModel.train_step expects (zero_grad / step / param_groups).  Hyper-parameters must be uniform
+  over the groups (they are in the reference's recipe, __main__.py:98-105)."""
+
+  def __init__(self, params, lr = 1e-3, momentum = 0.9, process_group = None, use_multicast = None, ctas_per_sm = 0):
+    os.environ.setdefault("TORCH_SYMMMEM_IMPLICIT_POOL", "0")   # one allocation per arena: the mappings then start at the tensor (offset 0)
+    import torch.distributed._symmetric_memory as symm
+    assert dist.is_initialized(), "NvlsShardedSGD needs an initialised process group (one process per GPU)"
+    group = process_group if process_group is not None else dist.group.WORLD
+    self.group, self.world_size, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+    assert 1 <= self.world_size <= 8, "one NVSwitch domain: at most 8 ranks"
+    self.param_groups = [dict(g) for g in params]
+    for g in self.param_groups:
+      g.setdefault("lr", lr); g.setdefault("momentum", momentum); g.setdefault("weight_decay", 0.0)
+    hp = {(g["lr"], g["momentum"], g["weight_decay"]) for g in self.param_groups}
+    assert len(hp) == 1, "NvlsShardedSGD: lr / momentum / weight_decay must be the same for every group"
+    self.lr, self.momentum, self.weight_decay = hp.pop()
+    self.params = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+    assert self.params and all(p.is_cuda and p.dtype == t.float32 for p in self.params)
+    dev = self.params[0].device
+    # flat layout: every tensor starts on a 16-byte boundary; the whole space is cut into world equal shards of whole float4s
+    self.offsets, total = [], 0
+    for p in self.params:
+      assert p.is_contiguous() or p.is_contiguous(memory_format = t.channels_last), "parameters must be dense"
+      self.offsets.append(total)
+      total += (p.numel() + 3) // 4 * 4
+    self.shard = (total + 4 * self.world_size - 1) // (4 * self.world_size) * 4
+    self.total = self.shard * self.world_size
+    self.W = symm.empty(self.total, dtype = t.float32, device = dev)
+    self.G = symm.empty(self.total, dtype = t.float32, device = dev)
+    self.W.zero_(); self.G.zero_()
+    symm.enable_symm_mem_for_group(group.group_name)
+    self.hW, self.hG = symm.rendezvous(self.W, group), symm.rendezvous(self.G, group)
+    with t.no_grad():
+      for p, off in zip(self.params, self.offsets):
+        view = self._view(self.W, off, p)
+        view.copy_(p)
+        p.data = view                                            # same shape, same strides; storage = this rank's weight arena
+    self._gviews = {id(p): self._view(self.G, off, p) for p, off in zip(self.params, self.offsets)}
+    self.momentum_shard = t.zeros((self.shard,), dtype = t.float32, device = dev)
+    self._first = True
+    self.ctas_per_sm = int(ctas_per_sm)
+    self.sm_reserve = 0
+    self.bytes_reduced_last_step = 0
+    # mappings: multicast (in-switch reduction / broadcast) when the fabric offers it, else every rank's arena through peer pointers
+    mc_w, mc_g = int(self.hW.multicast_ptr or 0), int(self.hG.multicast_ptr or 0)
+    if use_multicast is None:
+      use_multicast = os.environ.get("FRCNN_DP_FUSED_MULTICAST", "1") not in ("", "0")
+    self.use_multicast = bool(use_multicast) and mc_w != 0 and mc_g != 0
+    self._mc = (mc_g + int(self.hG.offset), mc_w + int(self.hW.offset)) if self.use_multicast else (None, None)
+    import ctypes
+    peers_g = [self.hG.get_buffer(r, (self.total,), t.float32, 0) for r in range(self.world_size)]
+    peers_w = [self.hW.get_buffer(r, (self.total,), t.float32, 0) for r in range(self.world_size)]
+    assert peers_w[self.rank].data_ptr() == self.W.data_ptr() and peers_g[self.rank].data_ptr() == self.G.data_ptr(), "symmetric-memory mapping does not start at the tensor"
+    self._peer_tensors = (peers_g, peers_w)                      # keep the mappings alive
+    vp = ctypes.c_void_p * self.world_size
+    self._peers = (vp(*[x.data_ptr() for x in peers_g]), vp(*[x.data_ptr() for x in peers_w]))
+    self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad_ready) for p in self.params]
+    dist.barrier(group)
+
+  @staticmethod
+  def _view(buf, off, p):
+    return buf[off:off + p.numel()].as_strided(p.shape, p.stride())
+
+  @t.no_grad()
+  def _on_grad_ready(self, p):
+    self._gviews[id(p)].copy_(p.grad)                            # on the compute stream, right behind the kernel that produced the gradient
+    self.bytes_reduced_last_step += p.grad.numel() * 4
+
+  def zero_grad(self, set_to_none = True):
+    self.bytes_reduced_last_step = 0
+    for p in self.params:
+      if set_to_none:
+        p.grad = None
+      elif p.grad is not None:
+        p.grad.zero_()
+
+  @t.no_grad()
+  def step(self):
+    from . import _lib
+    self.hG.barrier(channel = 0)                                 # every rank's gradients are in its arena
+    _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W), _lib.ptr(self.momentum_shard),
+                                             self.rank * self.shard, self.shard, float(self.lr), float(self.momentum), float(self.weight_decay),
+                                             1.0 / self.world_size, 1 if self._first else 0, self.ctas_per_sm, _lib.stream()), "frcnn_dp_sgd_fused")
+    _lib.count()
+    self.hG.barrier(channel = 0)                                 # every shard delivered everywhere; every arena's gradients consumed
+    self._first = False
+
+  def remove_hooks(self):
+    for h in self._hooks:
+      h.remove()
+    self._hooks = []
+
+
+def optimizer_param_groups(model, weight_decay = 5e-4):
+  """The reference's parameter groups (__main__.py:98-105): one per tensor that requires grad and has "weight" in its name."""
+  return [{"params": [value], "weight_decay": weight_decay} for key, value in dict(model.named_parameters()).items() if value.requires_grad and "weight" in key]
+
+
 def create_optimizer(model, learning_rate = 1e-3, momentum = 0.9, weight_decay = 5e-4, fused = True):
   """The reference's recipe (__main__.py:98-105): one group per tensor that requires grad and has
   "weight" in its name."""

@@ -327,6 +327,19 @@ int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *gra
                             const float *lrs, const float *momenta, const float *weight_decays, const int *first_steps, void *const *param_splits,
                             int split_format, float grad_scale, int ctas_per_sm, void *stream);
 
+/* ---- 8e: the data-parallel optimizer step as one kernel over NVLink / NVSwitch (EXPERIMENT; optim.NvlsShardedSGD) --------------------
+ * Replaces, for W > 1 replicas, the pair "NCCL all-reduce of the weight gradients + optimizer.step()" (the reference has no multi-GPU
+ * path; models/faster_rcnn.py:356-359 is the single-GPU backward + step it extends).  Weights and gradients of the optimizer's tensors live
+ * in two flat symmetric-memory arenas with the same layout on every rank.  This rank updates the shard [shard_begin, shard_begin +
+ * shard_count) (elements, multiples of 4): gradient = sum over ranks (multimem.ld_reduce on grad_multicast -- reduced inside the NVSwitch --
+ * or, when the multicast pointers are NULL, loads through grad_peers[0..world)), times grad_scale; torch.optim.SGD update with the shard's
+ * own momentum buffer (momentum_shard, shard_count floats); the new weights are written to every rank (multimem.st on weight_multicast, or
+ * stores through weight_peers).  weight_local = this rank's own arena (read side).  The caller brackets the launch with two cross-rank
+ * barriers: every rank's gradients complete before | every rank's stores delivered and gradients consumed after.  world <= 8. */
+int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_multicast, const void *const *grad_peers, void *const *weight_peers, int world,
+                       const float *weight_local, float *momentum_shard, size_t shard_begin, size_t shard_count,
+                       float lr, float momentum, float weight_decay, float grad_scale, int first_step, int ctas_per_sm, void *stream);
+
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one
  * launch: decode in fp64 with stds (0.1,0.1,0.2,0.2), clip to [0,img_h-1]x[0,img_w-1], keep

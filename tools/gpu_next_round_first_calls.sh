@@ -16,7 +16,9 @@ if [ "${1:-1}" = "1" ]; then
 else
   N=${1}
   run() { env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 8; }
-  for cfg in "FRCNN_PDL=0" "FRCNN_PDL=1" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16" "FRCNN_DP_SM_RESERVE=8 NCCL_MAX_CTAS=8" "FRCNN_DP_SM_RESERVE=32 NCCL_MAX_CTAS=32" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16 FRCNN_PDL=1"; do
+  FRCNN_TEST_EXPERIMENTS=1 timeout 900 python -m pytest tests/test_zz_experiments_gpu.py -q -k fused_dp -p no:cacheprovider > gpurun_out/pytest_fused_dp.log 2>&1
+  echo "fused DP step vs NCCL + SGD: exit $?"; tail -n 3 gpurun_out/pytest_fused_dp.log | cut -c1-200
+  for cfg in "FRCNN_PDL=0" "FRCNN_DP_FUSED=1" "FRCNN_DP_FUSED=1 FRCNN_DP_FUSED_MULTICAST=0" "FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_PDL=1" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16" "FRCNN_DP_SM_RESERVE=8 NCCL_MAX_CTAS=8" "FRCNN_DP_SM_RESERVE=32 NCCL_MAX_CTAS=32" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16 FRCNN_PDL=1"; do
     tag=$(echo "$cfg" | tr ' =' '__')
     run $cfg > gpurun_out/bench_n${N}_$tag.json 2> gpurun_out/bench_n${N}_$tag.err
     echo "N=$N $cfg: $(python -c "import json; d=json.load(open('gpurun_out/bench_n${N}_$tag.json')); print(round(d['value'],1), 'images/s', round(d['ms_per_step'],3), 'ms')" 2>&1 | tail -n 1)"
