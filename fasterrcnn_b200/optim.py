@@ -196,7 +196,7 @@ class NvlsShardedSGD:
     self._gviews = {id(p): self._view(self.G, off, p) for p, off in zip(self.params, self.offsets)}
     self.momentum_shard = t.zeros((self.shard,), dtype = t.float32, device = dev)
     self._first = True
-    self.ctas_per_sm = int(ctas_per_sm)
+    self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "0"))   # 0: the kernel's default (4 CTAs of 256 threads per SM)
     self.sm_reserve = 0
     self.bytes_reduced_last_step = 0
     # mappings: multicast (in-switch reduction / broadcast) when the fabric offers it, else every rank's arena through peer pointers
