@@ -196,6 +196,7 @@ class NvlsShardedSGD:
     self._gviews = {id(p): self._view(self.G, off, p) for p, off in zip(self.params, self.offsets)}
     self.momentum_shard = t.zeros((self.shard,), dtype = t.float32, device = dev)
     self._first = True
+    self._seen = set()
     self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "0"))   # 0: the kernel's default (4 CTAs of 256 threads per SM)
     self.sm_reserve = 0
     self.bytes_reduced_last_step = 0
@@ -222,10 +223,12 @@ class NvlsShardedSGD:
   @t.no_grad()
   def _on_grad_ready(self, p):
     self._gviews[id(p)].copy_(p.grad)                            # on the compute stream, right behind the kernel that produced the gradient
+    self._seen.add(id(p))
     self.bytes_reduced_last_step += p.grad.numel() * 4
 
   def zero_grad(self, set_to_none = True):
     self.bytes_reduced_last_step = 0
+    self._seen = set()
     for p in self.params:
       if set_to_none:
         p.grad = None
@@ -235,6 +238,9 @@ class NvlsShardedSGD:
   @t.no_grad()
   def step(self):
     from . import _lib
+    for p in self.params:
+      if id(p) not in self._seen:
+        self._gviews[id(p)].zero_()                              # no gradient on this rank this step (e.g. an empty RoI sample): contribute zero, not last step's values
     self.hG.barrier(channel = 0)                                 # every rank's gradients are in its arena
     _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W), _lib.ptr(self.momentum_shard),
                                              self.rank * self.shard, self.shard, float(self.lr), float(self.momentum), float(self.weight_decay),
