@@ -290,8 +290,19 @@ def run_ours(args, rank, local_rank, world):
       ms = float(tt.item())
     return ms, loss
 
-  for _ in range(max(args.warmup, 3)):
-    step(False)
+  try:
+    for _ in range(max(args.warmup, 3)):
+      step(False)
+    t.cuda.synchronize()
+  except Exception as e:                                          # insurance for the single-GPU default: a launch attribute this driver rejects
+    if not (pdl and world == 1):
+      raise
+    print("bench: warm-up with programmatic dependent launch failed (%s); measuring with it off" % str(e)[:200], file = sys.stderr)
+    pdl = False
+    _lib.set_pdl(False)
+    step = make_train_step(dev, rank, world)
+    for _ in range(max(args.warmup, 3)):
+      step(False)
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
