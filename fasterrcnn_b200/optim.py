@@ -201,18 +201,25 @@ class NvlsShardedSGD:
     self.sm_reserve = 0
     self.bytes_reduced_last_step = 0
     # mappings: multicast (in-switch reduction / broadcast) when the fabric offers it, else every rank's arena through peer pointers
-    mc_w, mc_g = int(self.hW.multicast_ptr or 0), int(self.hG.multicast_ptr or 0)
+    def mapping(handle, tensor):
+      """(peer pointers of `tensor` on every rank, multicast pointer or 0): the handle describes an allocation block, the tensor sits at
+      handle.offset inside it (0 with one allocation per arena) -- checked against the one address known for sure, this rank's."""
+      base = [int(x) for x in handle.buffer_ptrs]
+      off = int(handle.offset)
+      if base[self.rank] + off != tensor.data_ptr():
+        assert base[self.rank] == tensor.data_ptr(), "symmetric-memory mapping does not contain the tensor where expected"
+        off = 0
+      mc = int(handle.multicast_ptr or 0)
+      return [b + off for b in base], (mc + off if mc else 0)
+    peers_g, mc_g = mapping(self.hG, self.G)
+    peers_w, mc_w = mapping(self.hW, self.W)
     if use_multicast is None:
       use_multicast = os.environ.get("FRCNN_DP_FUSED_MULTICAST", "1") not in ("", "0")
     self.use_multicast = bool(use_multicast) and mc_w != 0 and mc_g != 0
-    self._mc = (mc_g + int(self.hG.offset), mc_w + int(self.hW.offset)) if self.use_multicast else (None, None)
+    self._mc = (mc_g, mc_w) if self.use_multicast else (None, None)
     import ctypes
-    peers_g = [self.hG.get_buffer(r, (self.total,), t.float32, 0) for r in range(self.world_size)]
-    peers_w = [self.hW.get_buffer(r, (self.total,), t.float32, 0) for r in range(self.world_size)]
-    assert peers_w[self.rank].data_ptr() == self.W.data_ptr() and peers_g[self.rank].data_ptr() == self.G.data_ptr(), "symmetric-memory mapping does not start at the tensor"
-    self._peer_tensors = (peers_g, peers_w)                      # keep the mappings alive
     vp = ctypes.c_void_p * self.world_size
-    self._peers = (vp(*[x.data_ptr() for x in peers_g]), vp(*[x.data_ptr() for x in peers_w]))
+    self._peers = (vp(*peers_g), vp(*peers_w))
     self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad_ready) for p in self.params]
     dist.barrier(group)
 
