@@ -204,12 +204,13 @@ class NvlsShardedSGD:
     def mapping(handle, tensor):
       """(peer pointers of `tensor` on every rank, multicast pointer or 0): the handle describes an allocation block, the tensor sits at
       handle.offset inside it (0 with one allocation per arena) -- checked against the one address known for sure, this rank's."""
-      base = [int(x) for x in handle.buffer_ptrs]
-      off = int(handle.offset)
+      get = lambda name: (lambda v: v() if callable(v) else v)(getattr(handle, name))     # properties in current torch
+      base = [int(x) for x in get("buffer_ptrs")]
+      off = int(get("offset"))
       if base[self.rank] + off != tensor.data_ptr():
         assert base[self.rank] == tensor.data_ptr(), "symmetric-memory mapping does not contain the tensor where expected"
         off = 0
-      mc = int(handle.multicast_ptr or 0)
+      mc = int(get("multicast_ptr") or 0)
       return [b + off for b in base], (mc + off if mc else 0)
     peers_g, mc_g = mapping(self.hG, self.G)
     peers_w, mc_w = mapping(self.hW, self.W)
