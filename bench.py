@@ -219,7 +219,11 @@ def make_train_step(dev, rank = 0, world = 1):
   model = model.cuda()
   if world > 1 and os.environ.get("FRCNN_DP_FUSED", "0") not in ("", "0"):
     # EXPERIMENT (unmeasured in round 1): reduce-scatter + SGD + all-gather as one kernel over NVLink / NVSwitch (csrc/dp_sgd.cu)
-    optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9)
+    try:
+      optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9)
+    except Exception as e:                                        # e.g. no symmetric-memory support on this box: every rank fails alike
+      print("bench: fused data-parallel step unavailable (%s); NCCL all-reduce + SGD instead" % str(e)[:300], file = sys.stderr)
+      optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
   else:
     optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
 
