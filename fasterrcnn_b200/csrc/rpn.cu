@@ -418,7 +418,7 @@ __global__ void append_rows_kernel(float *__restrict__ dst, const int32_t *__res
                                    const float *__restrict__ src, int m)
 {
   pdl_enter();
-  int n = *dst_count;
+  int n = __ldcg(dst_count);        // coherent, see gather_rows_kernel
   if (n < 0) n = 0;
   const int total = m * row_floats;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -431,7 +431,7 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int row_floats
                                    int capacity, float *__restrict__ dst)
 {
   pdl_enter();
-  int n = *count;
+  int n = __ldcg(count);            // a coherent load: ptxas may move a non-coherent (ld.global.nc) one above griddepcontrol.wait, and the count is the previous kernel's output
   if (n > capacity) n = capacity;
   size_t total = (size_t)n * row_floats;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {

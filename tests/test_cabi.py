@@ -75,6 +75,22 @@ def test_sass_carries_the_blackwell_instructions():
   count = lambda op: len(re.findall(r"\b%s\b" % op, sass))
   assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0
   assert count("PREEXIT") == kernels and count("ACQBULK") == kernels            # one griddepcontrol pair per kernel
+  # PDL safety, statically: in every kernel nothing touches global memory before griddepcontrol.wait (ACQBULK).  ptxas is free to move
+  # non-coherent loads (ld.global.nc, what `const __restrict__` turns into) above the wait -- it did so once for a device-side count --
+  # so the order is checked on the SASS of every build.  The tcgen05 kernel reads its TMEM slot from shared memory through a generic
+  # pointer before the wait (LD.E), nothing else; a branch before the wait may only jump within the pre-wait region.
+  strict = re.compile(r"\b(LDG|STG|ATOMG|REDG|ATOM|RED|LDGSTS|UTMALDG|UTMASTG|LDGMC|UBLKCP)\b")
+  generic = re.compile(r"\b(LD|ST)(\.E)?\b")
+  for body in re.split(r"^\s*Function : ", sass, flags = re.M)[1:]:
+    name = body.split("\n", 1)[0].strip()
+    ins = [(int(m.group(1), 16), re.sub(r"/\*.*?\*/", "", line).strip()) for line in body.split("\n") for m in [re.search(r"/\*([0-9a-f]{4,})\*/", line)] if m]
+    at = next(i for i, (_, op) in enumerate(ins) if "ACQBULK" in op)
+    wait_addr = ins[at][0]
+    for addr, op in ins[:at]:
+      assert not strict.search(op), (name, op)
+      assert "tc_conv_kernel" in name or not generic.search(op), (name, op)
+      m = re.search(r"\bBRA\s+(0x[0-9a-f]+)", op)
+      assert m is None or int(m.group(1), 16) <= wait_addr, (name, op)
 
 
 def test_sm_reserve_changes_neither_workspace_sizes_nor_amax_slots():
