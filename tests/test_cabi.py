@@ -75,6 +75,8 @@ def test_sass_carries_the_blackwell_instructions():
   count = lambda op: len(re.findall(r"\b%s\b" % op, sass))
   assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0
   assert count("PREEXIT") == kernels and count("ACQBULK") == kernels            # one griddepcontrol pair per kernel
+  # determinism: the only atomics are integer ones (order-independent); no floating-point RED / ATOM anywhere
+  assert not re.search(r"\b(RED|REDG|ATOM|ATOMG|ATOMS)\.[A-Z0-9.]*F(16|32|64)", sass)
   # PDL safety, statically: in every kernel nothing touches global memory before griddepcontrol.wait (ACQBULK).  ptxas is free to move
   # non-coherent loads (ld.global.nc, what `const __restrict__` turns into) above the wait -- it did so once for a device-side count --
   # so the order is checked on the SASS of every build.  The tcgen05 kernel reads its TMEM slot from shared memory through a generic
