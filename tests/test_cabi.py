@@ -118,3 +118,32 @@ def test_sm_reserve_changes_neither_workspace_sizes_nor_amax_slots():
   finally:
     assert _lib.set_sm_reserve(0) == 132          # 1000 was clamped to 148 - 16
   assert max(s[0] for s in base[2::3]) <= 148     # amax slots = CTAs of an unreserved launch
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+  """Every binding in fasterrcnn_b200/_lib.py has the argument list of its prototype in include/frcnn_b200.h: same count, and per argument
+  pointer -> c_void_p, int -> c_int, float -> c_float, double -> c_double, size_t -> c_size_t (a mismatch would only show on the GPU box,
+  as a corrupted call)."""
+  import ctypes
+  from fasterrcnn_b200 import _lib
+  text = open(os.path.join(ROOT, "include", "frcnn_b200.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags = re.S)
+  protos = dict((m.group(2), (m.group(1).strip(), m.group(3))) for m in re.finditer(r"^([A-Za-z_][\w \*]*?)\b(frcnn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags = re.M | re.S))
+  assert set(protos) == set(_lib._SIGNATURES), set(protos) ^ set(_lib._SIGNATURES)
+
+  def ctype_of(param):
+    param = " ".join(param.split())
+    if "*" in param:
+      return ctypes.c_void_p
+    base = param.rsplit(" ", 1)[0] if " " in param else param
+    base = base.replace("const ", "").strip()
+    return {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t, "int32_t": ctypes.c_int}[base]
+
+  for name, (ret, params) in protos.items():
+    restype, argtypes = _lib._SIGNATURES[name]
+    plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+    assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+    for i, (p, a) in enumerate(zip(plist, argtypes)):
+      assert ctype_of(p) is a, (name, i, p.strip(), a)
+    want = ctypes.c_char_p if ("char" in ret and "*" in ret) else (None if ret == "void" else {"int": ctypes.c_int, "size_t": ctypes.c_size_t}[ret.replace("const ", "").strip()])
+    assert restype is want, (name, ret, restype)
