@@ -147,3 +147,29 @@ def test_ctypes_signatures_match_the_header_prototypes():
       assert ctype_of(p) is a, (name, i, p.strip(), a)
     want = ctypes.c_char_p if ("char" in ret and "*" in ret) else (None if ret == "void" else {"int": ctypes.c_int, "size_t": ctypes.c_size_t}[ret.replace("const ", "").strip()])
     assert restype is want, (name, ret, restype)
+
+
+def test_call_sites_pass_the_bound_number_of_arguments():
+  """Static count of the arguments at every `...frcnn_xxx(...)` call in the package against the binding (`*geom` = the 9 geometry
+  integers): ctypes would raise only when the call is reached -- on the GPU box."""
+  import ast
+  import glob
+  from fasterrcnn_b200 import _lib
+  checked = 0
+  for path in glob.glob(os.path.join(ROOT, "fasterrcnn_b200", "*.py")) + [os.path.join(ROOT, "bench.py")] + glob.glob(os.path.join(ROOT, "tools", "*.py")):
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+      if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in _lib._SIGNATURES:
+        n, known = 0, True
+        for a in node.args:
+          if isinstance(a, ast.Starred):
+            if isinstance(a.value, ast.Name) and a.value.id in ("geom", "g9"):
+              n += 9
+            else:
+              known = False
+          else:
+            n += 1
+        if known and not node.keywords:
+          assert n == len(_lib._SIGNATURES[node.func.attr][1]), (os.path.basename(path), node.lineno, node.func.attr, n, len(_lib._SIGNATURES[node.func.attr][1]))
+          checked += 1
+  assert checked >= 60
