@@ -173,3 +173,13 @@ def test_call_sites_pass_the_bound_number_of_arguments():
           assert n == len(_lib._SIGNATURES[node.func.attr][1]), (os.path.basename(path), node.lineno, node.func.attr, n, len(_lib._SIGNATURES[node.func.attr][1]))
           checked += 1
   assert checked >= 60
+
+
+def test_python_constants_match_the_header_defines():
+  from fasterrcnn_b200 import _lib
+  text = open(os.path.join(ROOT, "include", "frcnn_b200.h")).read()
+  defs = {m.group(1): int(m.group(2).strip("()")) for m in re.finditer(r"^#define (FRCNN_[A-Z0-9_]+) (\(?-?\d+\)?)", text, flags = re.M)}
+  assert (defs["FRCNN_ACT_NONE"], defs["FRCNN_ACT_RELU"], defs["FRCNN_ACT_SIGMOID"]) == (_lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_SIGMOID)
+  assert (defs["FRCNN_ENGINE_AUTO"], defs["FRCNN_ENGINE_SIMT_FP32"], defs["FRCNN_ENGINE_TC_3XTF32"], defs["FRCNN_ENGINE_TC_3XF16"]) == \
+         (_lib.ENGINE_AUTO, _lib.ENGINE_SIMT_FP32, _lib.ENGINE_TC_3XTF32, _lib.ENGINE_TC_3XF16)
+  assert defs["FRCNN_OK"] == 0 and defs["FRCNN_E_BADARG"] < 0
