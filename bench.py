@@ -4,6 +4,8 @@ bench.py -- BASELINE.json's metric: images/sec, VGG-16 Faster R-CNN train_step (
 backward + SGD) on a synthetic 3x600x1000 image, batch 1 per GPU, N in {1,2,4,8} B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--backbone vgg16|resnet50|resnet101] [--batch B] [--roi-op pool|align] [--rois R]     other BASELINE configs (3, 4)
+                  [--micro]                                                                            BASELINE config 5 (HBM kernels)
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 One JSON line on rank 0.  `value` = whole-job images/s with the step's inputs resident in HBM;
@@ -32,6 +34,31 @@ sys.path.insert(0, ROOT)
 IMAGE_HW = (600, 1000)
 WORKLOAD = "VGG-16 Faster R-CNN train_step (fwd+bwd+SGD), synthetic 3x600x1000 image, batch 1/GPU, 2 GT boxes, 128 RoIs"
 METRIC = "images/sec fwd+bwd @ 1000x600, batch=1/GPU"
+PDL_DEFAULT_MULTI_GPU = "0"                     # until measured next to the overlapped collectives (profiles/r02_dp_sweep*.md)
+BACKBONE_NAMES = {"vgg16": "VGG-16", "resnet50": "ResNet-50", "resnet101": "ResNet-101"}
+
+
+def workload_name(args):
+  """BASELINE.json's headline workload by default (config 2); the other configs through --backbone / --batch / --roi-op / --rois."""
+  if args.backbone == "vgg16" and args.batch == 1 and args.roi_op == "pool" and args.rois == 128:
+    return WORKLOAD
+  return "%s Faster R-CNN train_step (fwd+bwd+SGD), synthetic 3x600x1000 image%s, batch %d/GPU, 2 GT boxes, %d RoIs per image, %s" % (
+    BACKBONE_NAMES[args.backbone], "s" if args.batch > 1 else "", args.batch, args.rois, "RoIAlign (sampling_ratio 2)" if args.roi_op == "align" else "RoIPool")
+
+
+def metric_name(args):
+  return METRIC if args.batch == 1 else "images/sec fwd+bwd @ 1000x600, batch=%d/GPU" % args.batch
+
+
+def cpu_model():
+  try:
+    with open("/proc/cpuinfo") as f:
+      for line in f:
+        if line.startswith("model name"):
+          return line.split(":", 1)[1].strip()
+  except OSError:
+    pass
+  return "unknown"
 # algorithmic GEMM work of one step (SURVEY.md 8d): conv fwd 366.32 + conv bwd 485.20 + RPN 32.8 + detector fc 92.1 GFLOP
 GT = [((100.0, 150.0, 400.0, 600.0), 7), ((50.0, 650.0, 500.0, 850.0), 15)]
 
@@ -82,7 +109,13 @@ def init_weights(model, seed):
   g = t.Generator(device = "cpu").manual_seed(seed)
   with t.no_grad():
     for key, p in model.named_parameters():
-      if key.startswith("_stage1") or "_fc" in key:
+      if ".bn" in key or ".downsample.1." in key or key.endswith("_feature_extractor.1.weight") or key.endswith("_feature_extractor.1.bias"):
+        # frozen BatchNorm affine (ResNet): gamma 1 / beta 0, the last BN of every bottleneck scaled down -- dozens of residual blocks
+        # with unit-gain branches overflow a random init
+        if key.endswith("bn3.weight"):
+          p.fill_(0.25)
+        continue
+      if key.startswith("_stage1") or "_fc" in key or "_layer4" in key:
         if p.dim() > 1:
           fan_in = int(np.prod(p.shape[1:]))
           w = t.randn(p.shape, generator = g) * (2.0 / fan_in) ** 0.5
@@ -176,19 +209,36 @@ def host_threads():
   return int(env) if env else n
 
 
-def cpu_port_times(steps, warmup):
+def cpu_port_times(steps, warmup, args = None):
+  """Per-step seconds of the CPU oracle port on this workload (every step processes args.batch images)."""
   from oracle import frcnn_oracle as orc
   cores = host_threads()
   t.set_num_threads(cores)
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 0, heads = "reference")
-  model = orc.OracleModel(params)
-  smp = orc.synthetic_sample(IMAGE_HW, seed = 0)
+  backbone = args.backbone if args is not None else "vgg16"
+  batch = args.batch if args is not None else 1
+  rois = args.rois if args is not None else 128
+  roi_op = args.roi_op if args is not None else "pool"
+  if backbone == "vgg16":
+    shapes = orc.vgg16_param_shapes()
+  else:
+    from oracle import resnet_oracle
+    shapes = resnet_oracle.param_shapes(backbone)
+  params = orc.synth_params(shapes, seed = 0, heads = "reference")
+  for k in params:
+    if k.endswith("bn3.weight"):
+      params[k] = params[k] * 0.3
+  model = orc.OracleModel(params, backbone = backbone, proposal_batch_size = rois)
+  smps = [orc.synthetic_sample(IMAGE_HW, seed = b, backbone = backbone) for b in range(batch)]
   random.seed(0); np.random.seed(0); t.manual_seed(0)
   times = []
   for i in range(warmup + steps):
     t0 = time.perf_counter()
-    model.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
-                     smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"])
+    if batch == 1 and roi_op == "pool":
+      smp = smps[0]
+      model.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                       smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"])
+    else:
+      model.train_step_batch(t.cat([s["image"] for s in smps], dim = 0), smps, roi_op = roi_op)
     if i >= warmup:
       times.append(time.perf_counter() - t0)
   return times, cores
@@ -197,43 +247,50 @@ def cpu_port_times(steps, warmup):
 def run_reference(args, rank):
   if rank != 0:
     return
-  times, cores = cpu_port_times(args.steps, args.warmup)
+  times, cores = cpu_port_times(args.steps, args.warmup, args)
   total = sum(times)
-  value = len(times) / total
-  sample = "%d train_steps of the CPU oracle port (torch-CPU conv/linear + C NMS/RoIPool restatement), %d threads" % (len(times), cores)
-  line = dict(impl = "reference", metric = METRIC, value = value, unit = "images/s", n_gpus = args.gpus, steps = args.steps, warmup = args.warmup,
+  value = args.batch * len(times) / total
+  sample = "%d train_steps of the CPU oracle port (torch-CPU conv/linear + C NMS/RoIPool restatement), %d threads, %s" % (len(times), cores, cpu_model())
+  line = dict(impl = "reference", metric = metric_name(args), value = value, unit = "images/s", n_gpus = args.gpus, steps = args.steps, warmup = args.warmup,
               ms_per_step = 1e3 * total / len(times), higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = "f32", data = "synthetic",
-              config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", parallelism = "host CPU, %d threads" % cores),
-              cpu_baseline = dict(value = value, unit = "images/s", cores = cores, kind = "port", sample = sample),
+              config = dict(workload = workload_name(args), image = "%dx3x600x1000" % args.batch, backbone = args.backbone, parallelism = "host CPU, %d threads" % cores, cpu = cpu_model()),
+              cpu_baseline = dict(value = value, unit = "images/s", cores = cores, kind = "port", sample = sample, cpu = cpu_model()),
               e2e = dict(value = value, unit = "images/s", h2d_bytes_per_step = 0, d2h_bytes_per_step = 0), gpu_launches = 0)
   print(json.dumps(line), flush = True)
 
 
-def make_train_step(dev, rank = 0, world = 1):
-  """Builds the benchmark workload on `dev`: model + fused optimizer + one synthetic sample.  Returns step(from_host) -> Loss."""
+def make_train_step(dev, args, rank = 0, world = 1):
+  """Builds the benchmark workload on `dev`: model + optimizer + synthetic sample(s).  Returns step(from_host) -> Loss."""
   import fasterrcnn_b200 as f
-  from fasterrcnn_b200 import anchors as fanchors, optim
+  from fasterrcnn_b200 import anchors as fanchors, optim, resnet
 
-  model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
+  if args.backbone == "vgg16":
+    backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  else:
+    backbone = resnet.ResNetBackbone({"resnet50": resnet.Architecture.ResNet50, "resnet101": resnet.Architecture.ResNet101}[args.backbone])
+  model = f.FasterRCNNModel(num_classes = 21, backbone = backbone, allow_edge_proposals = True, proposal_batch_size = args.rois, roi_op = args.roi_op)
   init_weights(model, seed = 0)                                   # identical replicas
   model = model.cuda()
-  if world > 1 and os.environ.get("FRCNN_DP_FUSED", "0") not in ("", "0"):
-    # EXPERIMENT (unmeasured in round 1): reduce-scatter + SGD + all-gather as one kernel over NVLink / NVSwitch (csrc/dp_sgd.cu)
+  named = list(model.named_parameters())
+  fused_dp = world > 1 and os.environ.get("FRCNN_DP_FUSED", "0") not in ("", "0")
+  if fused_dp:
+    # reduce-scatter + SGD + all-gather as one kernel per bucket over NVLink / NVSwitch (csrc/dp_sgd.cu), overlapped with the backward.
+    # The constructor agrees on success across ranks before it touches the parameters, so every rank takes the same branch here.
     try:
-      optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9)
-    except Exception as e:                                        # e.g. no symmetric-memory support on this box: every rank fails alike
+      optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9, named_params = named)
+    except Exception as e:                                        # e.g. no symmetric-memory support on this box
       print("bench: fused data-parallel step unavailable (%s); NCCL all-reduce + SGD instead" % str(e)[:300], file = sys.stderr)
-      optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
-  else:
-    optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
+      fused_dp = False
+  if not fused_dp:
+    optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True), named_params = named)
 
-  # per-rank synthetic sample (each rank its own image, SURVEY.md 8e)
-  g = t.Generator(device = "cpu").manual_seed(1000 + rank)
+  # per-rank synthetic samples (each rank its own images, SURVEY.md 8e)
   h, w = IMAGE_HW
-  image_host = (t.randn((1, 3, h, w), generator = g) * 50.0).pin_memory()
   boxes = [Box(b, c) for b, c in GT]
   anchor_map, anchor_valid_map = fanchors.generate_anchor_maps((3, h, w), model.backbone.compute_feature_map_shape((3, h, w)), 16)
   rpn_map, obj_idx, bg_idx = fanchors.generate_rpn_map(anchor_map, anchor_valid_map, boxes)
+  g = t.Generator(device = "cpu").manual_seed(1000 + rank)
+  image_host = (t.randn((args.batch, 3, h, w), generator = g) * 50.0).pin_memory()
   gt_map_host = t.from_numpy(rpn_map).unsqueeze(0).pin_memory()
   image_dev, gt_map_dev = image_host.cuda(), gt_map_host.cuda()
   random.seed(rank); t.manual_seed(rank)
@@ -244,8 +301,12 @@ def make_train_step(dev, rank = 0, world = 1):
       gmap = gt_map_host.to(dev, non_blocking = True)
     else:
       img, gmap = image_dev, gt_map_dev
-    return model.train_step(optimizer = optimizer, image_data = img, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map, gt_rpn_map = gmap,
-                            gt_rpn_object_indices = [obj_idx], gt_rpn_background_indices = [bg_idx], gt_boxes = [boxes])
+    if args.batch == 1:
+      return model.train_step(optimizer = optimizer, image_data = img, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map, gt_rpn_map = gmap,
+                              gt_rpn_object_indices = [obj_idx], gt_rpn_background_indices = [bg_idx], gt_boxes = [boxes])
+    samples = [dict(anchor_map = anchor_map, anchor_valid_map = anchor_valid_map, gt_rpn_map = gmap, gt_rpn_object_indices = obj_idx,
+                    gt_rpn_background_indices = bg_idx, gt_boxes = boxes) for _ in range(args.batch)]
+    return model.train_step_batch(optimizer, img, samples)
 
   step.h2d_bytes = image_host.numel() * 4 + gt_map_host.numel() * 4
   step.model = model
@@ -256,6 +317,43 @@ def make_train_step(dev, rank = 0, world = 1):
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
+def run_micro(args):
+  """BASELINE config 5: the HBM-bound kernels at a scale where bandwidth, not launch latency, is measured (6000 RoIs, 6000 boxes x 20
+  classes, 5.3 M anchors, fc1-sized SGD) -- ONE JSON line whose `micro` list holds a roofline record per kernel."""
+  sys.path.insert(0, os.path.join(ROOT, "tools"))
+  import microbench
+  t.cuda.set_device(0)
+  rows = microbench.run()
+  peaks = measured_peaks()
+  top = max((r for r in rows if "frac" in r), key = lambda r: r["ms"])
+  line = dict(metric = "config 5 microbench: achieved HBM GB/s per kernel", value = top["achieved_GBs"], unit = "GB/s", n_gpus = 1, steps = 20, warmup = 3, ms_per_step = top["ms"],
+              higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = "f32", data = "synthetic",
+              config = dict(workload = "NMS / RoIPool / RoIAlign / decode / SGD microbench: 6000 proposals x 20 classes, fm 512x37x62 and 1024x38x63", l2 = "160 MB buffer written between timed iterations (L2 flush)"),
+              roofline = dict(bound = "hbm", kernel = top["kernel"] + " " + top["shape"], achieved = top["achieved_GBs"], peak = peaks["hbm_gbs"], unit = "GB/s", frac = top["achieved_GBs"] / peaks["hbm_gbs"],
+                              traffic = None, peak_source = "MEASURED_PEAKS.json" if "MEASURED" in peaks["source"] else peaks["source"]),
+              micro = rows)
+  print(json.dumps(line), flush = True)
+
+
+def gpu_eager_baseline():
+  """The reference's step through eager PyTorch on this GPU (oracle/eager_gpu.py): cuDNN / cuBLAS / ATen / torchvision CUDA ops, fp32
+  (TF32 off -- the CPU path's arithmetic) and with torch's default TF32 convolutions (how the reference would run out of the box)."""
+  from oracle import eager_gpu
+  out = {}
+  for name, tf32, steps in (("fp32", False, 6), ("tf32_convs_torch_default", None, 6)):
+    try:
+      if tf32 is None:
+        times, last = eager_gpu.time_train_steps(IMAGE_HW, steps, 3, tf32 = False, torch_default = True)
+      else:
+        times, last = eager_gpu.time_train_steps(IMAGE_HW, steps, 3, tf32 = tf32)
+      out[name] = dict(value = len(times) / sum(times), unit = "images/s", ms_per_step = 1e3 * sum(times) / len(times), steps = len(times), last_total_loss = last[4])
+    except Exception as e:                                        # noqa: BLE001  (torchvision CUDA ops missing, out of memory ...)
+      out[name] = dict(unavailable = str(e)[:200])
+    t.cuda.empty_cache()
+  out["what"] = "reference train_step restated on eager PyTorch CUDA ops (cuDNN/cuBLAS convs and linears, ATen elementwise, torchvision nms/roi_pool, torch.optim.SGD, host-side sampling)"
+  return out
+
+
 def run_ours(args, rank, local_rank, world):
   import torch.distributed as dist
   import fasterrcnn_b200 as f
@@ -267,12 +365,10 @@ def run_ours(args, rank, local_rank, world):
     dist.init_process_group("nccl", device_id = dev)
 
   # programmatic dependent launch (frcnn_set_pdl): results are bit-identical either way (profiles/r01_pdl_ab.json: same losses over
-  # 35 steps, same detections; 5.68 -> 5.43 ms/step on one GPU).  Default: on for the single-GPU line, where it was measured; off at
-  # N > 1 until its interplay with the overlapped NCCL all-reduce (early-resident CTAs compete with NCCL's for SM slots) has been
-  # measured too.  FRCNN_PDL=0 / 1 overrides.
-  pdl = os.environ.get("FRCNN_PDL", "1" if world == 1 else "0") not in ("", "0")
+  # 35 steps, same detections; 5.68 -> 5.43 ms/step on one GPU).  FRCNN_PDL=0 / 1 overrides.
+  pdl = os.environ.get("FRCNN_PDL", "1" if world == 1 else PDL_DEFAULT_MULTI_GPU) not in ("", "0")
   _lib.set_pdl(pdl)
-  step = make_train_step(dev, rank, world)
+  step = make_train_step(dev, args, rank, world)
 
   def barrier():
     if world > 1:
@@ -304,21 +400,35 @@ def run_ours(args, rank, local_rank, world):
     print("bench: warm-up with programmatic dependent launch failed (%s); measuring with it off" % str(e)[:200], file = sys.stderr)
     pdl = False
     _lib.set_pdl(False)
-    step = make_train_step(dev, rank, world)
+    step = make_train_step(dev, args, rank, world)
     for _ in range(max(args.warmup, 3)):
       step(False)
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
+  # The headline: regions of EXACTLY K steps each (barrier + synchronize on both sides, max over ranks), repeated back to back until
+  # --min-seconds of device time have been spent, so that the reported number is a sustained one (clocks and power settle); `value` is
+  # the MEDIAN region, every region's ms/step is listed.
   _lib.launch_counter["calls"] = 0
-  ms_dev, loss = timed(args.steps, False)                         # the headline: K steps, nothing else in the timed region
+  regions = []
+  ms_dev, loss = timed(args.steps, False)
   launches = _lib.launch_counter["calls"]
+  regions.append(ms_dev)
+  want = int(min(60, max(0, (1e3 * args.min_seconds - ms_dev) / max(ms_dev, 1e-3))))
+  if world > 1:
+    wt = t.tensor([want], device = dev)
+    dist.broadcast(wt, 0)
+    want = int(wt.item())
+  for _ in range(want):
+    regions.append(timed(args.steps, False)[0])
+  ms_dev = statistics.median(regions)
   clocks = sampler.stop() if rank == 0 else None
   rois = step.model.last_step_info.get("num_rois")
   # end-to-end leg: host buffers in, loss out (the loss read-back is part of train_step's return value)
   for _ in range(2):
     step(True)
-  ms_e2e, _ = timed(args.steps, True)
+  e2e_regions = [timed(args.steps, True)[0] for _ in range(max(1, min(5, len(regions))))]
+  ms_e2e = statistics.median(e2e_regions)
   # roofline leg: the same K steps again with a CUDA-event pair around every conv / linear launch (on the launching stream).
   # Kept out of the headline region: two event records per launch cost host time the step is sensitive to.
   ops.kernel_timer.enable(True)
@@ -332,8 +442,9 @@ def run_ours(args, rank, local_rank, world):
     return
   peaks = measured_peaks()
   engine_name = {_lib.ENGINE_TC_3XF16: "f16", _lib.ENGINE_AUTO: "tf32", _lib.ENGINE_TC_3XTF32: "tf32", _lib.ENGINE_SIMT_FP32: "simt"}[ops.get_engine()]
-  value = world * args.steps / (ms_dev / 1e3)
-  e2e_value = world * args.steps / (ms_e2e / 1e3)
+  images = world * args.batch * args.steps
+  value = images / (ms_dev / 1e3)
+  e2e_value = images / (ms_e2e / 1e3)
   h2d = step.h2d_bytes
   d2h = 5 * 4 + 4 + 4 * 2100                                     # losses (5 fp32) + proposal count + class indices for the sampler
   # dominant kernel family = implicit-GEMM convolution / linear
@@ -350,22 +461,30 @@ def run_ours(args, rank, local_rank, world):
                     mma_products_per_mac = 1 if engine_name == "simt" else 3,
                     tensor_pipe_frac = (1 if engine_name == "simt" else 3) * achieved / peaks["tflops"],
                     families = {k: dict(tflops = v["gflop"] / v["ms"], ms_per_step = v["ms"] / args.steps, launches = v["launches"]) for k, v in gemm_stats.items()})
+  default_workload = args.backbone == "vgg16" and args.batch == 1 and args.roi_op == "pool" and args.rois == 128
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
-    times, cores = cpu_port_times(10, 2)                           # ~10-20 s of CPU work on the box's cores
-    cpu = dict(value = len(times) / sum(times), unit = "images/s", cores = cores, kind = "port",
-               sample = "10 timed + 2 warm-up train_steps of the CPU oracle port on the same 600x1000 workload, %d threads" % cores)
-  line = dict(metric = METRIC, value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
+    n_cpu = 10 if default_workload else 4
+    times, cores = cpu_port_times(n_cpu, 2, args)                  # ~10-20 s of CPU work on the box's cores
+    cpu = dict(value = args.batch * len(times) / sum(times), unit = "images/s", cores = cores, kind = "port", cpu = cpu_model(),
+               sample = "%d timed + 2 warm-up train_steps of the CPU oracle port on the same 600x1000 workload, %d threads" % (n_cpu, cores))
+  eager = gpu_eager_baseline() if (world == 1 and default_workload and not args.no_gpu_eager) else None
+  fused = isinstance(step.optimizer, optim.NvlsShardedSGD)
+  line = dict(metric = metric_name(args), value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
               higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = ENGINE_NOTES[engine_name][2], data = "synthetic",
-              config = dict(workload = WORKLOAD, image = "1x3x600x1000", backbone = "vgg16", global_batch = world, rois_per_image = rois,
-                            parallelism = ("dp%d (one process per GPU, fused reduce-scatter + SGD + all-gather kernel over NVLink multimem)" if isinstance(step.optimizer, optim.NvlsShardedSGD)
-                                           else "dp%d (one process per GPU, NCCL gradient all-reduce overlapped with backward)") % world,
+              config = dict(workload = workload_name(args), image = "%dx3x600x1000" % args.batch, backbone = args.backbone, global_batch = world * args.batch, rois_per_image = rois,
+                            parallelism = ("dp%d (one process per GPU; per bucket ONE fused reduce-scatter + SGD + all-gather kernel over NVLink multimem, overlapped with the backward)" if fused
+                                           else "dp%d (one process per GPU, bucketed NCCL gradient all-reduce on the gradient arena, overlapped with the backward)") % world,
+                            dp_buckets = (len(step.optimizer.arena.buckets) if getattr(step.optimizer, "arena", None) is not None else 0),
                             engine = ENGINE_NOTES[engine_name][0],
                             sm_reserve = step.optimizer.sm_reserve,     # SMs the GEMMs leave to NCCL while reductions are in flight (FRCNN_DP_SM_RESERVE)
                             pdl = "on (programmatic dependent launch between the library's kernels; FRCNN_PDL=0 turns it off)" if pdl else "off",
+                            timed_regions = "%d regions of %d steps back to back (%.2f s of device time); value = median region" % (len(regions), args.steps, sum(regions) / 1e3),
                             l2 = "per-step working set (~1.7 GB of weights, activations, gradients) exceeds the 126 MB L2; no explicit flush"),
+              regions = dict(count = len(regions), ms_per_step_min = min(regions) / args.steps, ms_per_step_median = ms_dev / args.steps, ms_per_step_max = max(regions) / args.steps,
+                             first_region_ms_per_step = regions[0] / args.steps),
               e2e = dict(value = e2e_value, unit = "images/s", h2d_bytes_per_step = h2d, d2h_bytes_per_step = d2h, ms_per_step = ms_e2e / args.steps),
-              gpu_launches = launches, clocks = clocks, roofline = roofline, cpu_baseline = cpu,
+              gpu_launches = launches, clocks = clocks, roofline = roofline, cpu_baseline = cpu, gpu_eager_baseline = eager,
               last_loss = dict(total = loss.total, rpn_class = loss.rpn_class, detector_class = loss.detector_class))
   print(json.dumps(line), flush = True)
   if world > 1:
@@ -379,6 +498,13 @@ def main():
   ap.add_argument("--warmup", type = int, default = 5)
   ap.add_argument("--impl", default = "ours", choices = ["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action = "store_true")
+  ap.add_argument("--no-gpu-eager", action = "store_true", help = "skip the eager-PyTorch-on-this-GPU comparator leg")
+  ap.add_argument("--backbone", default = "vgg16", choices = ["vgg16", "resnet50", "resnet101"])
+  ap.add_argument("--batch", type = int, default = 1, help = "images per GPU per step (> 1: train_step_batch, BASELINE config 3)")
+  ap.add_argument("--roi-op", default = "pool", choices = ["pool", "align"])
+  ap.add_argument("--rois", type = int, default = 128, help = "sampled RoIs per image (proposal_batch_size)")
+  ap.add_argument("--min-seconds", type = float, default = 2.0, help = "keep repeating K-step regions until this much device time is spent")
+  ap.add_argument("--micro", action = "store_true", help = "BASELINE config 5: HBM-kernel microbench instead of the train step")
   args = ap.parse_args()
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -388,6 +514,10 @@ def main():
     return
   if not t.cuda.is_available():
     raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU path")
+  if args.micro:
+    if rank == 0:
+      run_micro(args)
+    return
   if world != args.gpus:
     if args.gpus > 1 and world == 1:
       raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ..." % (args.gpus, args.gpus))

@@ -70,6 +70,9 @@ _SIGNATURES = {
   "frcnn_gather_filtered": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
   "frcnn_nms_workspace_bytes": (_sz, [_i]),
   "frcnn_nms_sorted_f32": (_i, [_vp, _vp, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
+  "frcnn_iou_matrix_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+  "frcnn_decode_boxes_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+  "frcnn_nms_sorted_f64": (_i, [_vp, _vp, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
   "frcnn_nms_batched_workspace_bytes": (_sz, [_i, _i, _i]),
   "frcnn_nms_batched_f32": (_i, [_vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
   "frcnn_gather_rows_f32": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp]),

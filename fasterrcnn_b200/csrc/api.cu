@@ -9,6 +9,19 @@ thread_local char g_last_error[512] = "";
 std::atomic<int> g_pdl{-1};
 std::atomic<int> g_sm_reserve{0};
 
+int device_sm_count()
+{
+  static std::atomic<int> cached{0};
+  int v = cached.load(std::memory_order_relaxed);
+  if (v <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    v = n > kNumSMs ? kNumSMs : n;
+    cached.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 bool pdl_enabled()
 {
   int v = g_pdl.load(std::memory_order_relaxed);

@@ -58,10 +58,15 @@ bool pdl_enabled();
 // SMs the persistent (one CTA per SM) GEMM launches may occupy: kNumSMs minus the ones the caller set aside for a concurrent
 // collective's CTAs (frcnn_set_sm_reserve; api.cu).  A persistent grid that finds some SMs taken runs a second, nearly empty wave.
 extern std::atomic<int> g_sm_reserve;
+// SMs of the current device (cudaDevAttrMultiProcessorCount, looked up once per process: one process drives one GPU), capped at the
+// kNumSMs the workspace layouts are sized for.  A part with fewer SMs (or an MPS / green-context partition reporting fewer) gets
+// persistent grids that still fit in one wave; kNumSMs remains the layout constant (grid_max).
+int device_sm_count();
 inline int sm_budget()
 {
-  int n = kNumSMs - g_sm_reserve.load(std::memory_order_relaxed);
-  return n < 16 ? 16 : (n > kNumSMs ? kNumSMs : n);
+  const int sms = device_sm_count();
+  int n = sms - g_sm_reserve.load(std::memory_order_relaxed);
+  return n < 16 ? (sms < 16 ? sms : 16) : (n > kNumSMs ? kNumSMs : n);
 }
 
 // the one way kernels are launched: <<<>>> semantics, plus the programmatic-serialization attribute when PDL is on

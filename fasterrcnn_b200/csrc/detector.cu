@@ -52,6 +52,42 @@ __global__ void label_proposals_kernel(const float *__restrict__ proposals, int 
   }
 }
 
+// ---- models/math_utils.py:39-63 (t_intersection_over_union) and :99-128 (t_convert_deltas_to_boxes) as standalone operators --------
+// The hot path has both fused into larger kernels (label_proposals above, rpn_decode); these are the helpers under the reference's names.
+__global__ void iou_matrix_kernel(const float *__restrict__ boxes1, int n, const float *__restrict__ boxes2, int m, float *__restrict__ out)
+{
+  pdl_enter();
+  const size_t total = (size_t)n * m;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / m), j = (int)(idx - (size_t)i * m);
+    const float4 p = __ldg(reinterpret_cast<const float4 *>(boxes1) + i);
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(boxes2) + j);
+    const float t0 = fmaxf(p.x, g.x), t1 = fmaxf(p.y, g.y), t2 = fminf(p.z, g.z), t3 = fminf(p.w, g.w);
+    const float inter = (t0 < t2 && t1 < t3) ? __fmul_rn(__fsub_rn(t2, t0), __fsub_rn(t3, t1)) : 0.f;       // strict well-ordered mask
+    const float area_p = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
+    const float area_g = __fmul_rn(__fsub_rn(g.z, g.x), __fsub_rn(g.w, g.y));
+    out[idx] = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(area_p, area_g), inter), 1e-7f));             // eps in the denominator
+  }
+}
+
+struct Vec4f { float v[4]; };
+
+__global__ void decode_boxes_kernel(const float *__restrict__ deltas, const float *__restrict__ anchors, int n, Vec4f means, Vec4f stds, float *__restrict__ boxes)
+{
+  pdl_enter();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4 *>(deltas) + i);
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(anchors) + i);                                   // (cy, cx, h, w)
+    // d = d * stds + means; c = a_hw * d_yx + a_yx; s = a_hw * exp(d_hw); box = c -/+ 0.5 s -- separate roundings, exp correctly rounded
+    const float dy = __fadd_rn(__fmul_rn(d0.x, stds.v[0]), means.v[0]), dx = __fadd_rn(__fmul_rn(d0.y, stds.v[1]), means.v[1]);
+    const float dh = __fadd_rn(__fmul_rn(d0.z, stds.v[2]), means.v[2]), dw = __fadd_rn(__fmul_rn(d0.w, stds.v[3]), means.v[3]);
+    const float cy = __fadd_rn(__fmul_rn(a.z, dy), a.x), cx = __fadd_rn(__fmul_rn(a.w, dx), a.y);
+    const float sh = __fmul_rn(a.z, __double2float_rn(exp((double)dh))), sw = __fmul_rn(a.w, __double2float_rn(exp((double)dw)));
+    reinterpret_cast<float4 *>(boxes)[i] = make_float4(__fsub_rn(cy, __fmul_rn(0.5f, sh)), __fsub_rn(cx, __fmul_rn(0.5f, sw)),
+                                                       __fadd_rn(cy, __fmul_rn(0.5f, sh)), __fadd_rn(cx, __fmul_rn(0.5f, sw)));
+  }
+}
+
 // ---- block reduction helper (double, fixed tree order -> deterministic) -------------------------
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double *scratch)
@@ -360,6 +396,24 @@ int frcnn_detector_losses(const float *probs, const float *deltas, const float *
   FRCNN_REQUIRE(probs && deltas && y_classes && y_deltas && losses_out && n > 0 && C > 1, "detector_losses: bad argument");
   launch(detector_losses_kernel, 1, 1024, 0, as_stream(stream), probs, deltas, y_classes, y_deltas, n, C, losses_out, d_probs, d_deltas);
   FRCNN_CHECK_LAUNCH("detector_losses_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_iou_matrix_f32(const float *boxes1, int n, const float *boxes2, int m, float *out, void *stream)
+{
+  FRCNN_REQUIRE(boxes1 && boxes2 && out && n > 0 && m > 0, "iou_matrix_f32: bad argument");
+  launch(iou_matrix_kernel, elementwise_grid((size_t)n * m, 256, 4), 256, 0, as_stream(stream), boxes1, n, boxes2, m, out);
+  FRCNN_CHECK_LAUNCH("iou_matrix_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_decode_boxes_f32(const float *deltas, const float *anchors, int n, const float *means4, const float *stds4, float *boxes, void *stream)
+{
+  FRCNN_REQUIRE(deltas && anchors && boxes && means4 && stds4 && n > 0, "decode_boxes_f32: bad argument");
+  Vec4f mu, sd;
+  for (int k = 0; k < 4; k++) { mu.v[k] = means4[k]; sd.v[k] = stds4[k]; }                                   // host arrays (4 floats each)
+  launch(decode_boxes_kernel, elementwise_grid((size_t)n, 256, 4), 256, 0, as_stream(stream), deltas, anchors, n, mu, sd, boxes);
+  FRCNN_CHECK_LAUNCH("decode_boxes_kernel");
   return FRCNN_OK;
 }
 

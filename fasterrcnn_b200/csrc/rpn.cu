@@ -257,6 +257,46 @@ nms_mask_kernel(const float *__restrict__ boxes, const int32_t *__restrict__ cou
   }
 }
 
+// fp64 twin of nms_mask_kernel for the per-class call site (models/faster_rcnn.py:216-220: float64 boxes, torchvision's kernel
+// instantiated for double): same tiles, every operation an explicit IEEE double operation, exact division, strict compare.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel_f64(const double *__restrict__ boxes, const int32_t *__restrict__ count, int capacity, double thr, unsigned long long *__restrict__ mask, int col_blocks)
+{
+  pdl_enter();
+  int n = *count;
+  if (n > capacity) n = capacity;
+  const int row_b = blockIdx.y, col_b = blockIdx.x;
+  if (col_b < row_b) return;
+  if (row_b * 64 >= n || col_b * 64 >= n) return;
+  __shared__ double cb[64][4];
+  __shared__ double ca[64];
+  const int t = threadIdx.x;
+  {
+    const int j = col_b * 64 + t;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    if (j < n) { b0 = boxes[(size_t)j * 4]; b1 = boxes[(size_t)j * 4 + 1]; b2 = boxes[(size_t)j * 4 + 2]; b3 = boxes[(size_t)j * 4 + 3]; }
+    cb[t][0] = b0; cb[t][1] = b1; cb[t][2] = b2; cb[t][3] = b3;
+    ca[t] = __dmul_rn(__dsub_rn(b2, b0), __dsub_rn(b3, b1));
+  }
+  __syncthreads();
+  const int i = row_b * 64 + t;
+  if (i < n) {
+    const double a0 = boxes[(size_t)i * 4], a1 = boxes[(size_t)i * 4 + 1], a2 = boxes[(size_t)i * 4 + 2], a3 = boxes[(size_t)i * 4 + 3];
+    const double area = __dmul_rn(__dsub_rn(a2, a0), __dsub_rn(a3, a1));
+    const int cols = n - col_b * 64 < 64 ? n - col_b * 64 : 64;
+    const int start = (row_b == col_b) ? t + 1 : 0;
+    unsigned long long bits = 0;
+    for (int q = start; q < cols; q++) {
+      const double w = fmax(0.0, __dsub_rn(fmin(a2, cb[q][2]), fmax(a0, cb[q][0])));
+      const double h = fmax(0.0, __dsub_rn(fmin(a3, cb[q][3]), fmax(a1, cb[q][1])));
+      const double inter = __dmul_rn(w, h);
+      const double ovr = __ddiv_rn(inter, __dsub_rn(__dadd_rn(area, ca[q]), inter));
+      if (ovr > thr) bits |= 1ull << q;                        // NaN (0/0) -> false, as in the reference op
+    }
+    mask[(size_t)i * col_blocks + col_b] = bits;
+  }
+}
+
 // Stage 2: the greedy scan, one CTA, software-pipelined over the 64-box blocks so that no global-memory round trip sits on
 // the serial chain.  Block c may be resolved once its "removed" word holds the rows of every box kept in blocks < c:
 //   * kept boxes of blocks < c-2: a column gather (one 8-byte load per kept box) ISSUED at iteration c-2 into registers and
@@ -587,6 +627,28 @@ int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity,
   const int keep_cap = max_keep < capacity ? max_keep : capacity;
   size_t smem = (size_t)keep_cap * sizeof(int32_t);
   FRCNN_REQUIRE(smem <= 200 * 1024, "nms_sorted_f32: max_keep too large for the scan's kept list");
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");
+  }
+  launch(nms_scan_kernel, 1, kScanThreads, smem, st, mask, count, 0, capacity, col_blocks, keep_cap, keep_out, 0, kept_count_out);
+  FRCNN_CHECK_LAUNCH("nms_scan_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_nms_sorted_f64(const double *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
+                         int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+  FRCNN_REQUIRE(boxes && count && keep_out && kept_count_out && capacity > 0 && max_keep > 0, "nms_sorted_f64: bad argument");
+  if (workspace == nullptr || workspace_bytes < frcnn_nms_workspace_bytes(capacity)) return fail(FRCNN_E_WORKSPACE, "nms_sorted_f64: workspace too small");
+  const int col_blocks = ceil_div(capacity, 64);
+  cudaStream_t st = as_stream(stream);
+  unsigned long long *mask = reinterpret_cast<unsigned long long *>(workspace);
+  launch(nms_mask_kernel_f64, dim3(col_blocks, col_blocks), 64, 0, st, boxes, count, capacity, iou_threshold, mask, col_blocks);
+  FRCNN_CHECK_LAUNCH("nms_mask_kernel_f64");
+  const int keep_cap = max_keep < capacity ? max_keep : capacity;
+  size_t smem = (size_t)keep_cap * sizeof(int32_t);
+  FRCNN_REQUIRE(smem <= 200 * 1024, "nms_sorted_f64: max_keep too large for the scan's kept list");
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "nms_scan_kernel: smem attribute");

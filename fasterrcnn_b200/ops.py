@@ -228,6 +228,70 @@ def weight_split_buffer(param):
   return e
 
 
+def invalidate_weight_splits(param = None):
+  """Drops the carried operand split of `param` (or of every parameter): the next GEMM that reads it re-splits from the fp32 values.
+  REQUIRED after any write to a parameter that bypasses torch's version counter -- ``p.data.copy_()`` / ``.data.normal_()``,
+  ``dist.broadcast(p.data)``, a raw-pointer kernel -- because the carried split is validated by address + ``_version`` only; in-place
+  ops on the parameter itself (``p.copy_()``, ``load_state_dict``) bump the version and need nothing.  state.load, the sharded
+  data-parallel optimizer and FusedSGD.load_state_dict call it."""
+  if param is None:
+    _weight_splits.clear()
+    return
+  for k in [k for k, v in _weight_splits.items() if v["ref"]() is param or v["ref"]() is None]:
+    del _weight_splits[k]
+
+
+# Gradient destinations (data parallel): the optimizer wrapper lays the weight gradients out in one flat arena, in the order backward
+# produces them, and registers each parameter's slot here; the filter-gradient kernels then write straight into the arena, so a bucket of
+# consecutive tensors is reduced in place (NCCL all-reduce or the fused NVLink kernel) with no gather / scatter copies.
+_grad_dest = {}                # id(param) -> (weakref(param), arena (flat fp32), offset in elements)
+
+
+def register_grad_destination(param, arena, offset):
+  assert arena.dtype == t.float32 and arena.dim() == 1 and offset % 4 == 0 and offset + param.numel() <= arena.numel()
+  _grad_dest[id(param)] = (weakref.ref(param), arena, int(offset))
+
+
+def clear_grad_destinations(params = None):
+  if params is None:
+    _grad_dest.clear()
+  else:
+    for q in params:
+      _grad_dest.pop(id(q), None)
+
+
+def grad_destination(param):
+  """The registered arena view for `param` with the given parameter's own shape / strides, or None."""
+  e = _grad_dest.get(id(param))
+  if e is None or e[0]() is not param:
+    return None
+  return e[1][e[2]:e[2] + param.numel()].as_strided(param.shape, param.stride())
+
+
+def _new_grad(key, shape, device, channels_last = False):
+  """Storage for a weight gradient in the layout the kernels write (row-major, or OHWI for k x k filters): a FRESH view of the
+  registered arena slot (fresh, so that autograd's AccumulateGrad still sees a uniquely referenced tensor and adopts it without a copy)
+  or a new tensor."""
+  shape = tuple(shape)
+  if channels_last:
+    o, i, kh, kw = shape
+    stride = (kh * kw * i, 1, kw * i, i)
+  else:
+    stride, acc = [], 1
+    for d in reversed(shape):
+      stride.append(acc); acc *= d
+    stride = tuple(reversed(stride))
+  e = _grad_dest.get(key) if key is not None else None
+  if e is not None:
+    q = e[0]()
+    numel = 1
+    for d in shape:
+      numel *= d
+    if q is not None and q.numel() == numel and e[1].device == device:
+      return e[1][e[2]:e[2] + numel].as_strided(shape, stride)
+  return t.empty_strided(shape, stride, dtype = t.float32, device = device)
+
+
 def tf32_split(x, cache = True):
   """Returns the [hi | lo] split buffer of x (frcnn_tf32_split), computing it at most once per tensor version."""
   e = _weight_splits.get((x.data_ptr(), x.numel()))
@@ -349,12 +413,10 @@ def conv2d_dgrad_raw(dy, w, x_shape, stride, pad, addend = None, reuse_dy = Fals
   return dx
 
 
-def conv2d_wgrad_raw(dy, x, w_shape, stride, pad, dy_split = None):
+def conv2d_wgrad_raw(dy, x, w_shape, stride, pad, dy_split = None, w_key = None):
   n, cin, h, wd = x.shape
   cout, _, kh, kw = w_shape
-  dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = x.device, memory_format = t.channels_last)
-  if kh == 1 and kw == 1:
-    dw = t.empty((cout, cin, 1, 1), dtype = t.float32, device = x.device)
+  dw = _new_grad(w_key, (cout, cin, kh, kw), x.device, channels_last = not (kh == 1 and kw == 1))
   geom = (n, h, wd, cin, cout, kh, kw, stride, pad)
   ds = xs = None
   if _uses_tc(2, geom):
@@ -444,7 +506,7 @@ def _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, act, rows, c):
   return bool(lib().frcnn_act_bwd_fused_supported(rows, c))
 
 
-def _conv_bwd_fused(dy, y, act, pool, xp, wp, geom, w_shape, want_dx, want_bias):
+def _conv_bwd_fused(dy, y, act, pool, xp, wp, geom, w_shape, want_dx, want_bias, w_key = None):
   """-> (dx, dw, db) of one conv / linear layer through frcnn_conv2d_bwd_f16.  dy / y / xp are NHWC-physical maps or (rows, C) matrices."""
   L = lib()
   dev = y.device
@@ -456,10 +518,10 @@ def _conv_bwd_fused(dy, y, act, pool, xp, wp, geom, w_shape, want_dx, want_bias)
   if y.dim() == 4:
     dx = _empty_nhwc(*xp.shape, dev) if want_dx else None
     cout, cin, kh, kw = w_shape
-    dw = t.empty((cout, cin, kh, kw), dtype = t.float32, device = dev) if (kh == 1 and kw == 1) else t.empty((cout, cin, kh, kw), dtype = t.float32, device = dev, memory_format = t.channels_last)
+    dw = _new_grad(w_key, (cout, cin, kh, kw), dev, channels_last = not (kh == 1 and kw == 1))
   else:
     dx = t.empty(tuple(xp.shape), dtype = t.float32, device = dev) if want_dx else None
-    dw = t.empty(tuple(w_shape), dtype = t.float32, device = dev)
+    dw = _new_grad(w_key, tuple(w_shape), dev)
   h = _amax_hint(dy)
   dx_amax = _amax_buffer(1, geom, dev) if want_dx else None
   w_split = tf32_split(wp)
@@ -495,6 +557,7 @@ class _ConvAct(t.autograd.Function):
     ctx.stride, ctx.pad, ctx.act, ctx.pool = stride, pad, act, pool
     ctx.has_bias = b is not None
     ctx.w_shape = tuple(w.shape)
+    ctx.w_key = id(w)                                                       # the parameter object: its gradient may have a registered destination
     if pool:
       assert act == ACT_RELU, "fused pooling is defined for the ReLU convs of VGG-16"
       n, c, h, wd = y.shape
@@ -519,7 +582,7 @@ class _ConvAct(t.autograd.Function):
     want_bias = ctx.has_bias and ctx.needs_input_grad[2]
     act = ctx.act
     if _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, act, y.numel() // c, c):
-      return _conv_bwd_fused(dy, y, act, ctx.pool, xp, wp, geom, ctx.w_shape, want_dx, want_bias) + (None, None, None, None)
+      return _conv_bwd_fused(dy, y, act, ctx.pool, xp, wp, geom, ctx.w_shape, want_dx, want_bias, ctx.w_key) + (None, None, None, None)
     if ctx.pool:
       dz = t.empty_like(y)
       check(lib().frcnn_maxpool2x2_relu_bwd(ptr(dy), ptr(y), ptr(dz), n, h, wd, c, stream()), "frcnn_maxpool2x2_relu_bwd")
@@ -531,13 +594,14 @@ class _ConvAct(t.autograd.Function):
     if want_dx:
       dx = conv2d_dgrad_raw(dz, wp, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = want_dw, dy_split = dz_split if tc_dx else None)
     if want_dw:
-      dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad, dy_split = dz_split if tc_dw else None)
+      dw = conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad, dy_split = dz_split if tc_dw else None, w_key = ctx.w_key)
     return dx, dw, db, None, None, None, None
 
 
 class _NoGradCtx:
   """Stand-in for the autograd context when nothing upstream needs a gradient (frozen VGG-16 blocks 1-2, inference)."""
   needs_input_grad = (False,) * 8
+  w_key = None
 
   def save_for_backward(self, *tensors):
     pass
@@ -562,6 +626,7 @@ class _LinearAct(t.autograd.Function):
     y = t.empty((m, nout), dtype = t.float32, device = x.device)
     ctx.act = act
     ctx.has_bias = b is not None
+    ctx.w_key = id(w)
     if m > 0:
       geom = (m, 1, 1, k, nout, 1, 1, 1, 0)
       xs = ws_ = None
@@ -587,7 +652,7 @@ class _LinearAct(t.autograd.Function):
     want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     tc_dx, tc_dw = want_dx and _uses_tc(1, geom), want_dw and _uses_tc(2, geom)
     if _fused_bwd_ok(geom, want_dx, want_dw, tc_dx, tc_dw, ctx.act, m, nout):
-      return _conv_bwd_fused(dy, y, ctx.act, False, x2, w2, geom, tuple(w2.shape), want_dx, ctx.has_bias and ctx.needs_input_grad[2]) + (None,)
+      return _conv_bwd_fused(dy, y, ctx.act, False, x2, w2, geom, tuple(w2.shape), want_dx, ctx.has_bias and ctx.needs_input_grad[2], ctx.w_key) + (None,)
     need_fp32 = (want_dx and not tc_dx) or (want_dw and not tc_dw)
     dz, dz_split, db = _act_bwd(dy, y, ctx.act, nout, tc_dx or tc_dw, ctx.has_bias and ctx.needs_input_grad[2], need_fp32)
     dx = dw = None
@@ -601,7 +666,7 @@ class _LinearAct(t.autograd.Function):
       _gemm(1, dz, w2, dx, geom, "linear_dgrad", 2e-9 * m * k * nout, ds, ws_, amax_out = amax)
       _set_amax_hint(dx, amax)
     if want_dw:
-      dw = t.empty((nout, k), dtype = t.float32, device = x2.device)
+      dw = _new_grad(ctx.w_key, (nout, k), x2.device)
       ds = xs = None
       if tc_dw:
         kd, kx = (dz.data_ptr(), dz.numel(), dz._version), (x2.data_ptr(), x2.numel(), x2._version)
@@ -637,6 +702,7 @@ class _TwoHeads(t.autograd.Function):
                               ptr(w2.detach()), ptr(b2.detach()) if b2 is not None else None, n2, act2, ptr(y1), ptr(y2), ws, ws_n, stream()), "frcnn_heads_fwd")
       _lib.count(2)
     ctx.acts = (act1, act2)
+    ctx.w_keys = (id(w1), id(w2))
     ctx.has_bias = (b1 is not None, b2 is not None)
     ctx.x_is_map = x.dim() == 4
     ctx.save_for_backward(xp, w1.detach(), w2.detach(), y1, y2)
@@ -649,8 +715,8 @@ class _TwoHeads(t.autograd.Function):
     m = xp.numel() // k
     n1, n2 = w1.shape[0], w2.shape[0]
     dev = xp.device
-    dw1 = t.empty_strided(w1.shape, w1.stride(), dtype = t.float32, device = dev)
-    dw2 = t.empty_strided(w2.shape, w2.stride(), dtype = t.float32, device = dev)
+    dw1 = _new_grad(ctx.w_keys[0], w1.shape, dev) if w1.is_contiguous() else t.empty_strided(w1.shape, w1.stride(), dtype = t.float32, device = dev)
+    dw2 = _new_grad(ctx.w_keys[1], w2.shape, dev) if w2.is_contiguous() else t.empty_strided(w2.shape, w2.stride(), dtype = t.float32, device = dev)
     db1 = t.empty((n1,), dtype = t.float32, device = dev) if ctx.has_bias[0] else None
     db2 = t.empty((n2,), dtype = t.float32, device = dev) if ctx.has_bias[1] else None
     dx = None
@@ -841,13 +907,15 @@ def detector_losses(probs, deltas, y_classes, y_deltas):
 # ------------------------------------------------------------------------------------------------
 
 def nms(boxes, scores, iou_threshold):
-  """torchvision.ops.nms replacement for fp32 boxes (models/rpn.py:147-151): returns int64 indices
-  of the kept boxes in descending score order (ties: lower index first)."""
+  """torchvision.ops.nms replacement (models/rpn.py:147-151: fp32 boxes; models/faster_rcnn.py:216-220: float64 boxes with float32
+  scores -- IoU then runs in IEEE double, frcnn_nms_sorted_f64): returns int64 indices of the kept boxes in descending score order
+  (ties: lower index first)."""
   _require_cuda(boxes, scores)
   n = boxes.shape[0]
   if n == 0:
     return t.empty((0,), dtype = t.int64, device = boxes.device)
-  b = boxes.detach().contiguous().float()
+  f64 = boxes.dtype == t.float64
+  b = boxes.detach().contiguous() if f64 else boxes.detach().contiguous().float()
   s = scores.detach().contiguous().float()
   dev = b.device
   # stable descending order == rank counting with ties -> LOWER index first: negate the tie rule
@@ -858,12 +926,14 @@ def nms(boxes, scores, iou_threshold):
   check(lib().frcnn_topk_order(ptr(rev), None, n, n, ptr(order), ptr(cnt), stream()), "frcnn_topk_order")
   _lib.count(3)
   order = (n - 1) - order                                        # back to original indices
-  sorted_boxes = t.empty((n, 4), dtype = t.float32, device = dev)
-  check(lib().frcnn_gather_rows_f32(ptr(b), 4, ptr(order.contiguous()), ptr(cnt), n, ptr(sorted_boxes), stream()), "frcnn_gather_rows_f32")
+  sorted_boxes = t.empty((n, 4), dtype = b.dtype, device = dev)
+  # (a float64 row is gathered as eight 32-bit words)
+  check(lib().frcnn_gather_rows_f32(ptr(b), 8 if f64 else 4, ptr(order.contiguous()), ptr(cnt), n, ptr(sorted_boxes), stream()), "frcnn_gather_rows_f32")
   keep = t.empty((n,), dtype = t.int32, device = dev)
   kept = t.empty((1,), dtype = t.int32, device = dev)
   ws, ws_n = workspace(lib().frcnn_nms_workspace_bytes(n), slot = 2)
-  check(lib().frcnn_nms_sorted_f32(ptr(sorted_boxes), ptr(cnt), n, float(iou_threshold), n, ptr(keep), ptr(kept), ws, ws_n, stream()), "frcnn_nms_sorted_f32")
+  entry = lib().frcnn_nms_sorted_f64 if f64 else lib().frcnn_nms_sorted_f32
+  check(entry(ptr(sorted_boxes), ptr(cnt), n, float(iou_threshold), n, ptr(keep), ptr(kept), ws, ws_n, stream()), "frcnn_nms_sorted_f64" if f64 else "frcnn_nms_sorted_f32")
   _lib.count(3)
   k = int(kept.item())
   return order[keep[:k].long()].long()

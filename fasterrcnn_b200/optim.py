@@ -86,11 +86,155 @@ class FusedSGD(t.optim.Optimizer):
       self._eager_done.clear()
 
 
-class DataParallel:
-  """Optimizer wrapper: overlapped gradient all-reduce + (optionally fused) update.  Quacks like the
-  optimizer ``FasterRCNNModel.train_step`` expects (zero_grad / step / param_groups)."""
+def backward_order(named_params):
+  """Optimizer tensors in the order train_step's backward produces their gradients (faster_rcnn.py: the RPN branch is back-propagated
+  first, then the detector head, then the shared backbone -- each in reverse layer order).  Only overlap depends on this being right:
+  buckets are launched strictly in order on every rank whatever order the hooks fire in."""
+  groups = {"_stage2": [], "_stage3": [], "_stage1": []}
+  other = []
+  for name, p in named_params:
+    for prefix, lst in groups.items():
+      if name.startswith(prefix):
+        lst.append(p)
+        break
+    else:
+      other.append(p)
+  return list(reversed(groups["_stage2"])) + list(reversed(groups["_stage3"])) + list(reversed(groups["_stage1"])) + list(reversed(other))
 
-  def __init__(self, optimizer, process_group = None, sm_reserve = None):
+
+class GradArena:
+  """One flat fp32 buffer holding the weight gradients of the optimizer's tensors back to back, in backward order, cut into a few
+  buckets of consecutive tensors.  The filter-gradient kernels write straight into it (ops.register_grad_destination), so a bucket is
+  one contiguous range: reduced in place by ONE collective, read in place by the optimizer kernel -- no flatten / unflatten copies.
+  Every tensor starts on a 128-byte boundary; every bucket on a (128 x world)-byte one, so that bucket / world is a whole number of
+  float4s (the fused kernel's shards)."""
+
+  def __init__(self, params, world, bucket_bytes = 48 << 20, last_bucket_bytes = 8 << 20, allocate = None):
+    self.params = list(params)
+    assert self.params and all(p.dtype == t.float32 for p in self.params)
+    self.world = int(world)
+    align_t, align_b = 32, 32 * self.world
+    # greedy buckets: close one as soon as it holds >= bucket_bytes; then carve a small final bucket off the tail (the last collective
+    # cannot overlap anything: backward ends with it)
+    cuts, acc = [], 0
+    for i, p in enumerate(self.params):
+      acc += p.numel() * 4
+      if acc >= bucket_bytes:
+        cuts.append(i + 1); acc = 0
+    if not cuts or cuts[-1] != len(self.params):
+      cuts.append(len(self.params))
+    start = cuts[-2] if len(cuts) > 1 else 0
+    if sum(p.numel() * 4 for p in self.params[start:]) > last_bucket_bytes:
+      tail, j = 0, len(self.params)
+      while j > start + 1 and tail + self.params[j - 1].numel() * 4 <= last_bucket_bytes:
+        j -= 1; tail += self.params[j].numel() * 4
+      if start < j < len(self.params):
+        cuts.insert(len(cuts) - 1, j)
+    self.offsets, self.buckets = [], []                      # element offset per tensor | (first tensor, end tensor, begin elem, end elem)
+    at, first = 0, 0
+    for end in cuts:
+      begin = at
+      for p in self.params[first:end]:
+        self.offsets.append(at)
+        at += (p.numel() + align_t - 1) // align_t * align_t
+      at = (at + align_b - 1) // align_b * align_b
+      self.buckets.append((first, end, begin, at))
+      first = end
+    self.total = at
+    self.payload_bytes = [sum(p.numel() * 4 for p in self.params[f0:f1]) for f0, f1, _, _ in self.buckets]   # without the alignment padding
+    self.bucket_of = {}
+    for b, (f0, f1, _, _) in enumerate(self.buckets):
+      for i in range(f0, f1):
+        self.bucket_of[id(self.params[i])] = b
+    dev = self.params[0].device
+    self.flat = (allocate or (lambda n: t.zeros((n,), dtype = t.float32, device = dev)))(self.total)
+    self.index = {id(p): i for i, p in enumerate(self.params)}
+
+  def register(self):
+    from . import ops
+    for p, off in zip(self.params, self.offsets):
+      ops.register_grad_destination(p, self.flat, off)
+
+  def unregister(self):
+    from . import ops
+    ops.clear_grad_destinations(self.params)
+
+  def view(self, p, buf = None):
+    off = self.offsets[self.index[id(p)]]
+    return (self.flat if buf is None else buf)[off:off + p.numel()].as_strided(p.shape, p.stride())
+
+  def adopt(self, p):
+    """Makes p.grad the arena view (copying only if the producing kernel did not write there already)."""
+    v = self.view(p)
+    if p.grad.data_ptr() != v.data_ptr() or p.grad.stride() != v.stride():
+      v.copy_(p.grad)
+      p.grad = v
+    return v
+
+
+class _BucketedHooks:
+  """Shared machinery of the two data-parallel optimizers: post-accumulate hooks count a bucket's tensors; a bucket is handed to
+  ``_launch_bucket`` as soon as it AND every earlier bucket is complete (same launch order on every rank, whatever fires when);
+  ``_flush`` at step() zero-fills the tensors that received no gradient on this rank and launches what is left."""
+
+  def _init_hooks(self, arena):
+    self.arena = arena
+    self._fired = [0] * len(arena.buckets)
+    self._seen = set()
+    self._next = 0
+    self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad_ready) for p in arena.params if p.requires_grad]
+    self.hook_order = []                                   # (debug) firing order of the last step, as arena indices
+
+  @t.no_grad()
+  def _on_grad_ready(self, p):
+    if id(p) in self._seen:
+      return
+    self.arena.adopt(p)
+    self._seen.add(id(p))
+    self.hook_order.append(self.arena.index[id(p)])
+    b = self.arena.bucket_of[id(p)]
+    self._fired[b] += 1
+    while self._next < len(self.arena.buckets) and self._fired[self._next] == self.arena.buckets[self._next][1] - self.arena.buckets[self._next][0]:
+      self._launch_bucket(self._next)
+      self._next += 1
+
+  @t.no_grad()
+  def _flush(self):
+    for p in self.arena.params:
+      if id(p) not in self._seen:
+        v = self.arena.view(p)
+        v.zero_()                                          # no gradient on this rank this step (e.g. an empty RoI sample): contribute zeros
+        p.grad = v
+    while self._next < len(self.arena.buckets):
+      self._launch_bucket(self._next)
+      self._next += 1
+
+  def _reset_step(self):
+    self._fired = [0] * len(self.arena.buckets)
+    self._seen = set()
+    self._next = 0
+    self.hook_order = []
+
+  def remove_hooks(self):
+    for h in self._hooks:
+      h.remove()
+    self._hooks = []
+    self.arena.unregister()
+
+
+class DataParallel(_BucketedHooks):
+  """Optimizer wrapper for one-process-per-GPU data parallelism: bucketed, overlapped gradient all-reduce + update.
+  Quacks like the optimizer ``FasterRCNNModel.train_step`` expects (zero_grad / step / param_groups).
+
+  The weight gradients live in a GradArena (written there directly by the filter-gradient kernels); each bucket -- VGG-16: {RPN, heads,
+  fc2} 78 MB | fc1 411 MB | blocks 5-4 52 MB | block 3 6 MB -- is all-reduced in place (NCCL over NVLink, sum, fp32) the moment its last
+  gradient exists, on NCCL's own stream, so fc1's reduction overlaps the convolution backward; ``step()`` waits for the handles and the
+  fused SGD applies 1 / world.  Every rank reduces every bucket every step, in the same order (a tensor without a gradient on this
+  rank contributes zeros -- the semantics of torch's DistributedDataParallel).  While reductions are in flight the persistent tcgen05
+  GEMMs leave ``sm_reserve`` SMs to NCCL's CTAs (frcnn_set_sm_reserve; FRCNN_DP_SM_RESERVE): a one-CTA-per-SM grid that finds SMs
+  taken would run a second, nearly empty wave.  With world_size 1 (or no process group) it is a transparent wrapper."""
+
+  def __init__(self, optimizer, process_group = None, sm_reserve = None, named_params = None, bucket_bytes = None):
     self.optimizer = optimizer
     self.group = process_group
     self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -101,11 +245,22 @@ class DataParallel:
     self._handles = []
     self._hooks = []
     self.bytes_reduced_last_step = 0
+    self.arena = None
     if self.world_size > 1:
-      for group in optimizer.param_groups:
-        for p in group["params"]:
-          if p.requires_grad:
-            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+      owned = [p for group in optimizer.param_groups for p in group["params"] if p.requires_grad]
+      if named_params is not None:
+        ids = {id(p) for p in owned}
+        ordered = [p for p in backward_order(named_params) if id(p) in ids]
+        owned = ordered + [p for p in owned if id(p) not in {id(q) for q in ordered}]
+      else:
+        owned = list(reversed(owned))
+      if bucket_bytes is None:
+        bucket_bytes = int(os.environ.get("FRCNN_DP_BUCKET_MB", "48")) << 20
+      cuda = all(p.is_cuda for p in owned)
+      arena = GradArena(owned, self.world_size, bucket_bytes = bucket_bytes)
+      if cuda:
+        arena.register()                                     # CUDA parameters: the wgrad kernels write into the arena
+      self._init_hooks(arena)
     if isinstance(optimizer, FusedSGD):
       optimizer.grad_scale = 1.0 / self.world_size
 
@@ -113,53 +268,58 @@ class DataParallel:
   def param_groups(self):
     return self.optimizer.param_groups
 
-  def _on_grad_ready(self, p):
+  def _launch_bucket(self, b):
     if self.sm_reserve > 0 and not self._reserved:
       from . import _lib
       _lib.set_sm_reserve(self.sm_reserve)                      # GEMMs launched from here on leave room for NCCL's CTAs
       self._reserved = True
-    # the gradient was produced on the current (compute) stream; NCCL orders itself after it
-    self._handles.append((p, dist.all_reduce(p.grad, op = dist.ReduceOp.SUM, group = self.group, async_op = True)))
+    _, _, begin, end = self.arena.buckets[b]
+    # the gradients were produced on the current (compute) stream; NCCL orders itself after it
+    self._handles.append((self.arena.payload_bytes[b], dist.all_reduce(self.arena.flat[begin:end], op = dist.ReduceOp.SUM, group = self.group, async_op = True)))
 
   def zero_grad(self, set_to_none = True):
     self._handles = []
-    self.optimizer.zero_grad(set_to_none = set_to_none)
+    if self.arena is not None:
+      self._reset_step()
+    self.optimizer.zero_grad(set_to_none = True if self.arena is not None else set_to_none)
 
   def step(self):
     nbytes = 0
-    for p, h in self._handles:
+    if self.arena is not None:
+      self._flush()
+    for n, h in self._handles:
       h.wait()                                                  # compute stream waits for the reduction
-      nbytes += p.grad.numel() * p.grad.element_size()
+      nbytes += n
     self.bytes_reduced_last_step = nbytes
     if self._reserved:
       from . import _lib
       _lib.set_sm_reserve(0)                                    # the reductions are behind the compute stream now: all SMs again
       self._reserved = False
     if self.world_size > 1 and not isinstance(self.optimizer, FusedSGD):
-      for p, _ in self._handles:
-        p.grad.div_(self.world_size)
+      self.arena.flat.div_(self.world_size)
     self._handles = []
     self.optimizer.step()
 
   def remove_hooks(self):
-    for h in self._hooks:
-      h.remove()
-    self._hooks = []
+    if self.arena is not None:
+      _BucketedHooks.remove_hooks(self)
 
 
-class NvlsShardedSGD:
-  """EXPERIMENT (opt-in, written after round 1's GPU budget had ended -- unmeasured; bench.py: FRCNN_DP_FUSED=1 at N > 1).
-
-  The data-parallel optimizer step as ONE hand-written kernel per rank over NVLink / NVSwitch instead of "NCCL all-reduce, then
-  optimizer.step()": reduce-scatter of the weight gradients (multimem.ld_reduce: summed inside the switch), torch.optim.SGD on this
-  rank's 1 / world shard (the momentum buffer exists only for the shard), all-gather of the updated weights (multimem.st) -- see
-  csrc/dp_sgd.cu.  The optimizer's tensors are moved into two flat symmetric-memory arenas (torch.distributed._symmetric_memory gives
-  the peer / multicast mappings and the stream-ordered cross-rank barrier): ``W`` -- the parameters become views of it -- and ``G``, into
-  which each gradient is copied from a post-accumulate hook the moment autograd has produced it.
+class NvlsShardedSGD(_BucketedHooks):
+  """The data-parallel optimizer step as hand-written kernels over NVLink / NVSwitch instead of "NCCL all-reduce, then optimizer.step()"
+  (csrc/dp_sgd.cu): per bucket ONE kernel per rank does the reduce-scatter of the weight gradients (multimem.ld_reduce: summed inside the
+  switch), torch.optim.SGD on this rank's 1 / world shard of the bucket (the momentum buffer exists only for the shards: 1 / world of its
+  memory and traffic) and the all-gather of the updated weights (multimem.st).  The optimizer's tensors live in two flat symmetric-memory
+  arenas with one layout (GradArena): ``W`` -- the parameters become views of it -- and ``G`` -- the filter-gradient kernels write into it
+  directly.  A bucket's kernel is launched on a side stream the moment its last gradient exists, bracketed by stream-ordered cross-rank
+  barriers (torch.distributed._symmetric_memory), in 128-thread CTAs that fit beside a resident GEMM CTA, so reduce + update + broadcast of
+  fc1's 411 MB run UNDER the convolution backward and no optimizer pass is left after it; ``step()`` only joins the side stream.
   Quacks like the optimizer FasterRCNNModel.train_step expects (zero_grad / step / param_groups).  Hyper-parameters must be uniform
-  over the groups (they are in the reference's recipe, __main__.py:98-105)."""
+  over the groups (they are in the reference's recipe, __main__.py:98-105).  A tensor that received no gradient on any rank still gets
+  weight decay + momentum (zeros are reduced: DistributedDataParallel's semantics, not torch.optim.SGD's skip)."""
 
-  def __init__(self, params, lr = 1e-3, momentum = 0.9, process_group = None, use_multicast = None, ctas_per_sm = 0):
+  def __init__(self, params, lr = 1e-3, momentum = 0.9, process_group = None, use_multicast = None, ctas_per_sm = 0, named_params = None, bucket_bytes = None,
+               overlap = None):
     os.environ.setdefault("TORCH_SYMMMEM_IMPLICIT_POOL", "0")   # one allocation per arena: the mappings then start at the tensor (offset 0)
     import torch.distributed._symmetric_memory as symm
     assert dist.is_initialized(), "NvlsShardedSGD needs an initialised process group (one process per GPU)"
@@ -172,48 +332,36 @@ class NvlsShardedSGD:
     hp = {(g["lr"], g["momentum"], g["weight_decay"]) for g in self.param_groups}
     assert len(hp) == 1, "NvlsShardedSGD: lr / momentum / weight_decay must be the same for every group"
     self.lr, self.momentum, self.weight_decay = hp.pop()
-    self.params = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
-    assert self.params and all(p.is_cuda and p.dtype == t.float32 for p in self.params)
-    dev = self.params[0].device
-    # flat layout: every tensor starts on a 16-byte boundary; the whole space is cut into world equal shards of whole float4s
-    self.offsets, total = [], 0
-    for p in self.params:
+    owned = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+    assert owned and all(p.is_cuda and p.dtype == t.float32 for p in owned)
+    for p in owned:
       assert p.is_contiguous() or p.is_contiguous(memory_format = t.channels_last), "parameters must be dense"
-      self.offsets.append(total)
-      total += (p.numel() + 3) // 4 * 4
-    self.shard = (total + 4 * self.world_size - 1) // (4 * self.world_size) * 4
-    self.total = self.shard * self.world_size
-    self.W = symm.empty(self.total, dtype = t.float32, device = dev)
-    self.G = symm.empty(self.total, dtype = t.float32, device = dev)
-    self.W.zero_(); self.G.zero_()
-    symm.enable_symm_mem_for_group(group.group_name)
-    self.hW, self.hG = symm.rendezvous(self.W, group), symm.rendezvous(self.G, group)
-    with t.no_grad():
-      for p, off in zip(self.params, self.offsets):
-        view = self._view(self.W, off, p)
-        view.copy_(p)
-        p.data = view                                            # same shape, same strides; storage = this rank's weight arena
-    self._gviews = {id(p): self._view(self.G, off, p) for p, off in zip(self.params, self.offsets)}
-    self.momentum_shard = t.zeros((self.shard,), dtype = t.float32, device = dev)
-    self._first = True
-    self._seen = set()
-    self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "0"))   # 0: the kernel's default (4 CTAs of 256 threads per SM)
-    self.sm_reserve = 0
-    self.bytes_reduced_last_step = 0
-    # mappings: multicast (in-switch reduction / broadcast) when the fabric offers it, else every rank's arena through peer pointers
-    def mapping(handle, tensor):
-      """(peer pointers of `tensor` on every rank, multicast pointer or 0): the handle describes an allocation block, the tensor sits at
-      handle.offset inside it (0 with one allocation per arena) -- checked against the one address known for sure, this rank's."""
-      get = lambda name: (lambda v: v() if callable(v) else v)(getattr(handle, name))     # properties in current torch
-      base = [int(x) for x in get("buffer_ptrs")]
-      off = int(get("offset"))
-      if base[self.rank] + off != tensor.data_ptr():
-        assert base[self.rank] == tensor.data_ptr(), "symmetric-memory mapping does not contain the tensor where expected"
-        off = 0
-      mc = int(get("multicast_ptr") or 0)
-      return [b + off for b in base], (mc + off if mc else 0)
-    peers_g, mc_g = mapping(self.hG, self.G)
-    peers_w, mc_w = mapping(self.hW, self.W)
+    if named_params is not None:
+      ids = {id(p) for p in owned}
+      ordered = [p for p in backward_order(named_params) if id(p) in ids]
+      owned = ordered + [p for p in owned if id(p) not in {id(q) for q in ordered}]
+    else:
+      owned = list(reversed(owned))
+    self.params = owned
+    dev = owned[0].device
+    if bucket_bytes is None:
+      bucket_bytes = int(os.environ.get("FRCNN_DP_BUCKET_MB", "48")) << 20
+    # every fallible step first; the parameters are re-pointed into the arena only once all ranks agree that the set-up succeeded
+    error = None
+    try:
+      symm.enable_symm_mem_for_group(group.group_name)
+      arena = GradArena(owned, self.world_size, bucket_bytes = bucket_bytes, allocate = lambda n: symm.empty(n, dtype = t.float32, device = dev).zero_())
+      self.W = symm.empty(arena.total, dtype = t.float32, device = dev).zero_()
+      self.G = arena.flat
+      self.hW, self.hG = symm.rendezvous(self.W, group), symm.rendezvous(self.G, group)
+      peers_g, mc_g = self._mapping(self.hG, self.G)
+      peers_w, mc_w = self._mapping(self.hW, self.W)
+    except Exception as e:                                     # noqa: BLE001
+      error = e
+    ok = t.tensor([0 if error is not None else 1], dtype = t.int32, device = dev)
+    dist.all_reduce(ok, op = dist.ReduceOp.MIN, group = group)
+    if int(ok.item()) == 0:
+      raise RuntimeError("NvlsShardedSGD: symmetric-memory set-up failed on at least one rank (%s)" % (error,))
     if use_multicast is None:
       use_multicast = os.environ.get("FRCNN_DP_FUSED_MULTICAST", "1") not in ("", "0")
     self.use_multicast = bool(use_multicast) and mc_w != 0 and mc_g != 0
@@ -221,46 +369,86 @@ class NvlsShardedSGD:
     import ctypes
     vp = ctypes.c_void_p * self.world_size
     self._peers = (vp(*peers_g), vp(*peers_w))
-    self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad_ready) for p in self.params]
+    with t.no_grad():
+      for p in owned:
+        view = arena.view(p, self.W)
+        view.copy_(p)
+        p.data = view                                            # same shape, same strides; storage = this rank's weight arena
+    from . import ops
+    ops.invalidate_weight_splits()                               # the parameters moved
+    # momentum: one shard per bucket, back to back
+    self._shards, at = [], 0
+    for (_, _, begin, end) in arena.buckets:
+      n = (end - begin) // self.world_size
+      self._shards.append((begin + self.rank * n, n, at))
+      at += n
+    self.momentum_shard = t.zeros((at,), dtype = t.float32, device = dev)
+    self._first = [True] * len(arena.buckets)
+    self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "1"))
+    if overlap is None:
+      overlap = os.environ.get("FRCNN_DP_FUSED_OVERLAP", "1") not in ("", "0")
+    self.overlap = bool(overlap)                                 # False: every bucket at step(), on the compute stream
+    self._side = t.cuda.Stream(device = dev) if self.overlap else None
+    self._used_side = False
+    self.sm_reserve = 0
+    self.bytes_reduced_last_step = 0
+    arena.register()
+    self._init_hooks(arena)
     dist.barrier(group)
+
+  def _mapping(self, handle, tensor):
+    """(peer pointers of `tensor` on every rank, multicast pointer or 0): the handle describes an allocation block, the tensor sits at
+    handle.offset inside it (0 with one allocation per arena) -- checked against the one address known for sure, this rank's."""
+    get = lambda name: (lambda v: v() if callable(v) else v)(getattr(handle, name))     # properties in current torch
+    base = [int(x) for x in get("buffer_ptrs")]
+    off = int(get("offset"))
+    if base[self.rank] + off != tensor.data_ptr():
+      assert base[self.rank] == tensor.data_ptr(), "symmetric-memory mapping does not contain the tensor where expected"
+      off = 0
+    mc = int(get("multicast_ptr") or 0)
+    return [b + off for b in base], (mc + off if mc else 0)
 
   @staticmethod
   def _view(buf, off, p):
     return buf[off:off + p.numel()].as_strided(p.shape, p.stride())
 
-  @t.no_grad()
-  def _on_grad_ready(self, p):
-    self._gviews[id(p)].copy_(p.grad)                            # on the compute stream, right behind the kernel that produced the gradient
-    self._seen.add(id(p))
-    self.bytes_reduced_last_step += p.grad.numel() * 4
+  def _fused(self, b):
+    from . import _lib
+    begin, n, mom_at = self._shards[b]
+    self.hG.barrier(channel = 0)                                 # every rank's gradients of this bucket are in its arena
+    _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W),
+                                             _lib.ptr(self.momentum_shard[mom_at:mom_at + n]), begin, n, float(self.lr), float(self.momentum), float(self.weight_decay),
+                                             1.0 / self.world_size, 1 if self._first[b] else 0, self.ctas_per_sm, _lib.stream()), "frcnn_dp_sgd_fused")
+    _lib.count()
+    self.hG.barrier(channel = 0)                                 # every shard delivered everywhere; every arena's gradients consumed
+    self._first[b] = False
+    self.bytes_reduced_last_step += self.arena.payload_bytes[b]
+
+  def _launch_bucket(self, b):
+    if self._side is None:
+      self._fused(b)
+      return
+    ready = t.cuda.Event()
+    ready.record()                                               # behind the bucket's last filter-gradient kernel (and every reader of its weights)
+    with t.cuda.stream(self._side):
+      self._side.wait_event(ready)
+      self._fused(b)
+    self._used_side = True
 
   def zero_grad(self, set_to_none = True):
     self.bytes_reduced_last_step = 0
-    self._seen = set()
+    self._reset_step()
     for p in self.params:
-      if set_to_none:
-        p.grad = None
-      elif p.grad is not None:
-        p.grad.zero_()
+      p.grad = None
 
   @t.no_grad()
   def step(self):
-    from . import _lib
-    for p in self.params:
-      if id(p) not in self._seen:
-        self._gviews[id(p)].zero_()                              # no gradient on this rank this step (e.g. an empty RoI sample): contribute zero, not last step's values
-    self.hG.barrier(channel = 0)                                 # every rank's gradients are in its arena
-    _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W), _lib.ptr(self.momentum_shard),
-                                             self.rank * self.shard, self.shard, float(self.lr), float(self.momentum), float(self.weight_decay),
-                                             1.0 / self.world_size, 1 if self._first else 0, self.ctas_per_sm, _lib.stream()), "frcnn_dp_sgd_fused")
-    _lib.count()
-    self.hG.barrier(channel = 0)                                 # every shard delivered everywhere; every arena's gradients consumed
-    self._first = False
-
-  def remove_hooks(self):
-    for h in self._hooks:
-      h.remove()
-    self._hooks = []
+    from . import ops
+    self._flush()
+    if self._used_side:
+      t.cuda.current_stream().wait_stream(self._side)            # the next forward reads the updated weights
+      self._used_side = False
+    ops.invalidate_weight_splits()                               # written through the multicast mapping: no version bump, no carried split
 
 
 def optimizer_param_groups(model, weight_decay = 5e-4):

@@ -4,6 +4,8 @@ Region proposal network (reference: pytorch/FasterRCNN/models/rpn.py).  3x3 conv
 whose NHWC output IS the (1,H,W,9)/(1,H,W,36) map layout the reference permutes into
 (rpn.py:95-96); proposals through ops.rpn_proposals (decode+anchors, top-N, size filter, NMS).
 """
+import hashlib
+
 import numpy as np
 import torch as t
 from torch import nn
@@ -79,15 +81,17 @@ class RegionProposalNetwork(nn.Module):
       elif am.shape == entry["std_anchors"].shape and np.array_equal(am, entry["std_anchors"]):
         entry["verified_standard"] = am                                   # holding the reference keeps the identity test sound
       else:
-        ck = (am.shape, am.tobytes()[:4096])
+        ck = (am.shape, hashlib.blake2b(np.ascontiguousarray(am).tobytes(), digest_size = 16).digest())   # the WHOLE map: two maps sharing their first rows must not alias
         anchors_dev = entry["custom"].get(ck)
         if anchors_dev is None:
           anchors_dev = t.from_numpy(np.ascontiguousarray(am.reshape(-1, 4), dtype = np.float32)).to(device)
-          entry["custom"] = {ck: anchors_dev}
+          if len(entry["custom"]) >= 8:
+            entry["custom"].clear()                                       # bounded: a handful of alternating custom maps stay resident
+          entry["custom"][ck] = anchors_dev
     keep_mask = None
     if not self._allow_edge_proposals:
       av = entry["std_valid"] if anchor_valid_map is None else (anchor_valid_map if isinstance(anchor_valid_map, np.ndarray) else anchor_valid_map.detach().cpu().numpy())
-      mk = ("mask", av.tobytes()[:4096], av.shape)
+      mk = ("mask", hashlib.blake2b(np.ascontiguousarray(av).tobytes(), digest_size = 16).digest(), av.shape)
       keep_mask = entry.get(mk)
       if keep_mask is None:
         keep_mask = t.from_numpy((av.reshape(-1) > 0).astype(np.uint8)).to(device)

@@ -15,6 +15,8 @@ The three accepted file formats and their probing order (Keras h5 -> Caffe VGG-1
 import numpy as np
 import torch as t
 
+from . import ops
+
 _KERAS_CONV_LAYERS = [
   "block1_conv1", "block1_conv2", "block2_conv1", "block2_conv2", "block3_conv1", "block3_conv2", "block3_conv3",
   "block4_conv1", "block4_conv2", "block4_conv3", "block5_conv1", "block5_conv2", "block5_conv3",
@@ -125,6 +127,7 @@ def load(model, filepath):
     print("Some layers were missing from '%s' and not loaded: %s" % (filepath, ", ".join(missing)))
   try:
     model.load_state_dict(state, strict = not partial)
+    ops.invalidate_weight_splits()               # (load_state_dict bumps the version counters; explicit for loaders that write through .data)
     print("Loaded initial weights from '%s'" % filepath)
   except Exception as e:
     print(e)

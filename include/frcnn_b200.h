@@ -225,6 +225,11 @@ int frcnn_gather_filtered(const float *boxes, const float *scores, const uint8_t
 size_t frcnn_nms_workspace_bytes(int capacity);
 int frcnn_nms_sorted_f32(const float *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
                          int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
+/* fp64 twin for the per-class call site (models/faster_rcnn.py:216-220: float64 boxes, float32 scores already used for the
+ * ordering): boxes (n,4) fp64 in descending score order; IoU and the compare in IEEE double, as torchvision's CPU op
+ * instantiated for double computes them.  Same workspace, same outputs. */
+int frcnn_nms_sorted_f64(const double *boxes, const int32_t *count, int capacity, double iou_threshold, int max_keep,
+                         int32_t *keep_out, int32_t *kept_count_out, void *workspace, size_t workspace_bytes, void *stream);
 /* Batched variant (BASELINE config 5: 6000 boxes x 20 classes; the per-class loop of models/faster_rcnn.py:196-220 at a size where
  * it is worth a grid): B independent problems of n boxes each, UNSORTED -- boxes (B,n,4) fp32, scores (B,n) fp32 -- solved in
  * one stream-ordered sequence with no host round trip: stable descending order per problem (ties -> lower index first, as
@@ -339,6 +344,14 @@ int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *gra
 int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_multicast, const void *const *grad_peers, void *const *weight_peers, int world,
                        const float *weight_local, float *momentum_shard, size_t shard_begin, size_t shard_count,
                        float lr, float momentum, float weight_decay, float grad_scale, int first_step, int ctas_per_sm, void *stream);
+
+/* ---- helpers under the reference's names (models/math_utils.py) -----------------------------------------------------------------
+ * t_intersection_over_union (math_utils.py:39-63): boxes1 (n,4), boxes2 (m,4) fp32 (y1,x1,y2,x2) -> out (n,m): intersection (strict
+ * top-left < bottom-right mask) / (area1 + area2 - intersection + 1e-7), every operation a separate fp32 rounding. */
+int frcnn_iou_matrix_f32(const float *boxes1, int n, const float *boxes2, int m, float *out, void *stream);
+/* t_convert_deltas_to_boxes (math_utils.py:99-128): deltas (n,4) (ty,tx,th,tw), anchors (n,4) (cy,cx,h,w), means4 / stds4 = HOST arrays of
+ * four floats -> boxes (n,4) (y1,x1,y2,x2); d*std+mean, a_hw*d_yx+a_yx, a_hw*exp(d_hw), c -/+ 0.5 s with separate roundings. */
+int frcnn_decode_boxes_f32(const float *deltas, const float *anchors, int n, const float *means4, const float *stds4, float *boxes, void *stream);
 
 /* ---- a13: inference post-processing (FasterRCNNModel.predict, models/faster_rcnn.py:179-226)
  * proposals (n,4) fp32, classes (n,C) fp32, deltas (n,4(C-1)) fp32.  For every class c>=1 in one

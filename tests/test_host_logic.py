@@ -225,3 +225,34 @@ def test_proposal_sampling_draws_match_the_restated_reference():
     assert np.array_equal(idx, ref_rows[:, 0].numpy().astype(np.int64)), (n, pos_rate)
     assert after == after_ref
   assert model._sample_proposal_indices(np.zeros((7,), np.int32), 0, 0.25) is None       # max_proposals <= 0: keep every row
+
+
+def test_math_utils_host_helpers_equal_the_reference_bit_for_bit():
+  """math_utils.intersection_over_union / convert_deltas_to_boxes (NumPy, host) against the oracle's restatement and -- where the
+  reference tree exists -- against the reference's own functions on the same inputs, bit for bit, float32 and float64."""
+  import importlib.util
+  import os
+  from fasterrcnn_b200 import math_utils
+  from oracle import frcnn_oracle as orc
+  from oracle import golden_inputs as gi
+  rng = np.random.default_rng(5)
+  ref = None
+  path = "/root/reference/pytorch/FasterRCNN/models/math_utils.py"
+  if os.path.exists(path):
+    spec = importlib.util.spec_from_file_location("ref_math_utils", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+  for dtype in (np.float32, np.float64):
+    b1 = gi.random_boxes(rng, 200, dtype = dtype)
+    b2 = np.concatenate([gi.random_boxes(rng, 7, dtype = dtype), b1[:3], np.array([[5, 5, 5, 9], [0, 0, 0, 0]], dtype = dtype)])    # identical + degenerate boxes
+    got = math_utils.intersection_over_union(b1, b2)
+    assert np.array_equal(got, orc.iou_np(b1, b2))
+    deltas = (rng.normal(0, 0.4, (200, 4))).astype(dtype)
+    anchors = np.stack([rng.uniform(0, 600, 200), rng.uniform(0, 1000, 200), rng.uniform(16, 512, 200), rng.uniform(16, 512, 200)], axis = 1).astype(dtype)
+    means, stds = np.array([0, 0, 0, 0], dtype = dtype), np.array([0.1, 0.1, 0.2, 0.2], dtype = dtype)
+    boxes = math_utils.convert_deltas_to_boxes(deltas, anchors, means, stds)
+    assert boxes.dtype == np.float64                                    # np.empty's default, as in the reference (predict relies on float64)
+    assert np.array_equal(boxes, orc.deltas_to_boxes_np(deltas, anchors, means, stds))
+    if ref is not None:
+      assert np.array_equal(got, ref.intersection_over_union(b1, b2))
+      assert np.array_equal(boxes, ref.convert_deltas_to_boxes(deltas, anchors, means, stds))

@@ -13,6 +13,8 @@ import torch.nn.functional as F
 from oracle import frcnn_oracle as orc
 from oracle import golden_inputs as gi
 
+import _margins
+
 pytestmark = pytest.mark.gpu
 
 
@@ -195,31 +197,72 @@ def test_rpn_proposal_stage_matches_reference_golden(ops, golden_dir, tag):
   props, dbg = ops.rpn_proposals(_cuda(c["score_map"]), _cuda(c["delta_map"]), c["image_shape"], 16, c["pre_nms"], c["post_nms"], return_debug = True)
   # ordering: bit-exact indices (scores are distinct by construction)
   assert np.array_equal(dbg["order"].cpu().numpy().astype(np.int64), taps["order"])
-  # decode: <= 1e-4 px on clipped coordinates (expf is correctly rounded here, SLEEF u10 on the CPU)
+  # decode: <= 1e-4 px on clipped coordinates.  The one transcendental is exp(): correctly rounded on the device, but ATen's CPU exp is
+  # a <= 1 ulp approximation whose BITS depend on the host's SIMD dispatch (DEFAULT / AVX2 / AVX512 kernels differ in the last place:
+  # ATEN_CPU_CAPABILITY=default vs avx2 changes 2198 -> 2148 of 200000 last-bit disagreements with the correctly rounded value on the
+  # same inputs).  That is what round 1 saw as a "host glitch" on one gpurun box.  The bar therefore allows, on top of 1e-4 px, the one
+  # ulp of exp() scaled to the box: 2^-23 * the UNCLIPPED side length (fp64 decode of the same deltas), which only matters for boxes
+  # larger than ~800 px -- everything else is held to 1e-4 as before.  No retry.
   got, want = dbg["boxes_sorted"].cpu().numpy(), taps["pre_nms_boxes"]
-  bad = np.argwhere(np.abs(got - want) > 1e-4)
-  if bad.shape[0] != 0:
-    # one gpurun host once returned a CPU-side value that neither the committed golden proposals nor any other run of the same
-    # restatement reproduces (the GPU value was the right one): rule out a host glitch by recomputing the checker once
-    taps2 = {}
-    orc.rpn_proposals(t.from_numpy(c["score_map"]), t.from_numpy(c["delta_map"]), am, av, c["image_shape"], c["pre_nms"], c["post_nms"], taps = taps2)
-    if not np.array_equal(taps2["pre_nms_boxes"], want):
-      want = taps2["pre_nms_boxes"]
-      bad = np.argwhere(np.abs(got - want) > 1e-4)
+  a64 = am.reshape(-1, 4).astype(np.float64)
+  d64 = c["delta_map"].reshape(-1, 4).astype(np.float64)
+  side = (a64[:, 2:4] * np.exp(d64[:, 2:4]))[taps["order"]][taps["size_ok"]]            # (rows, [h, w]) of the surviving boxes
+  tol = 1e-4 + 2.0 ** -23 * np.concatenate([side, side], axis = 1)                        # columns y1,x1,y2,x2 <- h,w,h,w
+  _margins.record("rpn_stage_" + tag, decode_max_abs_px = float(np.abs(got - want).max()), decode_rows = int(got.shape[0]),
+                  largest_unclipped_side_px = float(side.max()), rows_over_1e4_px = int((np.abs(got - want) > 1e-4).any(axis = 1).sum()))
+  bad = np.argwhere(np.abs(got - want) > tol)
   assert bad.shape[0] == 0, "decode mismatch at (row, col) %s: got %s want %s" % (bad[:4].tolist(), got[bad[:4, 0]].tolist(), want[bad[:4, 0]].tolist())
   assert props.shape == ref.shape
   np.testing.assert_allclose(props.cpu().numpy(), ref.numpy(), rtol = 0, atol = 1e-4)
 
 
+def test_math_utils_device_helpers_match_the_torch_expressions():
+  """math_utils.t_intersection_over_union / t_convert_deltas_to_boxes (one kernel each) against the reference's torch expressions as the
+  oracle restates them (frcnn_oracle.iou_t / deltas_to_boxes_t) on CPU: IoU bit for bit (only +, -, *, / with explicit roundings);
+  decoded boxes within 1e-4 px + one ulp of exp() scaled to the box (see test_rpn_proposal_stage_matches_reference_golden)."""
+  from fasterrcnn_b200 import math_utils
+  rng = np.random.default_rng(11)
+  b1 = gi.random_boxes(rng, 2000)
+  b2 = np.concatenate([gi.random_boxes(rng, 5), b1[:2], np.array([[5, 5, 5, 9], [0, 0, 0, 0]], dtype = np.float32)])
+  got = math_utils.t_intersection_over_union(_cuda(b1), _cuda(b2)).cpu().numpy()
+  want = orc.iou_t(t.from_numpy(b1), t.from_numpy(b2)).numpy()
+  assert np.array_equal(got, want)
+  assert math_utils.t_intersection_over_union(_cuda(b1[:0]), _cuda(b2)).shape == (0, 9)
+  deltas = rng.normal(0, 0.4, (3000, 4)).astype(np.float32)
+  anchors = np.stack([rng.uniform(0, 600, 3000), rng.uniform(0, 1000, 3000), rng.uniform(16, 512, 3000), rng.uniform(16, 512, 3000)], axis = 1).astype(np.float32)
+  for means, stds in (([0, 0, 0, 0], [1, 1, 1, 1]), ([0.0, 0.0, 0.0, 0.0], [0.1, 0.1, 0.2, 0.2]), ([0.01, -0.02, 0.03, 0.0], [0.5, 0.5, 0.25, 0.25])):
+    got = math_utils.t_convert_deltas_to_boxes(_cuda(deltas), _cuda(anchors), t.tensor(means, dtype = t.float32), t.tensor(stds, dtype = t.float32)).cpu().numpy()
+    want = orc.deltas_to_boxes_t(t.from_numpy(deltas), t.from_numpy(anchors), t.tensor(means, dtype = t.float32), t.tensor(stds, dtype = t.float32)).numpy()
+    side = anchors[:, 2:4].astype(np.float64) * np.exp(deltas[:, 2:4].astype(np.float64) * np.array(stds[2:4]) + np.array(means[2:4]))
+    tol = 1e-4 + 2.0 ** -23 * np.concatenate([side, side], axis = 1)
+    assert (np.abs(got - want) <= tol).all(), float(np.abs(got - want).max())
+
+
 @pytest.mark.parametrize("tag", gi.NMS_CASES)
 def test_nms_bit_exact_vs_oracle_and_golden(ops, golden_dir, tag):
-  boxes, scores, thr = gi.nms_case(tag)
-  if boxes.dtype != np.float32:
-    pytest.skip("fp64 NMS is exercised through detect_postprocess")
+  boxes, scores, thr = gi.nms_case(tag)                     # float64 boxes (faster_rcnn.py:216-220) run frcnn_nms_sorted_f64
   gold = np.load(os.path.join(golden_dir, "tv_ops.npz"))["nms_" + tag].astype(np.int64)
   keep = ops.nms(_cuda(boxes), _cuda(scores), thr).cpu().numpy()
   assert np.array_equal(keep, gold)
   assert np.array_equal(keep, orc.nms(boxes, scores, thr))
+
+
+def test_nms_fp64_standalone_vs_oracle(ops):
+  """The per-class call site's dtype (float64 boxes, float32 scores) at the per-class size (300) and at BASELINE config 5's (6000), plus
+  boxes whose IoU sits within an fp32 ulp of the threshold: decided differently in float and double, so the fp64 path must not round."""
+  rng = np.random.default_rng(7)
+  for n, thr in ((300, 0.3), (6000, 0.3), (2000, 0.7)):
+    b = gi.random_boxes(rng, n, dtype = np.float64)
+    s = rng.permutation(n).astype(np.float32) / n
+    keep = ops.nms(_cuda(b), _cuda(s), thr).cpu().numpy()
+    assert np.array_equal(keep, orc.nms(b, s, thr)), (n, thr)
+  # pairs at IoU = 0.5 exactly and one double-ulp either side of it (never distinguishable in fp32)
+  eps = 2.0 ** -40
+  b = np.array([[0, 0, 10, 10], [0, 0, 10, 5], [20, 20, 30, 30], [20, 20, 30, 25 + eps * 25], [40, 40, 50, 50], [40, 40, 50, 45 - eps * 45]], dtype = np.float64)
+  s = np.array([0.9, 0.8, 0.7, 0.6, 0.5, 0.4], dtype = np.float32)
+  keep = ops.nms(_cuda(b), _cuda(s), 0.5).cpu().numpy()
+  assert np.array_equal(keep, orc.nms(b, s, 0.5))
+  assert list(keep) == [0, 1, 2, 4, 5]                         # 0.5 is not > 0.5; 0.5 + ulp is; 0.5 - ulp is not
 
 
 def test_nms_full_size_properties(ops):

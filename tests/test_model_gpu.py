@@ -14,12 +14,27 @@ import torch as t
 from oracle import frcnn_oracle as orc
 from oracle import golden_inputs as gi
 
+import _margins
+
 pytestmark = pytest.mark.gpu
 
 
 class Box:
   def __init__(self, corners, class_index):
     self.corners, self.class_index, self.class_name = corners, class_index, str(class_index)
+
+
+# End-to-end bars.  Measured on the B200 (profiles/r02_parity_margins.md) and set to ~2x the measured worst case; the stage-isolated tests
+# (test_kernels_gpu.py) hold the bit-exact / 1e-4 bars of the north star, these bound what 13-16 stacked fp32 convolutions in another
+# summation order can move through exp() and the discontinuous selections.
+PX_BAR = 5e-2                                  # a produced box and its oracle partner (px, max over the 4 coordinates)
+ROWS_BAR = 3                                   # |#rows - #oracle rows|
+PRED_CLASSES_BAR = 18                          # classes (of 20) whose detection count equals the oracle's
+GRAD_BAR = 1e-2                                # relative L2 of every parameter gradient
+
+
+def UNMATCHED_BAR(rows):
+  return max(2, int(0.02 * rows))              # rows with no oracle partner within PX_BAR
 
 
 def _build(cfg):
@@ -58,14 +73,18 @@ def test_forward_and_predict_match_oracle(golden_dir, tag):
   fm_ref = taps["feature_map"].numpy()
   np.testing.assert_allclose(fm.cpu().numpy(), fm_ref, rtol = 1e-4, atol = 1e-4 * float(np.abs(fm_ref).max()))
   # proposals: the discontinuous steps (top-N cut, >=16 filter, IoU > 0.7) may flip an isolated box when the
-  # 13 stacked convs differ in the last bits, so rows are matched to their nearest oracle row: >= 98 % of the
-  # proposals must have a partner within 5e-2 px (the 1e-4 px bar is met stage-isolated, see test_kernels_gpu)
-  assert abs(props.shape[0] - p_ref.shape[0]) <= 3
+  # 13 stacked convs differ in the last bits, so rows are matched to their nearest oracle row; the measured deviation, the unmatched
+  # rows and the oracle's own decision margins go to the margin report (profiles/r02_parity_margins.md), the bars are 2x the measured
+  # values (the 1e-4 px bar is met stage-isolated, see test_kernels_gpu)
   pg, pr = props.cpu().numpy(), p_ref.numpy()
-  dist = np.abs(pg[:, None, :] - pr[None, :, :]).max(axis = 2)
-  partner = dist.argmin(axis = 1)
-  ok = dist[np.arange(pg.shape[0]), partner] <= 5e-2
-  assert ok.mean() >= 0.98, ok.mean()
+  partner, ok, m = _margins.proposal_margins(pg, pr, PX_BAR)
+  fm_err = float(np.abs(fm.cpu().numpy() - fm_ref).max() / np.abs(fm_ref).max())
+  cls_err = float(np.abs(classes.cpu().numpy()[ok] - c_ref.numpy()[partner[ok]]).max()) if ok.any() else 0.0
+  dlt_err = float(np.abs(deltas.cpu().numpy()[ok] - d_ref.numpy()[partner[ok]]).max()) if ok.any() else 0.0
+  _margins.record("forward_" + tag, feature_map_max_rel = fm_err, class_score_max_abs = cls_err, box_delta_max_abs = dlt_err,
+                  **m, **_margins.decision_margins(taps, 6000, cfg["hw"]))
+  assert abs(props.shape[0] - p_ref.shape[0]) <= ROWS_BAR
+  assert m["unmatched_rows"] <= UNMATCHED_BAR(pg.shape[0]), m
   np.testing.assert_allclose(classes.cpu().numpy()[ok], c_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)      # class scores within 1e-4
   np.testing.assert_allclose(deltas.cpu().numpy()[ok], d_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)
   g = np.load(os.path.join(golden_dir, "e2e_%s.npz" % cfg["backbone"]))
@@ -78,11 +97,22 @@ def test_forward_and_predict_match_oracle(golden_dir, tag):
   counts = np.array([pred[c].shape[0] for c in range(1, 21)])
   ref_counts = np.array([ref[c].shape[0] for c in range(1, 21)])
   assert np.array_equal(ref_counts, g[tag + "_pred_counts"])                     # oracle == reference
-  assert (counts == ref_counts).sum() >= 18 and abs(int(counts.sum()) - int(ref_counts.sum())) <= 3
+  worst_px, worst_score, unmatched = 0.0, 0.0, 0
   for c in range(1, 21):
-    if counts[c - 1] == ref_counts[c - 1] and counts[c - 1] > 0:
-      d = np.abs(pred[c][:, None, :4] - ref[c][None, :, :4]).max(axis = 2).min(axis = 1)
-      assert (d <= 5e-2).mean() >= 0.95, (c, d.max())
+    if counts[c - 1] > 0 and ref_counts[c - 1] > 0:
+      partner_c, dist_c = _margins.match_rows(pred[c][:, :4], ref[c][:, :4])
+      okc = dist_c <= PX_BAR
+      unmatched += int((~okc).sum())
+      if okc.any():
+        worst_px = max(worst_px, float(dist_c[okc].max()))
+        worst_score = max(worst_score, float(np.abs(pred[c][okc, 4] - ref[c][partner_c[okc], 4]).max()))
+    else:
+      unmatched += int(counts[c - 1])
+  _margins.record("predict_" + tag, classes_with_equal_count = int((counts == ref_counts).sum()), boxes = int(counts.sum()), ref_boxes = int(ref_counts.sum()),
+                  unmatched_boxes = unmatched, max_px_matched = worst_px, max_score_abs = worst_score)
+  assert (counts == ref_counts).sum() >= PRED_CLASSES_BAR and abs(int(counts.sum()) - int(ref_counts.sum())) <= ROWS_BAR
+  assert unmatched <= UNMATCHED_BAR(int(counts.sum())), unmatched
+  assert worst_score <= 1e-4
 
 
 @pytest.mark.parametrize("tag", list(gi.E2E_CASES))
@@ -116,10 +146,13 @@ def test_train_step_matches_oracle(golden_dir, tag):
   np.testing.assert_allclose(np.array(losses[0]), np.array(ref_losses[0]), rtol = 2e-4, atol = 1e-5)   # step 1: within 2e-4 relative
   np.testing.assert_allclose(np.array(losses[1]), np.array(ref_losses[1]), rtol = 5e-3, atol = 1e-4)   # step 2 (after an SGD update, re-sampled RoIs)
   assert set(grads) == set(ref_grads)
-  for k in ref_grads:
-    a, b = grads[k].double(), ref_grads[k].double()
-    rel = float((a - b).norm() / (b.norm() + 1e-12))
-    assert rel < 1e-2, (k, rel)                               # every parameter gradient: < 1 % relative L2 (isolated ReLU / RoI-argmax flips)
+  rels, gm = _margins.grad_margins(grads, ref_grads)
+  w_err = max(float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters())
+  _margins.record("train_step_" + tag, loss_rel_step1 = float(np.max(np.abs(np.array(losses[0]) - np.array(ref_losses[0])) / np.abs(np.array(ref_losses[0])))),
+                  loss_rel_step2 = float(np.max(np.abs(np.array(losses[1]) - np.array(ref_losses[1])) / np.abs(np.array(ref_losses[1])))),
+                  post_step_weight_max_abs = w_err, optimizer = "torch.optim.SGD", **gm)
+  for k, rel in rels.items():
+    assert rel < GRAD_BAR, (k, rel)                           # every parameter gradient (isolated ReLU / RoI-argmax flips)
   for k, p in model.named_parameters():                       # post-step weights
     ref_w = oracle.params[k].detach()
     np.testing.assert_allclose(p.detach().cpu().numpy(), ref_w.numpy(), rtol = 1e-4, atol = 2e-5)
@@ -150,24 +183,68 @@ def test_empty_and_ragged_inputs():
     model(image_data = t.zeros((2, 3, 64, 64), device = dev))
 
 
+def _forward_vs_oracle(name, model, oracle, smp, pre_nms = 6000):
+  """forward() against the oracle with the margin record; returns (partner, ok) of the proposal rows."""
+  taps = {}
+  with t.no_grad():
+    p_ref, c_ref, d_ref = oracle.forward(smp["image"], taps = taps)
+  model.eval()
+  with t.no_grad():
+    props, classes, deltas = model(image_data = smp["image"].cuda())
+  pg, pr = props.cpu().numpy(), p_ref.numpy()
+  partner, ok, m = _margins.proposal_margins(pg, pr, PX_BAR)
+  row_c = np.abs(classes.cpu().numpy()[ok] - c_ref.numpy()[partner[ok]]).max(axis = 1)
+  row_d = np.abs(deltas.cpu().numpy()[ok] - d_ref.numpy()[partner[ok]]).max(axis = 1)
+  _margins.record(name, class_score_max_abs = float(row_c.max()), box_delta_max_abs = float(row_d.max()), rows_over_1e4 = int(((row_c > 1e-4) | (row_d > 1e-4)).sum()),
+                  **m, **_margins.decision_margins(taps, pre_nms, tuple(smp["image"].shape[2:])))
+  assert abs(props.shape[0] - p_ref.shape[0]) <= ROWS_BAR
+  assert m["unmatched_rows"] <= UNMATCHED_BAR(pg.shape[0]), m
+  # a proposal within PX_BAR of its partner can still quantise to another RoIPool cell (round(x / 16) at a .5 boundary): such an isolated
+  # row gets different pooled features, so rows -- not elements -- are counted
+  assert ((row_c > 1e-4) | (row_d > 1e-4)).sum() <= max(1, int(0.01 * ok.sum())), (row_c.max(), row_d.max())
+  return partner, ok
+
+
+def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol = 1e-3, check_weights = False):
+  """One train_step against the oracle on the same RNG streams: losses, every parameter gradient, optionally post-step weights."""
+  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
+  random.seed(seed); np.random.seed(seed); t.manual_seed(seed)
+  ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = check_weights)
+  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
+  random.seed(seed); np.random.seed(seed); t.manual_seed(seed)
+  got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
+                         gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
+                         gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
+  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
+  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
+  grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+  rels, gm = _margins.grad_margins(grads, ref_grads)
+  extra = {}
+  if check_weights:
+    extra["post_step_weight_max_abs"] = max(float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters())
+  _margins.record(name, loss_rel = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6))), num_rois = model.last_step_info["num_rois"],
+                  optimizer = type(optimizer).__name__, **gm, **extra)
+  np.testing.assert_allclose(a, b, rtol = loss_rtol, atol = 1e-5)
+  assert set(grads) == set(ref_grads)
+  for k, rel in rels.items():
+    assert rel < 2 * GRAD_BAR, (k, rel)
+  if check_weights:
+    for k, p in model.named_parameters():
+      np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5, err_msg = k)
+  return got
+
+
+def _reference_optimizer(model):
+  return t.optim.SGD([{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k], lr = 1e-3, momentum = 0.9)
+
+
 def test_config1_full_size_forward_600x800():
   """BASELINE config 1: single 600x800 image, VGG-16, forward-only (RPN -> RoI -> NMS correctness) vs the CPU oracle."""
   cfg = dict(backbone = "vgg16", weight_seed = 3, heads = "spread", hw = (600, 800), sample_seed = 3)
   model, oracle, smp = _build(cfg)
   t.set_num_threads(min(16, os.cpu_count() or 8))
-  with t.no_grad():
-    p_ref, c_ref, d_ref = oracle.forward(smp["image"])
-  model.eval()
-  with t.no_grad():
-    props, classes, deltas = model(image_data = smp["image"].cuda())
-  assert abs(props.shape[0] - p_ref.shape[0]) <= 3
-  pg, pr = props.cpu().numpy(), p_ref.numpy()
-  dist = np.abs(pg[:, None, :] - pr[None, :, :]).max(axis = 2)
-  partner = dist.argmin(axis = 1)
-  ok = dist[np.arange(pg.shape[0]), partner] <= 5e-2
-  assert ok.mean() >= 0.97, ok.mean()
-  np.testing.assert_allclose(classes.cpu().numpy()[ok], c_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)
-  np.testing.assert_allclose(deltas.cpu().numpy()[ok], d_ref.numpy()[partner[ok]], rtol = 0, atol = 1e-4)
+  _forward_vs_oracle("config1_forward_600x800_vgg16", model, oracle, smp)
 
 
 def test_config2_full_size_train_step_600x1000():
@@ -175,27 +252,94 @@ def test_config2_full_size_train_step_600x1000():
   cfg = dict(backbone = "vgg16", weight_seed = 5, heads = "reference", hw = (600, 1000), sample_seed = 5)
   model, oracle, smp = _build(cfg)
   t.set_num_threads(min(16, os.cpu_count() or 8))
-  params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
-  optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)
-  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
-  random.seed(1); np.random.seed(1); t.manual_seed(1)
-  ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
-                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = False)
-  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
-  random.seed(1); np.random.seed(1); t.manual_seed(1)
-  got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
-                         gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
-                         gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
-  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
-  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
-  np.testing.assert_allclose(a, b, rtol = 1e-3, atol = 1e-5)
+  _train_step_vs_oracle("config2_train_step_600x1000_vgg16", model, oracle, smp, _reference_optimizer(model), seed = 1)
   assert model.last_step_info["num_rois"] == 128
+
+
+def test_config2_train_steps_with_the_fused_optimizer():
+  """The optimizer the benchmark uses (optim.FusedSGD: update + carried fp16 operand split of the new weights in one kernel) end to end:
+  TWO steps at 600x1000 against the oracle's SGD, so the second step's GEMMs read the splits the first step's optimizer kernel wrote."""
+  from fasterrcnn_b200 import optim
+  cfg = dict(backbone = "vgg16", weight_seed = 5, heads = "reference", hw = (600, 1000), sample_seed = 5)
+  model, oracle, smp = _build(cfg)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  optimizer = optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True)
+  assert isinstance(optimizer, optim.FusedSGD)
+  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
+  losses = {"ref": [], "gpu": []}
+  for who in ("ref", "gpu"):
+    random.seed(4); np.random.seed(4); t.manual_seed(4)
+    for _ in range(2):
+      if who == "ref":
+        l = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
+                              smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"])
+      else:
+        l = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
+                             gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
+                             gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
+      losses[who].append([l.rpn_class, l.rpn_regression, l.detector_class, l.detector_regression, l.total])
+  a, b = np.array(losses["gpu"]), np.array(losses["ref"])
+  w_err = {k: float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters()}
+  worst = max(w_err, key = w_err.get)
+  _margins.record("config2_two_steps_fused_sgd", loss_rel_step1 = float(np.max(np.abs(a[0] - b[0]) / np.abs(b[0]))), loss_rel_step2 = float(np.max(np.abs(a[1] - b[1]) / np.abs(b[1]))),
+                  post_step_weight_max_abs = w_err[worst], worst_weight = worst)
+  np.testing.assert_allclose(a[0], b[0], rtol = 1e-3, atol = 1e-5)
+  np.testing.assert_allclose(a[1], b[1], rtol = 5e-3, atol = 1e-4)
   for k, p in model.named_parameters():
-    if p.grad is None:
-      continue
-    ga, gb = p.grad.detach().cpu().double(), ref_grads[k].double()
-    rel = float((ga - gb).norm() / (gb.norm() + 1e-12))
-    assert rel < 2e-2, (k, rel)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5, err_msg = k)
+
+
+def test_out_of_band_weight_write_needs_invalidate_weight_splits():
+  """the fused optimizer carries each weight's fp16 operand split in a side buffer validated by address + torch's
+  version counter, which writes through ``p.data`` bypass.  The documented contract: call ops.invalidate_weight_splits() after such a
+  write.  After it, the model must behave exactly like a fresh model loaded with the same state dict."""
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import ops, optim
+  cfg = gi.E2E_CASES["small"]
+  model, _, smp = _build(cfg)
+  optimizer = optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True)
+  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
+  random.seed(0); np.random.seed(0); t.manual_seed(0)
+  model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
+                   gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
+                   gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])          # the carried splits now exist
+  with t.no_grad():
+    for k, p in model.named_parameters():
+      if "_block5_conv" in k or "_fc2" in k:
+        p.data.mul_(0.5)                                        # out-of-band: no version bump
+  ops.invalidate_weight_splits()
+  fresh = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
+  fresh.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+  fresh = fresh.cuda()
+  model.eval(); fresh.eval()
+  with t.no_grad():
+    a = model(image_data = smp["image"].cuda())
+    b = fresh(image_data = smp["image"].cuda())
+  for x, y in zip(a, b):
+    assert x.shape == y.shape and t.equal(x, y)
+
+
+def _build_resnet(kind, hw, seed, bn3_scale):
+  import fasterrcnn_b200 as f
+  from fasterrcnn_b200 import resnet
+  from oracle import resnet_oracle
+  params = orc.synth_params(resnet_oracle.param_shapes(kind), seed = seed, heads = "spread")
+  for k in params:
+    if k.endswith("bn3.weight"):
+      params[k] = params[k] * bn3_scale                # deep residual stacks with Kaiming-scale branches overflow the synthetic init otherwise
+  arch = {"resnet50": resnet.Architecture.ResNet50, "resnet101": resnet.Architecture.ResNet101, "resnet152": resnet.Architecture.ResNet152}[kind]
+  model = f.FasterRCNNModel(num_classes = 21, backbone = resnet.ResNetBackbone(arch), allow_edge_proposals = True)
+  model.load_state_dict(params)
+  return model.cuda(), orc.OracleModel(params, backbone = kind), orc.synthetic_sample(hw, seed = seed, backbone = kind)
+
+
+def test_config4_resnet101_full_size_600x1000():
+  """BASELINE config 4's per-GPU work at its real size: ResNet-101, one 600x1000 image (feature map 1024 x 38 x 63, 21,546 anchors) --
+  forward and one train step against the CPU oracle (the 8-GPU half of the config is tests/test_dp_gpu.py + bench.py --backbone resnet101)."""
+  model, oracle, smp = _build_resnet("resnet101", (600, 1000), 6, 0.3)
+  t.set_num_threads(min(16, os.cpu_count() or 8))
+  _forward_vs_oracle("config4_forward_600x1000_resnet101", model, oracle, smp)
+  _train_step_vs_oracle("config4_train_step_600x1000_resnet101", model, oracle, smp, _reference_optimizer(model), seed = 2)
 
 
 def _build_batch(kind, hw, roi_op, proposal_batch_size, weight_seed):
@@ -255,11 +399,12 @@ def test_batch2_forward_matches_oracle_and_single_image_path(kind, roi_op):
       assert (np.abs(cg[ok] - cs[partner[ok]]).max(axis = 1) <= 2e-5).mean() >= 0.99
 
 
-@pytest.mark.parametrize("kind,roi_op,rois", [("resnet50", "align", 300), ("vgg16", "pool", 128)])
-def test_batch2_train_step_matches_oracle(kind, roi_op, rois):
+@pytest.mark.parametrize("kind,roi_op,rois,hw", [("resnet50", "align", 300, (384, 512)), ("vgg16", "pool", 128, (384, 512)), ("resnet50", "align", 300, (600, 1000))])
+def test_batch2_train_step_matches_oracle(kind, roi_op, rois, hw):
   """EXTENSION, BASELINE config 3: ResNet-50, batch 2, 300 RoIs per image through RoIAlign -- losses, every parameter gradient and
-  the post-step weights against the oracle's batch restatement (same RNG order); VGG-16 / RoIPool as the second case."""
-  model, oracle, smps = _build_batch(kind, (384, 512), roi_op, rois, weight_seed = 4)
+  the post-step weights against the oracle's batch restatement (same RNG order), at a small size and at the config's own 600x1000
+  (feature maps 2 x 1024 x 38 x 63, 600 RoIs through layer4); VGG-16 / RoIPool as the second case."""
+  model, oracle, smps = _build_batch(kind, hw, roi_op, rois, weight_seed = 4)
   t.set_num_threads(min(16, os.cpu_count() or 8))
   images = t.cat([s["image"] for s in smps], dim = 0)
   params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
@@ -278,10 +423,12 @@ def test_batch2_train_step_matches_oracle(kind, roi_op, rois):
   assert model.last_step_info["rois_per_image"] == oracle.last_batch_rois
   grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
   assert set(grads) == set(ref_grads)
-  for k in ref_grads:
-    ga, gb = grads[k].double(), ref_grads[k].double()
-    rel = float((ga - gb).norm() / (gb.norm() + 1e-12))
-    assert rel < 2e-2, (k, rel)
+  rels, gm = _margins.grad_margins(grads, ref_grads)
+  w_err = max(float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters())
+  _margins.record("batch2_train_step_%s_%s_%dx%d" % (kind, roi_op, hw[0], hw[1]), loss_rel = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6))),
+                  rois_per_image = model.last_step_info["rois_per_image"], post_step_weight_max_abs = w_err, **gm)
+  for k, rel in rels.items():
+    assert rel < 2 * GRAD_BAR, (k, rel)
   for k, p in model.named_parameters():
     np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5)
 

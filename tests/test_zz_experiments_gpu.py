@@ -1,7 +1,6 @@
 """
-Opt-in schedule experiments that were written after the round's GPU budget had ended: they change WHEN work runs, not what
-is computed, so each is checked for equality against the default schedule on the same seeded train steps.  They run only with
-FRCNN_TEST_EXPERIMENTS=1 (first GPU call of the next round); nothing on the default path depends on them.
+Schedule options: they change WHEN work runs, not what is computed, so each is checked for equality against the default
+schedule on the same seeded train steps.  (The data-parallel optimizers have their own two-GPU test: tests/test_dp_gpu.py.)
   * optim.FusedSGD(eager = True): big tensors updated on a side stream from the gradient hook, overlapping the convolution backward
   * frcnn_set_sm_reserve(n): persistent GEMM grids of 148 - n CTAs (for co-residency with NCCL's CTAs)
 """
@@ -14,7 +13,7 @@ import torch as t
 
 from oracle import frcnn_oracle as orc
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("FRCNN_TEST_EXPERIMENTS") != "1", reason = "opt-in experiments (FRCNN_TEST_EXPERIMENTS=1)")]
+pytestmark = pytest.mark.gpu
 
 
 class Box:
@@ -68,54 +67,3 @@ def test_sm_reserve_same_results_up_to_summation_order(case):
   np.testing.assert_allclose(np.array(l2), np.array(losses), rtol = 1e-4, atol = 1e-6)
   for k in weights:
     np.testing.assert_allclose(w2[k], weights[k], rtol = 1e-4, atol = 1e-6, err_msg = k)
-
-
-# ---- fused reduce-scatter + SGD + all-gather over NVLink (optim.NvlsShardedSGD, csrc/dp_sgd.cu): needs two GPUs -------------------------
-def _dp_worker(rank, world, port, use_multicast, out):
-  import torch.distributed as dist
-  os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-  t.cuda.set_device(rank)
-  dist.init_process_group("nccl", rank = rank, world_size = world, device_id = t.device("cuda", rank))
-  import fasterrcnn_b200 as f
-  from fasterrcnn_b200 import optim
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 0, heads = "spread")
-  smp = orc.synthetic_sample((384, 512), seed = 100 + rank)            # every rank its own image
-  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
-  results = {}
-  for which in ("nccl", "fused"):
-    model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
-    model.load_state_dict(params)
-    model = model.cuda()
-    if which == "nccl":
-      optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True))
-    else:
-      optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9, use_multicast = use_multicast)
-    random.seed(rank); np.random.seed(rank); t.manual_seed(rank)
-    for _ in range(2):
-      model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
-                       gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
-                       gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
-    t.cuda.synchronize()
-    dist.barrier()
-    results[which] = {k: p.detach().float().cpu().clone() for k, p in model.named_parameters()}
-    optimizer.remove_hooks()
-  worst = max(float((results["fused"][k] - results["nccl"][k]).abs().max() / (results["nccl"][k].abs().max() + 1e-12)) for k in results["nccl"])
-  digest = float(sum(v.double().sum() for v in results["fused"].values()))
-  out[rank] = (worst, digest, bool(use_multicast))
-  dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("use_multicast", [False, True])
-def test_fused_dp_step_matches_nccl_allreduce_plus_sgd(use_multicast):
-  """Two ranks, two steps: NCCL all-reduce + fused SGD vs the one-kernel reduce-scatter + SGD + all-gather -- same weights up to the
-  fp32 summation order of the gradient sum, and the replicas stay identical."""
-  import socket
-  import torch.multiprocessing as mp
-  if t.cuda.device_count() < 2:
-    pytest.skip("needs two GPUs")
-  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-  mgr = mp.Manager(); out = mgr.dict()
-  mp.spawn(_dp_worker, args = (2, port, use_multicast, out), nprocs = 2, join = True)
-  (w0, d0, _), (w1, d1, _) = out[0], out[1]
-  assert w0 < 1e-5 and w1 < 1e-5, (w0, w1)
-  assert d0 == d1                                                # replicas identical after the broadcast

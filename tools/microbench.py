@@ -39,7 +39,8 @@ def boxes(rng, n, h = 600.0, w = 1000.0):
   return np.stack([y1, x1, np.minimum(y1 + rng.uniform(16, 300, n), h), np.minimum(x1 + rng.uniform(16, 300, n), w)], axis = 1).astype(np.float32)
 
 
-def main():
+def run():
+  """-> list of dicts, one per kernel (bench.py --micro prints them as ONE JSON line; python tools/microbench.py one line each)."""
   rng = np.random.default_rng(0)
   peak = peak_gbs()
   out = []
@@ -100,7 +101,11 @@ def main():
   ms = ev_time(lambda: ops.sgd_step(p, gr, buf, 1e-3, 0.9, 5e-4))
   alg = p.numel() * 20
   out.append(dict(kernel = "sgd_kernel", shape = "102.8 M elements (fc1)", ms = ms, algorithmic_MB = alg / 1e6, achieved_GBs = alg / ms / 1e6, peak_GBs = peak, frac = alg / ms / 1e6 / peak))
-  for o in out:
+  return out
+
+
+def main():
+  for o in run():
     print(json.dumps(o))
 
 
