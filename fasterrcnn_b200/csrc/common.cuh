@@ -88,6 +88,30 @@ inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through FRCNN_CHECK_LAUNCH (cudaGetLastError)
 }
 
+// same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it)
+template <typename... Params, typename... Args>
+inline void launch_cluster(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename T>
 inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

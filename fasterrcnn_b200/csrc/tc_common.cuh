@@ -138,6 +138,83 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v)
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of one cluster (the two SMs of a TPC) execute ONE M = 256 MMA -------------------------------
+// Each CTA stages its own 128 rows of A and HALF of the B tile (N / 2 columns) in its shared memory and owns the 128 accumulator lanes of
+// its rows in its own TMEM; the instruction is issued by the leader (cluster rank 0) only.  Per CTA the B operand traffic through shared
+// memory is halved -- the resource that bounds the single-CTA mainloop of the three-product scheme.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all()              // every thread of both CTAs, converged
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the barrier at `bar_cluster_addr`
+// (the leader's), which .cta_group::2 permits to live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void *dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void *dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4)
+{
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// one full warp of EACH CTA of the pair (same warp index, same destination offset)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols)
+{
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (256 rows: 128 per CTA) * B (N columns: N / 2 per CTA), issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs (mask 0b11) when the leader's previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
+{
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4

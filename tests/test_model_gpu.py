@@ -24,17 +24,22 @@ class Box:
     self.corners, self.class_index, self.class_name = corners, class_index, str(class_index)
 
 
-# End-to-end bars.  Measured on the B200 (profiles/r02_parity_margins.md) and set to ~2x the measured worst case; the stage-isolated tests
-# (test_kernels_gpu.py) hold the bit-exact / 1e-4 bars of the north star, these bound what 13-16 stacked fp32 convolutions in another
-# summation order can move through exp() and the discontinuous selections.
-PX_BAR = 5e-2                                  # a produced box and its oracle partner (px, max over the 4 coordinates)
-ROWS_BAR = 3                                   # |#rows - #oracle rows|
-PRED_CLASSES_BAR = 18                          # classes (of 20) whose detection count equals the oracle's
-GRAD_BAR = 1e-2                                # relative L2 of every parameter gradient
+# End-to-end bars = ~2x the worst value MEASURED on the B200 over every end-to-end case (profiles/r02_parity_margins.md: VGG-16 and
+# ResNet-50/101, 384x512 .. 600x1000, batch 1 and 2).  The stage-isolated tests (test_kernels_gpu.py) hold the bit-exact / 1e-4 bars of
+# the north star; these bound what 13-100 stacked fp32 convolutions in another summation order can move through exp() and the
+# discontinuous selections.  The oracle's own decision margins are recorded next to them (min |IoU - 0.7| down to 5e-7, top-N score gap
+# down to 1e-8): a decision inside the upstream floating-point agreement may legitimately flip, hence ONE unmatched row is tolerated.
+PX_BAR = 1e-2                                  # a produced box and its oracle partner, px, max over the 4 coordinates   (measured <= 4.6e-3)
+ROWS_BAR = 1                                   # |#rows - #oracle rows|                                                   (measured 0)
+PRED_CLASSES_BAR = 19                          # classes (of 20) whose detection count equals the oracle's                (measured 20)
+GRAD_BAR = 1.25e-3                             # relative L2 of every parameter gradient; full-size cases use 2x          (measured <= 5.5e-4 small, 1.2e-3 full size)
+LOSS_RTOL_STEP1 = 1e-4                         # each of the five losses, first step                                      (measured <= 3.4e-5)
+LOSS_RTOL_STEP2 = 3e-4                         # second step (after an SGD update, re-sampled RoIs)                       (measured <= 1.4e-4)
+WEIGHT_ATOL = 1.2e-5                           # post-step weights, with rtol 1e-4                                        (measured <= 5.8e-6)
 
 
 def UNMATCHED_BAR(rows):
-  return max(2, int(0.02 * rows))              # rows with no oracle partner within PX_BAR
+  return max(1, int(0.004 * rows))             # rows with no oracle partner within PX_BAR                                (measured 0)
 
 
 def _build(cfg):
@@ -143,8 +148,8 @@ def test_train_step_matches_oracle(golden_dir, tag):
         if step == 0:
           grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
   np.testing.assert_allclose(np.array(ref_losses), g[tag + "_losses"], rtol = 1e-5, atol = 1e-6)   # oracle == reference
-  np.testing.assert_allclose(np.array(losses[0]), np.array(ref_losses[0]), rtol = 2e-4, atol = 1e-5)   # step 1: within 2e-4 relative
-  np.testing.assert_allclose(np.array(losses[1]), np.array(ref_losses[1]), rtol = 5e-3, atol = 1e-4)   # step 2 (after an SGD update, re-sampled RoIs)
+  np.testing.assert_allclose(np.array(losses[0]), np.array(ref_losses[0]), rtol = LOSS_RTOL_STEP1, atol = 1e-6)
+  np.testing.assert_allclose(np.array(losses[1]), np.array(ref_losses[1]), rtol = LOSS_RTOL_STEP2, atol = 1e-6)   # (after an SGD update, re-sampled RoIs)
   assert set(grads) == set(ref_grads)
   rels, gm = _margins.grad_margins(grads, ref_grads)
   w_err = max(float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters())
@@ -155,7 +160,7 @@ def test_train_step_matches_oracle(golden_dir, tag):
     assert rel < GRAD_BAR, (k, rel)                           # every parameter gradient (isolated ReLU / RoI-argmax flips)
   for k, p in model.named_parameters():                       # post-step weights
     ref_w = oracle.params[k].detach()
-    np.testing.assert_allclose(p.detach().cpu().numpy(), ref_w.numpy(), rtol = 1e-4, atol = 2e-5)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), ref_w.numpy(), rtol = 1e-4, atol = WEIGHT_ATOL)
 
 
 def test_empty_and_ragged_inputs():
@@ -205,7 +210,7 @@ def _forward_vs_oracle(name, model, oracle, smp, pre_nms = 6000):
   return partner, ok
 
 
-def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol = 1e-3, check_weights = False):
+def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol = LOSS_RTOL_STEP1, check_weights = False):
   """One train_step against the oracle on the same RNG streams: losses, every parameter gradient, optionally post-step weights."""
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
   random.seed(seed); np.random.seed(seed); t.manual_seed(seed)
@@ -231,7 +236,7 @@ def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol =
     assert rel < 2 * GRAD_BAR, (k, rel)
   if check_weights:
     for k, p in model.named_parameters():
-      np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5, err_msg = k)
+      np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = WEIGHT_ATOL, err_msg = k)
   return got
 
 
@@ -283,10 +288,10 @@ def test_config2_train_steps_with_the_fused_optimizer():
   worst = max(w_err, key = w_err.get)
   _margins.record("config2_two_steps_fused_sgd", loss_rel_step1 = float(np.max(np.abs(a[0] - b[0]) / np.abs(b[0]))), loss_rel_step2 = float(np.max(np.abs(a[1] - b[1]) / np.abs(b[1]))),
                   post_step_weight_max_abs = w_err[worst], worst_weight = worst)
-  np.testing.assert_allclose(a[0], b[0], rtol = 1e-3, atol = 1e-5)
-  np.testing.assert_allclose(a[1], b[1], rtol = 5e-3, atol = 1e-4)
+  np.testing.assert_allclose(a[0], b[0], rtol = LOSS_RTOL_STEP1, atol = 1e-6)
+  np.testing.assert_allclose(a[1], b[1], rtol = LOSS_RTOL_STEP2, atol = 1e-6)
   for k, p in model.named_parameters():
-    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5, err_msg = k)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = WEIGHT_ATOL, err_msg = k)
 
 
 def test_out_of_band_weight_write_needs_invalidate_weight_splits():
@@ -361,7 +366,7 @@ def _build_batch(kind, hw, roi_op, proposal_batch_size, weight_seed):
   return model.cuda(), oracle, smps
 
 
-def _match_rows(pg, pr, tol = 5e-2):
+def _match_rows(pg, pr, tol = PX_BAR):
   dist = np.abs(pg[:, None, :] - pr[None, :, :]).max(axis = 2)
   partner = dist.argmin(axis = 1)
   return partner, dist[np.arange(pg.shape[0]), partner] <= tol
@@ -384,14 +389,16 @@ def test_batch2_forward_matches_oracle_and_single_image_path(kind, roi_op):
   for b in range(2):
     pg, cg, dg = [x.cpu().numpy() for x in got[b]]
     pr, cr, dr = [x.numpy() for x in ref[b]]
-    assert abs(pg.shape[0] - pr.shape[0]) <= 3
+    assert abs(pg.shape[0] - pr.shape[0]) <= ROWS_BAR
     partner, ok = _match_rows(pg, pr)
-    assert ok.mean() >= 0.97, (b, ok.mean())
-    # a proposal within 5e-2 px of its partner can still quantise to another RoIPool cell (round(x / 16) at a .5 boundary): such an
-    # isolated row gets different pooled features, so rows -- not elements -- are counted: >= 99 % of the matched rows within 1e-4
+    # a proposal within PX_BAR of its partner can still quantise to another RoIPool cell (round(x / 16) at a .5 boundary): such an
+    # isolated row gets different pooled features, so rows -- not elements -- are counted
     row_c = np.abs(cg[ok] - cr[partner[ok]]).max(axis = 1)
     row_d = np.abs(dg[ok] - dr[partner[ok]]).max(axis = 1)
-    assert (row_c <= 1e-4).mean() >= 0.99 and (row_d <= 1e-4).mean() >= 0.99, (b, (row_c > 1e-4).sum(), (row_d > 1e-4).sum())
+    _margins.record("batch2_forward_%s_%s_image%d" % (kind, roi_op, b), rows = int(pg.shape[0]), ref_rows = int(pr.shape[0]), unmatched_rows = int((~ok).sum()),
+                    class_score_max_abs = float(row_c.max()), box_delta_max_abs = float(row_d.max()), rows_over_1e4 = int(((row_c > 1e-4) | (row_d > 1e-4)).sum()))
+    assert (~ok).sum() <= UNMATCHED_BAR(pg.shape[0]), (b, (~ok).sum())
+    assert ((row_c > 1e-4) | (row_d > 1e-4)).sum() <= max(1, int(0.01 * ok.sum())), (b, (row_c > 1e-4).sum(), (row_d > 1e-4).sum())
     if single is not None:                     # same kernels, same weights: the batch path must reproduce the per-image path
       ps, cs, ds = [x.cpu().numpy() for x in single[b]]
       partner, ok = _match_rows(pg, ps, tol = 1e-3)
@@ -419,7 +426,7 @@ def test_batch2_train_step_matches_oracle(kind, roi_op, rois, hw):
   got = model.train_step_batch(optimizer, images.cuda(), samples)
   a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
   b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
-  np.testing.assert_allclose(a, b, rtol = 5e-4, atol = 1e-5)
+  np.testing.assert_allclose(a, b, rtol = LOSS_RTOL_STEP1, atol = 1e-6)
   assert model.last_step_info["rois_per_image"] == oracle.last_batch_rois
   grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
   assert set(grads) == set(ref_grads)
@@ -430,57 +437,17 @@ def test_batch2_train_step_matches_oracle(kind, roi_op, rois, hw):
   for k, rel in rels.items():
     assert rel < 2 * GRAD_BAR, (k, rel)
   for k, p in model.named_parameters():
-    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = 2e-5)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), oracle.params[k].detach().numpy(), rtol = 1e-4, atol = WEIGHT_ATOL)
 
 
 def test_resnet101_forward_and_train_step_match_oracle():
-  """BASELINE config 4's backbone (ResNet-101, batch 1 per GPU; the 8-GPU part of that config is bench.py --gpus 8): forward and one
-  train step against the CPU restatement -- 23 bottlenecks in layer3, frozen BN folded into the filters, stride-2 / 7x7 convs on the
-  CUDA-core engine, everything else on the tensor cores."""
-  import fasterrcnn_b200 as f
-  from fasterrcnn_b200 import resnet
-  from oracle import resnet_oracle
-  params = orc.synth_params(resnet_oracle.param_shapes("resnet101"), seed = 6, heads = "spread")
-  for k in params:
-    if k.endswith("bn3.weight"):
-      params[k] = params[k] * 0.3                      # 33 residual blocks with Kaiming-scale branches overflow the synthetic init otherwise
-  model = f.FasterRCNNModel(num_classes = 21, backbone = resnet.ResNetBackbone(resnet.Architecture.ResNet101), allow_edge_proposals = True)
-  model.load_state_dict(params)
-  model = model.cuda()
-  oracle = orc.OracleModel(params, backbone = "resnet101")
-  smp = orc.synthetic_sample((320, 416), seed = 6, backbone = "resnet101")
+  """BASELINE config 4's backbone at a small size (320x416; the full-size case is test_config4_resnet101_full_size_600x1000): forward
+  and one train step against the CPU restatement -- 23 bottlenecks in layer3, frozen BN folded into the filters, stride-2 / 7x7 convs on
+  the CUDA-core engine, everything else on the tensor cores."""
+  model, oracle, smp = _build_resnet("resnet101", (320, 416), 6, 0.3)
   t.set_num_threads(min(16, os.cpu_count() or 8))
-  with t.no_grad():
-    p_ref, c_ref, d_ref = oracle.forward(smp["image"])
-  model.eval()
-  with t.no_grad():
-    props, classes, deltas = model(image_data = smp["image"].cuda())
-  assert abs(props.shape[0] - p_ref.shape[0]) <= 3
-  partner, ok = _match_rows(props.cpu().numpy(), p_ref.numpy())
-  assert ok.mean() >= 0.97, ok.mean()
-  row = np.abs(classes.cpu().numpy()[ok] - c_ref.numpy()[partner[ok]]).max(axis = 1)
-  assert (row <= 1e-4).mean() >= 0.99, (row > 1e-4).sum()
-  params = [{"params": [p], "weight_decay": 5e-4} for k, p in model.named_parameters() if p.requires_grad and "weight" in k]
-  optimizer = t.optim.SGD(params, lr = 1e-3, momentum = 0.9)
-  boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
-  random.seed(2); np.random.seed(2); t.manual_seed(2)
-  ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
-                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = False)
-  ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
-  random.seed(2); np.random.seed(2); t.manual_seed(2)
-  got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
-                         gt_rpn_map = smp["gt_rpn_map"].cuda(), gt_rpn_object_indices = [smp["gt_rpn_object_indices"]],
-                         gt_rpn_background_indices = [smp["gt_rpn_background_indices"]], gt_boxes = [boxes])
-  a = np.array([got.rpn_class, got.rpn_regression, got.detector_class, got.detector_regression, got.total])
-  b = np.array([ref.rpn_class, ref.rpn_regression, ref.detector_class, ref.detector_regression, ref.total])
-  np.testing.assert_allclose(a, b, rtol = 1e-3, atol = 1e-5)
-  worst = 0.0
-  for k, p in model.named_parameters():
-    if p.grad is None:
-      continue
-    ga, gb = p.grad.detach().cpu().double(), ref_grads[k].double()
-    worst = max(worst, float((ga - gb).norm() / (gb.norm() + 1e-12)))
-  assert worst < 2e-2, worst
+  _forward_vs_oracle("resnet101_forward_320x416", model, oracle, smp)
+  _train_step_vs_oracle("resnet101_train_step_320x416", model, oracle, smp, _reference_optimizer(model), seed = 2)
 
 
 def test_checkpoint_round_trip_and_caffe_partial_load(tmp_path):
