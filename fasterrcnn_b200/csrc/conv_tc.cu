@@ -151,6 +151,7 @@ struct TcGeom {
   int kb_per_split, total_kb, splits;
   int mn_lbo, mn_sbo, mn_kstep;   // MN-major operand descriptor strides in bytes (4096 / 512 / 1024)
   int m_tiles, n_tiles, items;    // work items = m_tiles * n_tiles * (taps for WGRAD) * splits; CTAs loop over them (persistent grid)
+  int m_pairs;                    // CTA-pair kernels: ceil(m_tiles / 2) -- a work item is then TWO vertically adjacent 128-row tiles (rank 0 / 1)
   unsigned long long *trace;      // debug: per-CTA %globaltimer stamps (frcnn_debug_tc_trace), NULL in production
   // stream-K (streamk != 0): the launch's (tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per CTA, so
   // every SM gets the same number of k-blocks whatever the tile count.  A CTA whose range starts inside a tile parks its raw
@@ -174,12 +175,13 @@ struct TcItem {
   long long tile_end;             // stream-K: first unit after this tile
 };
 
-template <int MODE, int BN>
-__device__ __forceinline__ TcItem tc_decode_item(const TcGeom &g, int w)
+template <int MODE, int BN, bool PAIR>
+__device__ __forceinline__ TcItem tc_decode_item(const TcGeom &g, int w, int rank)
 {
   TcItem it;
-  const int mt = w % g.m_tiles;
-  int r = w / g.m_tiles;
+  const int mdiv = PAIR ? g.m_pairs : g.m_tiles;
+  const int mt = PAIR ? 2 * (w % mdiv) + rank : w % mdiv;       // (a pair's second tile may lie past the last one: TMA zero-fills, stores are masked)
+  int r = w / mdiv;
   const int nt = r % g.n_tiles;
   r /= g.n_tiles;                                    // FWD/DGRAD: split; WGRAD: tap * splits + split
   it.n0 = nt * BN;
@@ -210,27 +212,29 @@ struct TcCursor {
   long long pos, end;
 };
 
-__device__ __forceinline__ long long tc_sk_start(const TcGeom &g, int cta) { return (long long)cta * g.units / (long long)gridDim.x; }
+// work groups: CTAs (gid = blockIdx.x of G = gridDim.x) or, for the CTA-pair kernels, clusters (gid = %clusterid.x of G = gridDim.x / 2);
+// both CTAs of a pair walk the same range
+__device__ __forceinline__ long long tc_sk_start(const TcGeom &g, int gid, int G) { return (long long)gid * g.units / (long long)G; }
 
-__device__ __forceinline__ TcCursor tc_cursor(const TcGeom &g)
+__device__ __forceinline__ TcCursor tc_cursor(const TcGeom &g, int gid, int G)
 {
   TcCursor c;
-  if (g.streamk) { c.pos = tc_sk_start(g, blockIdx.x); c.end = tc_sk_start(g, blockIdx.x + 1); }
-  else { c.pos = blockIdx.x; c.end = g.items; }
+  if (g.streamk) { c.pos = tc_sk_start(g, gid, G); c.end = tc_sk_start(g, gid + 1, G); }
+  else { c.pos = gid; c.end = g.items; }
   return c;
 }
 
-template <int MODE, int BN>
-__device__ __forceinline__ bool tc_next(const TcGeom &g, TcCursor &c, TcItem &t)
+template <int MODE, int BN, bool PAIR>
+__device__ __forceinline__ bool tc_next(const TcGeom &g, TcCursor &c, TcItem &t, int rank, int G)
 {
   if (c.pos >= c.end) return false;
   if (!g.streamk) {
-    t = tc_decode_item<MODE, BN>(g, (int)c.pos);
-    c.pos += gridDim.x;
+    t = tc_decode_item<MODE, BN, PAIR>(g, (int)c.pos, rank);
+    c.pos += G;
     return true;
   }
   const int tile = (int)(c.pos / g.total_kb);
-  t = tc_decode_item<MODE, BN>(g, tile);               // splits == 1 in this mode: the tile's coordinates (and tap)
+  t = tc_decode_item<MODE, BN, PAIR>(g, tile, rank);   // splits == 1 in this mode: the tile's coordinates (and tap)
   t.kb_begin = (int)(c.pos - (long long)tile * g.total_kb);
   t.tile_end = (long long)(tile + 1) * g.total_kb;
   const long long stop = t.tile_end < c.end ? t.tile_end : c.end;
@@ -262,13 +266,21 @@ __device__ __forceinline__ float tc_act(float v, int act)
   return v;
 }
 
-template <int MODE, int BN, int STAGES, bool F16>
+// PAIR (fp16 engine only): the kernel runs as clusters of two CTAs on cta_group::2 -- one M = 256 MMA per pair.  Each CTA stages its own
+// 128 rows of A (hi, lo) and HALF of the B tile's columns (hi, lo: BN / 2 rows each); per k-step the leader issues three M = 256, N = BN
+// MMAs:  main += A_hi * B_hi,  corr += A_hi * B_lo,  corr += A_lo * B_hi  (the single-CTA kernel's N = 2 BN instruction cannot be kept:
+// a pair's B operand is split by COLUMNS across the CTAs, so [B_hi | B_lo] would put the main and corr columns in different CTAs' halves).
+// Shared-memory traffic per k-block and CTA drops from 144 KB (64 written by TMA + 80 read by the tensor core) to 120 KB (48 + 72) for the
+// same tensor work, and a stage is 48 KB instead of 64 KB (one more stage in flight).
+template <int MODE, int BN, int STAGES, bool F16, bool PAIR = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                TcGeom g, float *__restrict__ out, float *__restrict__ partial, Epilogue epi)
 {
-  constexpr int kBBytes = BN * kBK * 4;
+  static_assert(!PAIR || F16, "the CTA-pair variant exists for the fp16 engine");
+  constexpr int kBRows = PAIR ? BN / 2 : BN;   // B columns (= rows of the staged tile) per CTA
+  constexpr int kBBytes = kBRows * kBK * 4;
   constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   constexpr bool kAMajorMN = (MODE == TC_WGRAD);
   constexpr bool kBMajorMN = (MODE != TC_FWD);
@@ -284,22 +296,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KHW = g.KH * g.KW;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;               // 0 = leader: owns the `full` / `acc_empty` barriers and issues the MMAs
+  const int gid = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;     // work-group index (see tc_cursor)
+  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   pdl_trigger();                                                     // the next kernel's CTAs may become resident behind this one
   const unsigned long long t_entry = (g.trace && threadIdx.x == 0) ? tc_globaltimer() : 0ull;   // stored after the wait: no global access before it
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }      // full: one arrive.expect_tx per producer
-    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }   // pair: the epilogue warps of both CTAs
     fence_barrier_init();
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 4 * BN);                                   // 2 accumulator buffers x [main | corr] columns
+    if (PAIR) tmem_alloc_pair(tmem_slot, 4 * BN);                    // (issued by warp 1 of BOTH CTAs: same columns in both TMEMs)
+    else tmem_alloc(tmem_slot, 4 * BN);                              // 2 accumulator buffers x [main | corr] columns
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                      // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                                        // set-up above touched no global memory: it overlaps the previous kernel's tail
@@ -313,9 +330,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kElems;       // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
       int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
-      TcCursor cur = tc_cursor(g);
+      TcCursor cur = tc_cursor(g, gid, G);
       TcItem t;
-      while (tc_next<MODE, BN>(g, cur, t)) {
+      while (tc_next<MODE, BN, PAIR>(g, cur, t, rank, G)) {
+        const int nb0 = t.n0 + rank * kBRows;                                  // first B column staged by this CTA (pair: its half)
         for (int i = 0; i < t.nkb; i++, it++) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -324,18 +342,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint8_t *a_lo = a_hi + kABytes;
           uint8_t *b_hi = a_hi + 2 * kABytes;
           uint8_t *b_lo = b_hi + kBBytes;
-          mbar_expect_tx(&full[s], feed_a ? 2 * kABytes : 2 * kBBytes);
+          // pair: every load of both CTAs is counted on the LEADER's barrier, which its two producers arm with the bytes of both CTAs
+          const uint32_t fbar = PAIR ? mapa_u32(smem_u32(&full[s]), 0) : 0u;
+          if (!PAIR) mbar_expect_tx(&full[s], feed_a ? 2 * kABytes : 2 * kBBytes);
+          else if (rank == 0) mbar_expect_tx(&full[s], feed_a ? 4 * kABytes : 4 * kBBytes);
           if (MODE == TC_WGRAD) {
             const int im = (kb / patches_per_img) * g.pn;            // first image of the patch's image group
             const int prem = kb % patches_per_img;
             const int py = (prem / g.patches_w) * g.ph, px = (prem % g.patches_w) * g.pw;
             const int kh = t.tap_w / g.KW, kw = t.tap_w - kh * g.KW;
             if (feed_a) {                                                      // A: dy, 128 output channels = 4 atoms in one box
-              tma_load_5d(a_hi, &map_a_hi, &full[s], 0, px, py, im, t.m0 / kElems);
-              tma_load_5d(a_lo, &map_a_lo, &full[s], 0, px, py, im, t.m0 / kElems);
+              if (PAIR) {
+                tma_load_5d_pair(a_hi, &map_a_hi, fbar, 0, px, py, im, t.m0 / kElems);
+                tma_load_5d_pair(a_lo, &map_a_lo, fbar, 0, px, py, im, t.m0 / kElems);
+              } else {
+                tma_load_5d(a_hi, &map_a_hi, &full[s], 0, px, py, im, t.m0 / kElems);
+                tma_load_5d(a_lo, &map_a_lo, &full[s], 0, px, py, im, t.m0 / kElems);
+              }
             } else {                                                           // B: x shifted by the tap, BN / 32 atoms in one box
-              tma_load_5d(b_hi, &map_b_hi, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
-              tma_load_5d(b_lo, &map_b_lo, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
+              if (PAIR) {
+                tma_load_5d_pair(b_hi, &map_b_hi, fbar, 0, px + kw - g.pad, py + kh - g.pad, im, nb0 / kElems);
+                tma_load_5d_pair(b_lo, &map_b_lo, fbar, 0, px + kw - g.pad, py + kh - g.pad, im, nb0 / kElems);
+              } else {
+                tma_load_5d(b_hi, &map_b_hi, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
+                tma_load_5d(b_lo, &map_b_lo, &full[s], 0, px + kw - g.pad, py + kh - g.pad, im, t.n0 / kElems);
+              }
             }
           } else {
             const int tap = kb / kblocks_c, c0 = (kb - tap * kblocks_c) * kElems;
@@ -343,23 +374,43 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int dx = (MODE == TC_FWD) ? (kw - g.pad) : (g.pad - kw);
             const int dy = (MODE == TC_FWD) ? (kh - g.pad) : (g.pad - kh);
             if (feed_a) {
-              tma_load_4d(a_hi, &map_a_hi, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
-              tma_load_4d(a_lo, &map_a_lo, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+              if (PAIR) {
+                tma_load_4d_pair(a_hi, &map_a_hi, fbar, c0, t.ow0 + dx, t.oh0 + dy, t.img);
+                tma_load_4d_pair(a_lo, &map_a_lo, fbar, c0, t.ow0 + dx, t.oh0 + dy, t.img);
+              } else {
+                tma_load_4d(a_hi, &map_a_hi, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+                tma_load_4d(a_lo, &map_a_lo, &full[s], c0, t.ow0 + dx, t.oh0 + dy, t.img);
+              }
             } else if (MODE == TC_FWD) {
-              tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, t.n0);
-              tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, t.n0);
+              if (PAIR) {
+                tma_load_2d_pair(b_hi, &map_b_hi, fbar, tap * g.Cin + c0, nb0);
+                tma_load_2d_pair(b_lo, &map_b_lo, fbar, tap * g.Cin + c0, nb0);
+              } else {
+                tma_load_2d(b_hi, &map_b_hi, &full[s], tap * g.Cin + c0, t.n0);
+                tma_load_2d(b_lo, &map_b_lo, &full[s], tap * g.Cin + c0, t.n0);
+              }
             } else {                                                           // B: w[co0..+32][tap][n0 .. n0+BN) as BN / 32 atoms in one box
-              tma_load_4d(b_hi, &map_b_hi, &full[s], 0, tap, c0, t.n0 / kElems);
-              tma_load_4d(b_lo, &map_b_lo, &full[s], 0, tap, c0, t.n0 / kElems);
+              if (PAIR) {
+                tma_load_4d_pair(b_hi, &map_b_hi, fbar, 0, tap, c0, nb0 / kElems);
+                tma_load_4d_pair(b_lo, &map_b_lo, fbar, 0, tap, c0, nb0 / kElems);
+              } else {
+                tma_load_4d(b_hi, &map_b_hi, &full[s], 0, tap, c0, t.n0 / kElems);
+                tma_load_4d(b_lo, &map_b_lo, &full[s], 0, tap, c0, t.n0 / kElems);
+              }
             }
           }
           if (it == 0 && feed_a) TC_TRACE(2);
         }
       }
+      if (PAIR && feed_a) {
+        // producer tail: the leader's commits arrive on THIS CTA's `empty` barriers asynchronously; wait for the last one of every slot
+        // so that no arrival can land in the shared memory of a CTA that has already exited
+        for (int i = it > STAGES ? it - STAGES : 0; i < it; i++) mbar_wait(&empty[i % STAGES], (i / STAGES) & 1);
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (pair: the leader CTA's, for both) =====
       constexpr uint32_t idesc_main = F16 ? make_idesc_f16(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
                                           : make_idesc_tf32(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);   // A_hi x [B_hi | B_lo]
       constexpr uint32_t idesc_corr = F16 ? make_idesc_f16(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
@@ -369,10 +420,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t accumulate = 0;
       int it = 0, chunk = 0;                                         // ring position / accumulation chains started, across all items
       uint32_t tmem_acc = tmem_base;
-      TcCursor cur = tc_cursor(g);
+      constexpr uint32_t idesc_pair = make_idesc_f16(256, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);                // pair: M = 256, N = BN
+      TcCursor cur = tc_cursor(g, gid, G);
       TcItem t;
       bool first_item = true;
-      while (tc_next<MODE, BN>(g, cur, t)) {
+      while (tc_next<MODE, BN, PAIR>(g, cur, t, rank, G)) {
         for (int i = 0; i < t.nkb; i++, it++) {
           if (i % kChunk == 0) {                                     // new accumulation chain in the other TMEM buffer
             const int b = chunk & 1;
@@ -395,7 +447,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);   // covers b_hi then b_lo (contiguous)
-            if (F16) {
+            if (PAIR) {
+              const uint64_t db_lo = make_smem_desc(b_hi + kBBytes + k * b_kstep, b_lbo, b_sbo, b_lt);
+              umma_f16_pair(tmem_acc, da_hi, db, idesc_pair, accumulate);         // main (+)= A_hi * B_hi     (each CTA: its rows x all BN columns)
+              umma_f16_pair(tmem_acc + BN, da_hi, db_lo, idesc_pair, accumulate); // corr (+)= A_hi * B_lo
+              umma_f16_pair(tmem_acc + BN, da_lo, db, idesc_pair, 1);             // corr  += A_lo * B_hi
+            } else if (F16) {
               umma_f16(tmem_acc, da_hi, db, idesc_main, accumulate);
               umma_f16(tmem_acc + BN, da_lo, db, idesc_corr, 1);
             } else {
@@ -404,9 +461,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             accumulate = 1;
           }
-          umma_commit(&empty[s]);                                    // frees the operand slot when these MMAs retire
+          if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // frees the operand slot (pair: in both CTAs) when these MMAs retire
           if (i % kChunk == kChunk - 1 || i == t.nkb - 1) {
-            umma_commit(&acc_full[chunk & 1]);                       // chain complete -> epilogue warps may drain it
+            if (PAIR) umma_commit_pair(&acc_full[chunk & 1]); else umma_commit(&acc_full[chunk & 1]);   // chain complete -> epilogue warps may drain it
             chunk++;
           }
         }
@@ -431,10 +488,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     int cg = 0;                                                      // accumulation chains drained so far, across all items
     float out_max = 0.f;                                             // max |final output| written by this thread (amax_out)
-    TcCursor cur = tc_cursor(g);
+    TcCursor cur = tc_cursor(g, gid, G);
     TcItem t;
     bool first_item = true;
-    while (tc_next<MODE, BN>(g, cur, t)) {
+    while (tc_next<MODE, BN, PAIR>(g, cur, t, rank, G)) {
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; j++) acc[j] = 0.f;
@@ -455,7 +512,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[b]), 0));     // the leader's barrier counts the warps of both CTAs
+          else mbar_arrive(&acc_empty[b]);
+        }
       }
       if (first_item && threadIdx.x == 64) TC_TRACE(6);
       if (t.kind == TC_ITEM_PART) {
@@ -474,17 +534,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       if (t.kind == TC_ITEM_HEAD) {
         // the CTAs after this one hold the rest of the tile's K range as the FIRST item of their ranges: long done, or about to be
-        for (int j = blockIdx.x + 1; j < (int)gridDim.x && tc_sk_start(g, j) < t.tile_end; j++) {
+        for (int j = gid + 1; j < G && tc_sk_start(g, j, G) < t.tile_end; j++) {
+          const int pj = PAIR ? 2 * j + rank : j;                    // the CTA of work group j that holds the same 128 rows
           if (threadIdx.x == 64) {
             const long long t0 = clock64();
             unsigned long long seen;
             do {
-              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(g.sk_flags + j) : "memory");
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(g.sk_flags + pj) : "memory");
               if (seen != g.sk_tag && clock64() - t0 > 20000000000ll) __trap();    // ~10 s: a partner that never ran
             } while (seen != g.sk_tag);
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const float *slot = g.sk_slots + ((size_t)j * 128 + row) * BN;
+          const float *slot = g.sk_slots + ((size_t)pj * 128 + row) * BN;
 #pragma unroll
           for (int q = 0; q < BN; q += 4) {
             const float4 p = __ldcg(reinterpret_cast<const float4 *>(slot + q));
@@ -567,9 +628,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                      // both CTAs are done with each other's barriers and tensor memory
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 4 * BN);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 4 * BN); else tmem_dealloc(tmem_base, 4 * BN);
   }
   if (threadIdx.x == 0 && g.trace) {
     TC_TRACE(9);
@@ -657,6 +719,7 @@ struct TcPlan {
   int pw, ph, pn, patches_w, patches_h, pgroups;
   int total_kb, splits, kb_per_split;
   int m_tiles, n_tiles, items;       // persistent-loop work items (see TcGeom)
+  int pair, m_pairs;                 // CTA-pair kernel (fp16 engine): work items are pairs of 128-row tiles, the grid is made of 2-CTA clusters
   int streamk, grid;                 // stream-K decomposition (default) and its CTA count
   int grid_max;                      // the CTA count with no SMs reserved: sizes the workspace layout and the amax slots, whatever `grid` is
   long long units;
@@ -697,6 +760,11 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   if (mode == TC_WGRAD && (Cout % 128 != 0 || Cin % 64 != 0)) return false;
   p->BN = (ntot % 128 == 0) ? 128 : 64;
   p->stages = p->BN == 128 ? 3 : 4;
+  // CTA pairs (cta_group::2): fp16 engine; the forward pass takes both tile widths (its B operand is K-major: any row count splits in
+  // two), dgrad / wgrad need BN = 128 (an MN-major half must be a whole 64-column swizzle atom).  FRCNN_TC_PAIR=0 keeps single CTAs.
+  static const bool use_pair = !(getenv("FRCNN_TC_PAIR") && atoi(getenv("FRCNN_TC_PAIR")) == 0);
+  p->pair = (f16 && use_pair && (mode == TC_FWD || p->BN == 128)) ? 1 : 0;
+  if (p->pair) p->stages = p->BN == 128 ? 4 : 5;                          // 48 KB / 40 KB per stage
   p->tile_w = p->tile_h = p->tile_n = p->tiles_w = p->tiles_h = p->groups = 1;
   p->pw = p->ph = p->pn = p->patches_w = p->patches_h = p->pgroups = 1;
   const int taps = KH * KW;
@@ -709,7 +777,8 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->total_kb = p->pgroups * p->patches_w * p->patches_h;
     p->m_tiles = Cout / 128;
     p->n_tiles = Cin / p->BN;
-    ctas = p->m_tiles * p->n_tiles * taps;
+    p->m_pairs = ceil_div(p->m_tiles, 2);
+    ctas = (p->pair ? p->m_pairs : p->m_tiles) * p->n_tiles * taps;
   } else {
     best_patch(128, p->N, p->H, p->W, &p->tile_w, &p->tile_h, &p->tile_n);
     p->tiles_w = ceil_div(p->W, p->tile_w);
@@ -718,8 +787,12 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->total_kb = taps * ((mode == TC_FWD ? Cin : Cout) / kel);
     p->m_tiles = p->groups * p->tiles_w * p->tiles_h;
     p->n_tiles = ntot / p->BN;
-    ctas = p->m_tiles * p->n_tiles;
+    p->m_pairs = ceil_div(p->m_tiles, 2);
+    ctas = (p->pair ? p->m_pairs : p->m_tiles) * p->n_tiles;
   }
+  // from here on `ctas` counts WORK GROUPS' tiles: 128-row tiles for single CTAs, 256-row tile pairs for CTA pairs; `wg_max` is the number
+  // of work groups one wave holds (SMs, or 2-SM clusters)
+  const int wg_max = p->pair ? kNumSMs / 2 : kNumSMs;
   // Work decomposition.  Default = stream-K: the tiles * total_kb k-block units of the launch are cut into one equal contiguous
   // range per CTA (persistent grid <= one CTA per SM), so the SMs finish together whatever the tile count; a tile that straddles
   // two ranges is summed through a per-CTA slot in the workspace by the CTA owning its first k-block (no reduce kernel).
@@ -731,25 +804,26 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   // stream-K pays when a launch has between ~half a wave and a few waves of tiles: fewer tiles mean many CTAs share one tile and
   // the owner's serial fix-up (64 KB per partner) outweighs the balance -- the split-K + parallel reduce path is better there --
   // and with many waves of tiles the quantisation loss is below 1/8 of a tile per SM anyway.
-  p->streamk = (use_streamk && ctas >= kNumSMs / 2 && ctas < 8 * kNumSMs) ? 1 : 0;
+  p->streamk = (use_streamk && ctas >= wg_max / 2 && ctas < 8 * wg_max) ? 1 : 0;
   p->units = (long long)ctas * p->total_kb;
   // SMs this launch may occupy: all of them, minus the ones set aside for a concurrent collective (frcnn_set_sm_reserve).  Only the
   // CTA count follows it; the decomposition (stream-K or split-K, number of splits) and the workspace layout never change.
-  const int sms = sm_budget();
+  const int sms = p->pair ? sm_budget() / 2 : sm_budget();           // work groups this launch may occupy
+  const int per_wg = p->pair ? 2 : 1;                                // CTAs per work group
   if (p->streamk) {
-    long long gsz = p->units / chunk;                                // at least one accumulation chain per CTA
+    long long gsz = p->units / chunk;                                // at least one accumulation chain per work group
     if (gsz < 1) gsz = 1;
-    p->grid_max = (int)(gsz > kNumSMs ? kNumSMs : gsz);
-    p->grid = (int)(gsz > sms ? sms : gsz);
+    p->grid_max = per_wg * (int)(gsz > wg_max ? wg_max : gsz);
+    p->grid = per_wg * (int)(gsz > sms ? sms : gsz);
   } else {
-    const double t_kb = (p->BN == 128) ? 0.56 : 0.42;               // us per k-block (measured, smem-bandwidth bound mainloop)
+    const double t_kb = p->pair ? ((p->BN == 128) ? 0.48 : 0.36) : ((p->BN == 128) ? 0.56 : 0.42);   // us per k-block (smem-bandwidth bound mainloop)
     const double t_item = 2.5;                                       // us of per-item pipeline refill / final drain not overlapped
     double best_t = -1.0;
     const int max_splits = p->total_kb / chunk > 32 ? 32 : p->total_kb / chunk;
     for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); sp++) {
       const int kbs = ceil_div(p->total_kb, sp);
       if (ceil_div(p->total_kb, kbs) != sp) continue;                // slice lengths that do not produce exactly sp splits
-      const long long rounds = ((long long)ctas * sp + kNumSMs - 1) / kNumSMs;
+      const long long rounds = ((long long)ctas * sp + wg_max - 1) / wg_max;
       double tt = rounds * (kbs * t_kb + t_item);
       if (sp > 1) tt += 4.0 + (double)(sp + 2) * out_elems_plan * 4.0 / 4.0e6;   // reduce pass at ~4 TB/s effective + launch
       if (best_t < 0 || tt < best_t) { best_t = tt; splits = sp; }
@@ -759,8 +833,8 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->splits = ceil_div(p->total_kb, p->kb_per_split);
   p->items = ctas * p->splits;
   if (!p->streamk) {
-    p->grid_max = p->items > kNumSMs ? kNumSMs : p->items;
-    p->grid = p->items > sms ? sms : p->items;
+    p->grid_max = per_wg * (p->items > wg_max ? wg_max : p->items);
+    p->grid = per_wg * (p->items > sms ? sms : p->items);
   }
   const size_t act_in = (size_t)pixels * Cin, act_out = (size_t)pixels * Cout, filt = (size_t)Cout * taps * Cin;
   size_t out_elems;
@@ -784,13 +858,14 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   return true;
 }
 
-template <int MODE, int BN, int STAGES, bool F16>
+template <int MODE, int BN, int STAGES, bool F16, bool PAIR = false>
 static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float *out, float *partial, const Epilogue &epi, cudaStream_t st)
 {
-  constexpr int smem = STAGES * (2 * kABytes + 2 * BN * kBK * 4) + 1024 + 256;
-  static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  constexpr int smem = STAGES * (2 * kABytes + 2 * (PAIR ? BN / 2 : BN) * kBK * 4) + 1024 + 256;
+  static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
-  launch(tc_conv_kernel<MODE, BN, STAGES, F16>, grid, kTcThreads, smem, st, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  if (PAIR) launch_cluster(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, 2, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  else launch(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;
 }
@@ -876,18 +951,19 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   }
 
   const int taps = KH * KW, el = (int)esz, atom = 128 / el;
+  const int bn_cta = p.pair ? p.BN / 2 : p.BN;                       // B columns one CTA stages (a pair's CTA: its half)
   CUtensorMap maps[4];
   bool ok;
   dim3 grid;
   if (mode == TC_FWD) {
     ok = make_act_map(&maps[0], a_hi, el, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, el, p.N, p.H, p.W, Cin, p.tile_w, p.tile_h, p.tile_n) &&
-         make_mat_map(&maps[2], b_hi, el, Cout, taps * Cin, p.BN) && make_mat_map(&maps[3], b_lo, el, Cout, taps * Cin, p.BN);
+         make_mat_map(&maps[2], b_hi, el, Cout, taps * Cin, bn_cta) && make_mat_map(&maps[3], b_lo, el, Cout, taps * Cin, bn_cta);
   } else if (mode == TC_DGRAD) {
     ok = make_act_map(&maps[0], a_hi, el, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) && make_act_map(&maps[1], a_lo, el, p.N, p.H, p.W, Cout, p.tile_w, p.tile_h, p.tile_n) &&
-         make_filter_map_atoms(&maps[2], b_hi, el, Cout, taps, Cin, p.BN / atom) && make_filter_map_atoms(&maps[3], b_lo, el, Cout, taps, Cin, p.BN / atom);
+         make_filter_map_atoms(&maps[2], b_hi, el, Cout, taps, Cin, bn_cta / atom) && make_filter_map_atoms(&maps[3], b_lo, el, Cout, taps, Cin, bn_cta / atom);
   } else {
     ok = make_act_map_atoms(&maps[0], a_hi, el, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 128 / atom) && make_act_map_atoms(&maps[1], a_lo, el, p.N, p.H, p.W, Cout, p.pw, p.ph, p.pn, 128 / atom) &&
-         make_act_map_atoms(&maps[2], b_hi, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / atom) && make_act_map_atoms(&maps[3], b_lo, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, p.BN / atom);
+         make_act_map_atoms(&maps[2], b_hi, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, bn_cta / atom) && make_act_map_atoms(&maps[3], b_lo, el, p.N, p.H, p.W, Cin, p.pw, p.ph, p.pn, bn_cta / atom);
   }
   if (!ok) return fail(FRCNN_E_BADARG, "tcgen05 engine: cuTensorMapEncodeTiled failed");
 
@@ -900,7 +976,7 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   static std::atomic<unsigned long long> launch_serial{0};
   grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, g_tc_trace,
+           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
            0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp,
            (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr, p.grid_max};
@@ -908,7 +984,12 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
 #define TC_LAUNCH(M)                                                                                                                      \
   (f16 ? (p.BN == 128 ? launch_tc<M, 128, 3, true>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, true>(maps, g, grid, out, partial, epi, st)) \
        : (p.BN == 128 ? launch_tc<M, 128, 3, false>(maps, g, grid, out, partial, epi, st) : launch_tc<M, 64, 4, false>(maps, g, grid, out, partial, epi, st)))
-  if (mode == TC_FWD) rc = TC_LAUNCH(TC_FWD);
+  if (p.pair) {
+    if (mode == TC_FWD) rc = p.BN == 128 ? launch_tc<TC_FWD, 128, 4, true, true>(maps, g, grid, out, partial, epi, st) : launch_tc<TC_FWD, 64, 5, true, true>(maps, g, grid, out, partial, epi, st);
+    else if (mode == TC_DGRAD) rc = launch_tc<TC_DGRAD, 128, 4, true, true>(maps, g, grid, out, partial, epi, st);
+    else rc = launch_tc<TC_WGRAD, 128, 4, true, true>(maps, g, grid, out, partial, epi, st);
+  }
+  else if (mode == TC_FWD) rc = TC_LAUNCH(TC_FWD);
   else if (mode == TC_DGRAD) rc = TC_LAUNCH(TC_DGRAD);
   else rc = TC_LAUNCH(TC_WGRAD);
 #undef TC_LAUNCH

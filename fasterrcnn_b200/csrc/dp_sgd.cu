@@ -47,36 +47,53 @@ __device__ __forceinline__ float dp_sgd_one(float p, float g, float &buf, float 
 }
 
 // MC: reduce / broadcast through the multicast mapping; else through the peer pointers.  All offsets in float4 units.
-template <bool MC>
-__global__ void __launch_bounds__(256)
+// A thread keeps UNROLL independent float4 reductions in flight (a multimem.ld_reduce over NVLink has microseconds of latency: bytes in
+// flight, not threads, set the rate).  Two launch shapes: 256 threads x many CTAs when the kernel has the GPU to itself, and 128 threads
+// x ONE CTA per SM (<= 64 registers: 8192 per SM) when it runs UNDER the convolution backward -- that CTA fits beside a resident
+// 224-thread x 256-register GEMM CTA, so neither kernel waits for the other's SM slots.
+template <bool MC, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
 dp_sgd_kernel(const float *__restrict__ grad_mc, float *__restrict__ weight_mc, DpPeers peers, const float *__restrict__ weight_local,
               float *__restrict__ momentum_shard, size_t shard_begin4, size_t shard_count4, float lr, float mom, float wd, float gs, int first)
 {
   pdl_enter();
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < shard_count4; k += stride) {
-    const size_t i = shard_begin4 + k;
-    float4 g;
-    if (MC) {
-      g = multimem_ld_reduce_add(grad_mc + 4 * i);
-    } else {
-      g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < peers.world; r++) {                        // fixed rank order: every rank would form the same sum
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(peers.grad[r]) + i);
-        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+  const size_t stride = (size_t)gridDim.x * THREADS;
+  for (size_t k0 = blockIdx.x * (size_t)THREADS + threadIdx.x; k0 < shard_count4; k0 += stride * UNROLL) {
+    float4 g[UNROLL], p[UNROLL], b[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t k = k0 + (size_t)u * stride;
+      if (k < shard_count4) {
+        const size_t i = shard_begin4 + k;
+        if (MC) {
+          g[u] = multimem_ld_reduce_add(grad_mc + 4 * i);
+        } else {
+          g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < peers.world; r++) {                    // fixed rank order: every rank would form the same sum
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(peers.grad[r]) + i);
+            g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+          }
+        }
+        p[u] = __ldcs(reinterpret_cast<const float4 *>(weight_local) + i);
+        b[u] = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(reinterpret_cast<const float4 *>(momentum_shard) + k);
       }
     }
-    float4 p = __ldcg(reinterpret_cast<const float4 *>(weight_local) + i);
-    float4 b = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4 *>(momentum_shard)[k];
-    p.x = dp_sgd_one(p.x, g.x, b.x, lr, mom, wd, gs, first);
-    p.y = dp_sgd_one(p.y, g.y, b.y, lr, mom, wd, gs, first);
-    p.z = dp_sgd_one(p.z, g.z, b.z, lr, mom, wd, gs, first);
-    p.w = dp_sgd_one(p.w, g.w, b.w, lr, mom, wd, gs, first);
-    reinterpret_cast<float4 *>(momentum_shard)[k] = b;
-    if (MC) {
-      multimem_st(weight_mc + 4 * i, p);
-    } else {
-      for (int r = 0; r < peers.world; r++) __stcg(reinterpret_cast<float4 *>(peers.weight[r]) + i, p);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t k = k0 + (size_t)u * stride;
+      if (k < shard_count4) {
+        const size_t i = shard_begin4 + k;
+        p[u].x = dp_sgd_one(p[u].x, g[u].x, b[u].x, lr, mom, wd, gs, first);
+        p[u].y = dp_sgd_one(p[u].y, g[u].y, b[u].y, lr, mom, wd, gs, first);
+        p[u].z = dp_sgd_one(p[u].z, g[u].z, b[u].z, lr, mom, wd, gs, first);
+        p[u].w = dp_sgd_one(p[u].w, g[u].w, b[u].w, lr, mom, wd, gs, first);
+        __stcs(reinterpret_cast<float4 *>(momentum_shard) + k, b[u]);
+        if (MC) {
+          multimem_st(weight_mc + 4 * i, p[u]);
+        } else {
+          for (int r = 0; r < peers.world; r++) __stcg(reinterpret_cast<float4 *>(peers.weight[r]) + i, p[u]);
+        }
+      }
     }
   }
 }
@@ -108,9 +125,17 @@ extern "C" int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_mul
     }
   }
   const size_t n4 = shard_count / 4;
-  const int grid = elementwise_grid(n4, 256, ctas_per_sm > 0 ? ctas_per_sm : 4);
-  if (mc) launch(dp_sgd_kernel<true>, grid, 256, 0, as_stream(stream), grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
-  else launch(dp_sgd_kernel<false>, grid, 256, 0, as_stream(stream), grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+  cudaStream_t st = as_stream(stream);
+  if (ctas_per_sm < 0) {
+    // co-resident shape: one 128-thread CTA per SM, 8 float4 in flight per thread
+    const int grid = device_sm_count();
+    if (mc) launch(dp_sgd_kernel<true, 128, 8>, grid, 128, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+    else launch(dp_sgd_kernel<false, 128, 8>, grid, 128, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+  } else {
+    const int grid = elementwise_grid(ceil_div<size_t>(n4, 4), 256, ctas_per_sm > 0 ? ctas_per_sm : 8);
+    if (mc) launch(dp_sgd_kernel<true, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+    else launch(dp_sgd_kernel<false, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+  }
   FRCNN_CHECK_LAUNCH("dp_sgd_kernel");
   return FRCNN_OK;
 }

@@ -340,7 +340,9 @@ int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *gra
  * or, when the multicast pointers are NULL, loads through grad_peers[0..world)), times grad_scale; torch.optim.SGD update with the shard's
  * own momentum buffer (momentum_shard, shard_count floats); the new weights are written to every rank (multimem.st on weight_multicast, or
  * stores through weight_peers).  weight_local = this rank's own arena (read side).  The caller brackets the launch with two cross-rank
- * barriers: every rank's gradients complete before | every rank's stores delivered and gradients consumed after.  world <= 8. */
+ * barriers: every rank's gradients complete before | every rank's stores delivered and gradients consumed after.  world <= 8.
+ * ctas_per_sm > 0: 256-thread CTAs, that many per SM (0 = 8) -- the kernel alone on the GPU; ctas_per_sm < 0: ONE 128-thread CTA per SM that fits
+ * beside a resident GEMM CTA -- the shape for running under the convolution backward on a side stream. */
 int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_multicast, const void *const *grad_peers, void *const *weight_peers, int world,
                        const float *weight_local, float *momentum_shard, size_t shard_begin, size_t shard_count,
                        float lr, float momentum, float weight_decay, float grad_scale, int first_step, int ctas_per_sm, void *stream);

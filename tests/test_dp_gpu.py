@@ -98,11 +98,13 @@ def _worker(rank, world, port, which, out):
     err = float(((w - ref).abs() / (1e-4 * ref.abs() + 2e-5)).max())        # in units of the bar: rtol 1e-4, atol 2e-5
     if err > worst_w:
       worst_w, worst_w_key = err, k
-    if which == "nccl" and k in summed and p.grad is not None:               # the arena holds the all-reduced SUM of the last step
+    if which == "nccl" and k in summed and p.grad is not None and p.requires_grad and "weight" in k:
+      # an optimizer-owned tensor: its .grad is the arena view holding the all-reduced SUM of the last step (biases are not reduced)
       a, b = p.grad.detach().cpu().double(), summed[k].double()
       worst_g = max(worst_g, float((a - b).norm() / (b.norm() + 1e-12)))
+  bucket_order = [optimizer.arena.bucket_of[id(optimizer.arena.params[i])] for i in optimizer.hook_order]
   out[rank] = dict(worst_weight_err_in_bars = worst_w, worst_weight = worst_w_key, worst_summed_grad_rel_l2 = worst_g, digest = digest.hexdigest(),
-                   buckets = len(optimizer.arena.buckets), bytes_reduced = int(optimizer.bytes_reduced_last_step), hook_order = list(optimizer.hook_order),
+                   buckets = len(optimizer.arena.buckets), bytes_reduced = int(optimizer.bytes_reduced_last_step), hook_order = bucket_order,
                    multicast = bool(getattr(optimizer, "use_multicast", False)))
   optimizer.remove_hooks()
   dist.destroy_process_group()
@@ -118,8 +120,9 @@ def test_two_rank_step_matches_oracle_step_on_mean_gradient(which):
   mp.spawn(_worker, args = (2, port, which, out), nprocs = 2, join = True)
   r0, r1 = out[0], out[1]
   _margins.record("dp2_" + which, **{k: v for k, v in r0.items() if k not in ("digest", "hook_order")}, replicas_identical = r0["digest"] == r1["digest"],
-                  hook_order_is_arena_order = r0["hook_order"] == sorted(r0["hook_order"]))
+                  gradients_arrive_in_bucket_order = r0["hook_order"] == sorted(r0["hook_order"]), bucket_of_each_hook = str(r0["hook_order"]))
   assert r0["digest"] == r1["digest"]                                       # replicas bit-identical
+  assert r0["hook_order"] == sorted(r0["hook_order"]), r0["hook_order"]     # backward produces the buckets in arena order: each is launched the moment it is complete
   assert r0["worst_weight_err_in_bars"] <= 1.0 and r1["worst_weight_err_in_bars"] <= 1.0, (r0, r1)
   assert 5.4e8 < r0["bytes_reduced"] < 5.6e8                                # all 16 optimizer tensors (136.78 M elements, 547 MB) crossed the wire
   if which == "nccl":
