@@ -252,7 +252,16 @@ __device__ __forceinline__ unsigned long long tc_globaltimer()
 }
 #define TC_TRACE(slot) do { if (g.trace) g.trace[(size_t)blockIdx.x * 16 + (slot)] = tc_globaltimer(); } while (0)
 
-constexpr int kTcThreads = 224;                  // warp 0: TMA producer (A operand), 1: MMA issuer, 2-5: accumulate/epilogue, 6: TMA producer (B operand)
+// Two warpgroups: warps 0-3 = accumulate / epilogue (warp w owns TMEM lane quarter w), warps 4-7 = TMA producer (A operand), MMA issuer
+// + TMEM allocator, TMA producer (B operand), spare.  The kernel is LAUNCHED with kTcLaunchRegs registers per thread; the producer
+// warpgroup then shrinks to kTcProducerRegs and the epilogue warpgroup (128 fp32 partial sums per thread) grows to kTcEpilogueRegs
+// (setmaxnreg: 128 * 248 + 128 * 56 = 256 * 152).  A launch that reserved 255 registers for every thread would fill the register file
+// of every SM sub-partition (2 warps x 8192 of 16384) and nothing else could become resident next to a GEMM CTA; at 152 each
+// sub-partition keeps 6656 registers free -- room for the 256-thread CTAs of the optimizer / gradient-exchange kernels that run UNDER the
+// convolution backward on a side stream (optim.FusedSGD(eager), optim.NvlsShardedSGD).
+constexpr int kTcThreads = 256;
+constexpr int kTcLaunchRegs = 152, kTcProducerRegs = 56, kTcEpilogueRegs = 248;
+constexpr int kWarpTmaA = 4, kWarpMma = 5, kWarpTmaB = 6;
 constexpr int kBK = 32;                       // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = 128 * kBK * 4;        // 16 KB: one 128 x 32 A tile
 constexpr int kAtomBytes = 32 * kBK * 4;      // 4 KB: 32 x 32 fp32 block (one MN-major 32-column atom x 32 k-rows)
@@ -273,7 +282,7 @@ __device__ __forceinline__ float tc_act(float v, int act)
 // Shared-memory traffic per k-block and CTA drops from 144 KB (64 written by TMA + 80 read by the tensor core) to 120 KB (48 + 72) for the
 // same tensor work, and a stage is 48 KB instead of 64 KB (one more stage in flight).
 template <int MODE, int BN, int STAGES, bool F16, bool PAIR = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __maxnreg__(kTcLaunchRegs)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                TcGeom g, float *__restrict__ out, float *__restrict__ partial, Epilogue epi)
@@ -309,7 +318,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
   }
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     __syncwarp();
     if (PAIR) tmem_alloc_pair(tmem_slot, 4 * BN);                    // (issued by warp 1 of BOTH CTAs: same columns in both TMEMs)
     else tmem_alloc(tmem_slot, 4 * BN);                              // 2 accumulator buffers x [main | corr] columns
@@ -322,11 +331,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   pdl_wait();                                                        // set-up above touched no global memory: it overlaps the previous kernel's tail
 
   if (threadIdx.x == 0 && g.trace) { g.trace[(size_t)blockIdx.x * 16] = t_entry; TC_TRACE(1); }
-  if (warp == 0 || warp == 6) {
+  if (warp >= 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcProducerRegs));      // whole warpgroup, before its roles diverge
+  if (warp == kWarpTmaA || warp == kWarpTmaB) {
     if (lane == 0) {
       // ===== TMA producers: warp 0 feeds the A operand, warp 6 the B operand (up to 8 box loads each per k-block: issuing them
       // from one thread was the limit of the filter-gradient mainloop).  Both run ahead across work items. =====
-      const bool feed_a = (warp == 0);
+      const bool feed_a = (warp == kWarpTmaA);
       const int kblocks_c = (MODE == TC_FWD ? g.Cin : g.Cout) / kElems;       // channel blocks per tap (FWD/DGRAD)
       const int patches_per_img = g.patches_w * g.patches_h;
       int it = 0;                                                            // k-blocks issued by this CTA so far (ring position)
@@ -408,7 +419,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int i = it > STAGES ? it - STAGES : 0; i < it; i++) mbar_wait(&empty[i % STAGES], (i / STAGES) & 1);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     if (lane == 0 && rank == 0) {
       // ===== MMA issuer (pair: the leader CTA's, for both) =====
       constexpr uint32_t idesc_main = F16 ? make_idesc_f16(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
@@ -472,8 +483,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       TC_TRACE(5);
     }
+  }
   } else {
-    // ===== accumulate + epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== accumulate + epilogue: warps 0..3 own TMEM lane quarters (warp % 4) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpilogueRegs));
     // While these warps finish and store item i, the MMA warp is already up to two chains into item i+1.
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -517,7 +530,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           else mbar_arrive(&acc_empty[b]);
         }
       }
-      if (first_item && threadIdx.x == 64) TC_TRACE(6);
+      if (first_item && threadIdx.x == 0) TC_TRACE(6);
       if (t.kind == TC_ITEM_PART) {
         // park the raw partial sums of this (tile, k-range) and publish them; the tile's HEAD owner folds them in
         float *slot = g.sk_slots + ((size_t)blockIdx.x * 128 + row) * BN;
@@ -525,7 +538,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int j = 0; j < BN; j += 4) __stcg(reinterpret_cast<float4 *>(slot + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == 0) {
           asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(g.sk_flags + blockIdx.x), "l"(g.sk_tag) : "memory");
           if (first_item) TC_TRACE(7);
         }
@@ -536,7 +549,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // the CTAs after this one hold the rest of the tile's K range as the FIRST item of their ranges: long done, or about to be
         for (int j = gid + 1; j < G && tc_sk_start(g, j, G) < t.tile_end; j++) {
           const int pj = PAIR ? 2 * j + rank : j;                    // the CTA of work group j that holds the same 128 rows
-          if (threadIdx.x == 64) {
+          if (threadIdx.x == 0) {
             const long long t0 = clock64();
             unsigned long long seen;
             do {
@@ -609,7 +622,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
-      if (first_item && threadIdx.x == 64) TC_TRACE(7);
+      if (first_item && threadIdx.x == 0) TC_TRACE(7);
       first_item = false;
     }
     if (g.amax_out) {
@@ -619,17 +632,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       float *wmax = reinterpret_cast<float *>(tmem_slot + 1);        // 4 words behind the TMEM slot (inside the 256-byte tail)
       if (lane == 0) wmax[q] = out_max;
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) g.amax_out[kF16PartialsAt + blockIdx.x] = __float_as_uint(fmaxf(fmaxf(wmax[0], wmax[1]), fmaxf(wmax[2], wmax[3])));
+      if (threadIdx.x == 0) g.amax_out[kF16PartialsAt + blockIdx.x] = __float_as_uint(fmaxf(fmaxf(wmax[0], wmax[1]), fmaxf(wmax[2], wmax[3])));
       // a launch on fewer CTAs than the consumer expects partials from (frcnn_set_sm_reserve): the missing ones are zero
-      if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 192)
-        for (int sl = (int)gridDim.x + (threadIdx.x - 64); sl < g.amax_slots; sl += 128) g.amax_out[kF16PartialsAt + sl] = 0u;
+      if (blockIdx.x == 0)
+        for (int sl = (int)gridDim.x + threadIdx.x; sl < g.amax_slots; sl += 128) g.amax_out[kF16PartialsAt + sl] = 0u;
     }
-    if (threadIdx.x == 64) TC_TRACE(8);
+    if (threadIdx.x == 0) TC_TRACE(8);
   }
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                                      // both CTAs are done with each other's barriers and tensor memory
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     __syncwarp();
     if (PAIR) tmem_dealloc_pair(tmem_base, 4 * BN); else tmem_dealloc(tmem_base, 4 * BN);
   }
@@ -761,9 +774,10 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->BN = (ntot % 128 == 0) ? 128 : 64;
   p->stages = p->BN == 128 ? 3 : 4;
   // CTA pairs (cta_group::2): fp16 engine; the forward pass takes both tile widths (its B operand is K-major: any row count splits in
-  // two), dgrad / wgrad need BN = 128 (an MN-major half must be a whole 64-column swizzle atom).  FRCNN_TC_PAIR=0 keeps single CTAs.
-  static const bool use_pair = !(getenv("FRCNN_TC_PAIR") && atoi(getenv("FRCNN_TC_PAIR")) == 0);
-  p->pair = (f16 && use_pair && (mode == TC_FWD || p->BN == 128)) ? 1 : 0;
+  // two), dgrad / wgrad need BN = 128 (an MN-major half must be a whole 64-column swizzle atom).  Opt-in (FRCNN_TC_PAIR=1): parity-green
+  // (tests/test_kernels_gpu.py passes on it bit for bit) but measured SLOWER than the single-CTA kernels in round 2 (profiles/r02_pair_ab.md).
+  static const bool use_pair = getenv("FRCNN_TC_PAIR") && atoi(getenv("FRCNN_TC_PAIR")) != 0;
+  p->pair = (f16 && use_pair && (mode == TC_FWD || p->BN == 128)) ? 1 : 0;                  // (+ an even / large tile count, below)
   if (p->pair) p->stages = p->BN == 128 ? 4 : 5;                          // 48 KB / 40 KB per stage
   p->tile_w = p->tile_h = p->tile_n = p->tiles_w = p->tiles_h = p->groups = 1;
   p->pw = p->ph = p->pn = p->patches_w = p->patches_h = p->pgroups = 1;
@@ -789,6 +803,12 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
     p->n_tiles = ntot / p->BN;
     p->m_pairs = ceil_div(p->m_tiles, 2);
     ctas = (p->pair ? p->m_pairs : p->m_tiles) * p->n_tiles;
+  }
+  if (p->pair && (p->m_tiles & 1) && p->m_tiles < 16) {
+    // an odd tile count leaves one CTA of the last pair idle: nn.Linear on 128 RoIs (ONE row tile) would do twice the tensor work
+    p->pair = 0;
+    p->stages = p->BN == 128 ? 3 : 4;
+    ctas = (mode == TC_WGRAD) ? p->m_tiles * p->n_tiles * taps : p->m_tiles * p->n_tiles;
   }
   // from here on `ctas` counts WORK GROUPS' tiles: 128-row tiles for single CTAs, 256-row tile pairs for CTA pairs; `wg_max` is the number
   // of work groups one wave holds (SMs, or 2-SM clusters)

@@ -145,7 +145,7 @@ class FasterRCNNModel(nn.Module):
 
     loss_ready.synchronize()
     host = loss_host.numpy()
-    self.last_step_info = dict(num_rois = int(proposals.shape[0]))
+    self.last_step_info = dict(num_rois = int(proposals.shape[0]), sampled_proposals = proposals)      # (the RoIs the detector was trained on: device tensor, no copy)
     return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host[4]))
 
   # ---- EXTENSION: batch > 1 (BASELINE config 3).  The reference asserts batch == 1 everywhere; its loss formulas

@@ -214,8 +214,9 @@ def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol =
   """One train_step against the oracle on the same RNG streams: losses, every parameter gradient, optionally post-step weights."""
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
   random.seed(seed); np.random.seed(seed); t.manual_seed(seed)
+  taps = {}
   ref = oracle.train_step(smp["image"], smp["anchor_map"], smp["anchor_valid_map"], smp["gt_rpn_map"], smp["gt_rpn_object_indices"],
-                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = check_weights)
+                          smp["gt_rpn_background_indices"], smp["gt_corners"], smp["gt_class_idxs"], apply_update = check_weights, taps = taps)
   ref_grads = {k: v.grad.clone() for k, v in oracle.params.items() if v.grad is not None}
   random.seed(seed); np.random.seed(seed); t.manual_seed(seed)
   got = model.train_step(optimizer = optimizer, image_data = smp["image"].cuda(), anchor_map = smp["anchor_map"], anchor_valid_map = smp["anchor_valid_map"],
@@ -228,10 +229,23 @@ def _train_step_vs_oracle(name, model, oracle, smp, optimizer, seed, loss_rtol =
   extra = {}
   if check_weights:
     extra["post_step_weight_max_abs"] = max(float((p.detach().cpu() - oracle.params[k].detach()).abs().max()) for k, p in model.named_parameters())
+  # Did both sides train the detector on the SAME RoIs?  The proposal set feeds a seeded sampler, so one flipped NMS / top-N decision
+  # upstream (the oracle's own margins go down to |IoU - 0.7| = 5e-7, score gaps to 1e-8 -- inside the fp32 agreement of two summation
+  # orders) re-draws the sample: the step is then a different, equally valid one.  That case is recognised and held to the wide bars only
+  # if the oracle's margins really are that thin; with the same RoIs the tight bars (2x the measured values) apply.
+  sp_got, sp_ref = model.last_step_info["sampled_proposals"].detach().cpu().numpy(), taps["sampled_proposals"].numpy()
+  same_rois = sp_got.shape == sp_ref.shape and bool((_margins.match_rows(sp_got, sp_ref)[1] <= PX_BAR).all())
+  dm = _margins.decision_margins(taps, 12000, tuple(smp["image"].shape[2:]))
   _margins.record(name, loss_rel = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6))), num_rois = model.last_step_info["num_rois"],
-                  optimizer = type(optimizer).__name__, **gm, **extra)
-  np.testing.assert_allclose(a, b, rtol = loss_rtol, atol = 1e-5)
+                  optimizer = type(optimizer).__name__, same_sampled_rois = same_rois, **gm, **extra, **dm)
   assert set(grads) == set(ref_grads)
+  if not same_rois:
+    assert min(dm.get("min_iou_margin", 1.0), dm["topn_cut_gap"], dm["min_adjacent_gap"] + 1e-30) < 1e-4, ("RoI sets differ although every decision margin is wide", dm)
+    np.testing.assert_allclose(a, b, rtol = 5e-3, atol = 1e-4)
+    for k, rel in rels.items():
+      assert rel < 5e-2, (k, rel)
+    return got
+  np.testing.assert_allclose(a, b, rtol = loss_rtol, atol = 1e-5)
   for k, rel in rels.items():
     assert rel < 2 * GRAD_BAR, (k, rel)
   if check_weights:
