@@ -44,6 +44,7 @@ _SIGNATURES = {
   "frcnn_f16_split": (_i, [_vp, _sz, _vp, _vp]),
   "frcnn_conv2d_amax_slots": (_i, [_i] + _GEOM),
   "frcnn_f16_split_from_amax": (_i, [_vp, _sz, _vp, _i, _vp, _vp]),
+  "frcnn_f16_split_carried": (_i, [_vp, _sz, _vp, _i, _vp]),
   "frcnn_conv2d_fwd_f16": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _vp, _sz, _vp]),
   "frcnn_conv2d_dgrad_f16": (_i, [_vp] * 6 + _GEOM + [_vp, _vp, _sz, _vp]),
   "frcnn_conv2d_wgrad_f16": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),

@@ -59,6 +59,7 @@ size_t f16_split_bytes(size_t count);
 void tc_set_trace(void *buf);
 int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
 int f16_split(const float *x, size_t count, void *out, cudaStream_t st, const void *partials, int G);
+int f16_split_carried(const float *x, size_t count, void *out, int ctas_per_sm, cudaStream_t st);
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                     void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split, bool f16, void *amax_out = nullptr);
@@ -215,6 +216,13 @@ int frcnn_f16_split(const float *x, size_t count, void *out, void *stream)
   FRCNN_REQUIRE(x && out && count > 0, "f16_split: bad argument");
   FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0, "f16_split: x must be 16-byte, out 128-byte aligned");
   return f16_split(x, count, out, as_stream(stream), nullptr, 0);
+}
+
+int frcnn_f16_split_carried(const float *x, size_t count, void *out, int ctas_per_sm, void *stream)
+{
+  FRCNN_REQUIRE(x && out && count > 0, "f16_split_carried: bad argument");
+  FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0, "f16_split_carried: x must be 16-byte, out 128-byte aligned");
+  return f16_split_carried(x, count, out, ctas_per_sm, as_stream(stream));
 }
 
 int frcnn_f16_split_from_amax(const float *x, size_t count, const void *amax, int slots, void *out, void *stream)

@@ -138,6 +138,34 @@ split_f16_kernel(const float *__restrict__ x, unsigned *__restrict__ header, con
   for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) split16(x[i], s, hi[i], lo[i]);
 }
 
+// split with the exponent the buffer already carries (header word 1): ONE pass, for tensors that change slowly (weights after an optimizer
+// step whose update kernel could not write the split itself: the sharded data-parallel step).  Values are saturated, see f16_split.cuh.
+__global__ void __launch_bounds__(256)
+split_f16_carried_kernel(const float *__restrict__ x, const unsigned *__restrict__ header, __half *__restrict__ hi, __half *__restrict__ lo, size_t count)
+{
+  pdl_enter();
+  const float s = pow2i((int)__ldcg(header + 1));
+  const size_t n4 = count / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    uint2 h, l;
+    split16x4(__ldcs(reinterpret_cast<const float4 *>(x) + i), s, h, l);
+    reinterpret_cast<uint2 *>(hi)[i] = h;
+    reinterpret_cast<uint2 *>(lo)[i] = l;
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) split16(x[i], s, hi[i], lo[i]);
+}
+
+int f16_split_carried(const float *x, size_t count, void *out, int ctas_per_sm, cudaStream_t st)
+{
+  uint8_t *o = reinterpret_cast<uint8_t *>(out);
+  __half *hi = reinterpret_cast<__half *>(o + kF16Header);
+  __half *lo = reinterpret_cast<__half *>(o + kF16Header + f16_half_bytes(count));
+  launch(split_f16_carried_kernel, elementwise_grid(count / 4 + 1, 256, ctas_per_sm > 0 ? ctas_per_sm : 8), 256, 0, st, x, reinterpret_cast<const unsigned *>(o), hi, lo, count);
+  FRCNN_CHECK_LAUNCH("split_f16_carried_kernel");
+  return FRCNN_OK;
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
@@ -420,14 +448,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0 && rank == 0) {
-      // ===== MMA issuer (pair: the leader CTA's, for both) =====
+    if (rank == 0) {
+      // ===== MMA issuer (pair: the leader CTA's, for both).  The whole warp walks the loop (waits included); one elected lane issues. =====
       constexpr uint32_t idesc_main = F16 ? make_idesc_f16(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
                                           : make_idesc_tf32(128, 2 * BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);   // A_hi x [B_hi | B_lo]
       constexpr uint32_t idesc_corr = F16 ? make_idesc_f16(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0)
                                           : make_idesc_tf32(128, BN, kAMajorMN ? 1 : 0, kBMajorMN ? 1 : 0);       // A_lo x B_hi
       const uint32_t a_kstep = kAMajorMN ? g.mn_kstep : 32, a_lbo = kAMajorMN ? g.mn_lbo : 16, a_sbo = kAMajorMN ? g.mn_sbo : 1024;
       const uint32_t b_kstep = kBMajorMN ? g.mn_kstep : 32, b_lbo = kBMajorMN ? g.mn_lbo : 16, b_sbo = kBMajorMN ? g.mn_sbo : 1024;
+      constexpr uint32_t mn_lt = F16 ? kLayoutSW128 : kLayoutSW128Base32B;
+      const uint64_t a_desc = make_smem_desc_base(a_lbo, a_sbo, kAMajorMN ? mn_lt : kLayoutSW128);
+      const uint64_t b_desc = make_smem_desc_base(b_lbo, b_sbo, kBMajorMN ? mn_lt : kLayoutSW128);
       uint32_t accumulate = 0;
       int it = 0, chunk = 0;                                         // ring position / accumulation chains started, across all items
       uint32_t tmem_acc = tmem_base;
@@ -447,41 +478,43 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (it == 0) TC_TRACE(3);
+          if (it == 0 && lane == 0) TC_TRACE(3);
           const uint32_t a_hi = smem_u32(smem + s * kStageBytes);
           const uint32_t a_lo = a_hi + kABytes;
           const uint32_t b_hi = a_hi + 2 * kABytes;                  // b_lo follows at + kBBytes
+          const bool chain_end = (i % kChunk == kChunk - 1 || i == t.nkb - 1);
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {                              // four MMAs per k-block: K = 8 (tf32) / 16 (fp16) = 32 bytes of a K-major row each
-            constexpr uint32_t mn_lt = F16 ? kLayoutSW128 : kLayoutSW128Base32B;
-            constexpr uint32_t a_lt = kAMajorMN ? mn_lt : kLayoutSW128, b_lt = kBMajorMN ? mn_lt : kLayoutSW128;
-            const uint64_t da_hi = make_smem_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t da_lo = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t db = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);   // covers b_hi then b_lo (contiguous)
+            const uint64_t da_hi = smem_desc_at(a_desc, a_hi + k * a_kstep);
+            const uint64_t da_lo = smem_desc_at(a_desc, a_lo + k * a_kstep);
+            const uint64_t db = smem_desc_at(b_desc, b_hi + k * b_kstep);                 // covers b_hi then b_lo (contiguous)
             if (PAIR) {
-              const uint64_t db_lo = make_smem_desc(b_hi + kBBytes + k * b_kstep, b_lbo, b_sbo, b_lt);
-              umma_f16_pair(tmem_acc, da_hi, db, idesc_pair, accumulate);         // main (+)= A_hi * B_hi     (each CTA: its rows x all BN columns)
-              umma_f16_pair(tmem_acc + BN, da_hi, db_lo, idesc_pair, accumulate); // corr (+)= A_hi * B_lo
+              const uint64_t db_lo = smem_desc_at(b_desc, b_hi + kBBytes + k * b_kstep);
+              umma_f16_pair(tmem_acc, da_hi, db, idesc_pair, k ? 1u : accumulate);         // main (+)= A_hi * B_hi     (each CTA: its rows x all BN columns)
+              umma_f16_pair(tmem_acc + BN, da_hi, db_lo, idesc_pair, k ? 1u : accumulate); // corr (+)= A_hi * B_lo
               umma_f16_pair(tmem_acc + BN, da_lo, db, idesc_pair, 1);             // corr  += A_lo * B_hi
             } else if (F16) {
-              umma_f16(tmem_acc, da_hi, db, idesc_main, accumulate);
+              umma_f16(tmem_acc, da_hi, db, idesc_main, k ? 1u : accumulate);
               umma_f16(tmem_acc + BN, da_lo, db, idesc_corr, 1);
             } else {
-              umma_tf32(tmem_acc, da_hi, db, idesc_main, accumulate); // [main | corr] (+)= A_hi * [B_hi | B_lo]
+              umma_tf32(tmem_acc, da_hi, db, idesc_main, k ? 1u : accumulate); // [main | corr] (+)= A_hi * [B_hi | B_lo]
               umma_tf32(tmem_acc + BN, da_lo, db, idesc_corr, 1);     // corr += A_lo * B_hi
             }
-            accumulate = 1;
           }
           if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // frees the operand slot (pair: in both CTAs) when these MMAs retire
-          if (i % kChunk == kChunk - 1 || i == t.nkb - 1) {
+          if (chain_end) {
             if (PAIR) umma_commit_pair(&acc_full[chunk & 1]); else umma_commit(&acc_full[chunk & 1]);   // chain complete -> epilogue warps may drain it
-            chunk++;
           }
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (chain_end) chunk++;
         }
-        if (first_item) TC_TRACE(4);
+        if (first_item && lane == 0) TC_TRACE(4);
         first_item = false;
       }
-      TC_TRACE(5);
+      if (lane == 0) TC_TRACE(5);
     }
   }
   } else {

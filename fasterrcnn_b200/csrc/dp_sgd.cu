@@ -48,9 +48,9 @@ __device__ __forceinline__ float dp_sgd_one(float p, float g, float &buf, float 
 
 // MC: reduce / broadcast through the multicast mapping; else through the peer pointers.  All offsets in float4 units.
 // A thread keeps UNROLL independent float4 reductions in flight (a multimem.ld_reduce over NVLink has microseconds of latency: bytes in
-// flight, not threads, set the rate).  Two launch shapes: 256 threads x many CTAs when the kernel has the GPU to itself, and 128 threads
-// x ONE CTA per SM (<= 64 registers: 8192 per SM) when it runs UNDER the convolution backward -- that CTA fits beside a resident
-// 224-thread x 256-register GEMM CTA, so neither kernel waits for the other's SM slots.
+// flight, not threads, set the rate).  Launch shapes: many CTAs per SM when the kernel has the GPU to itself, ONE 256-thread CTA per SM
+// (~80 registers per thread) when it runs UNDER the convolution backward -- that CTA fits beside a resident GEMM CTA, which is launched
+// with 152 registers per thread for exactly this purpose (conv_tc.cu), so neither kernel waits for the other's SM slots.
 template <bool MC, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 dp_sgd_kernel(const float *__restrict__ grad_mc, float *__restrict__ weight_mc, DpPeers peers, const float *__restrict__ weight_local,
@@ -126,16 +126,11 @@ extern "C" int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_mul
   }
   const size_t n4 = shard_count / 4;
   cudaStream_t st = as_stream(stream);
-  if (ctas_per_sm < 0) {
-    // co-resident shape: one 128-thread CTA per SM, 8 float4 in flight per thread
-    const int grid = device_sm_count();
-    if (mc) launch(dp_sgd_kernel<true, 128, 8>, grid, 128, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
-    else launch(dp_sgd_kernel<false, 128, 8>, grid, 128, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
-  } else {
-    const int grid = elementwise_grid(ceil_div<size_t>(n4, 4), 256, ctas_per_sm > 0 ? ctas_per_sm : 8);
-    if (mc) launch(dp_sgd_kernel<true, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
-    else launch(dp_sgd_kernel<false, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
-  }
+  // 256 threads x 4 float4 in flight per thread; ctas_per_sm = 1 is the shape that runs UNDER the convolution backward (one such CTA,
+  // <= 104 registers per thread, fits beside a resident GEMM CTA: conv_tc.cu kTcLaunchRegs), 0 = 8 per SM when the kernel runs alone
+  const int grid = elementwise_grid(ceil_div<size_t>(n4, 4), 256, ctas_per_sm > 0 ? ctas_per_sm : 8);
+  if (mc) launch(dp_sgd_kernel<true, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
+  else launch(dp_sgd_kernel<false, 256, 4>, grid, 256, 0, st, grad_multicast, weight_multicast, peers, weight_local, momentum_shard, shard_begin / 4, n4, lr, momentum, weight_decay, grad_scale, first_step);
   FRCNN_CHECK_LAUNCH("dp_sgd_kernel");
   return FRCNN_OK;
 }

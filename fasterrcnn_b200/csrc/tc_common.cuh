@@ -165,9 +165,12 @@ __device__ __forceinline__ void cluster_sync_all()              // every thread 
 {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// (relaxed: the accumulator hand-over is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync on this side and
+// tcgen05.fence::after_thread_sync on the waiting side; a .release here compiles to ERRBAR, which also waits for the epilogue's
+// outstanding global stores -- 9 % of all stall samples in the first capture of the pair kernel)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
 {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the barrier at `bar_cluster_addr`
 // (the leader's), which .cta_group::2 permits to live in the peer CTA
@@ -240,6 +243,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
+}
+
+// descriptor = constant part (strides, version, layout) | start address field: the issue loop builds the constant part once
+__device__ __forceinline__ uint64_t make_smem_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) { return make_smem_desc(0u, lbo_bytes, sbo_bytes, layout_type); }
+__device__ __forceinline__ uint64_t smem_desc_at(uint64_t base, uint32_t smem_addr) { return base | (uint64_t)((smem_addr & 0x3FFFF) >> 4); }
+
+// one lane of a converged warp (the MMA / commit instructions are issued by it; the loop around them stays warp-uniform, so that the
+// operands live in uniform registers instead of being broadcast from a divergent lane before every instruction)
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
 }
 
 // Instruction descriptor for kind::tf32 with fp32 accumulation (upper 32 bits of the "idesc" operand):

@@ -384,10 +384,12 @@ class NvlsShardedSGD(_BucketedHooks):
       at += n
     self.momentum_shard = t.zeros((at,), dtype = t.float32, device = dev)
     self._first = [True] * len(arena.buckets)
-    self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "1"))
     if overlap is None:
       overlap = os.environ.get("FRCNN_DP_FUSED_OVERLAP", "1") not in ("", "0")
     self.overlap = bool(overlap)                                 # False: every bucket at step(), on the compute stream
+    # launch shapes: under the backward ONE 256-thread CTA per SM (it fits beside a resident GEMM CTA); alone on the GPU 8 per SM
+    self.ctas_per_sm = int(ctas_per_sm) if ctas_per_sm else int(os.environ.get("FRCNN_DP_FUSED_CTAS", "1" if self.overlap else "8"))
+    self.split_ctas_per_sm = int(os.environ.get("FRCNN_DP_SPLIT_CTAS", "2" if self.overlap else "8"))
     self._side = t.cuda.Stream(device = dev) if self.overlap else None
     self._used_side = False
     self.sm_reserve = 0
@@ -423,6 +425,31 @@ class NvlsShardedSGD(_BucketedHooks):
     self.hG.barrier(channel = 0)                                 # every shard delivered everywhere; every arena's gradients consumed
     self._first[b] = False
     self.bytes_reduced_last_step += self.arena.payload_bytes[b]
+    self._resplit(b)
+
+  def _resplit(self, b):
+    """The updated weights of bucket b arrived through the multicast mapping: bring the operand splits the tensor-core GEMMs read up to
+    date right here, on the stream the update ran on (under the backward), ONE pass per tensor with the exponent its buffer carries
+    (a full amax + split pass seeds it and refreshes it every 64 steps, as in FusedSGD)."""
+    from . import _lib, ops
+    if not ops._f16():
+      return
+    L = _lib.lib()
+    f0, f1, _, _ = self.arena.buckets[b]
+    for p in self.arena.params[f0:f1]:
+      if not (p.dim() >= 2 and p.numel() >= 4096):
+        continue                                               # (the narrow heads run on the CUDA cores and read fp32)
+      e = ops.weight_split_buffer(p)
+      age = e.get("age", 64)
+      if age >= 64:
+        _lib.check(L.frcnn_f16_split(_lib.ptr(p), p.numel(), _lib.ptr(e["buf"]), _lib.stream()), "frcnn_f16_split")
+        _lib.count(2)
+        age = 0
+      else:
+        _lib.check(L.frcnn_f16_split_carried(_lib.ptr(p), p.numel(), _lib.ptr(e["buf"]), self.split_ctas_per_sm, _lib.stream()), "frcnn_f16_split_carried")
+        _lib.count()
+      e["age"] = age + 1
+      e["version"] = p._version
 
   def _launch_bucket(self, b):
     if self._side is None:
@@ -448,7 +475,6 @@ class NvlsShardedSGD(_BucketedHooks):
     if self._used_side:
       t.cuda.current_stream().wait_stream(self._side)            # the next forward reads the updated weights
       self._used_side = False
-    ops.invalidate_weight_splits()                               # written through the multicast mapping: no version bump, no carried split
 
 
 def optimizer_param_groups(model, weight_decay = 5e-4):

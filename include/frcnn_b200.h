@@ -129,6 +129,10 @@ int frcnn_f16_split(const float *x, size_t count, void *out, void *stream);
  * without a pass over the tensor for its maximum.  The maxima may belong to a superset of x (an un-pooled map, an unmasked gradient). */
 int frcnn_conv2d_amax_slots(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int frcnn_f16_split_from_amax(const float *x, size_t count, const void *amax, int slots, void *out, void *stream);
+/* One-pass split that KEEPS the exponent `out` already carries (header word 1, left there by an earlier frcnn_f16_split of the same tensor):
+ * for weights after an update that moved them by a few lr * gradient (values are saturated at +-65504, so a stale exponent cannot emit
+ * inf; callers refresh it with a full frcnn_f16_split every few dozen steps).  ctas_per_sm: 0 = 8; small = a side-stream launch. */
+int frcnn_f16_split_carried(const float *x, size_t count, void *out, int ctas_per_sm, void *stream);
 int frcnn_conv2d_fwd_f16(const float *x, const float *w, const void *x_split, const void *w_split, const float *scale, const float *bias,
                          const float *residual, float *y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int act,
                          void *y_amax, void *workspace, size_t workspace_bytes, void *stream);
@@ -341,8 +345,8 @@ int frcnn_sgd_step_multi_ex(int n, float *const *params, const float *const *gra
  * own momentum buffer (momentum_shard, shard_count floats); the new weights are written to every rank (multimem.st on weight_multicast, or
  * stores through weight_peers).  weight_local = this rank's own arena (read side).  The caller brackets the launch with two cross-rank
  * barriers: every rank's gradients complete before | every rank's stores delivered and gradients consumed after.  world <= 8.
- * ctas_per_sm > 0: 256-thread CTAs, that many per SM (0 = 8) -- the kernel alone on the GPU; ctas_per_sm < 0: ONE 128-thread CTA per SM that fits
- * beside a resident GEMM CTA -- the shape for running under the convolution backward on a side stream. */
+ * ctas_per_sm: 256-thread CTAs per SM (0 = 8: the kernel alone on the GPU; 1 = the shape for running under the convolution backward on a side
+ * stream: one such CTA fits beside a resident GEMM CTA). */
 int frcnn_dp_sgd_fused(const float *grad_multicast, float *weight_multicast, const void *const *grad_peers, void *const *weight_peers, int world,
                        const float *weight_local, float *momentum_shard, size_t shard_begin, size_t shard_count,
                        float lr, float momentum, float weight_decay, float grad_scale, int first_step, int ctas_per_sm, void *stream);

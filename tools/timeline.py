@@ -15,7 +15,8 @@ import bench
 def main():
   steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
   dev = t.device("cuda:0")
-  step_fn = bench.make_train_step(dev)
+  import argparse
+  step_fn = bench.make_train_step(dev, argparse.Namespace(backbone = "vgg16", batch = 1, roi_op = "pool", rois = 128))
   for _ in range(4):
     step_fn()
   t.cuda.synchronize()
@@ -58,6 +59,20 @@ def main():
     a = tot.setdefault(n, [0, 0.0])
     a[0] += 1
     a[1] += e - s
+  # concurrency: for every optimizer / exchange kernel, how much of its run time other kernels were running too
+  for s0, e0, n0 in ks:
+    if "sgd_kernel" in n0 or "dp_sgd" in n0 or "split_f16_carried" in n0:
+      if e0 - s0 < 20:
+        continue
+      over = sum(max(0.0, min(e0, e) - max(s0, s)) for s, e, n in ks if n is not n0 and not (s == s0 and e == e0))
+      names = sorted({n.split("(")[0][-40:] for s, e, n in ks if min(e0, e) - max(s0, s) > 1 and not (s == s0 and e == e0)})
+      print("  overlap: %-28s %8.1f us long, %8.1f us of other kernels running meanwhile: %s" % (n0.split("(")[0][-28:], e0 - s0, over, ", ".join(names)[:160]))
+  if os.environ.get("TIMELINE_DUMP"):
+    t0 = ks[0][0]
+    last = ks[len(ks) * (steps - 1) // steps:] if steps > 1 else ks
+    print("kernels of the last step (start us, duration us, name):")
+    for s, e, n in last:
+      print("  %9.1f %8.1f  %s" % (s - t0, e - s, n.split("(")[0][-70:]))
   print("per-kernel totals per step (us):")
   for n, (c, us) in sorted(tot.items(), key = lambda kv: -kv[1][1])[:40]:
     print("  %9.1f  x%-4d %s" % (us / steps, c // steps, n[:110]))
