@@ -30,6 +30,7 @@ import torch as t
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T0 = time.perf_counter()
 
 IMAGE_HW = (600, 1000)
 WORKLOAD = "VGG-16 Faster R-CNN train_step (fwd+bwd+SGD), synthetic 3x600x1000 image, batch 1/GPU, 2 GT boxes, 128 RoIs"
@@ -369,6 +370,11 @@ def run_ours(args, rank, local_rank, world):
   pdl = os.environ.get("FRCNN_PDL", "1" if world == 1 else PDL_DEFAULT_MULTI_GPU) not in ("", "0")
   _lib.set_pdl(pdl)
   step = make_train_step(dev, args, rank, world)
+  verbose = os.environ.get("FRCNN_BENCH_VERBOSE", "0") not in ("", "0")
+
+  def say(what):
+    if verbose and rank == 0:
+      print("bench[%.1f s]: %s" % (time.perf_counter() - T0, what), file = sys.stderr, flush = True)
 
   def barrier():
     if world > 1:
@@ -391,8 +397,11 @@ def run_ours(args, rank, local_rank, world):
     return ms, loss
 
   try:
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
       step(False)
+      if verbose:
+        t.cuda.synchronize()
+        say("warm-up step %d done" % i)
     t.cuda.synchronize()
   except Exception as e:                                          # insurance for the single-GPU default: a launch attribute this driver rejects
     if not (pdl and world == 1):
@@ -412,6 +421,7 @@ def run_ours(args, rank, local_rank, world):
   _lib.launch_counter["calls"] = 0
   regions = []
   ms_dev, loss = timed(args.steps, False)
+  say("first timed region done: %.3f ms/step" % (ms_dev / args.steps))
   launches = _lib.launch_counter["calls"]
   regions.append(ms_dev)
   want = int(min(60, max(0, (1e3 * args.min_seconds - ms_dev) / max(ms_dev, 1e-3))))
@@ -427,14 +437,17 @@ def run_ours(args, rank, local_rank, world):
   # end-to-end leg: host buffers in, loss out (the loss read-back is part of train_step's return value)
   for _ in range(2):
     step(True)
+  say("all %d device-resident regions done" % len(regions))
   e2e_regions = [timed(args.steps, True)[0] for _ in range(max(1, min(5, len(regions))))]
   ms_e2e = statistics.median(e2e_regions)
+  say("end-to-end regions done")
   # roofline leg: the same K steps again with a CUDA-event pair around every conv / linear launch (on the launching stream).
   # Kept out of the headline region: two event records per launch cost host time the step is sensitive to.
   ops.kernel_timer.enable(True)
   timed(args.steps, False)
   gemm_stats = ops.kernel_timer.collect()
   ops.kernel_timer.enable(False)
+  say("roofline leg done")
 
   if rank != 0:
     if world > 1:

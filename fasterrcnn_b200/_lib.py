@@ -35,6 +35,7 @@ _SIGNATURES = {
   "frcnn_conv2d_wgrad": (_i, [_vp] * 3 + _GEOM + [_i, _vp, _sz, _vp]),
   "frcnn_conv2d_uses_tensor_cores": (_i, [_i] + _GEOM + [_i]),
   "frcnn_debug_tc_trace": (None, [_vp]),
+  "frcnn_debug_pair_max_active_clusters": (_i, []),
   "frcnn_tf32_split_bytes": (_sz, [_sz]),
   "frcnn_tf32_split": (_i, [_vp, _sz, _vp, _vp]),
   "frcnn_conv2d_fwd_presplit": (_i, [_vp] * 8 + _GEOM + [_i, _vp, _sz, _vp]),

@@ -60,6 +60,7 @@ void tc_set_trace(void *buf);
 int tf32_split(const float *x, size_t count, void *out, cudaStream_t st);
 int f16_split(const float *x, size_t count, void *out, cudaStream_t st, const void *partials, int G);
 int f16_split_carried(const float *x, size_t count, void *out, int ctas_per_sm, cudaStream_t st);
+int tc_pair_max_active_clusters();
 int tc_conv2d_dgrad(const float *dy, const float *w, const float *addend, float *dx,
                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                     void *workspace, size_t workspace_bytes, cudaStream_t st, const void *dy_split, const void *w_split, bool f16, void *amax_out = nullptr);
@@ -174,6 +175,7 @@ int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int C
 size_t frcnn_tf32_split_bytes(size_t count) { return tf32_split_bytes(count); }
 
 void frcnn_debug_tc_trace(void *buf) { tc_set_trace(buf); }
+int frcnn_debug_pair_max_active_clusters(void) { return tc_pair_max_active_clusters(); }
 
 int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream)
 {

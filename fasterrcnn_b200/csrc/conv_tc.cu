@@ -180,6 +180,7 @@ struct TcGeom {
   int mn_lbo, mn_sbo, mn_kstep;   // MN-major operand descriptor strides in bytes (4096 / 512 / 1024)
   int m_tiles, n_tiles, items;    // work items = m_tiles * n_tiles * (taps for WGRAD) * splits; CTAs loop over them (persistent grid)
   int m_pairs;                    // CTA-pair kernels: ceil(m_tiles / 2) -- a work item is then TWO vertically adjacent 128-row tiles (rank 0 / 1)
+  int pair_late_trigger;          // pair + stream-K: griddepcontrol.launch_dependents after the work loop instead of at the top
   unsigned long long *trace;      // debug: per-CTA %globaltimer stamps (frcnn_debug_tc_trace), NULL in production
   // stream-K (streamk != 0): the launch's (tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per CTA, so
   // every SM gets the same number of k-blocks whatever the tile count.  A CTA whose range starts inside a tile parks its raw
@@ -337,7 +338,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int gid = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;     // work-group index (see tc_cursor)
   const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  pdl_trigger();                                                     // the next kernel's CTAs may become resident behind this one
+  // The next kernel's CTAs may become resident behind this one.  A pair kernel whose CTAs spin on each other (stream-K) triggers LATE, after
+  // its work loop: with the early trigger the bench hung in round 2 whenever 2-CTA clusters, the stream-K spin protocol and programmatic
+  // dependent launch met (neither alone, nor any two of them); FRCNN_TC_PAIR_TRIGGER=early restores it for experiments.
+  const bool late_trigger = PAIR && g.streamk && g.pair_late_trigger;
+  if (!late_trigger) pdl_trigger();
   const unsigned long long t_entry = (g.trace && threadIdx.x == 0) ? tc_globaltimer() : 0ull;   // stored after the wait: no global access before it
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }      // full: one arrive.expect_tx per producer
@@ -672,6 +677,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     if (threadIdx.x == 0) TC_TRACE(8);
   }
+  if (late_trigger) pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                                      // both CTAs are done with each other's barriers and tensor memory
@@ -923,6 +929,26 @@ static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float 
   return FRCNN_OK;
 }
 
+// how many 2-CTA clusters of the pair kernel (forward, BN = 128) the device can hold at once: the persistent stream-K grid must not exceed
+// it -- a cluster that is not resident cannot publish the partial sums its neighbour spins on
+int tc_pair_max_active_clusters()
+{
+  auto kernel = tc_conv_kernel<TC_FWD, 128, 4, true, true>;
+  constexpr int smem = 4 * (2 * kABytes + 2 * 64 * kBK * 4) + 1024 + 256;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs, 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  return n;
+}
+
 static unsigned long long *g_tc_trace = nullptr;      // debug only (frcnn_debug_tc_trace); never set on the product path
 void tc_set_trace(void *buf) { g_tc_trace = reinterpret_cast<unsigned long long *>(buf); }
 
@@ -1027,9 +1053,10 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   static const int dbg_kstep = getenv("FRCNN_TC_MN_KSTEP") ? atoi(getenv("FRCNN_TC_MN_KSTEP")) : 0;
   const int mn_lbo = dbg_lbo ? dbg_lbo : (f16 ? 8192 : kAtomBytes), mn_sbo = dbg_sbo ? dbg_sbo : (f16 ? 1024 : 512), mn_kstep = dbg_kstep ? dbg_kstep : (f16 ? 2048 : 1024);
   static std::atomic<unsigned long long> launch_serial{0};
+  static const int pair_late = !(getenv("FRCNN_TC_PAIR_TRIGGER") && getenv("FRCNN_TC_PAIR_TRIGGER")[0] == 'e');
   grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, g_tc_trace,
+           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, pair_late, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
            0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp,
            (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr, p.grid_max};

@@ -103,6 +103,8 @@ int frcnn_conv2d_wgrad(const float *dy, const float *x, float *dw,
  * stamps (entry, setup done, first TMA, first MMA, first item issued, all MMAs issued, first item drained / stored, epilogue
  * done, exit, SM id) to buf[blockIdx * 16 ...]; buf must hold 148 * 16 * 8 bytes.  Pass NULL to switch it off again. */
 void frcnn_debug_tc_trace(void *buf);
+/* debug: 2-CTA clusters of the pair GEMM kernel the current device holds at once (cudaOccupancyMaxActiveClusters), -1 on error */
+int frcnn_debug_pair_max_active_clusters(void);
 int frcnn_conv2d_uses_tensor_cores(int pass, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int engine);
 size_t frcnn_tf32_split_bytes(size_t count);
 int frcnn_tf32_split(const float *x, size_t count, void *out, void *stream);

@@ -74,7 +74,9 @@ def test_sass_carries_the_blackwell_instructions():
   assert kernels >= 50
   count = lambda op: len(re.findall(r"\b%s\b" % op, sass))
   assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0
-  assert count("PREEXIT") == kernels and count("ACQBULK") == kernels            # one griddepcontrol pair per kernel
+  pair_kernels = len(re.findall(r"^\s*Function : \S*tc_conv_kernelILi\dELi\d+ELi\dELb1ELb1E", sass, flags = re.M))
+  assert count("ACQBULK") == kernels                                             # one griddepcontrol.wait per kernel
+  assert count("PREEXIT") == kernels + pair_kernels                              # one launch_dependents per kernel; the pair kernels carry an early AND a late one (one executes)
   # determinism: the only atomics are integer ones (order-independent); no floating-point RED / ATOM anywhere
   assert not re.search(r"\b(RED|REDG|ATOM|ATOMG|ATOMS)\.[A-Z0-9.]*F(16|32|64)", sass)
   # PDL safety, statically: in every kernel nothing touches global memory before griddepcontrol.wait (ACQBULK).  ptxas is free to move
