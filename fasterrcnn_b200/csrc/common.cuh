@@ -90,7 +90,7 @@ inline void launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem
 
 // same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it)
 template <typename... Params, typename... Args>
-inline void launch_cluster(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args &&...args)
+inline void launch_cluster(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, bool allow_pdl, Args &&...args)
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -103,7 +103,7 @@ inline void launch_cluster(void (*kernel)(Params...), dim3 grid, dim3 block, siz
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.numAttrs = 1;
-  if (pdl_enabled()) {
+  if (allow_pdl && pdl_enabled()) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;

@@ -685,6 +685,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     __syncwarp();
     if (PAIR) tmem_dealloc_pair(tmem_base, 4 * BN); else tmem_dealloc(tmem_base, 4 * BN);
   }
+  // tcgen05.dealloc.cta_group::2 is issued by one warp of EACH CTA for the columns of BOTH: neither CTA may exit (and hand its SM -- with
+  // programmatic dependent launch, instantly -- to a CTA of the next kernel that allocates the same columns) before the peer has issued its own
+  if (PAIR) cluster_sync_all();
   if (threadIdx.x == 0 && g.trace) {
     TC_TRACE(9);
     unsigned smid;
@@ -923,7 +926,10 @@ static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float 
   constexpr int smem = STAGES * (2 * kABytes + 2 * (PAIR ? BN / 2 : BN) * kBK * 4) + 1024 + 256;
   static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
-  if (PAIR) launch_cluster(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, 2, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
+  // FRCNN_TC_PAIR_PDL=0: the pair kernels themselves are launched without the programmatic-serialization attribute (they then start only
+  // after the previous kernel has completed), everything else keeps it
+  static const bool pair_pdl = !(getenv("FRCNN_TC_PAIR_PDL") && atoi(getenv("FRCNN_TC_PAIR_PDL")) == 0);
+  if (PAIR) launch_cluster(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, 2, pair_pdl, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   else launch(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");
   return FRCNN_OK;

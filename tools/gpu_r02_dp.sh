@@ -3,28 +3,28 @@
 #   bash tools/gpu_r02_dp.sh 2 [quick]
 N=${1:-2}
 mkdir -p gpurun_out
-if [ "$N" = "2" ]; then
-  timeout 1200 python -m pytest tests/test_dp_gpu.py -q -x --timeout 900 -p no:cacheprovider > gpurun_out/r02_pytest_dp2.log 2>&1
-  echo "two-rank numerics: exit $?"; tail -n 6 gpurun_out/r02_pytest_dp2.log | cut -c1-400
-  grep "\[margins\]" gpurun_out/r02_pytest_dp2.log | cut -c1-600
-  timeout 300 python tools/sm_reserve_debug.py 20 > gpurun_out/r02_sm_reserve_debug.log 2>&1
-  echo "sm reserve debug: exit $?"; grep "image\|block3_conv1\|fc1.weight\|rpn_conv1.weight" gpurun_out/r02_sm_reserve_debug.log | cut -c1-200
-fi
 run() { env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --min-seconds 1 --no-cpu-baseline; }
 summ() { python - "$1" <<'PY'
 import json, sys
 try:
-  d = json.load(open(sys.argv[1]))
+  d = [json.loads(l) for l in open(sys.argv[1]) if l.startswith("{")][-1]
   fam = d["roofline"]["families"]
   print(round(d["value"], 1), "images/s", round(d["ms_per_step"], 3), "ms |", " ".join("%s %.3f" % (k.replace("conv_", "c").replace("linear_", "l"), v["ms_per_step"]) for k, v in fam.items()), "| loss", round(d["last_loss"]["total"], 5), "|", d["config"]["parallelism"][:40])
 except Exception as e:
   print("no result:", e)
 PY
 }
+if [ "$N" = "2" ]; then
+  timeout 1200 python -m pytest tests/test_dp_gpu.py -q -x --timeout 900 -p no:cacheprovider > gpurun_out/r02_pytest_dp2.log 2>&1
+  echo "two-rank numerics: exit $?"; tail -n 6 gpurun_out/r02_pytest_dp2.log | cut -c1-400
+  grep "\[margins\]" gpurun_out/r02_pytest_dp2.log | cut -c1-600
+  FRCNN_TC_PAIR=1 FRCNN_PDL=1 FRCNN_TC_PAIR_PDL=0 FRCNN_BENCH_VERBOSE=1 timeout 90 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-eager --min-seconds 3 2> gpurun_out/r02_pair_nopdlattr.err | grep "^{" > gpurun_out/r02_pair_nopdlattr.json
+  echo "pair kernels launched without the PDL attribute: exit ${PIPESTATUS[0]} $(summ gpurun_out/r02_pair_nopdlattr.json)"; tail -n 2 gpurun_out/r02_pair_nopdlattr.err | cut -c1-200
+fi
 timeout 300 python bench.py --steps 20 --warmup 5 --min-seconds 1 --no-cpu-baseline --no-gpu-eager > gpurun_out/r02_dp_n1.json 2> gpurun_out/r02_dp_n1.err
 echo "N=1 on this box: $(summ gpurun_out/r02_dp_n1.json)"
-CONFIGS=("FRCNN_PDL=0" "FRCNN_PDL=1" "FRCNN_DP_SM_RESERVE=8 NCCL_MAX_CTAS=8" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16 FRCNN_PDL=1" "FRCNN_DP_FUSED=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_DP_FUSED_OVERLAP=0" "FRCNN_DP_FUSED=1 FRCNN_DP_FUSED_CTAS=2" "FRCNN_DP_FUSED=1 FRCNN_DP_FUSED_MULTICAST=0")
-if [ "$2" = "quick" ]; then CONFIGS=("FRCNN_PDL=0" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16 FRCNN_PDL=1" "FRCNN_DP_FUSED=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1"); fi
+CONFIGS=("FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_CTAS=2" "FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_OVERLAP=0" "FRCNN_DP_FUSED=1 FRCNN_PDL=0" "FRCNN_DP_SM_RESERVE=16 NCCL_MAX_CTAS=16 FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_BUCKET_MB=24")
+if [ "$2" = "quick" ]; then CONFIGS=("FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_OVERLAP=0"); fi
 for cfg in "${CONFIGS[@]}"; do
   tag=$(echo "$cfg" | tr ' =' '__')
   run $cfg > gpurun_out/r02_dp_n${N}_$tag.json 2> gpurun_out/r02_dp_n${N}_$tag.err
