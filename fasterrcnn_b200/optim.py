@@ -392,6 +392,7 @@ class NvlsShardedSGD(_BucketedHooks):
     self.split_ctas_per_sm = int(os.environ.get("FRCNN_DP_SPLIT_CTAS", "2" if self.overlap else "8"))
     self._side = t.cuda.Stream(device = dev) if self.overlap else None
     self._used_side = False
+    self._deferred = []
     self.sm_reserve = 0
     self.bytes_reduced_last_step = 0
     arena.register()
@@ -414,18 +415,20 @@ class NvlsShardedSGD(_BucketedHooks):
   def _view(buf, off, p):
     return buf[off:off + p.numel()].as_strided(p.shape, p.stride())
 
-  def _fused(self, b):
+  def _fused(self, b, pre_barrier = True, post_barrier = True):
     from . import _lib
     begin, n, mom_at = self._shards[b]
-    self.hG.barrier(channel = 0)                                 # every rank's gradients of this bucket are in its arena
+    if pre_barrier:
+      self.hG.barrier(channel = 0)                               # every rank's gradients of this bucket are in its arena
     _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W),
                                              _lib.ptr(self.momentum_shard[mom_at:mom_at + n]), begin, n, float(self.lr), float(self.momentum), float(self.weight_decay),
                                              1.0 / self.world_size, 1 if self._first[b] else 0, self.ctas_per_sm, _lib.stream()), "frcnn_dp_sgd_fused")
     _lib.count()
-    self.hG.barrier(channel = 0)                                 # every shard delivered everywhere; every arena's gradients consumed
     self._first[b] = False
     self.bytes_reduced_last_step += self.arena.payload_bytes[b]
-    self._resplit(b)
+    if post_barrier:
+      self.hG.barrier(channel = 0)                               # every shard delivered everywhere; every arena's gradients consumed
+      self._resplit(b)
 
   def _resplit(self, b):
     """The updated weights of bucket b arrived through the multicast mapping: bring the operand splits the tensor-core GEMMs read up to
@@ -453,7 +456,9 @@ class NvlsShardedSGD(_BucketedHooks):
 
   def _launch_bucket(self, b):
     if self._side is None:
-      self._fused(b)
+      # not overlapped: the buckets are only launched from step() (every gradient exists by then), back to back between ONE pair of
+      # cross-rank barriers
+      self._deferred.append(b)
       return
     ready = t.cuda.Event()
     ready.record()                                               # behind the bucket's last filter-gradient kernel (and every reader of its weights)
@@ -472,6 +477,13 @@ class NvlsShardedSGD(_BucketedHooks):
   def step(self):
     from . import ops
     self._flush()
+    if self._deferred:
+      for i, b in enumerate(self._deferred):
+        self._fused(b, pre_barrier = i == 0, post_barrier = False)
+      self.hG.barrier(channel = 0)
+      for b in self._deferred:
+        self._resplit(b)
+      self._deferred = []
     if self._used_side:
       t.cuda.current_stream().wait_stream(self._side)            # the next forward reads the updated weights
       self._used_side = False

@@ -91,6 +91,7 @@ def _worker(rank, world, port, which, out):
   t.cuda.synchronize()
   dist.barrier()
   worst_w, worst_w_key, worst_g, digest = 0.0, "", 0.0, hashlib.sha256()
+  grad_rels = []
   for k, p in named:
     w = p.detach().float().cpu()
     digest.update(np.ascontiguousarray(w.numpy()).tobytes())
@@ -101,11 +102,13 @@ def _worker(rank, world, port, which, out):
     if which == "nccl" and k in summed and p.grad is not None and p.requires_grad and "weight" in k:
       # an optimizer-owned tensor: its .grad is the arena view holding the all-reduced SUM of the last step (biases are not reduced)
       a, b = p.grad.detach().cpu().double(), summed[k].double()
-      worst_g = max(worst_g, float((a - b).norm() / (b.norm() + 1e-12)))
+      rel = float((a - b).norm() / (b.norm() + 1e-12))
+      grad_rels.append((rel, k, float(a.norm()), float(b.norm())))
+      worst_g = max(worst_g, rel)
   bucket_order = [optimizer.arena.bucket_of[id(optimizer.arena.params[i])] for i in optimizer.hook_order]
   out[rank] = dict(worst_weight_err_in_bars = worst_w, worst_weight = worst_w_key, worst_summed_grad_rel_l2 = worst_g, digest = digest.hexdigest(),
                    buckets = len(optimizer.arena.buckets), bytes_reduced = int(optimizer.bytes_reduced_last_step), hook_order = bucket_order,
-                   multicast = bool(getattr(optimizer, "use_multicast", False)))
+                   multicast = bool(getattr(optimizer, "use_multicast", False)), worst_grads = str(sorted(grad_rels, reverse = True)[:4]))
   optimizer.remove_hooks()
   dist.destroy_process_group()
 
