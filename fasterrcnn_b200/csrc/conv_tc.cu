@@ -926,9 +926,10 @@ static int launch_tc(const CUtensorMap *maps, const TcGeom &g, dim3 grid, float 
   constexpr int smem = STAGES * (2 * kABytes + 2 * (PAIR ? BN / 2 : BN) * kBK * 4) + 1024 + 256;
   static const cudaError_t attr = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (attr != cudaSuccess) return cuda_fail(attr, "tc_conv_kernel: smem attribute");
-  // FRCNN_TC_PAIR_PDL=0: the pair kernels themselves are launched without the programmatic-serialization attribute (they then start only
-  // after the previous kernel has completed), everything else keeps it
-  static const bool pair_pdl = !(getenv("FRCNN_TC_PAIR_PDL") && atoi(getenv("FRCNN_TC_PAIR_PDL")) == 0);
+  // The pair kernels themselves are launched WITHOUT the programmatic-serialization attribute (they start only after the previous kernel
+  // has completed; the kernel behind them still overlaps their tail): a 2-CTA cluster grid launched as a programmatic dependent hung or
+  // trapped within ~30 train steps in round 2 (profiles/r02_pair_ab.md), every other combination ran clean.  FRCNN_TC_PAIR_PDL=1 restores it.
+  static const bool pair_pdl = getenv("FRCNN_TC_PAIR_PDL") && atoi(getenv("FRCNN_TC_PAIR_PDL")) != 0;
   if (PAIR) launch_cluster(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, 2, pair_pdl, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   else launch(tc_conv_kernel<MODE, BN, STAGES, F16, PAIR>, grid, kTcThreads, smem, st, maps[0], maps[1], maps[2], maps[3], g, out, partial, epi);
   FRCNN_CHECK_LAUNCH("tc_conv_kernel");

@@ -363,7 +363,11 @@ class NvlsShardedSGD(_BucketedHooks):
     if int(ok.item()) == 0:
       raise RuntimeError("NvlsShardedSGD: symmetric-memory set-up failed on at least one rank (%s)" % (error,))
     if use_multicast is None:
-      use_multicast = os.environ.get("FRCNN_DP_FUSED_MULTICAST", "1") not in ("", "0")
+      # default = peer pointers: every element of the shard is read from each rank's arena and the result stored to each rank's, which
+      # moves 547 MB x (W - 1) / W per direction; the multicast path (multimem.ld_reduce / multimem.st) also sends every rank's OWN share
+      # through the switch and back: 547 MB x (1 + 1 / W) per direction -- 3x the bytes at W = 2, still 1.3x at W = 8 (measured:
+      # profiles/r02_dp_sweep_n2.md)
+      use_multicast = os.environ.get("FRCNN_DP_FUSED_MULTICAST", "0") not in ("", "0")
     self.use_multicast = bool(use_multicast) and mc_w != 0 and mc_g != 0
     self._mc = (mc_g, mc_w) if self.use_multicast else (None, None)
     import ctypes
