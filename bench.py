@@ -35,7 +35,7 @@ T0 = time.perf_counter()
 IMAGE_HW = (600, 1000)
 WORKLOAD = "VGG-16 Faster R-CNN train_step (fwd+bwd+SGD), synthetic 3x600x1000 image, batch 1/GPU, 2 GT boxes, 128 RoIs"
 METRIC = "images/sec fwd+bwd @ 1000x600, batch=1/GPU"
-PDL_DEFAULT_MULTI_GPU = "0"                     # until measured next to the overlapped collectives (profiles/r02_dp_sweep*.md)
+PDL_DEFAULT_MULTI_GPU = "1"                     # measured next to the overlapped exchange kernels: profiles/r02_dp_sweep_n2.md
 BACKBONE_NAMES = {"vgg16": "VGG-16", "resnet50": "ResNet-50", "resnet101": "ResNet-101"}
 
 
@@ -273,7 +273,7 @@ def make_train_step(dev, args, rank = 0, world = 1):
   init_weights(model, seed = 0)                                   # identical replicas
   model = model.cuda()
   named = list(model.named_parameters())
-  fused_dp = world > 1 and os.environ.get("FRCNN_DP_FUSED", "0") not in ("", "0")
+  fused_dp = world > 1 and os.environ.get("FRCNN_DP_FUSED", "1") not in ("", "0")    # default at N > 1 (FRCNN_DP_FUSED=0: bucketed NCCL all-reduce + fused SGD)
   if fused_dp:
     # reduce-scatter + SGD + all-gather as one kernel per bucket over NVLink / NVSwitch (csrc/dp_sgd.cu), overlapped with the backward.
     # The constructor agrees on success across ranks before it touches the parameters, so every rank takes the same branch here.

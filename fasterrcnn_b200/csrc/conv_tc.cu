@@ -816,9 +816,9 @@ static bool make_tc_plan(int mode, int N, int H, int W, int Cin, int Cout, int K
   p->BN = (ntot % 128 == 0) ? 128 : 64;
   p->stages = p->BN == 128 ? 3 : 4;
   // CTA pairs (cta_group::2): fp16 engine; the forward pass takes both tile widths (its B operand is K-major: any row count splits in
-  // two), dgrad / wgrad need BN = 128 (an MN-major half must be a whole 64-column swizzle atom).  Opt-in (FRCNN_TC_PAIR=1): parity-green
-  // (tests/test_kernels_gpu.py passes on it bit for bit) but measured SLOWER than the single-CTA kernels in round 2 (profiles/r02_pair_ab.md).
-  static const bool use_pair = getenv("FRCNN_TC_PAIR") && atoi(getenv("FRCNN_TC_PAIR")) != 0;
+  // two), dgrad / wgrad need BN = 128 (an MN-major half must be a whole 64-column swizzle atom).  Default on (FRCNN_TC_PAIR=0 = single CTAs):
+  // +10-15 % per layer on the 75x125 .. 300x500 convolutions once the MMA issue loop ran on uniform registers (profiles/r02_pair_ab.md).
+  static const bool use_pair = !(getenv("FRCNN_TC_PAIR") && atoi(getenv("FRCNN_TC_PAIR")) == 0);
   p->pair = (f16 && use_pair && (mode == TC_FWD || p->BN == 128)) ? 1 : 0;                  // (+ an even / large tile count, below)
   if (p->pair) p->stages = p->BN == 128 ? 4 : 5;                          // 48 KB / 40 KB per stage
   p->tile_w = p->tile_h = p->tile_n = p->tiles_w = p->tiles_h = p->groups = 1;
