@@ -319,10 +319,21 @@ class NvlsShardedSGD(_BucketedHooks):
   weight decay + momentum (zeros are reduced: DistributedDataParallel's semantics, not torch.optim.SGD's skip)."""
 
   def __init__(self, params, lr = 1e-3, momentum = 0.9, process_group = None, use_multicast = None, ctas_per_sm = 0, named_params = None, bucket_bytes = None,
-               overlap = None):
+               overlap = None, exchange = None):
+    """exchange: "peer" (default; csrc/dp_sgd.cu through peer pointers), "multicast" (same kernel through multimem instructions), or
+    "nccl": the same sharded step with the two transfers done by NCCL -- reduce-scatter of the bucket into this rank's shard, the
+    library's SGD kernel on the shard, all-gather of the updated shard -- for fabrics without peer mappings and as the measured
+    alternative at 8 ranks (profiles/r02_dp_n8.md).  FRCNN_DP_EXCHANGE overrides."""
     os.environ.setdefault("TORCH_SYMMMEM_IMPLICIT_POOL", "0")   # one allocation per arena: the mappings then start at the tensor (offset 0)
-    import torch.distributed._symmetric_memory as symm
     assert dist.is_initialized(), "NvlsShardedSGD needs an initialised process group (one process per GPU)"
+    if exchange is None:
+      exchange = os.environ.get("FRCNN_DP_EXCHANGE", "multicast" if use_multicast else "peer")
+    assert exchange in ("peer", "multicast", "nccl"), exchange
+    self.exchange = exchange
+    if exchange == "multicast":
+      use_multicast = True
+    if exchange != "nccl":
+      import torch.distributed._symmetric_memory as symm
     group = process_group if process_group is not None else dist.group.WORLD
     self.group, self.world_size, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
     assert 1 <= self.world_size <= 8, "one NVSwitch domain: at most 8 ranks"
@@ -348,14 +359,22 @@ class NvlsShardedSGD(_BucketedHooks):
       bucket_bytes = int(os.environ.get("FRCNN_DP_BUCKET_MB", "48")) << 20
     # every fallible step first; the parameters are re-pointed into the arena only once all ranks agree that the set-up succeeded
     error = None
+    peers_g = peers_w = [0] * self.world_size
+    mc_g = mc_w = 0
     try:
-      symm.enable_symm_mem_for_group(group.group_name)
-      arena = GradArena(owned, self.world_size, bucket_bytes = bucket_bytes, allocate = lambda n: symm.empty(n, dtype = t.float32, device = dev).zero_())
-      self.W = symm.empty(arena.total, dtype = t.float32, device = dev).zero_()
-      self.G = arena.flat
-      self.hW, self.hG = symm.rendezvous(self.W, group), symm.rendezvous(self.G, group)
-      peers_g, mc_g = self._mapping(self.hG, self.G)
-      peers_w, mc_w = self._mapping(self.hW, self.W)
+      if exchange == "nccl":
+        arena = GradArena(owned, self.world_size, bucket_bytes = bucket_bytes)
+        self.W = t.zeros((arena.total,), dtype = t.float32, device = dev)
+        self.G = arena.flat
+        self.hW = self.hG = None
+      else:
+        symm.enable_symm_mem_for_group(group.group_name)
+        arena = GradArena(owned, self.world_size, bucket_bytes = bucket_bytes, allocate = lambda n: symm.empty(n, dtype = t.float32, device = dev).zero_())
+        self.W = symm.empty(arena.total, dtype = t.float32, device = dev).zero_()
+        self.G = arena.flat
+        self.hW, self.hG = symm.rendezvous(self.W, group), symm.rendezvous(self.G, group)
+        peers_g, mc_g = self._mapping(self.hG, self.G)
+        peers_w, mc_w = self._mapping(self.hW, self.W)
     except Exception as e:                                     # noqa: BLE001
       error = e
     ok = t.tensor([0 if error is not None else 1], dtype = t.int32, device = dev)
@@ -423,6 +442,20 @@ class NvlsShardedSGD(_BucketedHooks):
   def _fused(self, b, pre_barrier = True, post_barrier = True):
     from . import _lib
     begin, n, mom_at = self._shards[b]
+    if self.exchange == "nccl":
+      # (blocking collectives: NCCL runs them on its own stream and makes the CURRENT stream -- the side stream when overlapped -- wait)
+      _, _, b0, b1 = self.arena.buckets[b]
+      dist.reduce_scatter_tensor(self.G[begin:begin + n], self.G[b0:b1], op = dist.ReduceOp.SUM, group = self.group)
+      _lib.check(_lib.lib().frcnn_sgd_step_split(_lib.ptr(self.W[begin:begin + n]), _lib.ptr(self.G[begin:begin + n]), _lib.ptr(self.momentum_shard[mom_at:mom_at + n]), n,
+                                                 float(self.lr), float(self.momentum), float(self.weight_decay), 1.0 / self.world_size, 1 if self._first[b] else 0, None,
+                                                 _lib.stream()), "frcnn_sgd_step_split")
+      _lib.count()
+      dist.all_gather_into_tensor(self.W[b0:b1], self.W[begin:begin + n], group = self.group)
+      self._first[b] = False
+      self.bytes_reduced_last_step += self.arena.payload_bytes[b]
+      if post_barrier:
+        self._resplit(b)
+      return
     if pre_barrier:
       self.hG.barrier(channel = 0)                               # every rank's gradients of this bucket are in its arena
     _lib.check(_lib.lib().frcnn_dp_sgd_fused(self._mc[0], self._mc[1], self._peers[0], self._peers[1], self.world_size, _lib.ptr(self.W),
@@ -485,7 +518,8 @@ class NvlsShardedSGD(_BucketedHooks):
     if self._deferred:
       for i, b in enumerate(self._deferred):
         self._fused(b, pre_barrier = i == 0, post_barrier = False)
-      self.hG.barrier(channel = 0)
+      if self.hG is not None:
+        self.hG.barrier(channel = 0)
       for b in self._deferred:
         self._resplit(b)
       self._deferred = []

@@ -4,8 +4,9 @@ After train steps through each data-parallel optimizer,
   * the post-all-reduce gradient equals the SUM of the two per-image oracle gradients (the fused SGD applies 1 / world),
   * the post-step weights equal an oracle SGD step on the MEAN of the two per-image oracle gradients (1e-4),
   * the replicas are bit-identical.
-Optimizers: DataParallel(FusedSGD) -- bucketed NCCL all-reduce on the gradient arena (what bench.py runs at N > 1) -- and NvlsShardedSGD --
-the fused reduce-scatter + SGD + all-gather kernel over NVLink multimem, with and without the multicast mapping.
+Optimizers: DataParallel(FusedSGD) -- bucketed NCCL all-reduce on the gradient arena -- and NvlsShardedSGD -- the sharded step: fused
+reduce-scatter + SGD + all-gather kernel over NVLink peer memory (bench.py's default at N > 1), the same through multimem instructions,
+and with NCCL doing the two transfers.
 Needs two devices (gpurun --gpus 2); skipped on a one-GPU box.
 """
 import os
@@ -82,7 +83,8 @@ def _worker(rank, world, port, which, out):
   if which == "nccl":
     optimizer = optim.DataParallel(optim.create_optimizer(model, 1e-3, 0.9, 5e-4, fused = True), named_params = named)
   else:
-    optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9, named_params = named, use_multicast = which == "nvls_multicast")
+    optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9, named_params = named,
+                                     exchange = {"nvls_multicast": "multicast", "nvls_peer": "peer", "nccl_sharded": "nccl"}[which])
   smp = _sample(rank)
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
   random.seed(rank); t.manual_seed(rank)
@@ -118,7 +120,7 @@ def _worker(rank, world, port, which, out):
   dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("which", ["nccl", "nvls_multicast", "nvls_peer"])
+@pytest.mark.parametrize("which", ["nccl", "nvls_multicast", "nvls_peer", "nccl_sharded"])
 def test_two_rank_step_matches_oracle_step_on_mean_gradient(which):
   import torch.multiprocessing as mp
   if t.cuda.device_count() < 2:

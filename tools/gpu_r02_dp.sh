@@ -15,14 +15,14 @@ except Exception as e:
 PY
 }
 if [ "$N" = "2" ]; then
-  timeout 1200 python -m pytest tests/test_dp_gpu.py -q -x --timeout 900 -p no:cacheprovider > gpurun_out/r02_pytest_dp2.log 2>&1
+  timeout 1200 python -m pytest tests/test_dp_gpu.py -q -x --timeout 900 -p no:cacheprovider -k "nccl_sharded" > gpurun_out/r02_pytest_dp2.log 2>&1
   echo "two-rank numerics: exit $?"; tail -n 6 gpurun_out/r02_pytest_dp2.log | cut -c1-400
   grep "\[margins\]" gpurun_out/r02_pytest_dp2.log | cut -c1-600
 fi
 FRCNN_TC_PAIR=1 timeout 300 python bench.py --steps 20 --warmup 5 --min-seconds 1 --no-cpu-baseline --no-gpu-eager > gpurun_out/r02_dp_n1.json 2> gpurun_out/r02_dp_n1.err
 echo "N=1 on this box: $(summ gpurun_out/r02_dp_n1.json)"
-CONFIGS=("FRCNN_TC_PAIR=1 FRCNN_PDL=1" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_OVERLAP=0" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_CTAS=2" "FRCNN_TC_PAIR=0 FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_MULTICAST=1 FRCNN_DP_FUSED_OVERLAP=0")
-if [ "$2" = "quick" ]; then CONFIGS=("FRCNN_TC_PAIR=1 FRCNN_PDL=1" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_OVERLAP=0" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1" "FRCNN_TC_PAIR=1 FRCNN_DP_FUSED=1 FRCNN_PDL=1 FRCNN_DP_FUSED_MULTICAST=1"); fi
+CONFIGS=("FRCNN_DP_FUSED=1" "FRCNN_DP_FUSED=1 FRCNN_DP_EXCHANGE=nccl" "FRCNN_DP_FUSED=1 FRCNN_DP_EXCHANGE=nccl FRCNN_DP_FUSED_OVERLAP=0" "FRCNN_DP_FUSED=0")
+if [ "$2" = "quick" ]; then CONFIGS=("FRCNN_DP_FUSED=1 FRCNN_DP_EXCHANGE=nccl" "FRCNN_DP_FUSED=0"); fi
 for cfg in "${CONFIGS[@]}"; do
   tag=$(echo "$cfg" | tr ' =' '__')
   run $cfg > gpurun_out/r02_dp_n${N}_$tag.json 2> gpurun_out/r02_dp_n${N}_$tag.err
