@@ -273,7 +273,10 @@ def make_train_step(dev, args, rank = 0, world = 1):
   init_weights(model, seed = 0)                                   # identical replicas
   model = model.cuda()
   named = list(model.named_parameters())
-  fused_dp = world > 1 and os.environ.get("FRCNN_DP_FUSED", "1") not in ("", "0")    # default at N > 1 (FRCNN_DP_FUSED=0: bucketed NCCL all-reduce + fused SGD)
+  # Default exchange by world size, from the round-2 measurements (profiles/r02_dp_sweep_n2.md, r02_dp_n8.md): at 2 ranks the fused
+  # peer-memory kernel under the backward (5.87 ms / step against 6.06 for the bucketed NCCL all-reduce); at 8 ranks the NCCL
+  # all-reduce on the gradient arena (6.57 against 6.66-6.70).  FRCNN_DP_FUSED=0 / 1 overrides.
+  fused_dp = world > 1 and os.environ.get("FRCNN_DP_FUSED", "1" if world <= 2 else "0") not in ("", "0")
   if fused_dp:
     # reduce-scatter + SGD + all-gather as one kernel per bucket over NVLink / NVSwitch (csrc/dp_sgd.cu), overlapped with the backward.
     # The constructor agrees on success across ranks before it touches the parameters, so every rank takes the same branch here.
