@@ -83,31 +83,42 @@ class FasterRCNNModel(nn.Module):
     # The two consumers of the shared feature map are back-propagated separately (the RPN branch early, see below), each leaving
     # its gradient on this detached leaf; the backbone then gets their sum -- the same two-term sum autograd would form.
     feature_map = backbone_map.detach().requires_grad_(True) if backbone_map.requires_grad else backbone_map
+    # The proposal path (decode, top-N, filter, NMS, GT append, labelling, the read-back of count + labels) is a serial chain of small,
+    # latency-bound launches that needs only the RPN head outputs; the RPN losses and the whole backward of the RPN branch need only those
+    # outputs too.  The chain therefore runs on a side stream and the RPN branch on the compute stream AT THE SAME TIME (the GEMM CTAs
+    # leave room for other kernels' CTAs on every SM, conv_tc.cu), instead of one after the other; the host waits for the chain's
+    # read-back -- the step's one mid-step synchronisation -- draws the samples, and the detector starts when both streams are done.
+    # FRCNN_PROPOSAL_STREAM=0 keeps everything on one stream.
+    main = t.cuda.current_stream()
+    side = self._proposal_stream(dev)
     rpn_score_map, rpn_box_deltas_map, (padded, count) = self._stage2_region_proposal_network(
       feature_map = feature_map, image_shape = image_shape, anchor_map = anchor_map, anchor_valid_map = anchor_valid_map,
-      max_proposals_pre_nms = 12000, max_proposals_post_nms = 2000, deferred_extra_rows = len(gt))
+      max_proposals_pre_nms = 12000, max_proposals_post_nms = 2000, deferred_extra_rows = len(gt), proposal_stream = side)
 
     # host work that needs nothing from the device overlaps the backbone / RPN kernels queued above
     gt_rpn_minibatch_map = self._sample_rpn_minibatch(rpn_map = gt_rpn_map, object_indices = gt_rpn_object_indices, background_indices = gt_rpn_background_indices)
-    # small host arrays go up through page-locked staging buffers: a cudaMemcpyAsync from PAGEABLE memory first synchronises the
-    # stream, which would stall the host here until the previous step's backward has drained
-    gt_box_corners = self._upload("gt_corners", np.array([box.corners for box in gt], dtype = np.float32).reshape(-1, 4), dev)
-    gt_box_class_idxs = self._upload("gt_classes", np.array([box.class_index for box in gt], dtype = np.int32), dev)
-    ops.append_rows(padded, count, gt_box_corners)
-    _, class_idx, gt_classes, gt_box_deltas = ops.label_proposals(padded, gt_box_corners, gt_box_class_idxs, self._num_classes, 0.5)
-
-    # the step's one mid-step synchronisation: proposal count + class labels in a single pinned read-back.  The RPN losses AND the
-    # whole backward of the RPN branch (which needs nothing from the detector) are queued behind it, so the device has ~0.4 ms of
-    # work while the host draws the samples and launches the detector
     fetch = self._pinned("fetch", (1 + padded.shape[0],), t.int32)
-    fetch[0:1].copy_(count, non_blocking = True)
-    fetch[1:].copy_(class_idx, non_blocking = True)
     fetched = t.cuda.Event()
-    fetched.record()
+    with t.cuda.stream(side if side is not None else main):
+      # small host arrays go up through page-locked staging buffers: a cudaMemcpyAsync from PAGEABLE memory first synchronises the
+      # stream, which would stall the host here until the previous step's backward has drained
+      gt_box_corners = self._upload("gt_corners", np.array([box.corners for box in gt], dtype = np.float32).reshape(-1, 4), dev)
+      gt_box_class_idxs = self._upload("gt_classes", np.array([box.class_index for box in gt], dtype = np.int32), dev)
+      ops.append_rows(padded, count, gt_box_corners)
+      _, class_idx, gt_classes, gt_box_deltas = ops.label_proposals(padded, gt_box_corners, gt_box_class_idxs, self._num_classes, 0.5)
+      # the step's one mid-step synchronisation: proposal count + class labels in a single pinned read-back
+      fetch[0:1].copy_(count, non_blocking = True)
+      fetch[1:].copy_(class_idx, non_blocking = True)
+      fetched.record()
+    if side is not None:
+      for x in (padded, gt_classes, gt_box_deltas, class_idx, gt_box_corners, gt_box_class_idxs):
+        x.record_stream(main)                                       # allocated on the side stream, consumed on the compute stream
     rpn_l = ops.rpn_losses(rpn_score_map, rpn_box_deltas_map, gt_rpn_minibatch_map)                # (class, regression)
     ones = self._ones2(dev)
     t.autograd.backward([rpn_l], [ones])                                                           # d(total)/d(loss) = 1 for every term
     fetched.synchronize()
+    if side is not None:
+      main.wait_event(fetched)                                      # the detector reads what the side stream produced
     n = int(fetch[0]) + len(gt)                                                                    # proposals + appended GT boxes
     indices = self._sample_proposal_indices(fetch[1:1 + n].numpy(), self._proposal_batch_size, 0.25)
     if indices is None or len(indices) == 0:
@@ -202,6 +213,16 @@ class FasterRCNNModel(nn.Module):
     host = t.cat([rpn_l.detach(), det_l.detach()]).cpu().numpy()
     self.last_step_info = dict(num_rois = int(sum(p.shape[0] for p in props_l)), rois_per_image = [int(p.shape[0]) for p in props_l])
     return FasterRCNNModel.Loss(rpn_class = float(host[0]), rpn_regression = float(host[1]), detector_class = float(host[2]), detector_regression = float(host[3]), total = float(host.sum()))
+
+  def _proposal_stream(self, device):
+    import os
+    if os.environ.get("FRCNN_PROPOSAL_STREAM", "1") in ("", "0"):
+      return None
+    cache = self.__dict__.setdefault("_proposal_streams", {})
+    key = str(device)
+    if key not in cache:
+      cache[key] = t.cuda.Stream(device = device)
+    return cache[key]
 
   def _ones2(self, device):
     cache = self.__dict__.setdefault("_ones2_cache", {})

@@ -28,10 +28,13 @@ class RegionProposalNetwork(nn.Module):
       layer.bias.data.zero_()
     self._anchor_cache = {}
 
-  def forward(self, feature_map, image_shape, anchor_map, anchor_valid_map, max_proposals_pre_nms, max_proposals_post_nms, deferred_extra_rows = None):
+  def forward(self, feature_map, image_shape, anchor_map, anchor_valid_map, max_proposals_pre_nms, max_proposals_post_nms, deferred_extra_rows = None,
+              proposal_stream = None):
     """-> objectness (1,H,W,9), box deltas (1,H,W,36), proposals (N,4) (y1,x1,y2,x2).
     deferred_extra_rows (not in the reference; used by FasterRCNNModel.train_step): when an int, the third result is the pair
-    (capacity-padded proposals with that many spare rows, device-side count) and no host synchronisation happens here."""
+    (capacity-padded proposals with that many spare rows, device-side count) and no host synchronisation happens here.
+    proposal_stream (train_step): the proposal kernels -- a serial, latency-bound chain of small launches -- are queued on that stream
+    behind the head outputs, so that the caller can run the RPN losses and the RPN branch's backward on the compute stream meanwhile."""
     assert feature_map.shape[0] == 1                                      # rpn.py:159
     y = ops.conv2d_act(feature_map, self._rpn_conv1.weight, self._rpn_conv1.bias, 1, 1, ops.ACT_RELU)
     # the two 1x1 heads (9 sigmoid scores, 36 deltas) are one narrow GEMM over the pixels' 512-channel rows; its row-major
@@ -42,6 +45,16 @@ class RegionProposalNetwork(nn.Module):
     box_deltas_map = deltas.view(1, fh, fw, deltas.shape[1])
 
     anchors_dev, keep_mask = self._resolve_anchors(anchor_map, anchor_valid_map, image_shape, objectness_score_map.shape[1:3], feature_map.device)
+    if proposal_stream is not None:
+      heads_done = t.cuda.Event()
+      heads_done.record()
+      with t.cuda.stream(proposal_stream):
+        proposal_stream.wait_event(heads_done)
+        proposals = ops.rpn_proposals(
+          objectness_score_map, box_deltas_map, image_shape, 16,
+          max_proposals_pre_nms, max_proposals_post_nms, anchors = anchors_dev, keep_mask = keep_mask,
+          defer_count = deferred_extra_rows is not None, extra_rows = deferred_extra_rows or 0)
+      return objectness_score_map, box_deltas_map, proposals
     proposals = ops.rpn_proposals(
       objectness_score_map, box_deltas_map, image_shape, 16,
       max_proposals_pre_nms, max_proposals_post_nms, anchors = anchors_dev, keep_mask = keep_mask,
