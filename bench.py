@@ -299,10 +299,17 @@ def make_train_step(dev, args, rank = 0, world = 1):
   image_dev, gt_map_dev = image_host.cuda(), gt_map_host.cuda()
   random.seed(rank); t.manual_seed(rank)
 
+  # end-to-end leg: every step's inputs come from page-locked HOST memory through the package's double-buffered feeder
+  # (fasterrcnn_b200.datasets.feeder.DeviceFeeder): the copy of step i + 1 runs on the copy engine while step i computes
+  from fasterrcnn_b200.datasets.feeder import DeviceFeeder
+  feeder = DeviceFeeder(dev)
+
   def step(from_host = False):
     if from_host:
-      img = image_host.to(dev, non_blocking = True)
-      gmap = gt_map_host.to(dev, non_blocking = True)
+      if not feeder.pending:
+        feeder.submit(image_host, gt_map_host)                    # first step of a region: nothing was prefetched
+      img, gmap = feeder.take()
+      feeder.submit(image_host, gt_map_host)                      # the next step's inputs (a loader would pass the next sample here)
     else:
       img, gmap = image_dev, gt_map_dev
     if args.batch == 1:

@@ -332,12 +332,12 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
   __shared__ unsigned long long ring[4][3][64];              // per block slot: [0] diagonal tile, [1] rows at column +1, [2] at column +2
   __shared__ unsigned long long removed[4];                  // removed[c & 3]: suppression word of block c, accumulated ahead of time
   __shared__ unsigned long long kept_bits_s;
-  __shared__ int kept_total;
+  __shared__ int kept_total[2];                              // double-buffered by block parity: thread 0 writes [b + 1] while slower threads may still read [b]
   int n = *count;
   if (n > capacity) n = capacity;
   const int nblocks = (n + 63) / 64;
   const int t = threadIdx.x;
-  if (t == 0) { kept_total = 0; kept_bits_s = 0ull; removed[0] = removed[1] = removed[2] = removed[3] = 0ull; }
+  if (t == 0) { kept_total[0] = kept_total[1] = 0; kept_bits_s = 0ull; removed[0] = removed[1] = removed[2] = removed[3] = 0ull; }
 
   // stream block `blk`'s three 64-word slices into ring slot blk & 3 (threads 64..255); one cp.async group per block
   auto prefetch_block = [&](int blk) {
@@ -358,8 +358,9 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
   unsigned long long pend[kScanDefer] = {0ull, 0ull, 0ull};  // gather issued last iteration, not yet folded
   unsigned long long pend_sync = 0ull;
   int pend_col = -1;
-  for (int b = 0; b < nblocks; b++) {
-    const int kept_before = kept_total;
+  int b = 0;
+  for (; b < nblocks; b++) {
+    const int kept_before = kept_total[b & 1];
     if (kept_before >= max_keep) break;                      // uniform (read after a barrier)
     if (t < 32) {
       // warp 0 resolves the block.  Only boxes that suppress something inside the block (non-zero diagonal row) have to be visited
@@ -392,7 +393,7 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
       __syncwarp();
       if (t == 0) {
         kept_bits_s = kept;
-        kept_total = kept_before + __popcll(kept);
+        kept_total[(b + 1) & 1] = kept_before + __popcll(kept);
         removed[b & 3] = 0ull;                                 // slot is reused by block b + 4 (first written at iteration b + 2)
       }
     } else if (t >= 32) {
@@ -430,7 +431,7 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
     __syncthreads();
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (t == 0) *kept_count_out = kept_total;
+  if (t == 0) *kept_count_out = kept_total[b & 1];              // (break at block b: the count it started with; ran out of blocks: what block nblocks - 1 left)
 }
 
 // batched NMS glue: sorted[z][r] = boxes[z][order[z][r]] (r < n), and keep[z][r] = order[z][keep_pos[z][r]] (r < kept[z])

@@ -1,7 +1,7 @@
 """
 Parity margin recorder (test infrastructure).  The end-to-end GPU tests assert ceilings; what they MEASURE -- largest deviation,
 unmatched rows, distance of the discontinuous decisions from their thresholds -- is appended here, one JSON object per line, to
-gpurun_out/parity_margins.jsonl (comes back from the GPU box) and summarised by tools/summarize_margins.py into
+gpurun_out/parity_margins_<test module>.jsonl (come back from the GPU box) and summarised by tools/summarize_margins.py into
 profiles/r02_parity_margins.md.  The bars in the tests are set from those measurements (2x the measured value).
 """
 import json
@@ -11,7 +11,12 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATH = os.path.join(ROOT, "gpurun_out", "parity_margins.jsonl")
+
+
+def _path():
+  """One file per test module (gpurun merges files by name: the two-GPU run's records must survive the next one-GPU run)."""
+  module = os.path.splitext(os.path.basename((os.environ.get("PYTEST_CURRENT_TEST") or "unknown").split("::")[0]))[0]
+  return os.path.join(ROOT, "gpurun_out", "parity_margins_%s.jsonl" % module)
 
 
 def record(test, **metrics):
@@ -21,8 +26,9 @@ def record(test, **metrics):
       v = v.item()
     row[k] = v
   try:
-    os.makedirs(os.path.dirname(PATH), exist_ok = True)
-    with open(PATH, "a") as f:
+    path = _path()
+    os.makedirs(os.path.dirname(path), exist_ok = True)
+    with open(path, "a") as f:
       f.write(json.dumps(row) + "\n")
   except OSError:
     pass

@@ -14,18 +14,22 @@ def fmt(v):
 
 
 def main():
-  path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "parity_margins.jsonl")
+  import glob
+  paths = sys.argv[1:] if len(sys.argv) > 1 else sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "parity_margins_*.jsonl")))
+  path = ", ".join(os.path.relpath(p, ROOT) for p in paths)
   latest = {}
-  with open(path) as f:
-    for line in f:
-      line = line.strip()
-      if line:
-        row = json.loads(line)
-        latest[row["test"]] = row
+  for one in paths:
+    with open(one) as f:
+      for line in f:
+        line = line.strip()
+        if line:
+          row = json.loads(line)
+          if row["test"] not in latest or row.get("when", "") >= latest[row["test"]].get("when", ""):
+            latest[row["test"]] = row
   print("# Parity margins measured on the B200 (round 2)\n")
   print("Written by the `-m gpu` tests themselves (`tests/_margins.py`): what each end-to-end comparison MEASURED, next to the oracle's own")
   print("distance from every discontinuous decision (top-N cut, 16-px size filter, IoU 0.7).  The bars asserted in `tests/test_model_gpu.py`")
-  print("are set from these numbers.  Source: `%s`.\n" % os.path.relpath(path, ROOT))
+  print("are set from these numbers.  Source: `%s`.\n" % path)
   for name in sorted(latest):
     row = latest[name]
     print("## %s  (%s)\n" % (name, row.get("when", "")))
