@@ -181,6 +181,7 @@ struct TcGeom {
   int m_tiles, n_tiles, items;    // work items = m_tiles * n_tiles * (taps for WGRAD) * splits; CTAs loop over them (persistent grid)
   int m_pairs;                    // CTA-pair kernels: ceil(m_tiles / 2) -- a work item is then TWO vertically adjacent 128-row tiles (rank 0 / 1)
   int pair_late_trigger;          // pair + stream-K: griddepcontrol.launch_dependents after the work loop instead of at the top
+  int paired_stores;              // epilogue: lane pairs write whole 32-byte sectors (see the store loop)
   unsigned long long *trace;      // debug: per-CTA %globaltimer stamps (frcnn_debug_tc_trace), NULL in production
   // stream-K (streamk != 0): the launch's (tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per CTA, so
   // every SM gets the same number of k-blocks whatever the tile count.  A CTA whose range starts inside a tile parks its raw
@@ -657,8 +658,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int j = 0; j < BN; j++) out_max = fmaxf(out_max, fabsf(acc[j]));
           }
         }
+        if (!g.paired_stores) {
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+      }
+      if (g.paired_stores) {
+        // Full-sector stores.  A thread owns one output row, so a plain 128-bit store instruction touches 32 rows x 16 bytes: 32 half
+        // sectors.  Lane pairs swap every other 4-column group (one shuffle per element) and then write 2 x 16 adjacent bytes of ONE row
+        // per instruction: every 32-byte sector is written whole, by one instruction.  (Worth it where the epilogue is not hidden: fc1's
+        // filter gradient -- 411 MB of output for 128 k-elements per tile.)
+        const bool odd = lane & 1;
+        float *base = raw ? partial : out;
+        const unsigned long long own_off = valid ? (unsigned long long)row_off : ~0ull;
+        const unsigned long long peer_off = __shfl_xor_sync(0xffffffffu, own_off, 1);
+#pragma unroll
+        for (int j = 0; j < BN; j += 8) {                              // groups (j .. j+3) and (j+4 .. j+7)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float send = odd ? acc[j + e] : acc[j + 4 + e];      // the even lane gives away its odd group, the odd lane its even group
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            if (odd) acc[j + e] = recv; else acc[j + 4 + e] = recv;
+          }
+          // slot j: even lane = own row, group j | odd lane = the even lane's row, group j + 4  -> 32 adjacent bytes of the even lane's row
+          const unsigned long long off0 = odd ? peer_off : own_off;
+          if (off0 != ~0ull) *reinterpret_cast<float4 *>(base + off0 + j + (odd ? 4 : 0)) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          // slot j + 4: even lane = the odd lane's row, group j | odd lane = own row, group j + 4   -> 32 adjacent bytes of the odd lane's row
+          const unsigned long long off1 = odd ? own_off : peer_off;
+          if (off1 != ~0ull) *reinterpret_cast<float4 *>(base + off1 + j + (odd ? 4 : 0)) = make_float4(acc[j + 4], acc[j + 5], acc[j + 6], acc[j + 7]);
+        }
       }
       if (first_item && threadIdx.x == 0) TC_TRACE(7);
       first_item = false;
@@ -1061,9 +1089,12 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   const int mn_lbo = dbg_lbo ? dbg_lbo : (f16 ? 8192 : kAtomBytes), mn_sbo = dbg_sbo ? dbg_sbo : (f16 ? 1024 : 512), mn_kstep = dbg_kstep ? dbg_kstep : (f16 ? 2048 : 1024);
   static std::atomic<unsigned long long> launch_serial{0};
   static const int pair_late = !(getenv("FRCNN_TC_PAIR_TRIGGER") && getenv("FRCNN_TC_PAIR_TRIGGER")[0] == 'e');
+  // FRCNN_TC_PAIRED_STORES: 0 = plain stores, 1 = everywhere, unset = where the epilogue is exposed (few k-blocks per tile)
+  static const int paired_env = getenv("FRCNN_TC_PAIRED_STORES") ? atoi(getenv("FRCNN_TC_PAIRED_STORES")) : -1;
+  const int paired_stores = paired_env >= 0 ? paired_env : (p.total_kb <= 12 ? 1 : 0);
   grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
-           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, pair_late, g_tc_trace,
+           p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, pair_late, paired_stores, g_tc_trace,
            p.streamk, p.units, partial, reinterpret_cast<unsigned long long *>(ws + p.flags_off),
            0xF1A6000000000000ull | (++launch_serial & 0xFFFFFFFFFFFFull), a_exp, b_exp,
            (p.splits == 1 && mode != TC_WGRAD) ? reinterpret_cast<unsigned *>(amax_out) : nullptr, p.grid_max};

@@ -24,19 +24,21 @@ from . import ops
 
 
 class FusedSGD(t.optim.Optimizer):
-  """eager (EXPERIMENT, off by default; FRCNN_EAGER_SGD=1): tensors of at least ``eager_min_numel`` elements (VGG-16: fc1, fc2 = 87 % of the
-  optimizer's bytes) are updated from a post-accumulate-grad hook on a side stream, as soon as their gradient exists, while the
-  tensor-pipe-bound convolution backward still runs on the compute stream -- the update is HBM-bound and its 256-thread / 32-register CTAs
-  fit beside a GEMM CTA.  ``step()`` then covers the remaining tensors and joins the side stream.  Same arithmetic, same result; only the
-  schedule differs.  Single-GPU only (with DataParallel the gradient is not final in the hook).  Unmeasured in round 1."""
+  """eager (default on; FRCNN_EAGER_SGD=0 turns it off): tensors of at least ``eager_min_numel`` elements (VGG-16: fc1, fc2 = 87 % of the
+  optimizer's bytes) are updated from a post-accumulate-grad hook on a side stream, as soon as their gradient exists, while the convolution
+  backward still runs on the compute stream -- the GEMM CTAs leave register room for the update kernel's 256-thread CTAs (conv_tc.cu), two
+  of which per SM measured best.  ``step()`` then covers the remaining tensors and joins the side stream.  Same arithmetic, same result
+  (tests/test_zz_experiments_gpu.py: bit-identical weights); only the schedule differs.  Single-GPU only (under DataParallel the gradient
+  is not final in the hook, and the update is skipped there).  Measured with the proposal chain on its own stream as well
+  (FasterRCNNModel.train_step): 5.325 -> 5.247 ms per step, two runs each on one box; either change alone is within noise."""
 
   def __init__(self, params, lr = 1e-3, momentum = 0.9, weight_decay = 0.0, eager = None, eager_min_numel = 1 << 23, eager_ctas_per_sm = None):
     super().__init__(params, dict(lr = lr, momentum = momentum, weight_decay = weight_decay))
     self.grad_scale = 1.0
     if eager is None:
-      eager = os.environ.get("FRCNN_EAGER_SGD", "0") not in ("", "0")
+      eager = os.environ.get("FRCNN_EAGER_SGD", "1") not in ("", "0")
     self.eager = bool(eager)
-    self.eager_ctas_per_sm = int(os.environ.get("FRCNN_EAGER_SGD_CTAS", "1")) if eager_ctas_per_sm is None else int(eager_ctas_per_sm)
+    self.eager_ctas_per_sm = int(os.environ.get("FRCNN_EAGER_SGD_CTAS", "2")) if eager_ctas_per_sm is None else int(eager_ctas_per_sm)
     self._side, self._eager_done, self._eager_hooks, self._group_of = None, set(), [], {}
     if self.eager:
       for group in self.param_groups:

@@ -544,3 +544,27 @@ def test_voc_dataset_with_device_anchor_kernels_matches_reference_golden(tmp_pat
                           anchor_valid_map = smp.anchor_valid_map, gt_rpn_map = t.from_numpy(smp.gt_rpn_map).unsqueeze(dim = 0).cuda(),
                           gt_rpn_object_indices = [smp.gt_rpn_object_indices], gt_rpn_background_indices = [smp.gt_rpn_background_indices], gt_boxes = [smp.gt_boxes])
   assert np.isfinite(loss.total) and loss.total > 0
+
+
+def test_device_feeder_delivers_every_step_its_own_inputs():
+  """datasets.feeder.DeviceFeeder (the end-to-end leg of bench.py): the copy of step i + 1 runs on the copy stream while step i computes;
+  every take() must return exactly the tensors submitted for that step, also when the host buffers are rewritten right after submit()
+  of the following step (two device slots, two pinned source buffers alternating as a loader would)."""
+  from fasterrcnn_b200.datasets.feeder import DeviceFeeder
+  dev = t.device("cuda", t.cuda.current_device())
+  feeder = DeviceFeeder(dev)
+  hosts = [(t.empty((1, 3, 64, 96)).pin_memory(), t.empty((1, 4, 6, 9, 6)).pin_memory()) for _ in range(2)]
+  burn = t.randn((2048, 2048), device = dev)
+  hosts[0][0].fill_(0.0); hosts[0][1].fill_(100.0)
+  feeder.submit(*hosts[0])
+  for step in range(6):
+    image, gmap = feeder.take()
+    nxt = hosts[(step + 1) % 2]
+    t.cuda.current_stream().synchronize()                    # (a loader refills a pinned buffer only after its previous copy has been consumed)
+    nxt[0].fill_(float(step + 1)); nxt[1].fill_(100.0 + step + 1)
+    feeder.submit(*nxt)
+    for _ in range(3):
+      burn = burn @ burn * 1e-3                              # compute-stream work the next copy overlaps with
+    assert float(image.min()) == float(image.max()) == float(step), (step, float(image.min()), float(image.max()))
+    assert float(gmap.min()) == float(gmap.max()) == 100.0 + step
+  assert DeviceFeeder.bytes_per_step(*hosts[0]) == (3 * 64 * 96 + 4 * 6 * 9 * 6) * 4

@@ -49,6 +49,33 @@ def main():
       ms = a.elapsed_time(e) / iters
       out.append(dict(shape = name, op = kind, ms = ms, tflops = gflop / ms))
       print("%-18s %-6s %8.3f ms  %6.1f TFLOP/s" % (name, kind, ms, gflop / ms), flush = True)
+  # the detector's fully connected layers on 128 RoIs: fc1 (25088 -> 4096) and fc2 (4096 -> 4096); wgrad writes 411 MB / 67 MB
+  for name, k, n in (("fc1 128x25088->4096", 25088, 4096), ("fc2 128x4096->4096", 4096, 4096)):
+    if only and only not in name:
+      continue
+    m = 128
+    x = t.randn((m, k), device = "cuda"); wt = t.randn((n, k), device = "cuda") * 0.01; dy = t.randn((m, n), device = "cuda")
+    y = t.empty((m, n), device = "cuda"); dx = t.empty((m, k), device = "cuda"); dw = t.empty((n, k), device = "cuda")
+    gflop = 2e-9 * m * k * n
+    ops.begin_step()
+    xs, ws, ds = ops.tf32_split(x), ops.tf32_split(wt), ops.tf32_split(dy)
+    geom = (m, 1, 1, k, n, 1, 1, 1, 0)
+    runs = {"fwd": lambda: ops._gemm(0, x, wt, y, geom, "probe", gflop, xs, ws),
+            "dgrad": lambda: ops._gemm(1, dy, wt, dx, geom, "probe", gflop, ds, ws),
+            "wgrad": lambda: ops._gemm(2, dy, x, dw, geom, "probe", gflop, ds, xs)}
+    for kind, fn in runs.items():
+      for _ in range(2 if iters > 1 else 0):
+        fn()
+      a, e = t.cuda.Event(enable_timing = True), t.cuda.Event(enable_timing = True)
+      a.record()
+      for _ in range(iters):
+        fn()
+      e.record()
+      t.cuda.synchronize()
+      ms = a.elapsed_time(e) / iters
+      hbm = (wt.numel() * 4 if kind != "wgrad" else dw.numel() * 4) / ms / 1e6
+      out.append(dict(shape = name, op = kind, ms = ms, tflops = gflop / ms, weight_side_GBs = hbm))
+      print("%-22s %-6s %8.3f ms  %6.1f TFLOP/s  %6.0f GB/s on the weight-sized operand" % (name, kind, ms, gflop / ms, hbm), flush = True)
   print(json.dumps(dict(pair = os.environ.get("FRCNN_TC_PAIR", "default"), rows = out)))
 
 
