@@ -666,8 +666,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (g.paired_stores) {
         // Full-sector stores.  A thread owns one output row, so a plain 128-bit store instruction touches 32 rows x 16 bytes: 32 half
         // sectors.  Lane pairs swap every other 4-column group (one shuffle per element) and then write 2 x 16 adjacent bytes of ONE row
-        // per instruction: every 32-byte sector is written whole, by one instruction.  (Worth it where the epilogue is not hidden: fc1's
-        // filter gradient -- 411 MB of output for 128 k-elements per tile.)
+        // per instruction: every 32-byte sector is written whole, by one instruction.  (Largest where the epilogue is not hidden -- fc1's
+        // filter gradient, 411 MB of output for 128 k-elements per tile: 0.188 -> 0.120 ms -- and never slower: profiles/r02_pair_ab.md.)
         const bool odd = lane & 1;
         float *base = raw ? partial : out;
         const unsigned long long own_off = valid ? (unsigned long long)row_off : ~0ull;
@@ -1089,9 +1089,8 @@ static int run_tc(int mode, const float *a, const float *b, float *out, const Ep
   const int mn_lbo = dbg_lbo ? dbg_lbo : (f16 ? 8192 : kAtomBytes), mn_sbo = dbg_sbo ? dbg_sbo : (f16 ? 1024 : 512), mn_kstep = dbg_kstep ? dbg_kstep : (f16 ? 2048 : 1024);
   static std::atomic<unsigned long long> launch_serial{0};
   static const int pair_late = !(getenv("FRCNN_TC_PAIR_TRIGGER") && getenv("FRCNN_TC_PAIR_TRIGGER")[0] == 'e');
-  // FRCNN_TC_PAIRED_STORES: 0 = plain stores, 1 = everywhere, unset = where the epilogue is exposed (few k-blocks per tile)
-  static const int paired_env = getenv("FRCNN_TC_PAIRED_STORES") ? atoi(getenv("FRCNN_TC_PAIRED_STORES")) : -1;
-  const int paired_stores = paired_env >= 0 ? paired_env : (p.total_kb <= 12 ? 1 : 0);
+  // FRCNN_TC_PAIRED_STORES=0: plain per-row stores (the A/B switch of profiles/r02_pair_ab.md; paired stores are equal or faster on every layer)
+  static const int paired_stores = getenv("FRCNN_TC_PAIRED_STORES") ? (atoi(getenv("FRCNN_TC_PAIRED_STORES")) != 0) : 1;
   grid = dim3(p.grid, 1, 1);
   TcGeom g{Cin, Cout, KH, KW, pad, p.H, p.W, p.N, p.tile_w, p.tile_h, p.tile_n, p.tiles_w, p.tiles_h, p.pw, p.ph, p.pn, p.patches_w, p.patches_h,
            p.kb_per_split, p.total_kb, p.splits, mn_lbo, mn_sbo, mn_kstep, p.m_tiles, p.n_tiles, p.items, p.m_pairs, pair_late, paired_stores, g_tc_trace,
