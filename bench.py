@@ -496,8 +496,9 @@ def run_ours(args, rank, local_rank, world):
   line = dict(metric = metric_name(args), value = value, unit = "images/s", n_gpus = world, steps = args.steps, warmup = max(args.warmup, 3), ms_per_step = ms_dev / args.steps,
               higher_is_better = True, scaling = "weak", vs_baseline = None, dtype = ENGINE_NOTES[engine_name][2], data = "synthetic",
               config = dict(workload = workload_name(args), image = "%dx3x600x1000" % args.batch, backbone = args.backbone, global_batch = world * args.batch, rois_per_image = rois,
-                            parallelism = ("dp%d (one process per GPU; per bucket ONE fused reduce-scatter + SGD + all-gather kernel over NVLink multimem, overlapped with the backward)" if fused
-                                           else "dp%d (one process per GPU, bucketed NCCL gradient all-reduce on the gradient arena, overlapped with the backward)") % world,
+                            parallelism = ("dp%%d (one process per GPU; per bucket ONE fused reduce-scatter + SGD + all-gather kernel over NVLink, exchange = %s, overlapped with the backward)" % step.optimizer.exchange if fused
+                                           else "dp%d (one process per GPU, bucketed NCCL gradient all-reduce on the gradient arena, overlapped with the backward)" if world > 1
+                                           else "dp%d (one process, one GPU: no gradient exchange)") % world,
                             dp_buckets = (len(step.optimizer.arena.buckets) if getattr(step.optimizer, "arena", None) is not None else 0),
                             engine = ENGINE_NOTES[engine_name][0],
                             sm_reserve = step.optimizer.sm_reserve,     # SMs the GEMMs leave to NCCL while reductions are in flight (FRCNN_DP_SM_RESERVE)

@@ -51,6 +51,7 @@ _SIGNATURES = {
   "frcnn_conv2d_wgrad_f16": (_i, [_vp] * 5 + _GEOM + [_vp, _sz, _vp]),
   "frcnn_conv2d_bwd_f16": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _GEOM + [_vp, _sz, _vp, _sz, _vp]),
   "frcnn_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
+  "frcnn_act_bwd_scale": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
   "frcnn_sigmoid_bwd": (_i, [_vp, _vp, _vp, _sz, _vp]),
   "frcnn_bias_grad_workspace_bytes": (_sz, [_sz, _i]),
   "frcnn_bias_grad": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _vp]),
@@ -62,6 +63,8 @@ _SIGNATURES = {
   "frcnn_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool2x2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+  "frcnn_subsample2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+  "frcnn_upsample2_zero": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_spatial_mean_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
   "frcnn_scale_rows": (_i, [_vp, _vp, _vp, _sz, _sz, _vp]),
   "frcnn_spatial_mean_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),

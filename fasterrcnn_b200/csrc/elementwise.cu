@@ -44,6 +44,27 @@ static int launch_transpose(const float *src, float *dst, int batch, int rows, i
 }
 
 // ---- relu backward / add / sgd ---------------------------------------------------------------
+// Backward of y = relu(conv * s[c] + shift[c] (+ residual)) (frozen BatchNorm as a per-channel epilogue factor, models/resnet.py:56-77):
+// dz = dy * (y > 0) is the gradient of the residual branch, dzs = dz * s[c] is what the convolution's dgrad / wgrad consume.  One pass
+// over (rows, C) row-major data; y == nullptr: no activation mask; dz == nullptr: only dzs is wanted.  C % 4 == 0.
+__global__ void act_bwd_scale_kernel(const float *__restrict__ dy, const float *__restrict__ y, const float *__restrict__ scale,
+                                     float *__restrict__ dz, float *__restrict__ dzs, size_t count4, int C4)
+{
+  pdl_enter();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count4; i += stride) {
+    float4 g = __ldg(reinterpret_cast<const float4 *>(dy) + i);
+    if (y) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(y) + i);
+      g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f;
+      g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    }
+    if (dz) reinterpret_cast<float4 *>(dz)[i] = g;
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + (i % C4));
+    reinterpret_cast<float4 *>(dzs)[i] = make_float4(__fmul_rn(g.x, sc.x), __fmul_rn(g.y, sc.y), __fmul_rn(g.z, sc.z), __fmul_rn(g.w, sc.w));
+  }
+}
+
 __global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz, size_t count)
 {
   pdl_enter();
@@ -377,6 +398,49 @@ __global__ void maxpool3x3s2_fwd_kernel(const float *__restrict__ x, float *__re
   }
 }
 
+// ---- stride-2 helpers (models/resnet.py:79-81,109-118: the 3x3 / 1x1 stride-2 convolutions of layer2-4) -----------------------------
+// A stride-2 convolution reads / produces every other pixel.  The tcgen05 engine is stride-1, so resnet.py runs
+//   1x1 s2:  conv1x1_s1(subsample2(x));   3x3 s2 pad 1:  subsample2(conv3x3_s1(x))
+// and, backwards, the stride-1 dgrad / wgrad on upsample2_zero(dy) -- the same sums of the same products as the strided form
+// (zeros contribute exact zeros).  V = floats per thread (4 when C % 4 == 0).
+template <int V>
+__global__ void subsample2_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int Ho, int Wo)
+{
+  pdl_enter();
+  const int Cv = C / V;
+  const size_t total = (size_t)N * Ho * Wo * Cv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cv);
+    size_t r = e / Cv;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const size_t src = ((((size_t)n * H + 2 * oh) * W + 2 * ow) * Cv + c) * V;
+    if (V == 4) *reinterpret_cast<float4 *>(y + e * 4) = __ldg(reinterpret_cast<const float4 *>(x + src));
+    else y[e] = __ldg(x + src);
+  }
+}
+
+// y (N, H, W, C) <- x (N, Ho, Wo, C): y[n, 2i, 2j, :] = x[n, i, j, :], every other pixel zero
+template <int V>
+__global__ void upsample2_zero_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, int Ho, int Wo)
+{
+  pdl_enter();
+  const int Cv = C / V;
+  const size_t total = (size_t)N * H * W * Cv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Cv);
+    size_t r = e / Cv;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const bool live = !((h | w) & 1);
+    const size_t src = ((((size_t)n * Ho + (h >> 1)) * Wo + (w >> 1)) * Cv + c) * V;
+    if (V == 4) *reinterpret_cast<float4 *>(y + e * 4) = live ? __ldg(reinterpret_cast<const float4 *>(x + src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else y[e] = live ? __ldg(x + src) : 0.f;
+  }
+}
+
 __global__ void spatial_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C)
 {
   pdl_enter();
@@ -431,6 +495,18 @@ int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, voi
   if (count == 0) return FRCNN_OK;
   launch(relu_bwd_kernel, elementwise_grid(count / 4 + 1, 256), 256, 0, as_stream(stream), dy, y, dz, count);
   FRCNN_CHECK_LAUNCH("relu_bwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_act_bwd_scale(const float *dy, const float *y, const float *scale, float *dz, float *dzs, size_t rows, int C, void *stream)
+{
+  FRCNN_REQUIRE(dy && scale && dzs && C > 0 && C % 4 == 0, "act_bwd_scale: bad argument (C must be a multiple of 4)");
+  FRCNN_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(dz) |
+                  reinterpret_cast<uintptr_t>(dzs)) & 15) == 0, "act_bwd_scale: pointers must be 16-byte aligned");
+  if (rows == 0) return FRCNN_OK;
+  const size_t count4 = rows * (size_t)(C / 4);
+  launch(act_bwd_scale_kernel, elementwise_grid(count4, 256), 256, 0, as_stream(stream), dy, y, scale, dz, dzs, count4, C / 4);
+  FRCNN_CHECK_LAUNCH("act_bwd_scale_kernel");
   return FRCNN_OK;
 }
 
@@ -654,6 +730,30 @@ int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C,
   size_t total = (size_t)N * Ho * Wo * C;
   launch(maxpool3x3s2_fwd_kernel, elementwise_grid(total, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
   FRCNN_CHECK_LAUNCH("maxpool3x3s2_fwd_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_subsample2(const float *x, float *y, int N, int H, int W, int C, void *stream)
+{
+  FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "subsample2: bad argument");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const bool v4 = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const size_t total = (size_t)N * Ho * Wo * C;
+  if (v4) launch(subsample2_kernel<4>, elementwise_grid(total / 4, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
+  else launch(subsample2_kernel<1>, elementwise_grid(total, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
+  FRCNN_CHECK_LAUNCH("subsample2_kernel");
+  return FRCNN_OK;
+}
+
+int frcnn_upsample2_zero(const float *x, float *y, int N, int H, int W, int C, void *stream)
+{
+  FRCNN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0, "upsample2_zero: bad argument");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const bool v4 = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const size_t total = (size_t)N * H * W * C;
+  if (v4) launch(upsample2_zero_kernel<4>, elementwise_grid(total / 4, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
+  else launch(upsample2_zero_kernel<1>, elementwise_grid(total, 256), 256, 0, as_stream(stream), x, y, N, H, W, C, Ho, Wo);
+  FRCNN_CHECK_LAUNCH("upsample2_zero_kernel");
   return FRCNN_OK;
 }
 

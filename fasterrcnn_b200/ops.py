@@ -228,6 +228,22 @@ def weight_split_buffer(param):
   return e
 
 
+def pin_split(x):
+  """Operand split of a long-lived tensor no optimizer updates (frozen filters: ResNet's conv1 / layer1, resnet.py:48-55): made once and kept until
+  the tensor's version, its address or the engine changes -- the same table the fused optimizer's carried splits live in, so
+  tf32_split() finds it.  In-place writes that bypass the version counter need invalidate_weight_splits(), as for any carried split."""
+  e = weight_split_buffer(x)
+  if e["version"] != x._version:
+    if _f16():
+      check(lib().frcnn_f16_split(ptr(x), x.numel(), ptr(e["buf"]), stream()), "frcnn_f16_split")
+      _lib.count(2)
+    else:
+      check(lib().frcnn_tf32_split(ptr(x), x.numel(), ptr(e["buf"]), stream()), "frcnn_tf32_split")
+      _lib.count()
+    e["version"] = x._version
+  return e["buf"]
+
+
 def invalidate_weight_splits(param = None):
   """Drops the carried operand split of `param` (or of every parameter): the next GEMM that reads it re-splits from the fp32 values.
   REQUIRED after any write to a parameter that bypasses torch's version counter -- ``p.data.copy_()`` / ``.data.normal_()``,

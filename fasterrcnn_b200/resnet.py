@@ -9,6 +9,7 @@ and ReLU are the epilogue too.  conv1 / bn1 / layer1 and every BN affine paramet
 requires_grad=False (resnet.py:48-55,96).  Parameter and buffer names equal torchvision's, so the
 reference's state dicts load unchanged.
 """
+import os
 from enum import Enum
 from math import ceil
 
@@ -52,48 +53,120 @@ class BNParams(nn.Module):
     return self._folded[1], self._folded[2]
 
 
-def _scale_rows(x, scale):
-  rows = x.shape[0]
-  out = t.empty_like(x)
-  check(lib().frcnn_scale_rows(ptr(x), ptr(scale), ptr(out), rows, x.numel() // rows, stream()), "frcnn_scale_rows")
-  _lib.count()
-  return out
+def _subsample2(x):
+  """x[:, :, ::2, ::2] of an NHWC tensor -- the pixels a stride-2 convolution keeps (frcnn_subsample2)."""
+  n, c, h, w = x.shape
+  y = t.empty((n, c, (h + 1) // 2, (w + 1) // 2), dtype = t.float32, device = x.device, memory_format = t.channels_last)
+  if y.numel() > 0:
+    check(lib().frcnn_subsample2(ptr(x), ptr(y), n, h, w, c, stream()), "frcnn_subsample2")
+    _lib.count()
+  ops._copy_amax_hint(x, y)                                    # a subset of x's values
+  return y
+
+
+def _upsample2_zero(x, h, w):
+  """The adjoint: an (n, c, h, w) NHWC tensor with x at the even pixels and zeros elsewhere (frcnn_upsample2_zero)."""
+  n, c = x.shape[0], x.shape[1]
+  assert x.shape[2] == (h + 1) // 2 and x.shape[3] == (w + 1) // 2
+  y = t.empty((n, c, h, w), dtype = t.float32, device = x.device, memory_format = t.channels_last)
+  if y.numel() > 0:
+    check(lib().frcnn_upsample2_zero(ptr(x), ptr(y), n, h, w, c, stream()), "frcnn_upsample2_zero")
+    _lib.count()
+  ops._copy_amax_hint(x, y)
+  return y
+
+
+def _strided_on_tensor_cores(x, w, stride, pad):
+  """The tcgen05 engine is stride-1.  The two stride-2 forms of a torchvision Bottleneck (resnet.py:79-81,109-118) are run on it as
+    1x1, stride 2         conv1x1_s1(x[::2, ::2])          -- same products, same count
+    3x3, stride 2, pad 1  conv3x3_s1(x)[::2, ::2]          -- 4x the products of three layers, still ~5x faster than the CUDA-core
+                                                              kernel they ran on (profiles/r02_resnet_launches.md)
+  and backwards as the stride-1 dgrad / wgrad of the zero-upsampled gradient (zeros add exact zeros: the sums are the strided form's).
+  FRCNN_RESNET_S2_TC=0 restores the CUDA-core strided kernels."""
+  if stride != 2 or os.environ.get("FRCNN_RESNET_S2_TC", "1") in ("", "0"):
+    return None
+  k = w.shape[2]
+  if k == 1 and pad == 0:
+    return "1x1"
+  if k == 3 and pad == 1 and w.shape[3] == 3:
+    return "3x3"
+  return None
+
+
+def _act_bwd_scale(dy, y, scale, want_dz):
+  """(dz, dzs) of frcnn_act_bwd_scale: dz = dy * (y > 0) (None unless want_dz), dzs = dz * scale[c]."""
+  n, c, h, w = dy.shape
+  dzs = t.empty_like(dy)
+  dz = t.empty_like(dy) if want_dz else None
+  if dy.numel() > 0:
+    check(lib().frcnn_act_bwd_scale(ptr(dy), ptr(y), ptr(scale), ptr(dz), ptr(dzs), n * h * w, c, stream()), "frcnn_act_bwd_scale")
+    _lib.count()
+  return dz, dzs
 
 
 class _ConvBNAct(t.autograd.Function):
-  """y = act(conv(x, w * s) + shift [+ residual]) with the frozen-BN factor s folded into the filter."""
+  """y = act(conv(x, w) * s + shift [+ residual]): the frozen BatchNorm is the GEMM's per-channel epilogue (factor s, offset shift), the
+  residual add and the ReLU too.  The filter the GEMM reads is the parameter itself, so the operand split the fused optimizer carries
+  with every weight (ops.weight_split_buffer) serves it, frozen filters keep theirs (ops.pin_split), and no scaled copy of the weights
+  is made per step.  Backward: one pass gives dz = dy * (y > 0) (the residual branch's gradient) and dz * s (the convolution's)."""
 
   @staticmethod
   def forward(ctx, x, w, scale, shift, residual, stride, pad, act):
     xp = ops.as_nhwc(x.detach())
     wp = ops._phys_filter(w.detach())
-    w_eff = _scale_rows(wp, scale)
+    if not w.requires_grad and wp.data_ptr() == w.data_ptr():
+      ops.pin_split(w)                                         # frozen filter (conv1, layer1): split once, not once per step
     res = ops.as_nhwc(residual.detach()) if residual is not None else None
-    y = ops.conv2d_fwd_raw(xp, w_eff, shift, stride, pad, act, residual = res, reuse_x = bool(ctx.needs_input_grad[1]))
-    ctx.stride, ctx.pad, ctx.act = stride, pad, act
+    want_dw = bool(ctx.needs_input_grad[1])
+    form = _strided_on_tensor_cores(xp, w, stride, pad)
+    ctx.x_shape = tuple(xp.shape)
+    if form == "1x1":
+      xp = _subsample2(xp)                                     # saved instead of x: the filter gradient reads the same pixels
+      y = ops.conv2d_fwd_raw(xp, wp, shift, 1, 0, act, scale = scale, residual = res, reuse_x = want_dw)
+    elif form == "3x3":
+      y = _subsample2(ops.conv2d_fwd_raw(xp, wp, shift, 1, 1, act, scale = scale, residual = res, reuse_x = want_dw))
+    else:
+      y = ops.conv2d_fwd_raw(xp, wp, shift, stride, pad, act, scale = scale, residual = res, reuse_x = want_dw)
+    ctx.stride, ctx.pad, ctx.act, ctx.form = stride, pad, act, form
     ctx.w_shape = tuple(w.shape)
+    ctx.w_key = id(w)
     ctx.has_residual = residual is not None
-    ctx.save_for_backward(xp, w_eff, scale, y)
+    ctx.save_for_backward(xp, wp, scale, y)
     return y
 
   @staticmethod
   def backward(ctx, dy):
-    xp, w_eff, scale, y = ctx.saved_tensors
+    xp, wp, scale, y = ctx.saved_tensors
     dy = ops.as_nhwc(dy)
-    if ctx.act == ops.ACT_RELU:
-      dz = t.empty_like(y)
-      check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
-      _lib.count()
+    want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    want_res = ctx.has_residual and ctx.needs_input_grad[4]
+    relu = ctx.act == ops.ACT_RELU
+    dz, dzs = _act_bwd_scale(dy, y if relu else None, scale, want_res and relu) if (want_dx or want_dw) else (None, None)
+    if want_res and dz is None:
+      if relu:                                                  # (only the residual branch needs a gradient)
+        dz = t.empty_like(y)
+        check(lib().frcnn_relu_bwd(ptr(dy), ptr(y), ptr(dz), y.numel(), stream()), "frcnn_relu_bwd")
+        _lib.count()
+      else:
+        dz = dy
+    dx = dw = None
+    if ctx.form == "1x1":
+      if want_dx:
+        dx = _upsample2_zero(ops.conv2d_dgrad_raw(dzs, wp, tuple(xp.shape), 1, 0, reuse_dy = want_dw), ctx.x_shape[2], ctx.x_shape[3])
+      if want_dw:
+        dw = ops.conv2d_wgrad_raw(dzs, xp, ctx.w_shape, 1, 0, w_key = ctx.w_key)
+    elif ctx.form == "3x3":
+      dz_full = _upsample2_zero(dzs, ctx.x_shape[2], ctx.x_shape[3]) if (want_dx or want_dw) else None
+      if want_dx:
+        dx = ops.conv2d_dgrad_raw(dz_full, wp, ctx.x_shape, 1, 1, reuse_dy = want_dw)
+      if want_dw:
+        dw = ops.conv2d_wgrad_raw(dz_full, xp, ctx.w_shape, 1, 1, w_key = ctx.w_key)
     else:
-      dz = dy
-    dx = dw = dres = None
-    if ctx.needs_input_grad[0]:
-      dx = ops.conv2d_dgrad_raw(dz, w_eff, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = ctx.needs_input_grad[1])
-    if ctx.needs_input_grad[1]:
-      dw = _scale_rows(ops.conv2d_wgrad_raw(dz, xp, ctx.w_shape, ctx.stride, ctx.pad), scale)
-    if ctx.has_residual and ctx.needs_input_grad[4]:
-      dres = dz
-    return dx, dw, None, None, dres, None, None, None
+      if want_dx:
+        dx = ops.conv2d_dgrad_raw(dzs, wp, tuple(xp.shape), ctx.stride, ctx.pad, reuse_dy = want_dw)
+      if want_dw:
+        dw = ops.conv2d_wgrad_raw(dzs, xp, ctx.w_shape, ctx.stride, ctx.pad, w_key = ctx.w_key)
+    return dx, dw, None, None, (dz if want_res else None), None, None, None
 
 
 def conv_bn_act(x, conv, bn, stride, pad, act, residual = None):

@@ -158,6 +158,10 @@ int frcnn_conv2d_bwd_f16(const float *dy, const float *y, int act, int pooled, c
 /* ---- elementwise / pooling pieces of the backward pass -------------------------------------
  * dz = dy * (y > 0)   (ReLU backward, models/vgg16.py:76-96 under autograd); in place allowed. */
 int frcnn_relu_bwd(const float *dy, const float *y, float *dz, size_t count, void *stream);
+/* Backward of y = relu(conv * s[c] + shift[c] (+ residual)) -- a frozen BatchNorm2d evaluated as the convolution's per-channel epilogue
+ * (models/resnet.py:56-77,100-107) -- over (rows, C) row-major data, C % 4 == 0:  dz = dy * (y > 0) (the residual branch's gradient;
+ * NULL = not wanted),  dzs = dz * s[c] (what dgrad / wgrad consume).  y == NULL: no activation. */
+int frcnn_act_bwd_scale(const float *dy, const float *y, const float *scale, float *dz, float *dzs, size_t rows, int C, void *stream);
 /* dbias[c] = sum over rows of dz[row, c]; workspace >= frcnn_bias_grad_workspace_bytes. */
 size_t frcnn_bias_grad_workspace_bytes(size_t rows, int C);
 int frcnn_bias_grad(const float *dz, float *dbias, size_t rows, int C, void *workspace, size_t workspace_bytes, void *stream);
@@ -182,6 +186,11 @@ int frcnn_maxpool2x2_fwd(const float *x, float *y, int N, int H, int W, int C, v
 int frcnn_maxpool2x2_relu_bwd(const float *dy, const float *x, float *dz, int N, int H, int W, int C, void *stream);
 /* 3x3 stride-2 pad-1 max pool (torchvision ResNet stem, models/resnet.py:42), NHWC. */
 int frcnn_maxpool3x3s2_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
+/* Stride-2 helpers for the stride-1 tensor-core engine (models/resnet.py:79-81,109-118: torchvision Bottleneck, stride on conv2 and on
+ * the 1x1 downsample), NHWC.  subsample2: y (N, ceil(H/2), ceil(W/2), C) = x[:, ::2, ::2, :] of x (N, H, W, C).  upsample2_zero: the
+ * adjoint -- y (N, H, W, C) gets x (N, ceil(H/2), ceil(W/2), C) at the even pixels and zeros elsewhere. */
+int frcnn_subsample2(const float *x, float *y, int N, int H, int W, int C, void *stream);
+int frcnn_upsample2_zero(const float *x, float *y, int N, int H, int W, int C, void *stream);
 /* y.mean(-1).mean(-1) of (N, H, W, C) -> (N, C) (models/resnet.py:117) and its gradient (HW = H*W). */
 int frcnn_spatial_mean_fwd(const float *x, float *y, int N, int H, int W, int C, void *stream);
 int frcnn_spatial_mean_bwd(const float *dy, float *dx, int N, int HW, int C, void *stream);

@@ -32,15 +32,31 @@ class Box:
     self.corners, self.class_index, self.class_name = corners, class_index, str(class_index)
 
 
-def _sample(rank):
+def _sample(rank, kind = "vgg16", hw = HW):
   gt = None if rank == 0 else [((60.0, 80.0, 300.0, 420.0), 3), ((200.0, 500.0, 560.0, 900.0), 12), ((20.0, 700.0, 180.0, 960.0), 9)]
-  return orc.synthetic_sample(HW, seed = 100 + rank, gt = gt)
+  if hw != HW and gt is not None:
+    gt = [(tuple(c * hw[0] / HW[0] if i % 2 == 0 else c * hw[1] / HW[1] for i, c in enumerate(b)), k) for b, k in gt]
+  return orc.synthetic_sample(hw, seed = 100 + rank, gt = gt, backbone = kind)
 
 
-def _oracle_reference(world, params):
+def _params_and_backbone(kind):
+  """(synthetic state dict, oracle backbone name, package backbone factory) for the two-rank tests."""
+  if kind == "vgg16":
+    import fasterrcnn_b200 as f
+    return orc.synth_params(orc.vgg16_param_shapes(), seed = 5, heads = "reference"), lambda: f.vgg16.VGG16Backbone(dropout_probability = 0.0)
+  from fasterrcnn_b200 import resnet
+  from oracle import resnet_oracle
+  params = orc.synth_params(resnet_oracle.param_shapes(kind), seed = 6, heads = "spread")
+  for k in params:
+    if k.endswith("bn3.weight"):
+      params[k] = params[k] * 0.3                      # as in tests/test_model_gpu.py: keeps the deep residual stack in range
+  return params, lambda: resnet.ResNetBackbone({"resnet50": resnet.Architecture.ResNet50, "resnet101": resnet.Architecture.ResNet101}[kind])
+
+
+def _oracle_reference(world, params, kind = "vgg16", hw = HW):
   """The oracle's data-parallel step: per-image train_step (no update) on every emulated rank's own RNG streams, SGD on the mean gradient."""
-  oracle = orc.OracleModel(params)
-  smps = [_sample(r) for r in range(world)]
+  oracle = orc.OracleModel(params, backbone = kind)
+  smps = [_sample(r, kind, hw) for r in range(world)]
   rng = []
   for r in range(world):
     random.seed(r); t.manual_seed(r)
@@ -65,7 +81,7 @@ def _oracle_reference(world, params):
   return oracle, summed, scale
 
 
-def _worker(rank, world, port, which, out):
+def _worker(rank, world, port, which, out, kind = "vgg16", hw = HW):
   import hashlib
   import torch.distributed as dist
   os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -74,9 +90,9 @@ def _worker(rank, world, port, which, out):
   import fasterrcnn_b200 as f
   from fasterrcnn_b200 import optim
   t.set_num_threads(max(1, min(16, (os.cpu_count() or 8) // world)))
-  params = orc.synth_params(orc.vgg16_param_shapes(), seed = 5, heads = "reference")
-  oracle, summed, scale = _oracle_reference(world, params)                         # every rank computes the same expectation
-  model = f.FasterRCNNModel(num_classes = 21, backbone = f.vgg16.VGG16Backbone(dropout_probability = 0.0), allow_edge_proposals = True)
+  params, make_backbone = _params_and_backbone(kind)
+  oracle, summed, scale = _oracle_reference(world, params, kind, hw)               # every rank computes the same expectation
+  model = f.FasterRCNNModel(num_classes = 21, backbone = make_backbone(), allow_edge_proposals = True)
   model.load_state_dict(params)
   model = model.cuda()
   named = list(model.named_parameters())
@@ -85,7 +101,7 @@ def _worker(rank, world, port, which, out):
   else:
     optimizer = optim.NvlsShardedSGD(optim.optimizer_param_groups(model, 5e-4), lr = 1e-3, momentum = 0.9, named_params = named,
                                      exchange = {"nvls_multicast": "multicast", "nvls_peer": "peer", "nccl_sharded": "nccl"}[which])
-  smp = _sample(rank)
+  smp = _sample(rank, kind, hw)
   boxes = [Box(b, c) for b, c in zip(smp["gt_corners"], smp["gt_class_idxs"])]
   random.seed(rank); t.manual_seed(rank)
   for _ in range(STEPS):
@@ -139,3 +155,23 @@ def test_two_rank_step_matches_oracle_step_on_mean_gradient(which):
     assert r0["worst_summed_grad_rel_l2"] < 2e-2 and r1["worst_summed_grad_rel_l2"] < 2e-2
   if which == "nvls_multicast":
     assert r0["multicast"], "this box has NVSwitch multicast: the multimem path must be the one that ran"
+
+
+@pytest.mark.parametrize("which", ["nccl", "nvls_peer"])
+def test_two_rank_resnet50_step_matches_oracle_step_on_mean_gradient(which):
+  """The same check on a ResNet backbone (BASELINE config 4's data-parallel path: frozen BatchNorm as the GEMM epilogue, stride-2
+  bottleneck convolutions on the tensor cores, filter gradients written straight into the gradient arena), ResNet-50 at 384x512."""
+  import torch.multiprocessing as mp
+  if t.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs (gpurun --gpus 2)")
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  mgr = mp.Manager(); out = mgr.dict()
+  mp.spawn(_worker, args = (2, port, which, out, "resnet50", (384, 512)), nprocs = 2, join = True)
+  r0, r1 = out[0], out[1]
+  _margins.record("dp2_resnet50_" + which, **{k: v for k, v in r0.items() if k not in ("digest", "hook_order")}, replicas_identical = r0["digest"] == r1["digest"],
+                  gradients_arrive_in_bucket_order = r0["hook_order"] == sorted(r0["hook_order"]))
+  assert r0["digest"] == r1["digest"]                                       # replicas bit-identical
+  assert r0["worst_weight_err_in_bars"] <= 1.0 and r1["worst_weight_err_in_bars"] <= 1.0, (r0, r1)
+  assert r0["bytes_reduced"] > 5e7                                          # the trainable filters of layer2-4 + heads crossed the wire
+  if which == "nccl":
+    assert r0["worst_summed_grad_rel_l2"] < 2e-2 and r1["worst_summed_grad_rel_l2"] < 2e-2

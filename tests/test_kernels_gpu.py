@@ -755,3 +755,67 @@ def test_two_heads_vs_torch(ops, m, k, n1, n2, act1):
       else:
         scale = max(float(want.abs().max()), 1e-6)
         assert float((got - want).abs().max()) <= 2e-5 * scale + 1e-6
+
+
+# ---------------------------------------------------------------- stride-2 convolutions of the ResNet bottlenecks on the tensor cores
+@pytest.mark.parametrize("n,h,w,c", [(1, 38, 63, 128), (3, 7, 7, 64), (2, 9, 12, 6), (1, 1, 1, 4)])
+def test_subsample2_upsample2_zero_bit_exact(ops, n, h, w, c):
+  """frcnn_subsample2 == x[:, :, ::2, ::2]; frcnn_upsample2_zero == its adjoint (odd extents, vector and scalar channel counts)."""
+  from fasterrcnn_b200 import resnet
+  g = t.Generator().manual_seed(5)
+  x = t.randn((n, c, h, w), generator = g).cuda().contiguous(memory_format = t.channels_last)
+  sub = resnet._subsample2(x)
+  assert sub.is_contiguous(memory_format = t.channels_last) or sub.numel() == sub.shape[1]
+  assert t.equal(sub, x[:, :, ::2, ::2])
+  up = resnet._upsample2_zero(sub, h, w)
+  want = t.zeros_like(x)
+  want[:, :, ::2, ::2] = x[:, :, ::2, ::2]
+  assert t.equal(up, want)
+
+
+S2_CASES = [
+  # k, n, h, w, cin, cout     (layer3.0 at 600x1000 scale, layer4.0 on 7x7 RoIs, odd maps)
+  (1, 1, 38, 63, 128, 256),
+  (3, 1, 38, 63, 128, 128),
+  (3, 6, 7, 7, 128, 128),
+  (1, 6, 7, 7, 128, 256),
+  (3, 1, 37, 61, 64, 64),
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES, ids = ["%dx%d_n%d_%dx%d_%d_%d" % (c[0], c[0], c[1], c[2], c[3], c[4], c[5]) for c in S2_CASES])
+def test_stride2_conv_bn_relu_vs_torch_fp64(ops, case, monkeypatch):
+  """resnet.conv_bn_act(stride = 2): the tensor-core forms (1x1 on the subsampled input; 3x3 at full resolution, subsampled; backward
+  through the zero-upsampled gradient) against torch's strided conv2d in fp64 -- output, dx, dw within 1e-5 of each tensor's scale --
+  and against the CUDA-core strided kernels they replace (FRCNN_RESNET_S2_TC=0) at the same bar."""
+  from fasterrcnn_b200 import resnet
+  k, n, h, w, cin, cout = case
+  pad = 1 if k == 3 else 0
+  g = t.Generator().manual_seed(11)
+  x = t.randn((n, cin, h, w), generator = g)
+  wt = t.randn((cout, cin, k, k), generator = g) * (2.0 / (cin * k * k)) ** 0.5
+  scale = t.rand((cout,), generator = g) + 0.5
+  shift = t.randn((cout,), generator = g) * 0.1
+  xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+  yr = F.relu(F.conv2d(xr, wr * scale.double()[:, None, None, None], shift.double(), stride = 2, padding = pad))
+  gy = t.randn(yr.shape, generator = g)
+  yr.backward(gy.double())
+
+  def run():
+    xc = x.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True)
+    wc = wt.cuda().contiguous(memory_format = t.channels_last).requires_grad_(True)
+    ops.begin_step()
+    y = resnet._ConvBNAct.apply(xc, wc, scale.cuda(), shift.cuda(), None, 2, pad, ops.ACT_RELU)
+    y.backward(gy.cuda())
+    return y.detach().cpu().double(), xc.grad.cpu().double(), wc.grad.cpu().double()
+
+  def close(a, b, what):
+    tol = 1e-5 * max(float(b.abs().max()), 1.0)
+    assert tuple(a.shape) == tuple(b.shape), what
+    assert float((a - b).abs().max()) <= tol, (what, float((a - b).abs().max()), tol)
+
+  y, dx, dw = run()
+  close(y, yr.detach(), "y"); close(dx, xr.grad, "dx"); close(dw, wr.grad, "dw")
+  monkeypatch.setenv("FRCNN_RESNET_S2_TC", "0")
+  y0, dx0, dw0 = run()
+  close(y0, yr.detach(), "y simt"); close(dx0, xr.grad, "dx simt"); close(dw0, wr.grad, "dw simt")
