@@ -256,3 +256,33 @@ def test_math_utils_host_helpers_equal_the_reference_bit_for_bit():
     if ref is not None:
       assert np.array_equal(got, ref.intersection_over_union(b1, b2))
       assert np.array_equal(boxes, ref.convert_deltas_to_boxes(deltas, anchors, means, stds))
+
+
+def test_resnet_frozen_bn_fold_and_stride2_form_selection(monkeypatch):
+  """Host logic of resnet._ConvBNAct: (1) the frozen-BN fold equals BatchNorm2d.eval()'s affine map and is cached until a tensor changes
+  (resnet.py:56-77: gamma / sqrt(var + eps), beta - mean * that); (2) which tensor-core form a strided convolution takes."""
+  from fasterrcnn_b200 import resnet
+  g = t.Generator().manual_seed(3)
+  bn = resnet.BNParams(16)
+  ref = t.nn.BatchNorm2d(16).eval()
+  with t.no_grad():
+    for name in ("weight", "bias", "running_mean"):
+      v = t.randn((16,), generator = g)
+      getattr(bn, name).copy_(v); getattr(ref, name).copy_(v)
+    v = t.rand((16,), generator = g) + 0.5
+    bn.running_var.copy_(v); ref.running_var.copy_(v)
+  x = t.randn((2, 16, 5, 7), generator = g)
+  scale, shift = bn.folded()
+  np.testing.assert_allclose((x * scale[None, :, None, None] + shift[None, :, None, None]).numpy(), ref(x).detach().numpy(), rtol = 1e-5, atol = 1e-6)
+  assert bn.folded()[0] is scale                                  # cached
+  with t.no_grad():
+    bn.weight.mul_(2.0)                                           # a version bump (what load_state_dict does) refolds
+  assert bn.folded()[0] is not scale and t.allclose(bn.folded()[0], 2.0 * scale)
+
+  w1, w3, w7 = t.empty((8, 4, 1, 1)), t.empty((8, 4, 3, 3)), t.empty((8, 3, 7, 7))
+  assert resnet._strided_on_tensor_cores(None, w1, 2, 0) == "1x1"      # downsample: conv1x1(x[::2, ::2])
+  assert resnet._strided_on_tensor_cores(None, w3, 2, 1) == "3x3"      # conv2: conv3x3(x)[::2, ::2]
+  assert resnet._strided_on_tensor_cores(None, w3, 1, 1) is None       # stride 1: the engine's own geometry
+  assert resnet._strided_on_tensor_cores(None, w7, 2, 3) is None       # the frozen 7x7 stem stays on the CUDA-core engine
+  monkeypatch.setenv("FRCNN_RESNET_S2_TC", "0")
+  assert resnet._strided_on_tensor_cores(None, w3, 2, 1) is None
