@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round 2, call 14 (one GPU): who calls torch.cuda.is_available() 187 times per ResNet-101 train step (62 us each)?
+# Round 2, call 14 (one GPU): who calls torch.cuda.is_available() 187 times per ResNet-101 train step?  (Answer: torch._utils.
+# _get_available_device_type under autograd.Function.apply, ~5 us each -- the 0.8 s in the profile is the FIRST call, the driver's cuInit.)
 mkdir -p gpurun_out
 timeout 600 python -m cProfile -o /tmp/resnet101.prof bench.py --backbone resnet101 --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager --min-seconds 0 > gpurun_out/r02_c14_bench.log 2>&1
 echo "exit $?"
